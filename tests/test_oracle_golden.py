@@ -1,0 +1,124 @@
+"""Pin the oracle (oracle/fsnet_oracle.py) against outputs of the reference itself.
+
+The fixtures under tests/golden were produced by tests/golden/make_golden.py, which imports and runs
+/root/reference.  Tolerances: the oracle uses the same torch CPU kernels as the reference, so the
+agreement is to rounding (1e-5 relative); the B200 path is held to 1e-3 elsewhere.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsnet_oracle as O
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def checksum(data):
+    return np.array([float(v.double().sum()) for k, v in sorted(data.items(), key=lambda kv: str(kv[0]))])
+
+
+def rel(a, b):
+    a = (a.detach() if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))).double()
+    b = (b.detach() if isinstance(b, torch.Tensor) else torch.as_tensor(np.asarray(b))).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+LOSS_CASES = {
+    "loss_a": dict(topo=O.Topology(height=96, width=160, overlapped_mask=True), B=3, seed=11),
+    "loss_b": dict(topo=O.Topology(height=64, width=96, overlapped_mask=False, scales=(0, 2)), B=2, seed=12, with_mask=False),
+    "loss_c": dict(topo=O.Topology(height=64, width=128, overlapped_mask=True), B=2, seed=13, mask_dtype=torch.float32,
+                   depth_lo=0.6, depth_hi=6.0),
+    "loss_mm": dict(topo=O.Topology(height=64, width=96, overlapped_mask=True, scales=(0, 1)), B=2, seed=14, motion_mask=True),
+}
+
+
+def build_loss_case(topo, B, seed, mask_dtype=torch.float64, with_mask=True, motion_mask=False, depth_lo=2.0, depth_hi=40.0):
+    data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype)
+    if not with_mask:
+        del data["patched_mask"]
+    outputs = O.synthetic_depth_outputs(B, topo.height, topo.width, topo.scales, seed + 1, depth_lo, depth_hi,
+                                        topo.min_depth, topo.max_depth)
+    if motion_mask:
+        data["motion_mask"] = O.synthetic_motion_mask(B, topo.height, topo.width, seed + 2)
+    noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+    return data, outputs, noise
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_CASES))
+def test_loss_chain_matches_reference(golden_dir, name):
+    g = load(golden_dir, name)
+    case = LOSS_CASES[name]
+    topo = case["topo"]
+    data, outputs, noise = build_loss_case(**case)
+    np.testing.assert_allclose(checksum(data), g["input_checksum"], rtol=1e-12)
+    for v in outputs.values():
+        v.requires_grad_(True)
+    cam_T = {f: data[("relative_pose", f)].clone().requires_grad_(True) for f in topo.frame_ids[1:]}
+    ret = O.loss_chain(outputs, data, cam_T, topo, noise, keep=True)
+    ret["loss"].backward()
+    assert abs(float(ret["loss"].detach()) - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    for k, v in ret["loss_dict"].items():
+        assert abs(float(v) - float(g["loss_dict/" + k])) <= 1e-5 * abs(float(g["loss_dict/" + k])) + 1e-12, k
+    for s in topo.scales:
+        assert rel(outputs[("depth", s, s)].grad, g[f"grad_depth/{s}"]) < 1e-4, s
+        assert rel(outputs[("disp", s)].grad, g[f"grad_disp/{s}"]) < 1e-4, s
+    for f in topo.frame_ids[1:]:
+        assert rel(cam_T[f].grad, g[f"grad_T/{f}"]) < 1e-4, f
+    if "loss_mask_0" in g.files and "motion_mask" not in data:
+        mine = np.packbits((ret["aux"][("idxs", 0)] >= 2)[0:1].unsqueeze(1).numpy().astype(np.uint8))
+        assert np.array_equal(mine, g["loss_mask_0"])
+
+
+FULL_CASES = {
+    "tiny4": dict(topo=O.Topology(height=64, width=128), B=2),
+    "cfg1": dict(topo=O.Topology(height=128, width=416, scales=(0,)), B=2),
+    "tiny_pose": dict(topo=O.Topology(height=64, width=128, posenet=True, overlapped_mask=False), B=2),
+    "tiny_sigmoid": dict(topo=O.Topology(height=64, width=96, multi_channel=False, n_bins=1, min_depth=0.1, scales=(0, 1, 2, 3)), B=2),
+    "tiny_r50": dict(topo=O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_CASES))
+def test_full_step_matches_reference(golden_dir, name):
+    g = load(golden_dir, name)
+    topo, B = FULL_CASES[name]["topo"], FULL_CASES[name]["B"]
+    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    np.testing.assert_allclose(checksum(data), g["input_checksum"], rtol=1e-12)
+    sd = O.make_state_dict(topo)
+    names = O.trainable(sd)
+    for k in names:
+        sd[k].requires_grad_(True)
+    noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+    ret = O.forward_train(sd, data, topo, noise)
+    assert (ret["loss"].dtype == torch.float64) == bool(g["loss_is_fp64"])
+    assert abs(float(ret["loss"].detach()) - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    for k, v in ret["loss_dict"].items():
+        assert abs(float(v) - float(g["loss_dict/" + k])) <= 1e-4 * abs(float(g["loss_dict/" + k])) + 1e-12, k
+    for s in topo.scales:
+        assert rel(ret["outputs"][("disp", s)], g[f"disp/{s}"]) < 1e-5
+        assert rel(ret["outputs"][("depth", s, s)], g[f"depth/{s}"]) < 1e-5
+    ret["loss"].backward()
+    gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    for k in names:
+        if k in gn:
+            mine = float(sd[k].grad.double().norm())
+            assert abs(mine - gn[k]) <= 2e-3 * gn[k] + 1e-9, (k, mine, gn[k])
+    for key in g.files:
+        if key.startswith("grad/"):
+            assert rel(sd[key[5:]].grad, g[key]) < 2e-3, key
+    if topo.posenet:
+        for f in topo.frame_ids[1:]:
+            assert rel(ret["cam_T"][f], g[f"cam_T_cam/{f}"]) < 1e-5
+    # eval-mode prediction; the train-mode forward above updated the running statistics once, as in the reference run
+    sd2 = O.make_state_dict(topo)
+    with torch.no_grad():
+        O.forward_train(sd2, data, topo, noise)
+        pred = O.forward_test(sd2, data, topo)
+    # the reference ran its train-mode forward on model2's backbone + decoder only (no PoseNet influence)
+    assert rel(pred["depth"], g["test_depth"]) < 1e-4
