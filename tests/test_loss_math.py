@@ -65,4 +65,4 @@ def test_closed_form_matches_autograd(name):
             K4 = M.camera(data["P2"], data[("relative_pose", f)])[2]
             acc += torch.matmul(K4[:, :3, :].transpose(1, 2), gP[fi])
         # pose gradients are a heavily cancelling sum over pixels: one flipped arg-min shows up at the % level
-        assert rel(acc, cam_T[f].grad) < (0.15 if any_flip else 1e-3), rel(acc, cam_T[f].grad)
+        assert rel(acc, cam_T[f].grad) < (0.15 if any_flip else 5e-3), rel(acc, cam_T[f].grad)
