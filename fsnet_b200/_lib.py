@@ -1,0 +1,94 @@
+"""ctypes binding of libfsnet_b200.so (C ABI declared in include/fsnet_b200.h).
+
+There is no CPU fallback: every call needs CUDA tensors and the built library; anything else raises.
+"""
+import ctypes
+import os
+import re
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfsnet_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fsnet_b200.h")
+
+_lock = threading.Lock()
+_lib = None
+launch_count = 0          # kernels' entry-point calls issued through this binding (bench.py reports it)
+
+
+class FsnetError(RuntimeError):
+    pass
+
+
+def declared_symbols():
+    """Entry points declared in the public header (used by the CPU-side ABI test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(fsnet_[a-z0-9_]+)\s*\(", text)))
+
+
+def load(build_if_missing=True):
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise FsnetError(f"{LIB_PATH} is missing: run `python -m fsnet_b200.build` (no CPU fallback exists)")
+            from . import build as _build
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.fsnet_last_error.restype = ctypes.c_char_p
+        lib.fsnet_abi_version.restype = ctypes.c_int
+        _lib = lib
+        return lib
+
+
+def _ptr(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    if isinstance(t, torch.Tensor):
+        if not t.is_cuda:
+            raise FsnetError("fsnet_b200 kernels take CUDA tensors only (there is no CPU path)")
+        if not t.is_contiguous():
+            raise FsnetError("fsnet_b200 kernels take contiguous tensors")
+        return ctypes.c_void_p(t.data_ptr())
+    raise TypeError(type(t))
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; tensors -> device pointers, ints/floats by value.
+    Python floats are passed as C float, ints as C int.  The current torch stream is appended."""
+    global launch_count
+    lib = load()
+    fn = getattr(lib, name)
+    cargs = []
+    for a in args:
+        if a is None or isinstance(a, torch.Tensor):
+            cargs.append(_ptr(a))
+        elif hasattr(a, "t") and isinstance(getattr(a, "t"), torch.Tensor):   # dense, non-'contiguous' (channels_last)
+            if not a.t.is_cuda:
+                raise FsnetError("fsnet_b200 kernels take CUDA tensors only (there is no CPU path)")
+            cargs.append(ctypes.c_void_p(a.t.data_ptr()))
+        elif isinstance(a, bool):
+            cargs.append(ctypes.c_int(int(a)))
+        elif isinstance(a, int):
+            cargs.append(ctypes.c_int(a))
+        elif isinstance(a, float):
+            cargs.append(ctypes.c_float(a))
+        elif isinstance(a, (ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t, ctypes.c_longlong, ctypes.c_double)):
+            cargs.append(a)
+        else:
+            raise TypeError(f"{name}: unsupported argument type {type(a)}")
+    cargs.append(stream_ptr())
+    rc = fn(*cargs)
+    launch_count += 1
+    if rc != 0:
+        raise FsnetError(f"{name} failed ({rc}): {lib.fsnet_last_error().decode()}")
+    return rc

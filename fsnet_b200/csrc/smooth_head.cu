@@ -1,0 +1,259 @@
+// Edge-aware disparity smoothness, the softmax-over-bins / sigmoid depth head and the loss finaliser.
+// Reference: monodepth_utils.py:168-181 + monodepth2_decoder.py:214-219,294-303 (smoothness),
+// depth_encoder.py:76-88,104-109,115-121 + monodepth_utils.py:8-24 (heads).
+#include "common.cuh"
+
+namespace fsnet {
+namespace {
+
+constexpr int TX = 32, TY = 8;     // low-resolution tile of one block
+
+// Loads the (TY+2) x (TX+2) halo tile of disparity and of the k x k box-averaged colour image
+// (== adaptive_avg_pool2d for H = h*k) into shared memory; out-of-range positions are clamped and
+// never used by the callers.
+__device__ __forceinline__ void load_tile(const float* __restrict__ disp, const float* __restrict__ img,
+                                          int b, int h, int w, int H, int W, int k, int ty0, int tx0,
+                                          float (&sd)[TY + 2][TX + 2], float (&sc)[3][TY + 2][TX + 2]) {
+  const float inv = 1.f / (float)(k * k);
+  for (int i = threadIdx.x; i < (TY + 2) * (TX + 2); i += blockDim.x) {
+    int ly = i / (TX + 2), lx = i % (TX + 2);
+    int y = min(max(ty0 + ly - 1, 0), h - 1), x = min(max(tx0 + lx - 1, 0), w - 1);
+    sd[ly][lx] = __ldg(disp + ((size_t)b * h + y) * w + x);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* base = img + (((size_t)b * 3 + c) * H + (size_t)y * k) * W + (size_t)x * k;
+      float s = 0.f;
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) s += __ldg(base + (size_t)dy * W + dx);
+      sc[c][ly][lx] = k == 1 ? s : s * inv;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float edge_weight(const float (&sc)[3][TY + 2][TX + 2], int y0, int x0, int y1, int x1) {
+  float g = fabsf(sc[0][y0][x0] - sc[0][y1][x1]) + fabsf(sc[1][y0][x0] - sc[1][y1][x1]) + fabsf(sc[2][y0][x0] - sc[2][y1][x1]);
+  return __expf(-g * (1.f / 3.f));
+}
+
+// sums[b] = { sum(disp), sum_x-edges w|d_i-d_j|, sum_y-edges w|d_i-d_j| }  (un-normalised disparity)
+__global__ void __launch_bounds__(TX * TY) smooth_fwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
+                                                             int h, int w, int H, int W, int k, double* __restrict__ sums) {
+  __shared__ float sd[TY + 2][TX + 2];
+  __shared__ float sc[3][TY + 2][TX + 2];
+  __shared__ float red[3][TX * TY / 32];
+  const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
+  load_tile(disp, img, b, h, w, H, W, k, ty0, tx0, sd, sc);
+  const int lx = threadIdx.x % TX + 1, ly = threadIdx.x / TX + 1;
+  const int x = tx0 + lx - 1, y = ty0 + ly - 1;
+  float s0 = 0.f, sx = 0.f, sy = 0.f;
+  if (x < w && y < h) {
+    float d = sd[ly][lx];
+    s0 = d;
+    if (x + 1 < w) sx = fabsf(d - sd[ly][lx + 1]) * edge_weight(sc, ly, lx, ly, lx + 1);
+    if (y + 1 < h) sy = fabsf(d - sd[ly + 1][lx]) * edge_weight(sc, ly, lx, ly + 1, lx);
+  }
+  s0 = warp_sum(s0); sx = warp_sum(sx); sy = warp_sum(sy);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s0; red[1][warp] = sx; red[2][warp] = sy; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int i = 0; i < TX * TY / 32; ++i) t += (double)red[threadIdx.x][i];
+    atomicAdd(sums + (size_t)b * 3 + threadIdx.x, t);
+  }
+}
+
+__global__ void smooth_finalize_kernel(const double* __restrict__ sums, int B, int h, int w, float weight, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double nx = (double)B * h * (w - 1), ny = (double)B * (h - 1) * w;
+  double acc = 0.0;
+  for (int b = 0; b < B; ++b) {
+    float mean = (float)(sums[b * 3] / ((double)h * w));
+    double m = (double)(mean + 1e-7f);
+    acc += (sums[b * 3 + 1] / nx + sums[b * 3 + 2] / ny) / m;
+  }
+  *out += acc * (double)weight;
+}
+
+__global__ void __launch_bounds__(TX * TY) smooth_bwd_kernel(const float* __restrict__ disp, const float* __restrict__ img,
+                                                             int B, int h, int w, int H, int W, int k, float weight,
+                                                             const double* __restrict__ sums, const float* __restrict__ gout,
+                                                             float* __restrict__ grad) {
+  __shared__ float sd[TY + 2][TX + 2];
+  __shared__ float sc[3][TY + 2][TX + 2];
+  const int b = blockIdx.z, ty0 = blockIdx.y * TY, tx0 = blockIdx.x * TX;
+  load_tile(disp, img, b, h, w, H, W, k, ty0, tx0, sd, sc);
+  const int lx = threadIdx.x % TX + 1, ly = threadIdx.x / TX + 1;
+  const int x = tx0 + lx - 1, y = ty0 + ly - 1;
+  if (x >= w || y >= h) return;
+  const double nx = (double)B * h * (w - 1), ny = (double)B * (h - 1) * w;
+  const float g = __ldg(gout) * weight;
+  const float cx = (float)((double)g / nx), cy = (float)((double)g / ny);
+  const float mean = (float)(sums[b * 3] / ((double)h * w));
+  const float m = mean + 1e-7f;
+  const float d = sd[ly][lx];
+  auto sgn = [](float v) { return (v > 0.f ? 1.f : 0.f) - (v < 0.f ? 1.f : 0.f); };
+  float gn = 0.f;      // d L / d normalised disparity at this pixel (times m)
+  if (x + 1 < w) gn += cx * sgn(d - sd[ly][lx + 1]) * edge_weight(sc, ly, lx, ly, lx + 1);
+  if (x > 0) gn -= cx * sgn(sd[ly][lx - 1] - d) * edge_weight(sc, ly, lx - 1, ly, lx);
+  if (y + 1 < h) gn += cy * sgn(d - sd[ly + 1][lx]) * edge_weight(sc, ly, lx, ly + 1, lx);
+  if (y > 0) gn -= cy * sgn(sd[ly - 1][lx] - d) * edge_weight(sc, ly - 1, lx, ly, lx);
+  // sum_i gnd_i d_i = g * (Sx/nx + Sy/ny) / m  -- each edge contributes coefficient * |d_i - d_j|
+  const double dot = (double)g * (sums[b * 3 + 1] / nx + sums[b * 3 + 2] / ny) / (double)m;
+  grad[((size_t)b * h + y) * w + x] = gn / m - (float)(dot / ((double)m * (double)h * w));
+}
+
+__global__ void depth_head_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ bins,
+                                      const float* __restrict__ scale, int B, int n, int hw, int channels_last,
+                                      int sigmoid_head, float min_depth, float max_depth,
+                                      float* __restrict__ depth, float* __restrict__ disp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * hw) return;
+  int b = (int)(i / hw);
+  size_t pix = i % hw;
+  const float sc = scale ? __ldg(scale + b) : 1.f;
+  const size_t base = channels_last ? i * n : (size_t)b * n * hw + pix;
+  const size_t cs = channels_last ? 1 : hw;
+  if (sigmoid_head) {
+    float l = __ldg(logits + base);
+    float s = 1.f / (1.f + __expf(-l));
+    disp[i] = s;
+    depth[i] = sc / (1.f / max_depth + (1.f / min_depth - 1.f / max_depth) * s);
+    return;
+  }
+  float se = 0.f, sb = 0.f;
+  for (int c = 0; c < n; ++c) {
+    float l = fminf(fmaxf(__ldg(logits + base + c * cs), -10.f), 10.f);
+    float e = __expf(l);
+    se += e;
+    sb = fmaf(e, __ldg(bins + c), sb);
+  }
+  float d = sb / se * sc;
+  const float mn = min_depth * sc, mx = max_depth * sc;
+  depth[i] = d;
+  disp[i] = (1.f / d - 1.f / mx) / (1.f / mn - 1.f / mx);
+}
+
+__global__ void depth_head_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ bins,
+                                      const float* __restrict__ scale, int B, int n, int hw, int channels_last,
+                                      int sigmoid_head, float min_depth, float max_depth,
+                                      const float* __restrict__ gdepth, const float* __restrict__ gdisp,
+                                      float* __restrict__ glogits) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * hw) return;
+  int b = (int)(i / hw);
+  size_t pix = i % hw;
+  const float sc = scale ? __ldg(scale + b) : 1.f;
+  const size_t base = channels_last ? i * n : (size_t)b * n * hw + pix;
+  const size_t cs = channels_last ? 1 : hw;
+  const float gd = gdepth ? __ldg(gdepth + i) : 0.f, gs = gdisp ? __ldg(gdisp + i) : 0.f;
+  if (sigmoid_head) {
+    float l = __ldg(logits + base);
+    float s = 1.f / (1.f + __expf(-l));
+    float span = 1.f / min_depth - 1.f / max_depth;
+    float raw = 1.f / (1.f / max_depth + span * s);
+    float g = gs + gd * (-raw * raw * span * sc);
+    glogits[base] = g * s * (1.f - s);
+    return;
+  }
+  float se = 0.f, sb = 0.f;
+  for (int c = 0; c < n; ++c) {
+    float l = fminf(fmaxf(__ldg(logits + base + c * cs), -10.f), 10.f);
+    float e = __expf(l);
+    se += e;
+    sb = fmaf(e, __ldg(bins + c), sb);
+  }
+  const float raw = sb / se;
+  const float d = raw * sc;
+  const float mn = min_depth * sc, mx = max_depth * sc;
+  const float g = (gd + gs * (-1.f / (d * d)) / (1.f / mn - 1.f / mx)) * sc;     // d L / d raw
+  const float rse = 1.f / se;
+  for (int c = 0; c < n; ++c) {
+    float lr = __ldg(logits + base + c * cs);
+    float l = fminf(fmaxf(lr, -10.f), 10.f);
+    float pc = __expf(l) * rse;
+    float live = (lr >= -10.f && lr <= 10.f) ? 1.f : 0.f;
+    glogits[base + c * cs] = g * pc * (__ldg(bins + c) - raw) * live;
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, int S, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double total = 0.0;
+  for (int s = 0; s < S; ++s) {
+    double ls = acc[4 * s] / (acc[4 * s + 1] + 1e-6) + acc[4 * s + 2];
+    out[s] = ls;
+    out[S + s] = acc[4 * s + 2];
+    total += ls;
+  }
+  out[2 * S] = total / (double)S;
+  out[2 * S + 1] = 0.0;
+}
+
+int smooth_check(const float* disp, const float* img, int B, int h, int w, int H, int W, const double* sums) {
+  FSNET_REQUIRE(disp && img && sums, "fsnet_smooth: null pointer");
+  FSNET_REQUIRE(B > 0 && h >= 2 && w >= 2 && H >= h && W >= w, "fsnet_smooth: bad shape");
+  FSNET_REQUIRE(H % h == 0 && W % w == 0 && H / h == W / w, "fsnet_smooth: image must be an integer multiple of the disparity (H=%d h=%d W=%d w=%d)", H, h, W, w);
+  return FSNET_OK;
+}
+
+}  // namespace
+}  // namespace fsnet
+
+using namespace fsnet;
+
+extern "C" int fsnet_smooth_fwd(const float* disp, const float* img, int B, int h, int w, int H, int W,
+                                float weight, double* sums, double* out, void* stream) {
+  int rc = smooth_check(disp, img, B, h, w, H, W, sums);
+  if (rc) return rc;
+  FSNET_REQUIRE(out, "fsnet_smooth_fwd: null output");
+  dim3 grid(ceil_div(w, TX), ceil_div(h, TY), B);
+  smooth_fwd_kernel<<<grid, TX * TY, 0, (cudaStream_t)stream>>>(disp, img, h, w, H, W, H / h, sums);
+  FSNET_LAUNCH_OK();
+  smooth_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, B, h, w, weight, out);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_smooth_bwd(const float* disp, const float* img, int B, int h, int w, int H, int W,
+                                float weight, double* sums, const float* gout, float* grad_disp, void* stream) {
+  int rc = smooth_check(disp, img, B, h, w, H, W, sums);
+  if (rc) return rc;
+  FSNET_REQUIRE(gout && grad_disp, "fsnet_smooth_bwd: null pointer");
+  dim3 grid(ceil_div(w, TX), ceil_div(h, TY), B);
+  smooth_bwd_kernel<<<grid, TX * TY, 0, (cudaStream_t)stream>>>(disp, img, B, h, w, H, W, H / h, weight, sums, gout, grad_disp);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_depth_head_fwd(const float* logits, const float* bins, const float* scale, int B, int n, int h, int w,
+                                    int channels_last, int sigmoid_head, float min_depth, float max_depth,
+                                    float* depth, float* disp, void* stream) {
+  FSNET_REQUIRE(logits && depth && disp && (sigmoid_head || bins), "fsnet_depth_head_fwd: null pointer");
+  FSNET_REQUIRE(B > 0 && n > 0 && h > 0 && w > 0 && (!sigmoid_head || n == 1), "fsnet_depth_head_fwd: bad shape");
+  size_t total = (size_t)B * h * w;
+  depth_head_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, bins, scale, B, n, h * w, channels_last, sigmoid_head, min_depth, max_depth, depth, disp);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* scale, int B, int n, int h, int w,
+                                    int channels_last, int sigmoid_head, float min_depth, float max_depth,
+                                    const float* grad_depth, const float* grad_disp, float* grad_logits, void* stream) {
+  FSNET_REQUIRE(logits && grad_logits && (sigmoid_head || bins), "fsnet_depth_head_bwd: null pointer");
+  FSNET_REQUIRE(B > 0 && n > 0 && h > 0 && w > 0 && (!sigmoid_head || n == 1), "fsnet_depth_head_bwd: bad shape");
+  size_t total = (size_t)B * h * w;
+  depth_head_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, bins, scale, B, n, h * w, channels_last, sigmoid_head, min_depth, max_depth, grad_depth, grad_disp, grad_logits);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_loss_finalize(const double* acc, int S, double* out, void* stream) {
+  FSNET_REQUIRE(acc && out && S > 0 && S <= 8, "fsnet_loss_finalize: bad arguments");
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, S, out);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}

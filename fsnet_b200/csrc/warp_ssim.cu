@@ -1,0 +1,705 @@
+// Fused photometric-reprojection loss for one scale: depth up-sample -> back-project -> project ->
+// bilinear border gather of both source frames -> nearest overlap-mask gather -> 3x3 reflect-padded
+// SSIM + L1 -> min over {identity, reprojection} x {+1,-1} -> patched-mask weighted sums; and its
+// backward by recomputation.  Replaces monodepth2_decoder.py:61-128,205-292 of the reference
+// (see include/fsnet_b200.h for the per-entry citations, tests/loss_math_ref.py for the derivation).
+//
+// Work decomposition ("marching warps"): one warp owns a strip of columns and walks down a chunk of
+// rows.  Lane l holds column x0+l-HALO; horizontal 3-tap sums take the neighbours' raw values with
+// warp shuffles, vertical 3-tap sums are rolling registers, so the 3x3 SSIM window never touches
+// shared memory and no block-level barrier exists.  The halo lanes/rows recompute the warp of the
+// reflected pixel, exactly what ReflectionPad2d(1) on the *warped* image means.
+#include "common.cuh"
+
+namespace fsnet {
+namespace {
+
+constexpr int kWarps = 4;                 // warps per block
+constexpr float k81C1 = 81.f * 1e-4f;     // 81 * 0.01^2   (sums instead of means: everything scaled by 9^2)
+constexpr float k81C2 = 81.f * 9e-4f;     // 81 * 0.03^2
+
+struct LossParams {
+  const float* depth; int hs, ws;
+  const float* tgt; const float* src0; const float* src1;
+  const void* mask; int mask_dtype;
+  const float* cam; const float* ident; const float* noise; const float* motion;
+  unsigned flags; int B, H, W;
+  double* accum; uint8_t* sel; float* pred0; float* ident_out;
+  const double* accum_in; const float* gout; float* grad_depth; float* grad_P;
+  int rows_per_item, n_strips, n_chunks;
+  float sy, sx;                           // (hs-1)/(H-1), (ws-1)/(W-1): align_corners=True scales
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  i = i < 0 ? -i : i;
+  i = i >= n ? 2 * n - 2 - i : i;
+  return min(max(i, 0), n - 1);
+}
+
+__device__ __forceinline__ const void* mask_dtype_ptr_add(const void* m, int dtype, size_t n) {
+  return reinterpret_cast<const char*>(m) + n * (dtype == FSNET_MASK_F64 ? 8 : 4);
+}
+__device__ __forceinline__ float load_mask(const void* m, int dtype, size_t i) {
+  if (dtype == FSNET_MASK_F64) return (float)__ldg(reinterpret_cast<const double*>(m) + i);
+  return __ldg(reinterpret_cast<const float*>(m) + i);
+}
+
+// align_corners=True bilinear read of the scale-s depth map at full-resolution pixel (y, x)
+struct UpW { int i0, i1; float l; };
+__device__ __forceinline__ UpW up_weights(int o, float scale, int n_in) {
+  UpW w;
+  float s = scale * (float)o;
+  w.i0 = min((int)s, n_in - 1);
+  w.i1 = w.i0 < n_in - 1 ? w.i0 + 1 : w.i0;
+  w.l = s - (float)w.i0;
+  return w;
+}
+__device__ __forceinline__ float depth_at(const float* d, int ws, const UpW& wy, const UpW& wx) {
+  const float* r0 = d + (size_t)wy.i0 * ws;
+  const float* r1 = d + (size_t)wy.i1 * ws;
+  float top = (1.f - wx.l) * __ldg(r0 + wx.i0) + wx.l * __ldg(r0 + wx.i1);
+  float bot = (1.f - wx.l) * __ldg(r1 + wx.i0) + wx.l * __ldg(r1 + wx.i1);
+  return (1.f - wy.l) * top + wy.l * bot;
+}
+
+struct Geo { float r[3]; float c[3]; };      // ray inv(K)(x,y,1) and camera point r*D
+__device__ __forceinline__ Geo geometry(const float* ik, float x, float y, float D) {
+  Geo g;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    g.r[i] = fmaf(ik[3 * i], x, fmaf(ik[3 * i + 1], y, ik[3 * i + 2]));
+    g.c[i] = g.r[i] * D;
+  }
+  return g;
+}
+
+// One source frame at one pixel.  GRAD=0: colour + validity.  GRAD=1: also d pred/d ix, d pred/d iy
+// (already zeroed where grid_sample's border clamp blocks the gradient) and d(u,v)/dD.
+template <int GRAD>
+struct Sample {
+  float pred[3];
+  bool valid;
+  float dix[GRAD ? 3 : 1], diy[GRAD ? 3 : 1];
+  float du, dv;                // d u / d D, d v / d D
+  float px, py, rz;            // projected point (x, y) and 1/(z+eps)
+};
+
+template <int GRAD>
+__device__ __forceinline__ Sample<GRAD> sample_frame(const float* __restrict__ src, const float* P, const Geo& g,
+                                                      const void* mask, int mask_dtype, bool want_valid,
+                                                      int H, int W) {
+  Sample<GRAD> o;
+  const size_t HW = (size_t)H * W;
+  float px = fmaf(P[0], g.c[0], fmaf(P[1], g.c[1], fmaf(P[2], g.c[2], P[3])));
+  float py = fmaf(P[4], g.c[0], fmaf(P[5], g.c[1], fmaf(P[6], g.c[2], P[7])));
+  float pz = fmaf(P[8], g.c[0], fmaf(P[9], g.c[1], fmaf(P[10], g.c[2], P[11])));
+  float rz = __frcp_rn(pz + 1e-7f);
+  float ix = px * rz, iy = py * rz;      // == grid_sample's un-normalised coordinate (align_corners=True)
+  const float xm = (float)(W - 1), ym = (float)(H - 1);
+  o.valid = true;
+  if (want_valid) {                       // nearest, zeros padding, "== 1" (monodepth2_decoder.py:113-116)
+    float xn = rintf(ix), yn = rintf(iy);
+    bool inb = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
+    o.valid = inb && (mask == nullptr || load_mask(mask, mask_dtype, (size_t)(int)yn * W + (int)xn) == 1.f);
+  }
+  float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);   // padding_mode='border'
+  float x0f = floorf(ixc), y0f = floorf(iyc);
+  float fx = ixc - x0f, fy = iyc - y0f;
+  int x0 = (int)x0f, y0 = (int)y0f;
+  int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float* r0 = src + (size_t)y0 * W;
+  const float* r1 = src + (size_t)y1 * W;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float nw = __ldg(r0 + c * HW + x0), ne = __ldg(r0 + c * HW + x1);
+    float sw = __ldg(r1 + c * HW + x0), se = __ldg(r1 + c * HW + x1);
+    float top = fmaf(fx, ne - nw, nw), bot = fmaf(fx, se - sw, sw);
+    o.pred[c] = fmaf(fy, bot - top, top);
+    if (GRAD) {
+      float dx_top = ne - nw, dx_bot = se - sw;
+      o.dix[c] = fmaf(fy, dx_bot - dx_top, dx_top);
+      o.diy[c] = bot - top;
+    }
+  }
+  o.px = px; o.py = py; o.rz = rz;
+  o.du = 0.f; o.dv = 0.f;
+  if (GRAD) {
+    // clip_coordinates_set_grad: zero gradient on and outside the border
+    bool mx = (ix > 0.f) && (ix < xm), my = (iy > 0.f) && (iy < ym);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o.dix[c] = mx ? o.dix[c] : 0.f;
+      o.diy[c] = my ? o.diy[c] : 0.f;
+    }
+    float ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
+    float ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
+    float az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
+    o.du = (ax - ix * az) * rz;          // (ax*z - px*az)/z^2
+    o.dv = (ay - iy * az) * rz;
+  }
+  return o;
+}
+
+// SSIM loss value of (x = pred, t = target) from the 3x3 SUMS (not means).
+__device__ __forceinline__ float ssim_sums(float Sx, float Sxx, float Sxt, float St, float Stt) {
+  float sxst = Sx * St;
+  float sq = fmaf(Sx, Sx, St * St);
+  float A1 = fmaf(2.f, sxst, k81C1);
+  float A2 = fmaf(18.f, Sxt, k81C2) - 2.f * sxst;
+  float B1 = sq + k81C1;
+  float B2 = fmaf(9.f, Sxx + Stt, k81C2) - sq;
+  return __saturatef(fmaf(-0.5f, __fdividef(A1 * A2, B1 * B2), 0.5f));
+}
+// value and partial derivatives with respect to Sx, Sxx, Sxt (tests/loss_math_ref.py::ssim_and_partials)
+__device__ __forceinline__ float ssim_sums_grad(float Sx, float Sxx, float Sxt, float St, float Stt,
+                                                float& dSx, float& dSxx, float& dSxt) {
+  float sxst = Sx * St;
+  float sq = fmaf(Sx, Sx, St * St);
+  float A1 = fmaf(2.f, sxst, k81C1);
+  float A2 = fmaf(18.f, Sxt, k81C2) - 2.f * sxst;
+  float B1 = sq + k81C1;
+  float B2 = fmaf(9.f, Sxx + Stt, k81C2) - sq;
+  float inv = __fdividef(1.f, B1 * B2);
+  float Q = A1 * A2 * inv;
+  float raw = fmaf(-0.5f, Q, 0.5f);
+  float live = (raw >= 0.f && raw <= 1.f) ? -0.5f : 0.f;
+  dSx = live * 2.f * inv * (St * (A2 - A1) - Q * Sx * (B2 - B1));
+  dSxx = live * (-9.f) * __fdividef(Q, B2);
+  dSxt = live * 18.f * A1 * inv;
+  return __saturatef(raw);
+}
+
+// horizontal 3-tap sums of the 24 SSIM moments from this lane's raw values and its two neighbours'
+// raw[0..2] = target, raw[3..5] = image 0, raw[6..8] = image 1
+__device__ __forceinline__ void hsum24(const float (&raw)[9], float (&h)[24]) {
+  float l[9], r[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    l[i] = __shfl_up_sync(0xffffffffu, raw[i], 1);
+    r[i] = __shfl_down_sync(0xffffffffu, raw[i], 1);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    h[c] = l[c] + raw[c] + r[c];                                           // St
+    h[3 + c] = fmaf(l[c], l[c], fmaf(raw[c], raw[c], r[c] * r[c]));        // Stt
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int j = 3 + 3 * k + c;
+      h[6 + 9 * k + c] = l[j] + raw[j] + r[j];                                       // Sx
+      h[6 + 9 * k + 3 + c] = fmaf(l[j], l[j], fmaf(raw[j], raw[j], r[j] * r[j]));    // Sxx
+      h[6 + 9 * k + 6 + c] = fmaf(l[j], l[c], fmaf(raw[j], raw[c], r[j] * r[c]));    // Sxt
+    }
+  }
+}
+
+struct Item { int b, y_begin, y_end, strip; };
+__device__ __forceinline__ bool decode_item(const LossParams& p, Item& it) {
+  int item = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (item >= p.B * p.n_strips * p.n_chunks) return false;
+  it.strip = item % p.n_strips;
+  int rest = item / p.n_strips;
+  int chunk = rest % p.n_chunks;
+  it.b = rest / p.n_chunks;
+  it.y_begin = chunk * p.rows_per_item;
+  it.y_end = min(it.y_begin + p.rows_per_item, p.H);
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward.  MODE 0: identity photometric map (pred_f := src_f at the same pixel, result stored);
+//           MODE 1: reprojection loss (pred_f := warped src_f, result reduced into accum).
+// Columns per warp: 30 (lanes 0 and 31 are the reflect / neighbour halo).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
+  __shared__ float s_cam[kWarps][42];
+  Item it;
+  if (!decode_item(p, it)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W;
+  const size_t HW = (size_t)H * W;
+  const int b = it.b;
+  const int x = it.strip * 30 + lane - 1;
+  const int xr = reflect_idx(x, W);
+  const bool out_lane = lane >= 1 && lane <= 30 && x < W;
+  const float* tgt = p.tgt + (size_t)b * 3 * HW;
+  const float* src0 = p.src0 + (size_t)b * 3 * HW;
+  const float* src1 = p.src1 + (size_t)b * 3 * HW;
+  const void* mask = p.mask;
+  const bool overlap = (p.flags & FSNET_FLAG_OVERLAP_MASK) != 0;
+  const bool use_ident = (p.flags & FSNET_FLAG_MOTION_MASK) == 0;
+
+  const float* ik = s_cam[warp];
+  UpW wx = {0, 0, 0.f};
+  const float* depth = nullptr;
+  if (MODE == 1) {
+    for (int i = lane; i < 42; i += 32) s_cam[warp][i] = __ldg(p.cam + (size_t)b * 42 + i);
+    __syncwarp();
+    wx = up_weights(xr, p.sx, p.ws);
+    depth = p.depth + (size_t)b * p.hs * p.ws;
+  }
+  const float* P0 = s_cam[warp] + 9;        // frame 0: inv(K) at [0,9), P at [9,21)
+  const float* P1 = s_cam[warp] + 21 + 9;   // frame 1: inv(K) at [21,30), P at [30,42)
+  const void* mask_b = mask ? mask_dtype_ptr_add(mask, p.mask_dtype, (size_t)b * HW) : nullptr;
+
+  float A1[24], A2[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { A1[i] = 0.f; A2[i] = 0.f; }
+  float l1_prev[2] = {0.f, 0.f};
+  bool valid_prev[2] = {true, true};
+  float acc_num = 0.f, acc_den = 0.f;
+
+  for (int yy = it.y_begin - 1; yy <= it.y_end; ++yy) {
+    const int yr = reflect_idx(yy, H);
+    float raw[9];
+    float l1[2];
+    bool valid[2] = {true, true};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) raw[c] = __ldg(tgt + c * HW + (size_t)yr * W + xr);
+    if (MODE == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        raw[3 + c] = __ldg(src0 + c * HW + (size_t)yr * W + xr);
+        raw[6 + c] = __ldg(src1 + c * HW + (size_t)yr * W + xr);
+      }
+    } else {
+      UpW wy = up_weights(yr, p.sy, p.hs);
+      float D = depth_at(depth, p.ws, wy, wx);
+      Geo g = geometry(ik, (float)xr, (float)yr, D);
+      Sample<0> s0 = sample_frame<0>(src0, P0, g, mask_b, p.mask_dtype, overlap, H, W);
+      Sample<0> s1 = sample_frame<0>(src1, P1, g, mask_b, p.mask_dtype, overlap, H, W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { raw[3 + c] = s0.pred[c]; raw[6 + c] = s1.pred[c]; }
+      valid[0] = s0.valid; valid[1] = s1.valid;
+      if (p.pred0 != nullptr && b == 0 && out_lane && yy >= it.y_begin && yy < it.y_end) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          p.pred0[c * HW + (size_t)yy * W + x] = s0.pred[c];
+          p.pred0[(3 + c) * HW + (size_t)yy * W + x] = s1.pred[c];
+        }
+      }
+    }
+    l1[0] = fabsf(raw[0] - raw[3]) + fabsf(raw[1] - raw[4]) + fabsf(raw[2] - raw[5]);
+    l1[1] = fabsf(raw[0] - raw[6]) + fabsf(raw[1] - raw[7]) + fabsf(raw[2] - raw[8]);
+
+    float h[24];
+    hsum24(raw, h);
+    if (yy >= it.y_begin + 1) {            // three rows in: centre row yc = yy - 1
+      const int yc = yy - 1;
+      float ph[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          s += ssim_sums(A2[6 + 9 * k + c] + h[6 + 9 * k + c], A2[6 + 9 * k + 3 + c] + h[6 + 9 * k + 3 + c],
+                         A2[6 + 9 * k + 6 + c] + h[6 + 9 * k + 6 + c], A2[c] + h[c], A2[3 + c] + h[3 + c]);
+        }
+        ph[k] = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_prev[k]);
+      }
+      if (out_lane) {
+        const size_t pix = (size_t)yc * W + x;
+        if (MODE == 0) {
+          p.ident_out[((size_t)b * 2 + 0) * HW + pix] = ph[0];
+          p.ident_out[((size_t)b * 2 + 1) * HW + pix] = ph[1];
+        } else {
+          if (overlap) {
+            ph[0] = valid_prev[0] ? ph[0] : 100.f;
+            ph[1] = valid_prev[1] ? ph[1] : 100.f;
+          }
+          float best;
+          int arg;
+          if (use_ident) {
+            float i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
+            float i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
+            if (p.noise) {
+              i0 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix), 1e-5f, i0);
+              i1 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix), 1e-5f, i1);
+            }
+            best = i0; arg = 0;
+            if (i1 < best) { best = i1; arg = 1; }
+            if (ph[0] < best) { best = ph[0]; arg = 2; }
+            if (ph[1] < best) { best = ph[1]; arg = 3; }
+          } else {
+            best = ph[0]; arg = 0;
+            if (ph[1] < best) { best = ph[1]; arg = 1; }
+          }
+          float m = mask ? load_mask(mask_b, p.mask_dtype, pix) : 1.f;
+          acc_num = fmaf(best, m, acc_num);
+          acc_den += m;
+          if (p.sel) p.sel[(size_t)b * HW + pix] = (uint8_t)arg;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { A2[i] = A1[i] + h[i]; A1[i] = h[i]; }
+    l1_prev[0] = l1[0]; l1_prev[1] = l1[1];
+    valid_prev[0] = valid[0]; valid_prev[1] = valid[1];
+  }
+  if (MODE == 1) {
+    double n = warp_sum((double)acc_num), d = warp_sum((double)acc_den);
+    if (lane == 0) {
+      atomicAdd(p.accum, n);
+      atomicAdd(p.accum + 1, d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward.  Columns per warp: 28 (two halo lanes each side: one for SSIM, one for its adjoint).
+// Pipeline per raw row yy: A) raw values + derivative bundle at row yy  B) SSIM partials and winner at
+// yc = yy-1  C) adjoint box filter -> d pred, chain to depth (and pose) at yq = yy-2.
+// POSE=1 additionally reduces d loss / d P (12 numbers per frame).
+// ------------------------------------------------------------------------------------------------
+template <int POSE>
+__global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
+  constexpr int NV = POSE ? 22 : 15;        // delayed values per pixel
+  __shared__ float s_cam[kWarps][42];
+  __shared__ float s_delay[kWarps][3][NV][32];
+  Item it;
+  if (!decode_item(p, it)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W;
+  const size_t HW = (size_t)H * W;
+  const int b = it.b;
+  const int x = it.strip * 28 + lane - 2;
+  const int xr = reflect_idx(x, W);
+  const bool x_in = x >= 0 && x < W;
+  const bool out_lane = lane >= 2 && lane <= 29 && x < W;
+  const float* tgt = p.tgt + (size_t)b * 3 * HW;
+  const float* src0 = p.src0 + (size_t)b * 3 * HW;
+  const float* src1 = p.src1 + (size_t)b * 3 * HW;
+  const bool overlap = (p.flags & FSNET_FLAG_OVERLAP_MASK) != 0;
+  const bool use_ident = (p.flags & FSNET_FLAG_MOTION_MASK) == 0;
+  const void* mask_b = p.mask ? mask_dtype_ptr_add(p.mask, p.mask_dtype, (size_t)b * HW) : nullptr;
+
+  for (int i = lane; i < 42; i += 32) s_cam[warp][i] = __ldg(p.cam + (size_t)b * 42 + i);
+  __syncwarp();
+  const float* ik = s_cam[warp];
+  const float* P0 = s_cam[warp] + 9;
+  const float* P1 = s_cam[warp] + 30;
+  const UpW wx = up_weights(xr, p.sx, p.ws);
+  const float* depth = p.depth + (size_t)b * p.hs * p.ws;
+  const bool full_res = (p.hs == H && p.ws == W);
+  // d total / d (min value at a pixel) = gout * mask / (sum(mask) + 1e-6)
+  const float gbase = (float)((double)__ldg(p.gout) / (__ldg(p.accum_in + 1) + 1e-6));
+
+  float A1[24], A2[24], B1[18], B2[18];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { A1[i] = 0.f; A2[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 18; ++i) { B1[i] = 0.f; B2[i] = 0.f; }
+  float l1_prev[2] = {0.f, 0.f};
+  bool valid_prev[2] = {true, true};
+  float gf_prev[2] = {0.f, 0.f};
+  float gP[POSE ? 24 : 1];
+#pragma unroll
+  for (int i = 0; i < (POSE ? 24 : 1); ++i) gP[i] = 0.f;
+
+  for (int yy = it.y_begin - 2; yy <= it.y_end + 1; ++yy) {
+    // ---- A: raw values at row yy (reflected / clamped) -------------------------------------------
+    const int yr = reflect_idx(yy, H);
+    float raw[9];
+    float l1[2];
+    bool valid[2];
+    {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) raw[c] = __ldg(tgt + c * HW + (size_t)yr * W + xr);
+      UpW wy = up_weights(yr, p.sy, p.hs);
+      float D = depth_at(depth, p.ws, wy, wx);
+      Geo g = geometry(ik, (float)xr, (float)yr, D);
+      Sample<1> s0 = sample_frame<1>(src0, P0, g, mask_b, p.mask_dtype, overlap, H, W);
+      Sample<1> s1 = sample_frame<1>(src1, P1, g, mask_b, p.mask_dtype, overlap, H, W);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { raw[3 + c] = s0.pred[c]; raw[6 + c] = s1.pred[c]; }
+      valid[0] = s0.valid; valid[1] = s1.valid;
+      float(*slot)[32] = s_delay[warp][(yy + 3) % 3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) slot[i][lane] = raw[i];
+      if (POSE) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          slot[9 + c][lane] = s0.dix[c];  slot[12 + c][lane] = s0.diy[c];
+          slot[15 + c][lane] = s1.dix[c]; slot[18 + c][lane] = s1.diy[c];
+        }
+        slot[21][lane] = D;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          slot[9 + c][lane] = fmaf(s0.dix[c], s0.du, s0.diy[c] * s0.dv);
+          slot[12 + c][lane] = fmaf(s1.dix[c], s1.du, s1.diy[c] * s1.dv);
+        }
+      }
+    }
+    l1[0] = fabsf(raw[0] - raw[3]) + fabsf(raw[1] - raw[4]) + fabsf(raw[2] - raw[5]);
+    l1[1] = fabsf(raw[0] - raw[6]) + fabsf(raw[1] - raw[7]) + fabsf(raw[2] - raw[8]);
+    float h[24];
+    hsum24(raw, h);
+
+    // ---- B: SSIM partials and arg-min at the centre row yc = yy - 1 ------------------------------
+    const int yc = yy - 1;
+    float w[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) w[i] = 0.f;
+    float gf[2] = {0.f, 0.f};
+    if (yy >= it.y_begin && yc >= 0 && yc < H && x_in && lane >= 1 && lane <= 30) {
+      float ph[2], da[2][3], db[2][3], dc[2][3];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          s += ssim_sums_grad(A2[6 + 9 * k + c] + h[6 + 9 * k + c], A2[6 + 9 * k + 3 + c] + h[6 + 9 * k + 3 + c],
+                              A2[6 + 9 * k + 6 + c] + h[6 + 9 * k + 6 + c], A2[c] + h[c], A2[3 + c] + h[3 + c],
+                              da[k][c], db[k][c], dc[k][c]);
+        }
+        ph[k] = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_prev[k]);
+        if (overlap && !valid_prev[k]) ph[k] = 100.f;
+      }
+      const size_t pix = (size_t)yc * W + x;
+      int win;                               // 0 / 1 = reprojection frame that wins, -1 = none
+      float gate = 1.f;
+      if (use_ident) {
+        float i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
+        float i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
+        if (p.noise) {
+          i0 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix), 1e-5f, i0);
+          i1 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix), 1e-5f, i1);
+        }
+        float best = fminf(i0, i1);
+        win = -1;
+        if (ph[0] < best) { best = ph[0]; win = 0; }
+        if (ph[1] < best) { win = 1; }
+      } else {
+        win = ph[1] < ph[0] ? 1 : 0;
+        gate = 1.f - __ldg(p.motion + (size_t)b * HW + pix);
+      }
+      if (win >= 0 && (!overlap || valid_prev[win])) {
+        float m = p.mask ? load_mask(mask_b, p.mask_dtype, pix) : 1.f;
+        float gv = gbase * m * gate;
+        float ws_ = (0.85f / 3.f) * gv;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (k == win) {
+            gf[k] = gv;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              w[9 * k + c] = ws_ * da[k][c];
+              w[9 * k + 3 + c] = ws_ * db[k][c];
+              w[9 * k + 6 + c] = ws_ * dc[k][c];
+            }
+          }
+        }
+      }
+    }
+    // ---- C: adjoint of the reflect-padded box filter, then the chain to depth at yq = yy - 2 -----
+    const int yq = yy - 2;
+    float G[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      float wl = __shfl_up_sync(0xffffffffu, w[i], 1);
+      float wr = __shfl_down_sync(0xffffffffu, w[i], 1);
+      float hw = wl + w[i] + wr;
+      if (x == 1) hw += wl;                  // column 0 reflects onto column 1
+      if (x == W - 2) hw += wr;              // column W-1 reflects onto column W-2
+      float gsum = B2[i] + hw;
+      if (yq == 1) gsum += B2[i] - B1[i];    // row 0 reflects onto row 1   (B2 - B1 = HW(row 0))
+      if (yq == H - 2) gsum += hw;           // row H-1 reflects onto row H-2
+      G[i] = gsum;
+      B2[i] = B1[i] + hw;
+      B1[i] = hw;
+    }
+    if (yq >= it.y_begin && yq < it.y_end && out_lane) {
+      float(*slot)[32] = s_delay[warp][(yq + 3) % 3];
+      float t[3], gD = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t[c] = slot[c][lane];
+      float gu[2] = {0.f, 0.f}, gv2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float pr = slot[3 + 3 * k + c][lane];
+          float d = t[c] - pr;
+          float sgn = (d > 0.f ? 1.f : 0.f) - (d < 0.f ? 1.f : 0.f);
+          float gp = fmaf(2.f * pr, G[9 * k + 3 + c], fmaf(t[c], G[9 * k + 6 + c], G[9 * k + c]));
+          gp = fmaf(-(0.15f / 3.f) * gf_prev[k], sgn, gp);
+          if (POSE) {
+            gu[k] = fmaf(gp, slot[9 + 6 * k + c][lane], gu[k]);
+            gv2[k] = fmaf(gp, slot[12 + 6 * k + c][lane], gv2[k]);
+          } else {
+            gD = fmaf(gp, slot[9 + 3 * k + c][lane], gD);
+          }
+        }
+      }
+      if (POSE) {
+        float D = slot[21][lane];
+        Geo g = geometry(ik, (float)x, (float)yq, D);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float* P = k == 0 ? P0 : P1;
+          float px = fmaf(P[0], g.c[0], fmaf(P[1], g.c[1], fmaf(P[2], g.c[2], P[3])));
+          float py = fmaf(P[4], g.c[0], fmaf(P[5], g.c[1], fmaf(P[6], g.c[2], P[7])));
+          float pz = fmaf(P[8], g.c[0], fmaf(P[9], g.c[1], fmaf(P[10], g.c[2], P[11])));
+          float rz = __frcp_rn(pz + 1e-7f);
+          float u = px * rz, v = py * rz;
+          float ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
+          float ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
+          float az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
+          gD = fmaf(gu[k], (ax - u * az) * rz, fmaf(gv2[k], (ay - v * az) * rz, gD));
+          float r0 = gu[k] * rz, r1 = gv2[k] * rz, r2 = -(gu[k] * u + gv2[k] * v) * rz;
+          float hh[4] = {g.c[0], g.c[1], g.c[2], 1.f};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gP[12 * k + j] = fmaf(r0, hh[j], gP[12 * k + j]);
+            gP[12 * k + 4 + j] = fmaf(r1, hh[j], gP[12 * k + 4 + j]);
+            gP[12 * k + 8 + j] = fmaf(r2, hh[j], gP[12 * k + 8 + j]);
+          }
+        }
+      }
+      float* gd = p.grad_depth + (size_t)b * p.hs * p.ws;
+      if (full_res) {
+        gd[(size_t)yq * W + x] = gD;
+      } else {                               // transposed align_corners=True bilinear up-sample
+        UpW wy = up_weights(yq, p.sy, p.hs);
+        UpW wxx = up_weights(x, p.sx, p.ws);
+        float a = gD * (1.f - wy.l), c2 = gD * wy.l;
+        atomicAdd(gd + (size_t)wy.i0 * p.ws + wxx.i0, a * (1.f - wxx.l));
+        atomicAdd(gd + (size_t)wy.i0 * p.ws + wxx.i1, a * wxx.l);
+        atomicAdd(gd + (size_t)wy.i1 * p.ws + wxx.i0, c2 * (1.f - wxx.l));
+        atomicAdd(gd + (size_t)wy.i1 * p.ws + wxx.i1, c2 * wxx.l);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { A2[i] = A1[i] + h[i]; A1[i] = h[i]; }
+    l1_prev[0] = l1[0]; l1_prev[1] = l1[1];
+    valid_prev[0] = valid[0]; valid_prev[1] = valid[1];
+    gf_prev[0] = gf[0]; gf_prev[1] = gf[1];
+  }
+  if (POSE) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+      float v = warp_sum(gP[i]);
+      if (lane == 0) atomicAdd(p.grad_P + (size_t)b * 24 + i, v);
+    }
+  }
+}
+
+__global__ void camera_setup_kernel(const float* __restrict__ P2, const float* __restrict__ T0,
+                                    const float* __restrict__ T1, int B, float* __restrict__ cam) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2) return;
+  int b = i >> 1, f = i & 1;
+  const float* K = P2 + (size_t)b * 12;      // rows of 4; K = P2[:3,:3]
+  const float* T = (f == 0 ? T0 : T1) + (size_t)b * 16;
+  float* o = cam + (size_t)i * 21;
+  double k[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) k[r][c] = (double)K[r * 4 + c];
+  double c00 = k[1][1] * k[2][2] - k[1][2] * k[2][1];
+  double c01 = k[1][2] * k[2][0] - k[1][0] * k[2][2];
+  double c02 = k[1][0] * k[2][1] - k[1][1] * k[2][0];
+  double det = k[0][0] * c00 + k[0][1] * c01 + k[0][2] * c02;
+  double id = 1.0 / det;
+  o[0] = (float)(c00 * id);
+  o[1] = (float)((k[0][2] * k[2][1] - k[0][1] * k[2][2]) * id);
+  o[2] = (float)((k[0][1] * k[1][2] - k[0][2] * k[1][1]) * id);
+  o[3] = (float)(c01 * id);
+  o[4] = (float)((k[0][0] * k[2][2] - k[0][2] * k[2][0]) * id);
+  o[5] = (float)((k[0][2] * k[1][0] - k[0][0] * k[1][2]) * id);
+  o[6] = (float)(c02 * id);
+  o[7] = (float)((k[0][1] * k[2][0] - k[0][0] * k[2][1]) * id);
+  o[8] = (float)((k[0][0] * k[1][1] - k[0][1] * k[1][0]) * id);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) {
+      float s = 0.f;
+      for (int j = 0; j < 3; ++j) s = fmaf(K[r * 4 + j], T[j * 4 + c], s);   // K[r][3] = 0 in the 4x4 embedding
+      o[9 + r * 4 + c] = s;
+    }
+}
+
+int plan(LossParams& p, int cols_per_warp) {
+  p.n_strips = ceil_div(p.W, cols_per_warp);
+  int rows = 32;
+  while (rows > 8 && (long)p.B * p.n_strips * ceil_div(p.H, rows) < 148L * 16) rows >>= 1;
+  p.rows_per_item = rows;
+  p.n_chunks = ceil_div(p.H, rows);
+  p.sy = p.H > 1 ? (float)(p.hs - 1) / (float)(p.H - 1) : 0.f;
+  p.sx = p.W > 1 ? (float)(p.ws - 1) / (float)(p.W - 1) : 0.f;
+  return ceil_div(p.B * p.n_strips * p.n_chunks, kWarps);
+}
+
+}  // namespace
+}  // namespace fsnet
+
+using namespace fsnet;
+
+extern "C" int fsnet_camera_setup(const float* P2, const float* T0, const float* T1, int B, float* cam, void* stream) {
+  FSNET_REQUIRE(P2 && T0 && T1 && cam && B > 0, "fsnet_camera_setup: bad arguments");
+  camera_setup_kernel<<<ceil_div(B * 2, 64), 64, 0, (cudaStream_t)stream>>>(P2, T0, T1, B, cam);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
+                                          int B, int H, int W, float* ident, void* stream) {
+  FSNET_REQUIRE(tgt && src0 && src1 && ident, "fsnet_identity_photometric: null pointer");
+  FSNET_REQUIRE(B > 0 && H >= 3 && W >= 3, "fsnet_identity_photometric: need B>0, H>=3, W>=3 (got %d,%d,%d)", B, H, W);
+  LossParams p = {};
+  p.tgt = tgt; p.src0 = src0; p.src1 = src1; p.B = B; p.H = H; p.W = W; p.hs = H; p.ws = W;
+  p.ident_out = ident;
+  int blocks = plan(p, 30);
+  loss_fwd_kernel<0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+static int check_common(const float* depth_s, int hs, int ws, const float* tgt, const float* src0, const float* src1,
+                        const void* mask, int mask_dtype, const float* cam, const float* ident, const float* motion,
+                        unsigned flags, int B, int H, int W) {
+  FSNET_REQUIRE(depth_s && tgt && src0 && src1 && cam, "fsnet_warp_ssim: null pointer");
+  FSNET_REQUIRE(B > 0 && H >= 3 && W >= 3 && hs >= 1 && ws >= 1 && hs <= H && ws <= W,
+                "fsnet_warp_ssim: bad shape B=%d H=%d W=%d hs=%d ws=%d", B, H, W, hs, ws);
+  FSNET_REQUIRE((mask == nullptr) == (mask_dtype == FSNET_MASK_NONE), "fsnet_warp_ssim: mask pointer / dtype mismatch");
+  FSNET_REQUIRE(mask_dtype >= 0 && mask_dtype <= 2, "fsnet_warp_ssim: unknown mask dtype %d", mask_dtype);
+  if (flags & FSNET_FLAG_MOTION_MASK) FSNET_REQUIRE(motion != nullptr, "fsnet_warp_ssim: motion-mask flag without a motion mask");
+  else FSNET_REQUIRE(ident != nullptr, "fsnet_warp_ssim: identity terms required (no motion mask)");
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* tgt, const float* src0,
+                                   const float* src1, const void* mask, int mask_dtype, const float* cam,
+                                   const float* ident, const float* noise, const float* motion, unsigned flags,
+                                   int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
+  int rc = check_common(depth_s, hs, ws, tgt, src0, src1, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
+  if (rc) return rc;
+  FSNET_REQUIRE(accum, "fsnet_warp_ssim_fwd: null accumulator");
+  LossParams p = {};
+  p.depth = depth_s; p.hs = hs; p.ws = ws; p.tgt = tgt; p.src0 = src0; p.src1 = src1;
+  p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
+  p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum = accum; p.sel = sel; p.pred0 = pred0;
+  int blocks = plan(p, 30);
+  loss_fwd_kernel<1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* tgt, const float* src0,
+                                   const float* src1, const void* mask, int mask_dtype, const float* cam,
+                                   const float* ident, const float* noise, const float* motion, unsigned flags,
+                                   int B, int H, int W, const double* accum, const float* gout,
+                                   float* grad_depth, float* grad_P, void* stream) {
+  int rc = check_common(depth_s, hs, ws, tgt, src0, src1, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
+  if (rc) return rc;
+  FSNET_REQUIRE(accum && gout && grad_depth, "fsnet_warp_ssim_bwd: null pointer");
+  LossParams p = {};
+  p.depth = depth_s; p.hs = hs; p.ws = ws; p.tgt = tgt; p.src0 = src0; p.src1 = src1;
+  p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
+  p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
+  p.grad_depth = grad_depth; p.grad_P = grad_P;
+  int blocks = plan(p, 28);
+  if (grad_P) loss_bwd_kernel<1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  else loss_bwd_kernel<0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}

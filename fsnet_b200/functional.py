@@ -1,0 +1,186 @@
+"""torch.autograd Functions over the fsnet_b200 C ABI (include/fsnet_b200.h).
+
+Every Function here launches hand-written CUDA kernels through ctypes; none has a CPU or PyTorch
+fallback.  Reference citations (file:line) are relative to the FSNet checkout.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+MASK_NONE, MASK_F32, MASK_F64 = 0, 1, 2
+FLAG_OVERLAP, FLAG_MOTION = 1, 2
+
+
+def _mask_dtype(mask: Optional[torch.Tensor]) -> int:
+    if mask is None:
+        return MASK_NONE
+    if mask.dtype == torch.float64:
+        return MASK_F64
+    if mask.dtype == torch.float32:
+        return MASK_F32
+    raise _lib.FsnetError(f"patched_mask must be float32 or float64, got {mask.dtype}")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _ReprojectionLoss(torch.autograd.Function):
+    """MonoDepth2Decoder.compute_total_reprojection_loss (monodepth2_decoder.py:205-304) as
+    camera set-up + identity terms + one fused kernel per scale + smoothness + finalise.
+
+    Inputs: S depth maps, S disparity maps, the two cam_T_cam matrices, then constants.
+    Output: (total [0-d], stats [2S+2] fp64 = loss/s, smooth_loss/s, total, 0).
+    """
+
+    @staticmethod
+    def forward(ctx, S: int, cfg: dict, *tensors):
+        depths = [_f32c(t) for t in tensors[:S]]
+        disps = [_f32c(t) for t in tensors[S:2 * S]]
+        T0, T1, P2, tgt, src0, src1, mask, motion = tensors[2 * S:2 * S + 8]
+        noise = tensors[2 * S + 8:]
+        dev = tgt.device
+        B, _, H, W = tgt.shape
+        tgt, src0, src1 = _f32c(tgt), _f32c(src0), _f32c(src1)
+        P2c, T0c, T1c = _f32c(P2), _f32c(T0), _f32c(T1)
+        mask_c = None if mask is None else mask.detach().contiguous()
+        mdt = _mask_dtype(mask_c)
+        flags = (FLAG_OVERLAP if cfg["overlapped_mask"] else 0) | (FLAG_MOTION if motion is not None else 0)
+        motion_c = None if motion is None else _f32c(motion)
+        noise_c = [None] * S if len(noise) == 0 else [_f32c(n) for n in noise]
+
+        cam = torch.empty(B, 2, 21, device=dev, dtype=torch.float32)
+        _lib.call("fsnet_camera_setup", P2c, T0c, T1c, B, cam)
+        ident = None
+        if motion is None:
+            ident = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
+            _lib.call("fsnet_identity_photometric", tgt, src0, src1, B, H, W, ident)
+        acc = torch.zeros(S, 4, device=dev, dtype=torch.float64)
+        sums = torch.zeros(S, B, 3, device=dev, dtype=torch.float64)
+        sel = pred0 = None
+        if cfg.get("log_image"):
+            sel = torch.empty(B, H, W, device=dev, dtype=torch.uint8)
+            pred0 = torch.empty(2, 3, H, W, device=dev, dtype=torch.float32)
+        for i, s in enumerate(cfg["scales"]):
+            hs, ws = depths[i].shape[-2:]
+            want_log = sel is not None and s == 0
+            _lib.call("fsnet_warp_ssim_fwd", depths[i], hs, ws, tgt, src0, src1, mask_c, mdt, cam, ident, noise_c[i],
+                      motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
+                      pred0 if want_log else None)
+            h, w = disps[i].shape[-2:]
+            _lib.call("fsnet_smooth_fwd", disps[i], tgt, B, h, w, H, W, float(cfg["smooth_weight"] / (2 ** s)), sums[i], acc[i, 2:])
+        stats = torch.empty(2 * S + 2, device=dev, dtype=torch.float64)
+        _lib.call("fsnet_loss_finalize", acc, S, stats)
+        ctx.S, ctx.cfg, ctx.flags, ctx.mdt = S, cfg, flags, mdt
+        ctx.shapes = (B, H, W)
+        ctx.need_pose = any(ctx.needs_input_grad[2 + 2 * S + j] for j in range(2))
+        ctx.save_for_backward(*depths, *disps, tgt, src0, src1, cam, P2c, acc, sums,
+                              *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
+                              *( [motion_c] if motion_c is not None else []), *[n for n in noise_c if n is not None])
+        ctx.has = (ident is not None, mask_c is not None, motion_c is not None, noise_c[0] is not None)
+        ctx.aux = (sel, pred0)
+        # the reference's loss is fp64 exactly when patched_mask is fp64
+        total = stats[2 * S] if mdt == MASK_F64 else stats[2 * S].float()
+        ctx.mark_non_differentiable(stats)
+        return total.clone(), stats
+
+    @staticmethod
+    def backward(ctx, g_total, _g_stats):
+        S, cfg = ctx.S, ctx.cfg
+        B, H, W = ctx.shapes
+        sv = list(ctx.saved_tensors)
+        depths, disps = sv[:S], sv[S:2 * S]
+        tgt, src0, src1, cam, P2c, acc, sums = sv[2 * S:2 * S + 7]
+        rest = sv[2 * S + 7:]
+        has_ident, has_mask, has_motion, has_noise = ctx.has
+        ident = rest.pop(0) if has_ident else None
+        mask_c = rest.pop(0) if has_mask else None
+        motion_c = rest.pop(0) if has_motion else None
+        noise_c = rest if has_noise else [None] * S
+        dev = tgt.device
+        gout = (g_total.detach().to(torch.float32) / S).reshape(1).contiguous()
+        g_depths, g_disps = [], []
+        gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
+        for i, s in enumerate(cfg["scales"]):
+            hs, ws = depths[i].shape[-2:]
+            full = (hs == H and ws == W)
+            gd = (torch.empty if full else torch.zeros)(depths[i].shape, device=dev, dtype=torch.float32)
+            _lib.call("fsnet_warp_ssim_bwd", depths[i], hs, ws, tgt, src0, src1, mask_c, ctx.mdt, cam, ident, noise_c[i],
+                      motion_c, _lib.ctypes.c_uint(ctx.flags), B, H, W, acc[i], gout, gd, gP)
+            g_depths.append(gd)
+            h, w = disps[i].shape[-2:]
+            gs = torch.empty(disps[i].shape, device=dev, dtype=torch.float32)
+            _lib.call("fsnet_smooth_bwd", disps[i], tgt, B, h, w, H, W, float(cfg["smooth_weight"] / (2 ** s)), sums[i], gout, gs)
+            g_disps.append(gs)
+        gT = [None, None]
+        if gP is not None:
+            # P = (K4 @ T)[:3]  =>  dL/dT = K4[:3,:]^T @ dL/dP      (Project3D, monodepth_utils.py:155)
+            K3 = torch.zeros(B, 3, 4, device=dev, dtype=torch.float32)
+            K3[:, :, :3] = P2c[:, :3, :3]
+            for f in range(2):
+                if ctx.needs_input_grad[2 + 2 * S + f]:
+                    gT[f] = torch.matmul(K3.transpose(1, 2), gP[:, f].reshape(B, 3, 4))
+        n_noise = S if has_noise else 0
+        return (None, None, *g_depths, *g_disps, gT[0], gT[1], None, None, None, None, None, None, *([None] * n_noise))
+
+
+def reprojection_loss(depths: Sequence[torch.Tensor], disps: Sequence[torch.Tensor], T0, T1, P2, tgt, src0, src1,
+                      mask=None, motion=None, noise: Optional[Sequence[torch.Tensor]] = None, *, scales, overlapped_mask: bool,
+                      smooth_weight: float = 1e-5, log_image: bool = False):
+    """Returns (total, stats, aux) -- see _ReprojectionLoss.  ``noise[i]`` are standard-normal draws
+    of shape [B,2,H,W] for scale i (monodepth2_decoder.py:258); None => no tie-break noise."""
+    S = len(scales)
+    cfg = dict(scales=list(scales), overlapped_mask=bool(overlapped_mask), smooth_weight=float(smooth_weight), log_image=log_image)
+    extra = [] if noise is None else list(noise)
+    total, stats = _ReprojectionLoss.apply(S, cfg, *depths, *disps, T0, T1, P2, tgt, src0, src1, mask, motion, *extra)
+    return total, stats
+
+
+class _DepthHead(torch.autograd.Function):
+    """softmax-over-bins -> depth -> disparity (depth_encoder.py:76-88,115-121) or the sigmoid head
+    (:104-109).  logits may be NCHW-contiguous or channels_last."""
+
+    @staticmethod
+    def forward(ctx, logits, bins, scale, sigmoid_head: bool, min_depth: float, max_depth: float):
+        B, n, h, w = logits.shape
+        cl = logits.is_contiguous(memory_format=torch.channels_last) and not logits.is_contiguous()
+        lg = logits.detach()
+        if not cl:
+            lg = lg.contiguous()
+        dev = logits.device
+        depth = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
+        disp = torch.empty(B, 1, h, w, device=dev, dtype=torch.float32)
+        sc = None if scale is None else _f32c(scale).reshape(B)
+        lib_args = (_RawPtr(lg), None if bins is None else _f32c(bins), sc, B, n, h, w, int(cl), int(sigmoid_head),
+                    float(min_depth), float(max_depth))
+        _lib.call("fsnet_depth_head_fwd", *lib_args, depth, disp)
+        ctx.save_for_backward(lg, bins, sc)
+        ctx.meta = (B, n, h, w, cl, sigmoid_head, min_depth, max_depth)
+        return depth, disp
+
+    @staticmethod
+    def backward(ctx, g_depth, g_disp):
+        lg, bins, sc = ctx.saved_tensors
+        B, n, h, w, cl, sig, mn, mx = ctx.meta
+        gl = torch.empty_like(lg)      # preserves the memory format
+        gd = None if g_depth is None else _f32c(g_depth)
+        gs = None if g_disp is None else _f32c(g_disp)
+        _lib.call("fsnet_depth_head_bwd", _RawPtr(lg), None if bins is None else _f32c(bins), sc, B, n, h, w, int(cl), int(sig),
+                  float(mn), float(mx), gd, gs, _RawPtr(gl))
+        return gl, None, None, None, None, None
+
+
+class _RawPtr:
+    """Wraps a tensor whose memory is dense but not torch-'contiguous' (channels_last)."""
+
+    def __init__(self, t):
+        self.t = t
+
+
+def depth_head(logits, bins, scale, sigmoid_head, min_depth, max_depth):
+    return _DepthHead.apply(logits, bins, scale, sigmoid_head, min_depth, max_depth)

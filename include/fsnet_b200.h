@@ -1,0 +1,144 @@
+/*
+ * fsnet_b200 -- C ABI of the B200-native FSNet training-step hot path.
+ *
+ * The reference (Owen-Liuyuxuan/FSNet) has NO native interface on this path: every operation below is
+ * a chain of stock PyTorch ops in Python.  Each entry point therefore cites the reference Python it
+ * replaces (file:line relative to the reference checkout); INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the caller owns every buffer
+ *     (the kernels never allocate);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns
+ *     without synchronising;
+ *   - return value: 0 on success, a negative fsnet_status otherwise; fsnet_last_error() gives text;
+ *   - the library is re-entrant; it keeps no mutable global state except the last-error string
+ *     (thread-local) and lazily cached function attributes / tensor-map driver entry point.
+ *   - images are fp32 NCHW as the reference's data dict delivers them;
+ *     network activations are fp32/bf16 NHWC.
+ */
+#ifndef FSNET_B200_H
+#define FSNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  FSNET_OK = 0,
+  FSNET_ERR_INVALID = -1,   /* bad argument (null pointer, non-positive size, unsupported shape) */
+  FSNET_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+  FSNET_ERR_UNSUPPORTED = -3
+} fsnet_status;
+
+/* mask element types for `patched_mask` (the reference delivers fp64) */
+#define FSNET_MASK_NONE 0
+#define FSNET_MASK_F32 1
+#define FSNET_MASK_F64 2
+
+/* flags of the fused reprojection kernels */
+#define FSNET_FLAG_OVERLAP_MASK 1u   /* overlapped_mask=True: nearest-sample patched_mask, invalid := 100 */
+#define FSNET_FLAG_MOTION_MASK 2u    /* 'motion_mask' branch: min over the two reprojections only   */
+
+int fsnet_abi_version(void);
+const char* fsnet_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * camera set-up.  Replaces the per-(scale, frame) host round trip of
+ * monodepth2_decoder.py:82-90 (P2.cpu().numpy(), np.linalg.pinv, .cuda()) and Project3D's
+ * P = (K @ T)[:, :3, :] (monodepth_utils.py:155).
+ *   P2   [B,3,4] fp32     T0, T1 [B,4,4] fp32 (cam_T_cam for frame_ids[1], frame_ids[2])
+ *   cam  [B,2,21] fp32 out: inv(K) row-major (9) followed by P row-major (12), per source frame
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_camera_setup(const float* P2, const float* T0, const float* T1, int B, float* cam, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * identity photometric terms: 0.85*mean_c SSIM(src_f, tgt) + 0.15*mean_c |tgt - src_f| for both
+ * source frames.  monodepth2_decoder.py:248-254 (+ :118-128, monodepth_utils.py:184-215).  They do
+ * not depend on the scale, so they are computed once per step.
+ *   tgt, src0, src1 [B,3,H,W] fp32        ident [B,2,H,W] fp32 out
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
+                               int B, int H, int W, float* ident, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused per-scale reprojection loss, forward.  One launch replaces, for one scale,
+ * _generate_images_pred (monodepth2_decoder.py:61-116: F.interpolate, BackprojectDepth,
+ * Project3D, two F.grid_sample per frame), compute_reprojection_loss for both frames (:118-128),
+ * the 100.0 overwrite (:231-235), the tie-break noise and 4-way min (:257-263), the patched-mask
+ * product and the two sums of :292.
+ *   depth_s [B,1,hs,ws]   tgt/src0/src1 [B,3,H,W]   mask [B,H,W] (mask_dtype) or NULL
+ *   cam     [B,2,21] from fsnet_camera_setup
+ *   ident   [B,2,H,W] from fsnet_identity_photometric (ignored with FSNET_FLAG_MOTION_MASK)
+ *   noise   [B,2,H,W] fp32 standard-normal draws (scaled by 1e-5 in the kernel) or NULL
+ *   motion  [B,H,W] fp32 motion mask (only with FSNET_FLAG_MOTION_MASK) or NULL
+ *   accum   [2] fp64, must be zeroed by the caller: accum[0] += sum(min * mask), accum[1] += sum(mask)
+ *   sel     [B,H,W] uint8 arg-min index (0,1 identity; 2,3 reprojection) or NULL
+ *   pred0   [2,3,H,W] fp32 warped sources of batch sample 0 (the reference's `hm` images) or NULL
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws,
+                        const float* tgt, const float* src0, const float* src1,
+                        const void* mask, int mask_dtype, const float* cam,
+                        const float* ident, const float* noise, const float* motion,
+                        unsigned flags, int B, int H, int W,
+                        double* accum, uint8_t* sel, float* pred0, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fused per-scale reprojection loss, backward (recomputes the forward; nothing is saved).
+ * Autograd of the same reference lines.  d loss / d depth_s and, if grad_P != NULL, d loss / d P
+ * (the pose path of MonoDepthMeta, monodepth2_model.py:42-43).
+ *   accum      the forward's [2] fp64 (accum[1] = sum(mask) is read)
+ *   gout       [1] fp32 device scalar: d L / d (this scale's photometric term), i.e. the incoming
+ *              gradient of the total loss divided by num_scales
+ *   grad_depth [B,1,hs,ws] fp32, must be zeroed by the caller when hs != H (scatter-add)
+ *   grad_P     [B,2,12] fp32, zeroed by the caller, or NULL
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws,
+                        const float* tgt, const float* src0, const float* src1,
+                        const void* mask, int mask_dtype, const float* cam,
+                        const float* ident, const float* noise, const float* motion,
+                        unsigned flags, int B, int H, int W,
+                        const double* accum, const float* gout,
+                        float* grad_depth, float* grad_P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * edge-aware smoothness on mean-normalised disparity (monodepth2_decoder.py:214-219,294-296,
+ * monodepth_utils.py:168-181), forward and backward.  `img` is original_image_0 at full resolution;
+ * the 2^s x 2^s box average (adaptive_avg_pool2d) is taken inside the kernel.
+ *   disp [B,1,h,w]  img [B,3,H,W] with H = h*k, W = w*k
+ *   sums [B,3] fp64 workspace, zeroed by the caller: per-sample sum(disp), then backward scratch
+ *   out  [1] fp64, zeroed by the caller: += weight * (mean|dx|e^-|dIx| + mean|dy|e^-|dIy|)
+ *   gout [1] fp32 device scalar (d L / d smooth term); grad_disp [B,1,h,w] fp32 out (overwritten)
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_smooth_fwd(const float* disp, const float* img, int B, int h, int w, int H, int W,
+                     float weight, double* sums, double* out, void* stream);
+int fsnet_smooth_bwd(const float* disp, const float* img, int B, int h, int w, int H, int W,
+                     float weight, double* sums, const float* gout, float* grad_disp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * softmax-over-depth-bins head (depth_encoder.py:76-88,115-121; monodepth_utils.py:19-24) and the
+ * sigmoid head (depth_encoder.py:104-109), forward and backward.
+ *   logits [B,n,h,w] fp32 NCHW (channel stride = h*w) or NHWC (channels_last != 0)
+ *   bins [n] fp32; scale [B] fp32 (fx/base_fx) or NULL; depth, disp [B,1,h,w] out
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_depth_head_fwd(const float* logits, const float* bins, const float* scale, int B, int n, int h, int w,
+                         int channels_last, int sigmoid_head, float min_depth, float max_depth,
+                         float* depth, float* disp, void* stream);
+int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* scale, int B, int n, int h, int w,
+                         int channels_last, int sigmoid_head, float min_depth, float max_depth,
+                         const float* grad_depth, const float* grad_disp, float* grad_logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * loss finalisation: turns the per-scale accumulators into the reference's loss_dict entries
+ * (monodepth2_decoder.py:292-303).  acc [S,4] fp64 = {num, den, smooth, unused} per scale.
+ *   out [2*S+2] fp64: loss/s (S), smooth_loss/s (S), total_loss, spare
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_loss_finalize(const double* acc, int S, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSNET_B200_H */

@@ -1,0 +1,135 @@
+"""GPU parity of the fused loss kernels (through the C ABI) against the oracle and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsnet_oracle as O
+from test_oracle_golden import LOSS_CASES, build_loss_case, rel, load
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda(d):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+def run_gpu_loss(topo, data, outputs, noise, need_pose=True):
+    from fsnet_b200 import functional as Fn
+    dev = "cuda"
+    S = len(topo.scales)
+    depths = [outputs[("depth", s, s)].detach().to(dev).requires_grad_(True) for s in topo.scales]
+    disps = [outputs[("disp", s)].detach().to(dev).requires_grad_(True) for s in topo.scales]
+    T = [data[("relative_pose", f)].to(dev).requires_grad_(need_pose) for f in topo.frame_ids[1:]]
+    mask = data["patched_mask"].to(dev) if "patched_mask" in data else None
+    motion = data["motion_mask"].to(dev) if "motion_mask" in data else None
+    nz = None if motion is not None else [noise[s].to(dev) for s in topo.scales]
+    total, stats = Fn.reprojection_loss(
+        depths, disps, T[0], T[1], data["P2"].to(dev), data[("original_image", 0)].to(dev),
+        data[("original_image", topo.frame_ids[1])].to(dev), data[("original_image", topo.frame_ids[2])].to(dev),
+        mask, motion, nz, scales=topo.scales, overlapped_mask=topo.overlapped_mask)
+    total.backward()
+    return total, stats, depths, disps, T
+
+
+@pytest.mark.parametrize("name", sorted(LOSS_CASES))
+def test_fused_loss_matches_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    case = LOSS_CASES[name]
+    topo = case["topo"]
+    data, outputs, noise = build_loss_case(**case)
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise)
+    S = len(topo.scales)
+    stats = stats.cpu()
+    # loss scalars: north_star tolerance 1e-3 relative; the kernels are far inside it
+    assert abs(float(total) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    assert (total.dtype == torch.float64) == ("patched_mask" in data and data["patched_mask"].dtype == torch.float64)
+    for i, s in enumerate(topo.scales):
+        assert abs(float(stats[i]) - float(g[f"loss_dict/loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/loss/{s}"])), s
+        assert abs(float(stats[S + i]) - float(g[f"loss_dict/smooth_loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/smooth_loss/{s}"])), s
+        assert rel(disps[i].grad.cpu(), g[f"grad_disp/{s}"]) < 1e-3, s
+        # depth gradients flip with near-tie arg-mins: 3e-2 bound, typically ~1e-3
+        e = rel(depths[i].grad.cpu(), g[f"grad_depth/{s}"])
+        assert e < 3e-2, (s, e)
+    for fi, f in enumerate(topo.frame_ids[1:]):
+        e = rel(T[fi].grad.cpu(), g[f"grad_T/{f}"])
+        assert e < 0.15, (f, e)
+
+
+def test_fused_loss_vs_oracle_cfg2_shape():
+    """Full cfg2 image size (B=2 to keep the CPU oracle in seconds), all four scales."""
+    topo = O.Topology(height=192, width=640)
+    data, outputs, noise = build_loss_case(topo, 2, 21)
+    for v in outputs.values():
+        v.requires_grad_(True)
+    cam_T = {f: data[("relative_pose", f)] for f in topo.frame_ids[1:]}
+    ref = O.loss_chain(outputs, data, cam_T, topo, noise, keep=True)
+    ref["loss"].backward()
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, need_pose=False)
+    assert abs(float(total) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
+    for i, s in enumerate(topo.scales):
+        assert rel(disps[i].grad.cpu(), outputs[("disp", s)].grad) < 1e-3
+        e = rel(depths[i].grad.cpu(), outputs[("depth", s, s)].grad)
+        assert e < 3e-2, (s, e)
+
+
+def test_selection_and_warped_image_outputs():
+    from fsnet_b200 import functional as Fn
+    topo = LOSS_CASES["loss_a"]["topo"]
+    data, outputs, noise = build_loss_case(**LOSS_CASES["loss_a"])
+    cam_T = {f: data[("relative_pose", f)] for f in topo.frame_ids[1:]}
+    ref = O.loss_chain(outputs, data, cam_T, topo, noise, keep=True)
+    dev = "cuda"
+    depths = [outputs[("depth", s, s)].to(dev) for s in topo.scales]
+    disps = [outputs[("disp", s)].to(dev) for s in topo.scales]
+    S = len(topo.scales)
+    cfg = dict(scales=list(topo.scales), overlapped_mask=True, smooth_weight=1e-5, log_image=True)
+    args = [data[("relative_pose", 1)].to(dev), data[("relative_pose", -1)].to(dev), data["P2"].to(dev),
+            data[("original_image", 0)].to(dev), data[("original_image", 1)].to(dev), data[("original_image", -1)].to(dev),
+            data["patched_mask"].to(dev), None] + [noise[s].to(dev) for s in topo.scales]
+    ctx_holder = {}
+
+    class Probe(Fn._ReprojectionLoss):
+        @staticmethod
+        def forward(ctx, *a):
+            out = Fn._ReprojectionLoss.forward(ctx, *a)
+            ctx_holder["aux"] = ctx.aux
+            return out
+    Probe.apply(S, cfg, *depths, *disps, *args)
+    sel, pred0 = ctx_holder["aux"]
+    flips = float((sel.cpu().long() != ref["aux"][("idxs", 0)]).float().mean())
+    assert flips < 2e-3, flips
+    assert rel(pred0[0].cpu(), ref["aux"][("warped", 0)][1][0]) < 1e-4
+    assert rel(pred0[1].cpu(), ref["aux"][("warped", 0)][-1][0]) < 1e-4
+
+
+def test_depth_head_matches_oracle():
+    from fsnet_b200 import functional as Fn
+    torch.manual_seed(3)
+    for n, cl, scale in ((16, False, False), (64, True, True), (16, True, False)):
+        topo = O.Topology(n_bins=n, base_fx=(40.0 if scale else None))
+        logits = (torch.randn(3, n, 24, 40) * 6).requires_grad_(True)
+        bins = O.depth_bins(topo)
+        sc = (torch.rand(3) + 0.5) if scale else None
+        d_ref, s_ref = O.gather_depth(logits, bins, topo, sc.reshape(-1, 1, 1, 1) if scale else 1)
+        gd, gs = torch.randn_like(d_ref), torch.randn_like(s_ref)
+        (d_ref * gd + s_ref * gs).sum().backward()
+        lg = logits.detach().cuda()
+        if cl:
+            lg = lg.contiguous(memory_format=torch.channels_last)
+        lg.requires_grad_(True)
+        d, s = Fn.depth_head(lg, bins.cuda(), None if sc is None else sc.cuda(), False, topo.min_depth, topo.max_depth)
+        (d * gd.cuda() + s * gs.cuda()).sum().backward()
+        assert rel(d.cpu(), d_ref) < 1e-5 and rel(s.cpu(), s_ref) < 1e-5
+        assert rel(lg.grad.cpu(), logits.grad) < 1e-4
+    # sigmoid head (DepthDecoder)
+    logits = torch.randn(2, 1, 16, 24).requires_grad_(True)
+    disp_ref = torch.sigmoid(logits)
+    depth_ref = 1 / (1 / 100.0 + (1 / 0.1 - 1 / 100.0) * disp_ref)
+    (depth_ref.sum() * 0.01 + disp_ref.sum()).backward()
+    lg = logits.detach().cuda().requires_grad_(True)
+    d, s = Fn.depth_head(lg, None, None, True, 0.1, 100.0)
+    (d.sum() * 0.01 + s.sum()).backward()
+    assert rel(d.cpu(), depth_ref) < 1e-5 and rel(s.cpu(), disp_ref) < 1e-5
+    assert rel(lg.grad.cpu(), logits.grad) < 1e-4
