@@ -1,0 +1,242 @@
+"""Benchmark of the FSNet training-step hot path (BASELINE.json metric: images/sec on 640x192 triplets).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: cfg2a (configs/kitti_wpose_synthetic.py: ResNet-18, 192x640, 4 scales, 16 bins, B=12 per
+GPU), one step = BaseTrainingHook.__call__ (zero_grad, forward, backward, clip, Adam).  `value` is
+measured with the batch resident in HBM; `e2e` includes the pinned-host -> device copy of every step's
+batch and a device -> host read of the loss.  `roofline` is the fused warp-SSIM forward kernel
+(algorithmic bytes of SURVEY.md 8(d) / CUDA-event time of its launches inside the timed steps).
+`--impl reference` times the CPU restatement of the reference (oracle/, pinned to the reference by
+tests/golden) on the host cores.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+B_PER_GPU, H, W = 12, 192, 640
+SCALES = (0, 1, 2, 3)
+CONFIG = os.path.join(REPO, "configs", "kitti_wpose_synthetic.py")
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def oracle_step_rate(batch, steps, warmup):
+    """The oracle's full training step on the host cores -> triplets/s."""
+    from oracle import fsnet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    topo = O.Topology(height=H, width=W, scales=SCALES)
+    trainer = O.OracleTrainer(topo, seed=123, lr=1e-4, clip=35.0)
+    times = []
+    for i in range(warmup + steps):
+        data = O.synthetic_batch(batch, H, W, seed=1234 + i)
+        noise = O.tie_break_noise(batch, H, W, SCALES, seed=i)
+        t0 = time.perf_counter()
+        trainer.step(data, noise)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = 4 if (args.steps + args.warmup) <= 12 else 2
+    rate, sec = oracle_step_rate(batch, args.steps, args.warmup)
+    cores = os.cpu_count() or 1
+    sample = f"B={batch} of {B_PER_GPU} triplets per step (192x640, ResNet-18, 4 scales), full step fwd+bwd+clip+Adam"
+    line = {
+        "impl": "reference", "metric": "images/sec (640x192 triplets), full training step", "value": rate, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2a kitti_wpose 192x640 R18 4-scale n=16 (CPU restatement of the reference, oracle/)", "batch": batch},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="fsnet_b200", choices=["fsnet_b200", "reference"])
+    ap.add_argument("--backend", default=os.environ.get("FSNET_CONV_BACKEND", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", init_method="env://")
+
+    from fsnet_b200 import _lib
+    from fsnet_b200.networks import ops
+    from fsnet_b200.data.synthetic import make_batch
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file, set_random_seed
+
+    if args.backend in ("auto", "tc"):
+        ops.set_backend("tc" if ops.tc_available() else "torch")
+    else:
+        ops.set_backend(args.backend)
+    torch.backends.cudnn.allow_tf32 = False          # interim library convs must also meet the 1e-3 parity bar
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = cfg_from_file(CONFIG)
+    set_random_seed(123)
+    model = build(**cfg.meta_arch)
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+        model = torch.nn.parallel.DistributedDataParallel(model.to(dev), device_ids=[local_rank], output_device=local_rank)
+    else:
+        model = model.to(dev)
+    model.train()
+    optimizer = build("vision_base.networks.optimizers.optimizers.build_optimizer", model, **cfg.optimizer)
+    hook = build(**cfg.trainer.training_hook)
+
+    host = make_batch(B_PER_GPU, H, W, seed=1234 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, use_host):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for i in range(n):
+            data = dict(pinned) if use_host else dict(resident)
+            out = hook(data, model, optimizer, None, None, i, 0)
+            if use_host:
+                last = out["loss"].item()            # device -> host read of the step's result
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, last
+
+    timed(args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_counters()
+    _lib.profile_entry("fsnet_warp_ssim_fwd", True)
+    ms, _ = timed(args.steps, False)
+    launches = _lib.kernel_launches
+    kern_us = _lib.profile_results("fsnet_warp_ssim_fwd")        # per-launch CUDA-event times (us), scale order
+    _lib.profile_entry("fsnet_warp_ssim_fwd", False)
+    clocks = sampler.stop() if rank == 0 else None
+    timed(2, True)
+    ms_e2e, last_loss = timed(args.steps, True)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    imgs = B_PER_GPU * world * args.steps
+    value = imgs / (ms / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+    peak, peak_src = peaks()
+    bytes_per_launch = sum(B_PER_GPU * H * W * (40 + 8 / 4 ** s) for s in SCALES) / len(SCALES)
+    avg_us = sum(kern_us) / max(len(kern_us), 1) if kern_us else float("nan")
+    achieved = bytes_per_launch / (avg_us * 1e-6) / 1e9 if kern_us else None
+    line = {
+        "metric": "images/sec (640x192 triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (convs: " + ops.precision_note() + ")", "data": "synthetic",
+        "config": {"workload": "cfg2a kitti_wpose_synthetic: ResNet-18 depth net, 192x640, 4 scales, 16 bins, dataset poses, "
+                               "fwd+bwd+clip(35)+Adam", "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
+                   "parallelism": f"dp{world}" + (" (DDP + SyncBN over NCCL)" if world > 1 else ""), "conv_backend": ops.BACKEND,
+                   "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
+        "roofline": {"kernel": "loss_fwd_kernel<1> (fused warp-SSIM forward, one launch per scale)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
+                     "algorithmic_bytes_per_launch": bytes_per_launch},
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sec = oracle_step_rate(4, 2, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/, torch CPU fp32)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -15,7 +15,30 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fsnet_b200.h")
 
 _lock = threading.Lock()
 _lib = None
-launch_count = 0          # kernels' entry-point calls issued through this binding (bench.py reports it)
+launch_count = 0          # entry-point calls issued through this binding
+kernel_launches = 0       # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
+KERNELS_PER_ENTRY = {"fsnet_smooth_fwd": 2}          # everything else launches exactly one kernel
+_profiled = {}            # entry name -> list of (start_event, end_event) while profiling is on
+
+
+def reset_counters():
+    global launch_count, kernel_launches
+    launch_count = 0
+    kernel_launches = 0
+
+
+def profile_entry(name, on=True):
+    """Bracket every call of `name` with CUDA events on the launching stream (bench.py's roofline leg)."""
+    if on:
+        _profiled[name] = []
+    else:
+        _profiled.pop(name, None)
+
+
+def profile_results(name):
+    """Per-launch durations in microseconds (synchronises)."""
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) * 1e3 for a, b in _profiled.get(name, [])]
 
 
 class FsnetError(RuntimeError):
@@ -65,7 +88,7 @@ def stream_ptr():
 def call(name, *args):
     """Invoke an int-returning entry point; tensors -> device pointers, ints/floats by value.
     Python floats are passed as C float, ints as C int.  The current torch stream is appended."""
-    global launch_count
+    global launch_count, kernel_launches
     lib = load()
     fn = getattr(lib, name)
     cargs = []
@@ -87,8 +110,17 @@ def call(name, *args):
         else:
             raise TypeError(f"{name}: unsupported argument type {type(a)}")
     cargs.append(stream_ptr())
-    rc = fn(*cargs)
+    rec = _profiled.get(name)
+    if rec is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*cargs)
+        ev1.record()
+        rec.append((ev0, ev1))
+    else:
+        rc = fn(*cargs)
     launch_count += 1
+    kernel_launches += KERNELS_PER_ENTRY.get(name, 1)
     if rc != 0:
         raise FsnetError(f"{name} failed ({rc}): {lib.fsnet_last_error().decode()}")
     return rc

@@ -35,7 +35,9 @@ class _ReprojectionLoss(torch.autograd.Function):
     camera set-up + identity terms + one fused kernel per scale + smoothness + finalise.
 
     Inputs: S depth maps, S disparity maps, the two cam_T_cam matrices, then constants.
-    Output: (total [0-d], stats [2S+2] fp64 = loss/s, smooth_loss/s, total, 0).
+    Output: (total [0-d], stats [2S+2] fp64 = loss/s, smooth_loss/s, total, 0, sel, pred0) with
+    sel [B,H,W] uint8 = arg-min index at scale 0 and pred0 [2,3,H,W] = warped sources of sample 0
+    (both empty unless cfg['log_image']; they feed the reference's `hm` dict, :223,237-238,265-268).
     """
 
     @staticmethod
@@ -83,14 +85,16 @@ class _ReprojectionLoss(torch.autograd.Function):
                               *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
                               *( [motion_c] if motion_c is not None else []), *[n for n in noise_c if n is not None])
         ctx.has = (ident is not None, mask_c is not None, motion_c is not None, noise_c[0] is not None)
-        ctx.aux = (sel, pred0)
         # the reference's loss is fp64 exactly when patched_mask is fp64
         total = stats[2 * S] if mdt == MASK_F64 else stats[2 * S].float()
-        ctx.mark_non_differentiable(stats)
-        return total.clone(), stats
+        if sel is None:
+            sel = torch.empty(0, device=dev, dtype=torch.uint8)
+            pred0 = torch.empty(0, device=dev, dtype=torch.float32)
+        ctx.mark_non_differentiable(stats, sel, pred0)
+        return total.clone(), stats, sel, pred0
 
     @staticmethod
-    def backward(ctx, g_total, _g_stats):
+    def backward(ctx, g_total, _g_stats=None, _g_sel=None, _g_pred=None):
         S, cfg = ctx.S, ctx.cfg
         B, H, W = ctx.shapes
         sv = list(ctx.saved_tensors)
@@ -132,13 +136,12 @@ class _ReprojectionLoss(torch.autograd.Function):
 def reprojection_loss(depths: Sequence[torch.Tensor], disps: Sequence[torch.Tensor], T0, T1, P2, tgt, src0, src1,
                       mask=None, motion=None, noise: Optional[Sequence[torch.Tensor]] = None, *, scales, overlapped_mask: bool,
                       smooth_weight: float = 1e-5, log_image: bool = False):
-    """Returns (total, stats, aux) -- see _ReprojectionLoss.  ``noise[i]`` are standard-normal draws
+    """Returns (total, stats, sel, pred0) -- see _ReprojectionLoss; sel / pred0 are empty unless log_image.  ``noise[i]`` are standard-normal draws
     of shape [B,2,H,W] for scale i (monodepth2_decoder.py:258); None => no tie-break noise."""
     S = len(scales)
     cfg = dict(scales=list(scales), overlapped_mask=bool(overlapped_mask), smooth_weight=float(smooth_weight), log_image=log_image)
     extra = [] if noise is None else list(noise)
-    total, stats = _ReprojectionLoss.apply(S, cfg, *depths, *disps, T0, T1, P2, tgt, src0, src1, mask, motion, *extra)
-    return total, stats
+    return _ReprojectionLoss.apply(S, cfg, *depths, *disps, T0, T1, P2, tgt, src0, src1, mask, motion, *extra)
 
 
 class _DepthHead(torch.autograd.Function):

@@ -1,0 +1,67 @@
+"""PoseNet head (reference: monodepth/networks/models/heads/pose_decoder.py:5-45) and the
+axis-angle -> 4x4 conversion (monodepth/networks/utils/monodepth_utils.py:31-63,298-337)."""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class PoseDecoder(nn.Module):
+    def __init__(self, num_ch_enc, num_input_features, num_frames_to_predict_for=None, stride=1):
+        super().__init__()
+        self.num_ch_enc = num_ch_enc
+        self.num_input_features = num_input_features
+        if num_frames_to_predict_for is None:
+            num_frames_to_predict_for = num_input_features - 1
+        self.num_frames_to_predict_for = num_frames_to_predict_for
+        self.convs = OrderedDict()
+        self.convs[("squeeze")] = nn.Conv2d(int(num_ch_enc[-1]), 256, 1)
+        self.convs[("pose", 0)] = nn.Conv2d(num_input_features * 256, 256, 3, stride, 1)
+        self.convs[("pose", 1)] = nn.Conv2d(256, 256, 3, stride, 1)
+        self.convs[("pose", 2)] = nn.Conv2d(256, 6 * num_frames_to_predict_for, 1)
+        self.relu = nn.ReLU()
+        self.net = nn.ModuleList(list(self.convs.values()))
+
+    def forward(self, input_features):
+        last = [f[-1] for f in input_features]
+        cat = torch.cat([ops.conv_act(f, self.convs["squeeze"], relu=True) for f in last], 1)
+        out = ops.conv_act(cat, self.convs[("pose", 0)], relu=True)
+        out = ops.conv_act(out, self.convs[("pose", 1)], relu=True)
+        out = ops.conv_act(out, self.convs[("pose", 2)], relu=False)
+        out = out.float().mean(3).mean(2)
+        out = 0.01 * out.view(-1, self.num_frames_to_predict_for, 1, 6)
+        return out[..., :3], out[..., 3:]
+
+
+def rot_from_axisangle(vec):
+    """Rodrigues with the reference's ``axis = v / (|v| + 1e-7)``; vec is [B,1,3] -> [B,4,4]."""
+    angle = torch.norm(vec, 2, 2, True)
+    axis = vec / (angle + 1e-7)
+    ca, sa = torch.cos(angle), torch.sin(angle)
+    C = 1 - ca
+    x, y, z = axis[..., 0:1], axis[..., 1:2], axis[..., 2:3]
+    B = vec.shape[0]
+    zero, one = torch.zeros_like(ca), torch.ones_like(ca)
+    rows = [x * x * C + ca, x * y * C - z * sa, z * x * C + y * sa, zero,
+            x * y * C + z * sa, y * y * C + ca, y * z * C - x * sa, zero,
+            z * x * C - y * sa, y * z * C + x * sa, z * z * C + ca, zero,
+            zero, zero, zero, one]
+    return torch.cat(rows, dim=-1).reshape(B, 4, 4)
+
+
+def get_translation_matrix(t):
+    B = t.shape[0]
+    T = torch.eye(4, device=t.device, dtype=t.dtype).repeat(B, 1, 1)
+    return torch.cat([torch.cat([T[:, :3, :3], t.reshape(B, 3, 1)], 2), T[:, 3:4, :]], 1)
+
+
+def transformation_from_parameters(axisangle, translation, invert=False):
+    R = rot_from_axisangle(axisangle)
+    t = translation.clone()
+    if invert:
+        R = R.transpose(1, 2)
+        t = t * -1
+    T = get_translation_matrix(t)
+    return torch.matmul(R, T) if invert else torch.matmul(T, R)

@@ -1,0 +1,3 @@
+"""Reference-compatible dotted name; the implementation lives in fsnet_b200."""
+from fsnet_b200.networks.pose_decoder import (rot_from_axisangle, get_translation_matrix,  # noqa: F401
+                                              transformation_from_parameters)

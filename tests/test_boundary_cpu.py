@@ -1,0 +1,149 @@
+"""Host-side (no GPU) checks of the drop-in boundary: plugin names, constructor surface, state-dict
+layout, config loading / overriding, the C ABI's exported symbols, and that no CPU fallback exists."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+from easydict import EasyDict
+
+from oracle import fsnet_oracle as O
+from helpers import build_model, meta_arch_cfg
+
+DOTTED = [
+    "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthWPose",
+    "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthMeta",
+    "vision_base.networks.models.backbone.resnet.resnet",
+    "monodepth.networks.models.heads.monodepth2_decoder.MonoDepth2Decoder",
+    "monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoder",
+    "monodepth.networks.models.heads.depth_encoder.DepthDecoder",
+    "monodepth.networks.models.heads.pose_decoder.PoseDecoder",
+    "vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook",
+    "vision_base.pipeline_hooks.train_val_hooks.base_validation_hooks.BaseValidationHook",
+    "vision_base.utils.builder.Sequential", "vision_base.utils.builder.Shuffle", "vision_base.utils.builder.Parallel",
+    "vision_base.data.datasets.dataset_utils.ConcatDataset", "vision_base.data.datasets.dataset_utils.collate_fn",
+    "vision_base.data.dataloader.build_dataloader", "vision_base.data.dataloader.distributed_sampler.TrainingSampler",
+    "vision_base.networks.optimizers.optimizers.build_optimizer", "vision_base.networks.optimizers.schedulers.build_scheduler",
+    "vision_base.networks.utils.utils.save_models", "vision_base.networks.utils.utils.load_models",
+    "vision_base.networks.blocks.blocks.ConvBnReLU", "vision_base.networks.models.meta_archs.base_meta.BaseMetaArch",
+    "vision_base.utils.utils.cfg_from_file", "vision_base.utils.utils.update_cfg", "vision_base.utils.logger.LossLogger",
+    "vision_base.utils.timer.Timer",
+]
+
+
+@pytest.mark.parametrize("name", DOTTED)
+def test_dotted_names_resolve(name):
+    from vision_base.utils.utils import find_object
+    assert find_object(name) is not None
+
+
+def test_find_object_error_is_module_not_found():
+    from vision_base.utils.utils import find_object
+    with pytest.raises(ModuleNotFoundError) as e:
+        find_object("vision_base.nope.Missing")
+    assert "error traces" in str(e.value)
+
+
+@pytest.mark.parametrize("topo", [O.Topology(), O.Topology(posenet=True), O.Topology(depth=50), O.Topology(depth=34, n_bins=64),
+                                  O.Topology(multi_channel=False, n_bins=1, scales=(0, 2))])
+def test_state_dict_layout_matches_reference(topo):
+    """Keys, shapes and dtypes equal the oracle's list, which loads strictly into the reference
+    (tests/golden/make_golden.py ran ``load_state_dict(strict=True)`` on it)."""
+    model = build_model(topo)
+    mine = model.state_dict()
+    ref = O.make_state_dict(topo)
+    assert list(mine.keys()) == list(ref.keys())
+    for k in ref:
+        assert mine[k].shape == ref[k].shape and mine[k].dtype == ref[k].dtype, k
+    from vision_base.networks.models.meta_archs.base_meta import BaseMetaArch
+    assert isinstance(model, BaseMetaArch)
+    n = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    if topo == O.Topology():
+        assert n == 14_364_112 or abs(n - 14.36e6) < 0.01e6        # 14.36 M
+    # SyncBN conversion and re-wrapping must keep the key layout
+    conv = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo))
+    assert list(conv.state_dict().keys()) == list(ref.keys())
+
+
+def test_extra_head_kwargs_become_attributes():
+    cfg = meta_arch_cfg(O.Topology())
+    cfg.head_cfg.pose_loss_weight = 0.5
+    cfg.head_cfg.some_new_flag = "x"
+    from vision_base.utils.builder import build
+    m = build(**cfg)
+    assert m.head.pose_loss_weight == 0.5 and m.head.some_new_flag == "x" and m.head.overlapped_mask is True
+
+
+def test_wpose_with_pose_backbone_raises():
+    cfg = meta_arch_cfg(O.Topology())
+    cfg.pose_backbone_cfg = EasyDict(cfg.depth_backbone_cfg, num_input_images=2)
+    from vision_base.utils.builder import build
+    with pytest.raises(NotImplementedError):
+        build(**cfg)
+
+
+def test_cfg_from_file_and_update(tmp_path):
+    from vision_base.utils.utils import cfg_from_file, update_cfg
+    p = tmp_path / "c.py"
+    p.write_text("from easydict import EasyDict as edict\ncfg = edict()\ncfg.a = 1\ncfg.b = edict(c=0, f=2)\ncfg.c = 3\n")
+    cfg = cfg_from_file(str(p))
+    assert isinstance(cfg, EasyDict)
+    cfg = update_cfg(cfg, **{"a": 2, "b.c": 3, "d.e.f": 4, "c.g": 1})      # reference tests/test_cfg.py:18-39
+    assert cfg["b"]["f"] == 2 and cfg["a"] == 2 and cfg["b"]["c"] == 3
+    assert isinstance(cfg["d"]["e"], dict) and cfg["d"]["e"]["f"] == 4
+    assert isinstance(cfg["c"], dict) and cfg["c"]["g"] == 1
+    with pytest.raises(AssertionError):
+        cfg_from_file(str(tmp_path / "c.txt"))
+
+
+def test_shipped_configs_load():
+    from vision_base.utils.utils import cfg_from_file
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs")
+    names = [f for f in os.listdir(root) if f.endswith(".py")]
+    assert names
+    for f in names:
+        cfg = cfg_from_file(os.path.join(root, f))
+        assert isinstance(cfg, EasyDict) and "meta_arch" in cfg
+
+
+def test_abi_exports_every_declared_symbol():
+    from fsnet_b200 import _lib
+    lib = _lib.load()
+    for sym in _lib.declared_symbols():
+        assert hasattr(lib, sym), sym
+    assert lib.fsnet_abi_version() >= 1
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors -- never route through the oracle."""
+    from fsnet_b200 import _lib, functional as Fn
+    t = torch.zeros(1, 3, 8, 8)
+    with pytest.raises(_lib.FsnetError):
+        Fn.reprojection_loss([t[:, :1]], [t[:, :1]], torch.eye(4)[None], torch.eye(4)[None], torch.zeros(1, 3, 4), t, t, t,
+                             scales=[0], overlapped_mask=False)
+    with pytest.raises(_lib.FsnetError):
+        Fn.depth_head(torch.zeros(1, 4, 8, 8), torch.ones(4), None, False, 0.5, 100.0)
+    src = open(os.path.join(os.path.dirname(_lib.__file__), "functional.py")).read()
+    assert "oracle" not in src
+
+
+def test_sampler_and_collate():
+    from vision_base.data.dataloader.distributed_sampler import TrainingSampler
+    from vision_base.data.datasets.dataset_utils import collate_fn
+    a = list(TrainingSampler(10, rank=0, world_size=2))
+    b = list(TrainingSampler(10, rank=1, world_size=2))
+    assert sorted(a + b) == list(range(10)) and len(a) == 5
+    batch = collate_fn([{"x": torch.ones(2), ("k", 0): np.zeros(3), "s": "a", "only0": 1}, {"x": torch.ones(2), ("k", 0): np.ones(3), "s": "b"}])
+    assert batch["x"].shape == (2, 2) and batch[("k", 0)].shape == (2, 3) and batch["s"] == ["a", "b"] and "only0" not in batch
+
+
+def test_synthetic_dataset_schema():
+    from fsnet_b200.data.synthetic import SyntheticTripletDataset, make_batch
+    ds = SyntheticTripletDataset(length=4, height=32, width=64)
+    s = ds[1]
+    assert s[("image", 0)].shape == (3, 32, 64) and s["patched_mask"].dtype == torch.float64 and s["P2"].shape == (3, 4)
+    # the product's generator and the oracle's are the same recipe (the bench compares the two arms on equal inputs)
+    mine, ref = make_batch(2, 32, 64, seed=7), O.synthetic_batch(2, 32, 64, seed=7)
+    for k in ref:
+        assert torch.equal(mine[k], ref[k]), k

@@ -25,7 +25,7 @@ def run_gpu_loss(topo, data, outputs, noise, need_pose=True):
     mask = data["patched_mask"].to(dev) if "patched_mask" in data else None
     motion = data["motion_mask"].to(dev) if "motion_mask" in data else None
     nz = None if motion is not None else [noise[s].to(dev) for s in topo.scales]
-    total, stats = Fn.reprojection_loss(
+    total, stats, _, _ = Fn.reprojection_loss(
         depths, disps, T[0], T[1], data["P2"].to(dev), data[("original_image", 0)].to(dev),
         data[("original_image", topo.frame_ids[1])].to(dev), data[("original_image", topo.frame_ids[2])].to(dev),
         mask, motion, nz, scales=topo.scales, overlapped_mask=topo.overlapped_mask)
@@ -83,21 +83,11 @@ def test_selection_and_warped_image_outputs():
     dev = "cuda"
     depths = [outputs[("depth", s, s)].to(dev) for s in topo.scales]
     disps = [outputs[("disp", s)].to(dev) for s in topo.scales]
-    S = len(topo.scales)
-    cfg = dict(scales=list(topo.scales), overlapped_mask=True, smooth_weight=1e-5, log_image=True)
-    args = [data[("relative_pose", 1)].to(dev), data[("relative_pose", -1)].to(dev), data["P2"].to(dev),
-            data[("original_image", 0)].to(dev), data[("original_image", 1)].to(dev), data[("original_image", -1)].to(dev),
-            data["patched_mask"].to(dev), None] + [noise[s].to(dev) for s in topo.scales]
-    ctx_holder = {}
-
-    class Probe(Fn._ReprojectionLoss):
-        @staticmethod
-        def forward(ctx, *a):
-            out = Fn._ReprojectionLoss.forward(ctx, *a)
-            ctx_holder["aux"] = ctx.aux
-            return out
-    Probe.apply(S, cfg, *depths, *disps, *args)
-    sel, pred0 = ctx_holder["aux"]
+    _, _, sel, pred0 = Fn.reprojection_loss(
+        depths, disps, data[("relative_pose", 1)].to(dev), data[("relative_pose", -1)].to(dev), data["P2"].to(dev),
+        data[("original_image", 0)].to(dev), data[("original_image", 1)].to(dev), data[("original_image", -1)].to(dev),
+        data["patched_mask"].to(dev), None, [noise[s].to(dev) for s in topo.scales], scales=topo.scales,
+        overlapped_mask=True, log_image=True)
     flips = float((sel.cpu().long() != ref["aux"][("idxs", 0)]).float().mean())
     assert flips < 2e-3, flips
     assert rel(pred0[0].cpu(), ref["aux"][("warped", 0)][1][0]) < 1e-4

@@ -1,0 +1,2 @@
+"""Reference-compatible dotted name; the implementation lives in fsnet_b200."""
+from fsnet_b200.utils.builder import build, Sequential, Parallel, Shuffle  # noqa: F401
