@@ -155,7 +155,8 @@ def main():
     else:
         model = model.to(dev)
     model.train()
-    optimizer = build("vision_base.networks.optimizers.optimizers.build_optimizer", model, **cfg.optimizer)
+    from vision_base.networks.optimizers.optimizers import build_optimizer
+    optimizer = build_optimizer(model, **cfg.optimizer)
     hook = build(**cfg.trainer.training_hook)
 
     host = make_batch(B_PER_GPU, H, W, seed=1234 + rank)
