@@ -138,6 +138,25 @@ int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* sc
  * ------------------------------------------------------------------------------------------- */
 int fsnet_loss_finalize(const double* acc, int S, double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * convolution on the tcgen05 tensor cores (implicit GEMM, TMA-fed, fp32 accumulation in TMEM).
+ * Replaces nn.Conv2d as used by resnet.py:21-89,119 / blocks.py:43-45 / depth_encoder.py:62 /
+ * pose_decoder.py:18-21 of the reference.
+ *   in_hi, in_lo  NHWC bf16 planes (x ~ hi + lo) of a RINGED buffer [N, H+2*ring, W+2*ring, Cin]; the
+ *                 pointers address the ring origin; pitch_w = W+2*ring, pitch_h = H+2*ring (pixels)
+ *   use_ring      0: zero padding (TMA out-of-bounds fill over the interior view)
+ *                 1: the ring holds materialised (replicate) padding and is read as data
+ *   w_hi, w_lo    weights [Cout, KH, KW, Cin] bf16 planes
+ *   nprod         3: hi*hi + lo*hi + hi*lo (forward, ~fp32 accuracy)   1: hi*hi only (gradients)
+ *   bias          [Cout] fp32 added in the epilogue, or NULL;  relu != 0 applies max(.,0)
+ *   out           [N, Ho, Wo, Cout] fp32 NHWC
+ *   stats         [2*Cout] fp64, accumulated: per-channel sum and sum of squares of `out`
+ *                 (train-mode BatchNorm statistics), or NULL
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_conv_fwd(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, int pitch_w, int pitch_h,
+                   int ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW, int stride, int pad,
+                   int use_ring, int nprod, const float* bias, int relu, float* out, double* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
