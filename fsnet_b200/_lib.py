@@ -45,6 +45,12 @@ class FsnetError(RuntimeError):
     pass
 
 
+class View(ctypes.Structure):
+    """fsnet_view of include/fsnet_b200.h."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("n", ctypes.c_int), ("h", ctypes.c_int), ("w", ctypes.c_int), ("c", ctypes.c_int),
+                ("ring", ctypes.c_int), ("c_total", ctypes.c_int), ("c_off", ctypes.c_int)]
+
+
 def declared_symbols():
     """Entry points declared in the public header (used by the CPU-side ABI test)."""
     with open(HEADER_PATH) as f:
@@ -99,6 +105,8 @@ def call(name, *args):
             if not a.t.is_cuda:
                 raise FsnetError("fsnet_b200 kernels take CUDA tensors only (there is no CPU path)")
             cargs.append(ctypes.c_void_p(a.t.data_ptr()))
+        elif isinstance(a, View):
+            cargs.append(ctypes.byref(a))
         elif isinstance(a, bool):
             cargs.append(ctypes.c_int(int(a)))
         elif isinstance(a, int):

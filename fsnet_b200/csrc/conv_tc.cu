@@ -40,7 +40,8 @@ struct ConvParams {
   uint32_t a_bytes, b_bytes, stage_bytes, tx_bytes;
   uint32_t tmem_cols;
   uint32_t sbo, layout_type;   // UMMA smem descriptor fields for this swizzle
-  float* out;                  // [N,Ho,Wo,Cout] fp32
+  float* out;                  // fp32 NHWC view: element (n,y,x,c) at ((n*out_ph + y+out_ring)*out_pw + x+out_ring)*out_ct + out_coff + c
+  int out_pw, out_ph, out_ring, out_ct, out_coff, accumulate;
   const float* bias;           // [Cout] or null
   double* stats;               // [2*Cout] (sum, sumsq) or null
   int relu;
@@ -259,7 +260,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const int py = m / p.TW, px = m - py * p.TW;
       const int oy = ty * p.TH + py, ox = tx * p.TW + px;
       const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo;
-      float* orow = p.out + (((size_t)img * p.Ho + oy) * p.Wo + ox) * p.Cout + nt * p.BN;
+      float* orow = p.out + (((size_t)img * p.out_ph + oy + p.out_ring) * p.out_pw + ox + p.out_ring) * p.out_ct + p.out_coff + nt * p.BN;
       mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -280,7 +281,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 16; j += 4) {
+            float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (p.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+            *dst = o;
+          }
         }
         if (p.stats) {
           float sq[16];
@@ -352,30 +358,54 @@ void pick_tile(int Ho, int Wo, int& TH, int& TW) {
 
 using namespace fsnet;
 
-// ---------------------------------------------------------------------------------------------------
-// fsnet_conv_fwd -- see include/fsnet_b200.h
-// ---------------------------------------------------------------------------------------------------
-extern "C" int fsnet_conv_fwd(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, int pitch_w, int pitch_h,
-                              int ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW, int stride, int pad,
-                              int use_ring, int nprod, const float* bias, int relu, float* out, double* stats, void* stream) {
-  FSNET_REQUIRE(in_hi && w_hi && out, "fsnet_conv_fwd: null pointer");
-  FSNET_REQUIRE(nprod == 1 || (nprod == 3 && in_lo && w_lo), "fsnet_conv_fwd: nprod must be 1 or 3 (3 needs the lo planes)");
-  FSNET_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 16 == 0 && Cout % 16 == 0, "fsnet_conv_fwd: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
-  FSNET_REQUIRE(stride == 1 || stride == 2, "fsnet_conv_fwd: stride %d unsupported", stride);
-  FSNET_REQUIRE(!use_ring || (ring >= pad), "fsnet_conv_fwd: replicate padding needs a materialised ring >= pad");
+static int encode_act_map(CUtensorMap* map, const fsnet_view* v, int plane, int use_ring, int kc, int box_w, int box_h, int stride,
+                          const char* who) {
   EncodeTiledFn enc = encode_fn();
-  FSNET_REQUIRE(enc != nullptr, "fsnet_conv_fwd: cuTensorMapEncodeTiled not available from the driver");
+  FSNET_REQUIRE(enc != nullptr, "%s: cuTensorMapEncodeTiled not available from the driver", who);
+  const int pw = v->w + 2 * v->ring, ph = v->h + 2 * v->ring;
+  const size_t plane_elems = (size_t)v->n * ph * pw * v->c_total;
+  const char* base = (const char*)v->ptr + (plane_elems * plane + v->c_off) * 2;
+  if (!use_ring) base += ((size_t)v->ring * pw + v->ring) * v->c_total * 2;
+  const int Wm = use_ring ? pw : v->w, Hm = use_ring ? ph : v->h;
+  cuuint64_t dim[4] = {(cuuint64_t)v->c, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)v->n};
+  cuuint64_t str[3] = {(cuuint64_t)v->c_total * 2, (cuuint64_t)pw * v->c_total * 2, (cuuint64_t)ph * pw * v->c_total * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(box_w * stride), (cuuint32_t)(box_h * stride), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  FSNET_REQUIRE(box[1] <= 256 && box[2] <= 256, "%s: TMA box too large", who);
+  FSNET_REQUIRE(((uintptr_t)base & 15) == 0 && (str[0] & 15) == 0, "%s: activation view is not 16-byte aligned", who);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FSNET_REQUIRE(r == CUDA_SUCCESS, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)r);
+  return FSNET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fsnet_conv -- see include/fsnet_b200.h
+// ---------------------------------------------------------------------------------------------------
+extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW,
+                          int stride, int pad, int nprod, const float* bias, int relu, const fsnet_view* out, int accumulate,
+                          double* stats, void* stream) {
+  FSNET_REQUIRE(in && in->ptr && w_hi && out && out->ptr, "fsnet_conv: null pointer");
+  FSNET_REQUIRE(nprod == 1 || (nprod == 3 && w_lo), "fsnet_conv: nprod must be 1 or 3 (3 needs the lo planes)");
+  const int N = in->n, H = in->h, W = in->w, Cin = in->c;
+  FSNET_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 16 == 0 && Cout % 16 == 0, "fsnet_conv: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
+  FSNET_REQUIRE(stride == 1 || stride == 2, "fsnet_conv: stride %d unsupported", stride);
+  FSNET_REQUIRE(!use_ring || (in->ring >= pad), "fsnet_conv: replicate padding needs a materialised ring >= pad");
+  EncodeTiledFn enc = encode_fn();
+  FSNET_REQUIRE(enc != nullptr, "fsnet_conv: cuTensorMapEncodeTiled not available from the driver");
 
   ConvParams p = {};
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad; p.dil = 1;
   p.Ho = (H + 2 * pad - KH) / stride + 1;
   p.Wo = (W + 2 * pad - KW) / stride + 1;
-  p.org = use_ring ? ring : 0;
+  FSNET_REQUIRE(out->n == N && out->h == p.Ho && out->w == p.Wo && out->c == Cout, "fsnet_conv: output view is [%d,%d,%d,%d], expected [%d,%d,%d,%d]",
+                out->n, out->h, out->w, out->c, N, p.Ho, p.Wo, Cout);
+  FSNET_REQUIRE(out->c_off % 4 == 0 && out->c_total % 4 == 0, "fsnet_conv: output channel slice must be 16-byte aligned");
+  p.org = use_ring ? in->ring : 0;
   pick_tile(p.Ho, p.Wo, p.TH, p.TW);
   p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
-  p.BN = Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16));
-  if (Cout <= 128) p.BN = Cout;
-  FSNET_REQUIRE(p.BN % 16 == 0 && p.BN <= 128 && Cout % p.BN == 0, "fsnet_conv_fwd: cannot tile Cout=%d", Cout);
+  p.BN = Cout <= 128 ? Cout : 128;
+  FSNET_REQUIRE(Cout % p.BN == 0, "fsnet_conv: cannot tile Cout=%d", Cout);
   p.n_tiles = Cout / p.BN;
   p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
   p.KC = pick_kc(Cin); p.cchunks = Cin / p.KC; p.kiters = KH * KW * p.cchunks;
@@ -386,57 +416,38 @@ extern "C" int fsnet_conv_fwd(const void* in_hi, const void* in_lo, int N, int H
   const uint32_t stats_bytes = stats ? 2u * Cout * 4u : 0u;
   int stages = (int)((200u * 1024u - stats_bytes) / p.stage_bytes);
   p.stages = stages > kMaxStages ? kMaxStages : stages;
-  FSNET_REQUIRE(p.stages >= 2, "fsnet_conv_fwd: tile does not fit shared memory");
+  FSNET_REQUIRE(p.stages >= 2, "fsnet_conv: tile does not fit shared memory");
   uint32_t cols = 32;
   while (cols < 2u * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   p.sbo = 8u * p.KC * 2;
   p.layout_type = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);
-  p.out = out; p.bias = bias; p.stats = stats; p.relu = relu;
+  p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
+  p.out_ct = out->c_total; p.out_coff = out->c_off; p.accumulate = accumulate;
+  p.bias = bias; p.stats = stats; p.relu = relu;
 
-  // activation maps: dims (C, W', H', N) over the logical image (zero padding through OOB fill) or over
-  // the ringed tensor (materialised replicate padding)
-  const int Wm = use_ring ? W + 2 * ring : W, Hm = use_ring ? H + 2 * ring : H;
-  const char* base_hi = (const char*)in_hi;
-  const char* base_lo = (const char*)in_lo;
-  if (!use_ring) {            // caller passes the pointer to the ring origin; step to the interior
-    size_t off = ((size_t)ring * pitch_w + ring) * Cin * 2;
-    base_hi += off;
-    if (base_lo) base_lo += off;
-  }
-  cuuint64_t adim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wm, (cuuint64_t)Hm, (cuuint64_t)N};
-  cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)pitch_w * Cin * 2, (cuuint64_t)pitch_h * pitch_w * Cin * 2};
-  cuuint32_t abox[4] = {(cuuint32_t)p.KC, (cuuint32_t)(p.TW * stride), (cuuint32_t)(p.TH * stride), 1};
-  cuuint32_t aes[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-  FSNET_REQUIRE(abox[1] <= 256 && abox[2] <= 256, "fsnet_conv_fwd: TMA box too large");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  CUresult r = enc(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base_hi, adim, astr, abox, aes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv_fwd: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+  int rc = encode_act_map(&ma_hi, in, 0, use_ring, p.KC, p.TW, p.TH, stride, "fsnet_conv");
+  if (rc) return rc;
   ma_lo = ma_hi;
-  if (nprod == 3) {
-    r = enc(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base_lo, adim, astr, abox, aes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv_fwd: cuTensorMapEncodeTiled(A lo) failed with %d", (int)r);
-  }
+  if (nprod == 3) { rc = encode_act_map(&ma_lo, in, 1, use_ring, p.KC, p.TW, p.TH, stride, "fsnet_conv"); if (rc) return rc; }
   const int Ktot = KH * KW * Cin;
   cuuint64_t bdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t bstr[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t bbox[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.BN};
   cuuint32_t bes[2] = {1, 1};
-  r = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_hi, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv_fwd: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  CUresult r = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_hi, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   mb_lo = mb_hi;
   if (nprod == 3) {
     r = enc(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_lo, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv_fwd: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
+    FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
   }
 
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   const size_t smem = (size_t)p.stages * p.stage_bytes + stats_bytes + 1024;
   auto kern = nprod == 3 ? conv_tc_kernel<3> : conv_tc_kernel<1>;
@@ -446,6 +457,204 @@ extern "C" int fsnet_conv_fwd(const void* in_hi, const void* in_lo, int N, int H
     attr_set[nprod == 3] = true;
   }
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+// ===================================================================================================
+// weight gradient:  dW[co, r, s, ci] = sum_{n, yo, xo} dy[n, yo, xo, co] * x[n, yo*st + r - p, xo*st + s - p, ci]
+//
+// GEMM with M = Cout (128 rows, duplicated when Cout < 128), N = Cin tile, K = pixels.  Both operands are
+// read straight from the NHWC planes, i.e. MN-major (the contiguous dimension is the channel): one TMA box
+// per 64/32/16-channel swizzle atom, [channels, PW, PH] -> 64 pixel rows, UMMA descriptors with
+// a_major = b_major = MN.  One CTA per (tap, co tile, ci tile, K split); the fp32 tile is reduced into the
+// accumulator with atomics.
+// ===================================================================================================
+namespace fsnet {
+namespace {
+
+constexpr int kWgPix = 64;          // pixels (K) per pipeline stage
+
+struct WgradParams {
+  int N, Ho, Wo, KH, KW, stride, pad, org;
+  int Cout, Cin;                    // padded channel counts of the accumulator
+  int co_tiles, ci_tiles, ksplit, taps;
+  int BM_real, BN;                  // real rows (channels of dy) in the tile, ci tile width
+  int atomA, atomB, nA, nB;         // channels per swizzle atom, atoms actually loaded
+  int PW, PH, chunks_x, chunks_y, total_chunks, chunks_per_split;
+  int stages;
+  uint32_t a_atom_bytes, b_atom_bytes, a_bytes, b_bytes, stage_bytes, tx_bytes;
+  uint32_t tmem_cols;
+  uint32_t a_layout, b_layout;
+  float* acc;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // stride between swizzle atoms along M/N
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride between groups of 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item
+  int item = blockIdx.x;
+  const int ks = item % p.ksplit; item /= p.ksplit;
+  const int cit = item % p.ci_tiles; item /= p.ci_tiles;
+  const int cot = item % p.co_tiles; const int tap = item / p.co_tiles;
+  const int r = tap / p.KW, s = tap - r * p.KW;
+  const int chunk_begin = ks * p.chunks_per_split;
+  const int chunk_end = min(chunk_begin + p.chunks_per_split, p.total_chunks);
+  const int nchunks = max(chunk_end - chunk_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int ch = chunk_begin; ch < chunk_end; ++ch) {
+        int cx = ch % p.chunks_x; int rest = ch / p.chunks_x;
+        int cy = rest % p.chunks_y; int img = rest / p.chunks_y;
+        const int xo = cx * p.PW, yo = cy * p.PH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+        for (int a = 0; a < p.nA; ++a)
+          tma_load_4d(st + a * p.a_atom_bytes, &map_dy, &full_bar[stage], cot * 128 + a * p.atomA, xo, yo, img);
+        for (int b = 0; b < p.nB; ++b)
+          tma_load_4d(st + p.a_bytes + b * p.b_atom_bytes, &map_x, &full_bar[stage], cit * p.BN + b * p.atomB,
+                      xo * p.stride + s - p.pad + p.org, yo * p.stride + r - p.pad + p.org, img);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t rowA = (uint32_t)p.atomA * 2, rowB = (uint32_t)p.atomB * 2;
+      // when fewer than 128/atomA atoms exist, LBO = 0 makes the missing atoms alias atom 0 (duplicate rows, never stored)
+      const uint32_t lboA = (p.nA * p.atomA >= 128) ? p.a_atom_bytes : 0u;
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < nchunks; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        for (int k = 0; k < kWgPix / 16; ++k) {
+          const uint64_t da = make_desc_mn(st + k * 16 * rowA, lboA, 8 * rowA, p.a_layout);
+          const uint64_t db = make_desc_mn(st + p.a_bytes + k * 16 * rowB, p.b_atom_bytes, 8 * rowB, p.b_layout);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else if (nchunks > 0) {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;              // row = output channel within the tile
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int co = cot * 128 + m;
+    const bool valid = m < p.BM_real && co < p.Cout;
+    float* dst = p.acc + ((size_t)co * p.taps + tap) * p.Cin + cit * p.BN;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(taddr + c0, raw);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(raw[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+int atom_channels(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : 16); }
+uint32_t layout_for_atom(int a) { return a == 64 ? 2u : (a == 32 ? 4u : 6u); }
+
+}  // namespace
+}  // namespace fsnet
+
+extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, int KH, int KW, int stride, int pad,
+                                float* acc, void* stream) {
+  FSNET_REQUIRE(x && dy && x->ptr && dy->ptr && acc, "fsnet_conv_wgrad: null pointer");
+  FSNET_REQUIRE(x->c % 16 == 0 && dy->c % 16 == 0, "fsnet_conv_wgrad: channels must be multiples of 16");
+  FSNET_REQUIRE(stride == 1 || stride == 2, "fsnet_conv_wgrad: stride %d unsupported", stride);
+  WgradParams p = {};
+  p.N = dy->n; p.Ho = dy->h; p.Wo = dy->w; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
+  p.org = use_ring ? x->ring : 0;
+  p.Cout = dy->c; p.Cin = x->c; p.taps = KH * KW;
+  FSNET_REQUIRE((x->h + 2 * pad - KH) / stride + 1 == p.Ho && (x->w + 2 * pad - KW) / stride + 1 == p.Wo, "fsnet_conv_wgrad: shape mismatch");
+  p.atomA = atom_channels(p.Cout); p.atomB = atom_channels(p.Cin);
+  const int BMr = p.Cout < 128 ? p.Cout : 128;
+  FSNET_REQUIRE(p.Cout % BMr == 0, "fsnet_conv_wgrad: cannot tile Cout=%d", p.Cout);
+  p.BM_real = BMr; p.co_tiles = p.Cout / BMr;
+  p.nA = BMr / p.atomA;
+  FSNET_REQUIRE(p.nA == 1 || p.nA * p.atomA == 128, "fsnet_conv_wgrad: Cout=%d needs partial atom aliasing (unsupported)", p.Cout);
+  p.BN = p.Cin <= 128 ? p.Cin : 128;
+  FSNET_REQUIRE(p.Cin % p.BN == 0, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
+  p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
+  int pw = 1;
+  while (pw * 2 <= p.Wo && pw * 2 <= kWgPix) pw *= 2;
+  p.PW = pw; p.PH = kWgPix / pw;
+  p.chunks_x = ceil_div(p.Wo, p.PW); p.chunks_y = ceil_div(p.Ho, p.PH);
+  p.total_chunks = p.N * p.chunks_x * p.chunks_y;
+  const int base_items = p.taps * p.co_tiles * p.ci_tiles;
+  int ksplit = ceil_div(148 * 3, base_items);
+  if (ksplit > p.total_chunks) ksplit = p.total_chunks;
+  if (ksplit < 1) ksplit = 1;
+  p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
+  p.ksplit = ceil_div(p.total_chunks, p.chunks_per_split);
+  p.a_atom_bytes = (uint32_t)kWgPix * p.atomA * 2; p.b_atom_bytes = (uint32_t)kWgPix * p.atomB * 2;
+  p.a_bytes = ((uint32_t)p.nA * p.a_atom_bytes + 1023u) & ~1023u;
+  p.b_bytes = ((uint32_t)p.nB * p.b_atom_bytes + 1023u) & ~1023u;
+  p.stage_bytes = p.a_bytes + p.b_bytes;
+  p.tx_bytes = (uint32_t)p.nA * p.a_atom_bytes + (uint32_t)p.nB * p.b_atom_bytes;
+  int stages = (int)(200u * 1024u / p.stage_bytes);
+  p.stages = stages > kMaxStages ? kMaxStages : stages;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)p.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  p.a_layout = layout_for_atom(p.atomA); p.b_layout = layout_for_atom(p.atomB);
+  p.acc = acc;
+  CUtensorMap mdy, mx;
+  int rc = encode_act_map(&mdy, dy, 0, 0, p.atomA, p.PW, p.PH, 1, "fsnet_conv_wgrad");
+  if (rc) return rc;
+  rc = encode_act_map(&mx, x, 0, use_ring, p.atomB, p.PW, p.PH, stride, "fsnet_conv_wgrad");
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FSNET_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    attr_set = true;
+  }
+  const int grid = base_items * p.ksplit;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mdy, mx, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

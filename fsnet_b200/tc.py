@@ -1,0 +1,94 @@
+"""Thin Python handles for the tcgen05 path: ringed NHWC buffers and the calls of include/fsnet_b200.h.
+
+``Planes``  bf16 [2, N, H+2r, W+2r, C]  (hi, lo) -- what the convolutions read through TMA
+``Fp32``    fp32 [N, H+2r, W+2r, C]             -- conv outputs ("raw") and gradients
+Both hand out ``fsnet_view`` structs (optionally a channel slice).  Product code: CUDA only.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import View
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+class _Buf:
+    def __init__(self, t, n, h, w, c, ring):
+        self.t, self.n, self.h, self.w, self.c, self.ring = t, n, h, w, c, ring
+
+    def view(self, c_off=0, c=None) -> View:
+        return View(self.t.data_ptr(), self.n, self.h, self.w, self.c if c is None else c, self.ring, self.c, c_off)
+
+
+class Planes(_Buf):
+    def __init__(self, n, h, w, c, ring=1, device="cuda", zero=False):
+        t = (torch.zeros if zero else torch.empty)(2, n, h + 2 * ring, w + 2 * ring, c, device=device, dtype=torch.bfloat16)
+        super().__init__(t, n, h, w, c, ring)
+
+    def to_float(self):
+        """[N,C,H,W] fp32 reconstruction of the interior (tests / lazy feature export)."""
+        r = self.ring
+        x = self.t[0].float() + self.t[1].float()
+        return x[:, r:r + self.h, r:r + self.w, :].permute(0, 3, 1, 2)
+
+
+class Fp32(_Buf):
+    def __init__(self, n, h, w, c, ring=0, device="cuda", zero=False):
+        t = (torch.zeros if zero else torch.empty)(n, h + 2 * ring, w + 2 * ring, c, device=device, dtype=torch.float32)
+        super().__init__(t, n, h, w, c, ring)
+
+    def interior(self):
+        r = self.ring
+        return self.t[:, r:r + self.h, r:r + self.w, :]
+
+    def nchw(self):
+        return self.interior().permute(0, 3, 1, 2)
+
+
+class ConvWeights:
+    """bf16 operand planes of one convolution, refreshed from the fp32 parameter every step."""
+
+    def __init__(self, weight: torch.Tensor, need_dgrad=True):
+        co, ci, kh, kw = weight.shape
+        self.co, self.ci, self.kh, self.kw = co, ci, kh, kw
+        self.co_pad, self.ci_pad = pad16(co), pad16(ci)
+        dev = weight.device
+        self.fwd = torch.empty(2, self.co_pad, kh, kw, self.ci_pad, device=dev, dtype=torch.bfloat16)
+        self.dgrad = torch.empty(self.ci_pad, kh, kw, self.co_pad, device=dev, dtype=torch.bfloat16) if need_dgrad else None
+        self.acc = None
+
+    def refresh(self, weight: torch.Tensor):
+        _lib.call("fsnet_weight_planes", weight.detach(), self.co, self.ci, self.kh, self.kw, self.co_pad, self.ci_pad,
+                  self.fwd[0], self.fwd[1], self.dgrad)
+
+    def wgrad_acc(self):
+        if self.acc is None:
+            self.acc = torch.empty(self.co_pad, self.kh, self.kw, self.ci_pad, device=self.fwd.device, dtype=torch.float32)
+        return self.acc
+
+
+def conv(inp: Planes, w: ConvWeights, out: Fp32, stride=1, pad=1, use_ring=False, nprod=3, bias=None, relu=False, stats=None,
+         accumulate=False, in_view=None, out_view=None):
+    _lib.call("fsnet_conv", in_view or inp.view(), int(use_ring), w.fwd[0], w.fwd[1], w.co_pad, w.kh, w.kw, stride, pad, nprod,
+              bias, int(relu), out_view or out.view(), int(accumulate), stats)
+
+
+def conv_dgrad(dy: Planes, w: ConvWeights, out_view: View, pad, accumulate=False, dy_view=None):
+    """Data gradient of a stride-1 convolution = convolution of dy with the flipped, transposed weights."""
+    _lib.call("fsnet_conv", dy_view or dy.view(), 0, w.dgrad, None, w.ci_pad, w.kh, w.kw, 1, pad, 1, None, 0, out_view,
+              int(accumulate), None)
+
+
+def conv_wgrad(x_view: View, use_ring, dy_view: View, w: ConvWeights, stride, pad):
+    acc = w.wgrad_acc()
+    acc.zero_()
+    _lib.call("fsnet_conv_wgrad", x_view, int(use_ring), dy_view, w.kh, w.kw, stride, pad, acc)
+    return acc
+
+
+def c_double(x):
+    return ctypes.c_double(float(x))

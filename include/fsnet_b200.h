@@ -139,23 +139,86 @@ int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* sc
 int fsnet_loss_finalize(const double* acc, int S, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * NHWC views.  Element (n, y, x, c) of a view lives at
+ *     ((n*(h+2*ring) + y+ring) * (w+2*ring) + x+ring) * c_total + c_off + c
+ * `ptr` addresses the ring origin.  "planes" views are bf16: the hi plane at `ptr`, the lo plane
+ * (x - hi) right behind it (n*(h+2*ring)*(w+2*ring)*c_total elements later); fp32 views are single.
+ * The ring of a planes buffer holds the replicate padding of the interior.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  void* ptr;
+  int n, h, w, c;      /* logical size of the view */
+  int ring;            /* 0 or 1 pixel of materialised border around h x w */
+  int c_total, c_off;  /* channel stride of the underlying buffer and first channel of the view */
+} fsnet_view;
+
+/* ---------------------------------------------------------------------------------------------
  * convolution on the tcgen05 tensor cores (implicit GEMM, TMA-fed, fp32 accumulation in TMEM).
  * Replaces nn.Conv2d as used by resnet.py:21-89,119 / blocks.py:43-45 / depth_encoder.py:62 /
- * pose_decoder.py:18-21 of the reference.
- *   in_hi, in_lo  NHWC bf16 planes (x ~ hi + lo) of a RINGED buffer [N, H+2*ring, W+2*ring, Cin]; the
- *                 pointers address the ring origin; pitch_w = W+2*ring, pitch_h = H+2*ring (pixels)
- *   use_ring      0: zero padding (TMA out-of-bounds fill over the interior view)
- *                 1: the ring holds materialised (replicate) padding and is read as data
- *   w_hi, w_lo    weights [Cout, KH, KW, Cin] bf16 planes
- *   nprod         3: hi*hi + lo*hi + hi*lo (forward, ~fp32 accuracy)   1: hi*hi only (gradients)
- *   bias          [Cout] fp32 added in the epilogue, or NULL;  relu != 0 applies max(.,0)
- *   out           [N, Ho, Wo, Cout] fp32 NHWC
- *   stats         [2*Cout] fp64, accumulated: per-channel sum and sum of squares of `out`
- *                 (train-mode BatchNorm statistics), or NULL
+ * pose_decoder.py:18-21 of the reference; with transposed / flipped weights it is also the data
+ * gradient of those layers.
+ *   in        planes view (Cin = in->c, multiple of 16)
+ *   use_ring  0: zero padding (TMA out-of-bounds fill over the interior)
+ *             1: the ring holds materialised (replicate) padding and is read as data
+ *   w_hi/w_lo weights [Cout, KH, KW, Cin] bf16 planes (fsnet_weight_planes)
+ *   nprod     3: hi*hi + lo*hi + hi*lo (forward, ~fp32 accuracy)   1: hi*hi only (gradients)
+ *   bias      [Cout] fp32 added in the epilogue, or NULL;  relu != 0 applies max(.,0)
+ *   out       fp32 view [N, Ho, Wo, Cout]; accumulate != 0 adds to its current content
+ *   stats     [2*Cout] fp64, accumulated: per-channel sum and sum of squares of the result
+ *             (train-mode BatchNorm statistics, nn.BatchNorm2d in resnet.py / blocks.py), or NULL
+ * fsnet_conv_wgrad: acc[Cout, KH, KW, Cin] (fp32, zeroed by the caller) += dy^T * im2col(x); dy is a
+ * bf16 plane view [N, Ho, Wo, Cout], x the planes view the forward convolution read.
  * ------------------------------------------------------------------------------------------- */
-int fsnet_conv_fwd(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, int pitch_w, int pitch_h,
-                   int ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW, int stride, int pad,
-                   int use_ring, int nprod, const float* bias, int relu, float* out, double* stats, void* stream);
+int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW,
+               int stride, int pad, int nprod, const float* bias, int relu, const fsnet_view* out, int accumulate,
+               double* stats, void* stream);
+int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, int KH, int KW, int stride, int pad,
+                     float* acc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * element-wise / reduction kernels around the convolutions (fsnet_b200/csrc/act_tc.cu)
+ *   fsnet_image_to_planes  fp32 NCHW image [N,C,H,W] -> planes with dst->c >= C channels (extra = 0)
+ *   fsnet_weight_planes    fp32 [Cout,Cin,KH,KW] -> [Cout_pad,KH,KW,Cin_pad] hi/lo planes and the
+ *                          data-gradient operand [Cin_pad,KH,KW (flipped),Cout_pad] (hi), any may be NULL
+ *   fsnet_wgrad_to_param   fp32 [Cout_pad,KH,KW,Cin_pad] accumulator -> parameter gradient layout
+ *   fsnet_bn_finalize      nn.BatchNorm2d statistics: scale_shift[2C] = (gamma*invstd, beta-mean*gamma*invstd),
+ *                          mean_invstd[2C] saved for backward, running stats updated (momentum, unbiased var),
+ *                          `stats` re-zeroed; training == 0 uses the running statistics
+ *   fsnet_act_planes       dst planes = relu?(raw*scale+shift + residual), optional nearest x2 (`up`=2) into a
+ *                          channel slice of a concat buffer; residual: 0 none, 1 planes, 2 raw fp32 with its
+ *                          own scale_shift (the down-sample branch, resnet.py:138-145)
+ *   fsnet_copy_planes      planes -> channel slice of another planes buffer (skip connection, depth_encoder.py:99-101)
+ *   fsnet_maxpool_planes / fsnet_maxpool_bwd   nn.MaxPool2d(3, 2, 1) (resnet.py:122) and its gradient
+ *   fsnet_bn_bwd_reduce / fsnet_bn_bwd_apply   gradient of (ReLU o BatchNorm): sums[2C] = (sum g, sum g*xhat);
+ *                          dy (bf16 plane) = gamma*invstd*(g - mean g - xhat*mean g*xhat); mean_invstd == NULL
+ *                          means "no BatchNorm" (dy = masked g); `up`=2 reads the gradient through the adjoint
+ *                          of the nearest x2 up-sampling; res_mode 1/2 writes/accumulates the masked gradient
+ *                          into another fp32 view (identity residual)
+ *   fsnet_fold_ring        adjoint of replicate padding: adds the ring of a ringed fp32 gradient into its border
+ *   fsnet_add_slice        dst (+)= channel slice of src (fp32 views)
+ *   fsnet_zero_insert      bf16 plane -> zero-stuffed x2 plane (stride-2 data gradient as a stride-1 convolution)
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_image_to_planes(const float* img, int C, const fsnet_view* dst, void* stream);
+int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad,
+                        void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* stream);
+int fsnet_wgrad_to_param(const float* acc, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad, float* grad,
+                         int accumulate, void* stream);
+int fsnet_bn_finalize(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,
+                      float* running_mean, float* running_var, long long* num_batches, float momentum, float eps,
+                      int training, int C, float* scale_shift, float* mean_invstd, void* stream);
+int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift, int res_mode, const fsnet_view* res,
+                     const float* res_scale_shift, int relu, int up, const fsnet_view* dst, void* stream);
+int fsnet_copy_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
+int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
+int fsnet_maxpool_bwd(const fsnet_view* src, const fsnet_view* grad_dst, const fsnet_view* grad_src, int accumulate, void* stream);
+int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+                        const float* mean_invstd, double* sums, void* stream);
+int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+                       const float* mean_invstd, const float* gamma, double* sums, double count,
+                       const fsnet_view* dy, int res_mode, const fsnet_view* res, void* stream);
+int fsnet_fold_ring(const fsnet_view* g, void* stream);
+int fsnet_add_slice(const fsnet_view* dst, const fsnet_view* src, int accumulate, void* stream);
+int fsnet_zero_insert(const fsnet_view* src, const fsnet_view* dst, void* stream);
 
 #ifdef __cplusplus
 }
