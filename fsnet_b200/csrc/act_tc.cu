@@ -206,6 +206,7 @@ struct BnBwdParams {
   V g;                          // incoming gradient wrt the activation (fp32); `up`=2: adjoint of nearest x2
   int up;
   V mask; int has_mask;         // activation planes (ReLU output): gradient passes where value > 0
+  const float* mask_ss;         // alternative mask: raw*scale+shift > 0 (activation only stored up-sampled)
   V raw;                        // conv raw output (fp32)
   const float* mean_invstd;     // [2C] or null (no BN: plain masked gradient)
   const float* gamma;           // [C] or null
@@ -226,6 +227,9 @@ __device__ __forceinline__ float masked_g(const BnBwdParams& p, int n, int y, in
     const __nv_bfloat16* mh = (const __nv_bfloat16*)p.mask.ptr;
     size_t mi = vidx(p.mask, n, y, x, c);
     float a = __bfloat162float(mh[mi]) + __bfloat162float(mh[mi + plane_stride(p.mask)]);
+    g = a > 0.f ? g : 0.f;
+  } else if (p.mask_ss) {
+    float a = fmaf(((const float*)p.raw.ptr)[vidx(p.raw, n, y, x, c)], __ldg(p.mask_ss + c), __ldg(p.mask_ss + p.raw.c + c));
     g = a > 0.f ? g : 0.f;
   }
   return g;
@@ -435,19 +439,19 @@ extern "C" int fsnet_maxpool_bwd(const fsnet_view* src, const fsnet_view* grad_d
   return FSNET_OK;
 }
 
-static int fill_bn_bwd(BnBwdParams& p, const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+static int fill_bn_bwd(BnBwdParams& p, const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_ss, const fsnet_view* raw,
                        const float* mean_invstd, const float* gamma, double* sums, double count) {
   FSNET_REQUIRE(g && raw && g->ptr && raw->ptr && sums && (up == 1 || up == 2), "fsnet_bn_bwd: bad arguments");
   FSNET_REQUIRE(g->h == raw->h * up && g->w == raw->w * up && g->c == raw->c, "fsnet_bn_bwd: gradient / raw shape mismatch");
   p.g = *g; p.up = up; p.has_mask = mask != nullptr && mask->ptr != nullptr; if (p.has_mask) p.mask = *mask;
-  p.raw = *raw; p.mean_invstd = mean_invstd; p.gamma = gamma; p.sums = sums; p.count = count;
+  p.raw = *raw; p.mean_invstd = mean_invstd; p.gamma = gamma; p.sums = sums; p.count = count; p.mask_ss = mask_ss;
   return FSNET_OK;
 }
 
-extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_ss, const fsnet_view* raw,
                                    const float* mean_invstd, double* sums, void* stream) {
   BnBwdParams p = {};
-  int rc = fill_bn_bwd(p, g, up, mask, raw, mean_invstd, nullptr, sums, 1.0);
+  int rc = fill_bn_bwd(p, g, up, mask, mask_ss, raw, mean_invstd, nullptr, sums, 1.0);
   if (rc) return rc;
   size_t npix = (size_t)raw->n * raw->h * raw->w;
   unsigned grid = (unsigned)((npix + 8 * 16 - 1) / (8 * 16));
@@ -458,11 +462,11 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   return FSNET_OK;
 }
 
-extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_ss, const fsnet_view* raw,
                                   const float* mean_invstd, const float* gamma, double* sums, double count,
                                   const fsnet_view* dy, int res_mode, const fsnet_view* res, void* stream) {
   BnBwdParams p = {};
-  int rc = fill_bn_bwd(p, g, up, mask, raw, mean_invstd, gamma, sums, count);
+  int rc = fill_bn_bwd(p, g, up, mask, mask_ss, raw, mean_invstd, gamma, sums, count);
   if (rc) return rc;
   FSNET_REQUIRE(dy && dy->ptr && (res_mode == 0 || (res && res->ptr)), "fsnet_bn_bwd_apply: bad arguments");
   p.dy = *dy; p.res_mode = res_mode; if (res) p.res = *res;

@@ -1,0 +1,502 @@
+"""Whole-network executor of the tcgen05 path.
+
+The reference runs its depth net / PoseNet as ~hundreds of autograd nodes (cuDNN conv, BN, ReLU, add,
+interpolate, cat ...).  Here one ``torch.autograd.Function`` per network walks the module tree (which
+only holds parameters, in the reference's layout), launches the hand-written kernels of
+csrc/conv_tc.cu + csrc/act_tc.cu in forward order, and records a tape of backward closures that are
+replayed in reverse.  Activations never leave the device-resident bf16 "planes" / fp32 "raw" buffers.
+
+Per convolution: forward   conv (tcgen05, bf16x3, BN statistics in the epilogue) -> bn_finalize -> act_planes
+                 backward  bn_bwd_reduce -> bn_bwd_apply (-> dy plane) -> conv_wgrad + conv (data gradient)
+"""
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib, tc
+from .tc import Fp32, Planes, View, pad16
+
+MOMENTUM_DEFAULT = 0.1
+
+
+class Act:
+    """An activation tensor of the graph: a channel slice of a planes buffer plus its gradient buffer.
+    Slices of a concat buffer share the gradient buffer and its bookkeeping through ``root``."""
+
+    def __init__(self, planes: Planes, c_off=0, c=None, relu=True, grad_ring=0, root: Optional["Act"] = None):
+        self.planes, self.c_off, self.c = planes, c_off, planes.c if c is None else c
+        self.relu = relu
+        self.root = root if root is not None else self
+        self._grad: Optional[Fp32] = None
+        self._grad_ring = grad_ring
+        self._written = False
+        self._dirty = False
+
+    n = property(lambda self: self.planes.n)
+    h = property(lambda self: self.planes.h)
+    w = property(lambda self: self.planes.w)
+    grad = property(lambda self: self.root._grad)
+
+    @property
+    def grad_written(self):
+        return self.root._written
+
+    @grad_written.setter
+    def grad_written(self, v):
+        self.root._written = v
+
+    @property
+    def ring_dirty(self):
+        return self.root._dirty
+
+    @ring_dirty.setter
+    def ring_dirty(self, v):
+        self.root._dirty = v
+
+    def pview(self) -> View:
+        return self.planes.view(self.c_off, self.c)
+
+    def ensure_grad(self):
+        r = self.root
+        if r._grad is None:
+            r._grad = Fp32(r.n, r.h, r.w, r.planes.c, ring=r._grad_ring, device=r.planes.t.device)
+        return r._grad
+
+    def gview(self) -> View:
+        return self.grad.view(self.c_off, self.c)
+
+    def gview_full_ring(self) -> View:
+        """The ringed gradient buffer seen as a plain [N, H+2, W+2, C] tensor (target of a pad-(k-1) data gradient)."""
+        g = self.grad
+        assert g.ring == 1 and self.c_off == 0 and self.c == g.c
+        return View(g.t.data_ptr(), g.n, g.h + 2, g.w + 2, g.c, 0, g.c, 0)
+
+
+class LayerState:
+    """Per-convolution device state that persists across steps (operand planes, statistics, scale/shift)."""
+
+    def __init__(self, conv: nn.Conv2d, bn: Optional[nn.Module], need_dgrad=True):
+        self.conv, self.bn = conv, bn
+        w = conv.weight
+        self.w = tc.ConvWeights(w, need_dgrad)
+        C = self.w.co_pad
+        dev = w.device
+        self.C, self.c_real = C, w.shape[0]
+        self.stats = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+        self.sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+        self.ss = torch.zeros(2 * C, device=dev, dtype=torch.float32)
+        self.mi = torch.zeros(2 * C, device=dev, dtype=torch.float32)
+        self.kh, self.kw = conv.kernel_size
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+        self.replicate = getattr(conv, "padding_mode", "zeros") == "replicate"
+        assert conv.dilation[0] == 1 and conv.groups == 1, "tcgen05 path: dilation/groups unsupported"
+
+    def padded(self, t: Optional[torch.Tensor], fill=0.0):
+        if t is None:
+            return None
+        if t.shape[0] == self.C:
+            return t.detach()
+        out = torch.full((self.C,), fill, device=t.device, dtype=torch.float32)
+        out[: t.shape[0]] = t.detach()
+        return out
+
+
+def _sync_world(bn) -> int:
+    if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
+class Tape:
+    """Forward executor + backward tape for one network invocation."""
+
+    def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool):
+        self.states, self.training, self.need_grad = states, training, need_grad
+        self.backward_ops: List = []
+        self.param_grads: Dict[int, torch.Tensor] = {}      # id(parameter) -> gradient tensor
+
+    def state(self, conv, bn, need_dgrad=True) -> LayerState:
+        st = self.states.get(id(conv))
+        if st is None:
+            st = LayerState(conv, bn, need_dgrad)
+            self.states[id(conv)] = st
+        return st
+
+    # -------------------------------------------------------------------------------------------
+    def conv_bn_act(self, x: Act, conv: nn.Conv2d, bn, relu=True, residual: Optional[Act] = None, down=None,
+                    up=1, dst: Optional[Act] = None, need_dgrad=True, grad_ring=0) -> Act:
+        """conv -> BatchNorm (batch statistics when training) -> (+ residual | + BN(down conv)) -> ReLU -> planes.
+        ``down`` = (conv, bn) of the 1x1 down-sample branch applied to ``residual``'s source ``x_down``."""
+        st = self.state(conv, bn, need_dgrad)
+        st.w.refresh(conv.weight)
+        N = x.n
+        Ho = (x.h + 2 * st.pad - st.kh) // st.stride + 1
+        Wo = (x.w + 2 * st.pad - st.kw) // st.stride + 1
+        raw = Fp32(N, Ho, Wo, st.C, device=x.planes.t.device)
+        bn_train = bn is not None and (self.training and bn.training)
+        tc.conv(x.planes, st.w, raw, st.stride, st.pad, use_ring=st.replicate, stats=st.stats if bn_train else None, in_view=x.pview())
+        count = float(N * Ho * Wo)
+        self._finalize(st, bn, bn_train, count)
+        res_mode, res_view, res_ss = 0, None, None
+        down_state = None
+        if down is not None:
+            dconv, dbn, x_down = down
+            down_state = self._down_forward(x_down, dconv, dbn)
+            res_mode, res_view, res_ss = 2, down_state["raw"].view(), down_state["st"].ss
+        elif residual is not None:
+            res_mode, res_view = 1, residual.pview()
+        if dst is None:
+            out_planes = Planes(N, Ho * up, Wo * up, st.C, ring=1, device=raw.t.device)
+            out = Act(out_planes, relu=relu, grad_ring=grad_ring)
+        else:
+            out = dst
+        _lib.call("fsnet_act_planes", raw.view(), st.ss, res_mode, res_view, res_ss, int(relu), up, out.pview())
+        if self.need_grad:
+            if need_dgrad:
+                x.ensure_grad()
+            if residual is not None and down is None:
+                residual.ensure_grad()
+            if down_state is not None:
+                down_state["x"].ensure_grad()
+            self.backward_ops.append(lambda: self._conv_bn_act_bwd(x, st, bn, bn_train, raw, out, relu, residual, down_state, up, count, need_dgrad))
+        return out
+
+    def _finalize(self, st: LayerState, bn, bn_train: bool, count: float):
+        conv = st.conv
+        if bn is None:
+            # plain convolution with bias: scale = 1, shift = bias
+            st.ss[: st.C] = 1.0
+            st.ss[st.C:] = 0.0 if conv.bias is None else st.padded(conv.bias)
+            return
+        world = _sync_world(bn) if bn_train else 1
+        if world > 1:
+            dist.all_reduce(st.stats)
+            count = count * world
+        st.count = count
+        momentum = MOMENTUM_DEFAULT if bn.momentum is None else bn.momentum
+        _lib.call("fsnet_bn_finalize", st.stats, tc.c_double(count), st.padded(bn.weight, 1.0), st.padded(bn.bias),
+                  st.padded(conv.bias), self._buf(bn.running_mean, st), self._buf(bn.running_var, st),
+                  bn.num_batches_tracked if bn_train else None, float(momentum), float(bn.eps), int(bn_train), st.C,
+                  st.ss, st.mi)
+
+    @staticmethod
+    def _buf(t, st):
+        # running statistics are updated in place; channel counts of BN layers are always multiples of 16
+        assert t is None or t.shape[0] == st.C, "BatchNorm channels must be a multiple of 16 on the tcgen05 path"
+        return t
+
+    def _down_forward(self, x: Act, conv, bn):
+        st = self.state(conv, bn)
+        st.w.refresh(conv.weight)
+        Ho = (x.h - 1) // st.stride + 1
+        Wo = (x.w - 1) // st.stride + 1
+        raw = Fp32(x.n, Ho, Wo, st.C, device=x.planes.t.device)
+        bn_train = self.training and bn.training
+        tc.conv(x.planes, st.w, raw, st.stride, 0, stats=st.stats if bn_train else None, in_view=x.pview())
+        count = float(x.n * Ho * Wo)
+        self._finalize(st, bn, bn_train, count)
+        return dict(st=st, raw=raw, x=x, bn=bn, bn_train=bn_train, count=count)
+
+    # -------------------------------------------------------------------------------------------
+    def _bn_bwd(self, st: LayerState, bn, bn_train, g_view: View, up, mask_view, mask_ss, raw: Fp32, count, res_mode=0, res_view=None):
+        """(ReLU o BatchNorm) backward -> dy plane; fills the BN / bias parameter gradients."""
+        st.sums.zero_()
+        has_bn = bn is not None and bn_train
+        mi = st.mi if has_bn else None
+        _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, st.sums)
+        world = _sync_world(bn) if has_bn else 1
+        if world > 1:
+            dist.all_reduce(st.sums)
+        dy = Planes(raw.n, raw.h, raw.w, st.C, ring=0, device=raw.t.device)
+        gamma = st.padded(bn.weight, 1.0) if bn is not None else None
+        if bn is not None and not bn_train:
+            # BatchNorm in eval mode inside a training step (norm_eval=True): a fixed per-channel scale
+            raise NotImplementedError("norm_eval=True training is not implemented on the tcgen05 path")
+        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, st.sums, tc.c_double(getattr(st, "count", count)),
+                  dy.view(), res_mode, res_view)
+        C = st.c_real
+        if bn is not None:
+            if bn.weight is not None and bn.weight.requires_grad:
+                self.param_grads[id(bn.weight)] = st.sums[st.C:st.C + C].float()
+                self.param_grads[id(bn.bias)] = st.sums[:C].float()
+            if st.conv.bias is not None and st.conv.bias.requires_grad:
+                self.param_grads[id(st.conv.bias)] = torch.zeros_like(st.conv.bias)     # cancelled by the batch mean
+        elif st.conv.bias is not None and st.conv.bias.requires_grad:
+            self.param_grads[id(st.conv.bias)] = st.sums[:C].float()
+        return dy
+
+    def _conv_bwd(self, x: Act, st: LayerState, dy: Planes, need_dgrad=True):
+        """Weight gradient and (accumulated) data gradient of one convolution."""
+        conv = st.conv
+        if conv.weight.requires_grad:
+            acc = tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad)
+            gw = torch.empty_like(conv.weight)
+            _lib.call("fsnet_wgrad_to_param", acc, st.w.co, st.w.ci, st.kh, st.kw, st.w.co_pad, st.w.ci_pad, gw, 0)
+            self.param_grads[id(conv.weight)] = gw
+        if not need_dgrad or x.grad is None:
+            return
+        k = st.kh
+        if st.replicate:
+            # x_pad = replicate_pad(x): gradient of the padded tensor (pad k-1 correlation), then fold the ring
+            assert x.grad.ring == 1, "replicate consumers need a ringed gradient buffer"
+            tc.conv_dgrad(dy, st.w, x.gview_full_ring(), pad=k - 1, accumulate=x.grad_written)
+            x.grad_written = True
+            x.ring_dirty = True
+            return
+        if x.grad.ring == 1 and not x.grad_written:
+            x.grad.t.zero_()                       # interior-only writer on a ringed buffer: the ring must read as zero
+            x.grad_written = True
+        src = dy
+        if st.stride == 2:
+            src = Planes(x.n, x.h, x.w, st.C, ring=0, device=dy.t.device)
+            _lib.call("fsnet_zero_insert", dy.view(), src.view())
+        tc.conv_dgrad(src, st.w, x.gview(), pad=k - 1 - st.pad, accumulate=x.grad_written)
+        x.grad_written = True
+
+    def _fold_if_needed(self, a: Act):
+        if getattr(a, "ring_dirty", False):
+            _lib.call("fsnet_fold_ring", a.grad.view())
+            a.ring_dirty = False
+
+    def _conv_bn_act_bwd(self, x: Act, st, bn, bn_train, raw, out: Act, relu, residual, down_state, up, count, need_dgrad=True):
+        if out.grad is None or not out.grad_written:
+            return                                  # nothing downstream needs this activation's gradient
+        self._fold_if_needed(out)
+        g_view = out.gview()
+        mask_view = out.pview() if (relu and up == 1) else None
+        mask_ss = st.ss if (relu and up == 2) else None
+        res_mode, res_view = 0, None
+        if residual is not None and down_state is None and residual.grad is not None:
+            if residual.grad.ring == 1 and not residual.grad_written:
+                residual.grad.t.zero_()
+            res_mode = 2 if residual.grad_written else 1
+            res_view = residual.gview()
+            residual.grad_written = True
+        dy = self._bn_bwd(st, bn, bn_train, g_view, up, mask_view, mask_ss, raw, count, res_mode, res_view)
+        if down_state is not None:
+            ds = down_state
+            dyd = self._bn_bwd(ds["st"], ds["bn"], ds["bn_train"], g_view, 1, out.pview() if relu else None, None, ds["raw"], ds["count"])
+            self._conv_bwd(ds["x"], ds["st"], dyd)
+        self._conv_bwd(x, st, dy, need_dgrad)
+
+    # -------------------------------------------------------------------------------------------
+    def maxpool(self, x: Act) -> Act:
+        out = Act(Planes(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, ring=1, device=x.planes.t.device))
+        _lib.call("fsnet_maxpool_planes", x.pview(), out.pview())
+        if self.need_grad:
+            x.ensure_grad()
+
+            def bwd():
+                if out.grad is None or not out.grad_written or x.grad is None:
+                    return
+                _lib.call("fsnet_maxpool_bwd", x.pview(), out.gview(), x.gview(), int(x.grad_written))
+                x.grad_written = True
+            self.backward_ops.append(bwd)
+        return out
+
+    def copy_skip(self, skip: Act, dst: Act):
+        _lib.call("fsnet_copy_planes", skip.pview(), dst.pview())
+        if self.need_grad:
+            skip.ensure_grad()
+
+            def bwd():
+                if dst.grad is None or not dst.grad_written or skip.grad is None:
+                    return
+                self._fold_if_needed(dst)
+                _lib.call("fsnet_add_slice", skip.gview(), dst.gview(), int(skip.grad_written))
+                skip.grad_written = True
+            self.backward_ops.append(bwd)
+
+    def conv_out(self, x: Act, conv: nn.Conv2d, key) -> Fp32:
+        """Plain convolution + bias whose fp32 result leaves the tcgen05 graph (dispconv logits, pose output).
+        Its incoming gradient is looked up as ``self.out_grads[key]`` (fp32 NHWC, padded channels) at backward time."""
+        st = self.state(conv, None)
+        st.w.refresh(conv.weight)
+        Ho = (x.h + 2 * st.pad - st.kh) // st.stride + 1
+        Wo = (x.w + 2 * st.pad - st.kw) // st.stride + 1
+        out = Fp32(x.n, Ho, Wo, st.C, device=x.planes.t.device)
+        tc.conv(x.planes, st.w, out, st.stride, st.pad, use_ring=st.replicate, bias=st.padded(conv.bias), in_view=x.pview())
+        if self.need_grad:
+            x.ensure_grad()
+
+            def bwd():
+                g_out = self.out_grads.get(key)
+                if g_out is None:
+                    return
+                g = Fp32(out.n, out.h, out.w, st.C, device=out.t.device)
+                g.t.copy_(g_out)
+                dy = self._bn_bwd(st, None, False, g.view(), 1, None, None, out, float(out.n * out.h * out.w))
+                self._conv_bwd(x, st, dy)
+            self.backward_ops.append(bwd)
+        return out
+
+    def run_backward(self, out_grads: Dict):
+        self.out_grads = out_grads
+        for op in reversed(self.backward_ops):
+            op()
+
+
+# ---------------------------------------------------------------------------------------------------
+# network walkers
+# ---------------------------------------------------------------------------------------------------
+def _image_act(img: torch.Tensor) -> Act:
+    n, c, h, w = img.shape
+    p = Planes(n, h, w, pad16(c), ring=1, device=img.device)
+    _lib.call("fsnet_image_to_planes", img.detach().float().contiguous(), c, p.view())
+    return Act(p, relu=False)
+
+
+def resnet_forward(tape: Tape, net, img: torch.Tensor, want_grads: bool) -> List[Act]:
+    """ResNet.forward (fsnet_b200/networks/resnet.py) on the tcgen05 path -> the five feature Acts."""
+    from .networks.resnet import BasicBlock
+    x = _image_act(img)
+    feats = []
+    a = tape.conv_bn_act(x, net.conv1, net.bn1, relu=True, need_dgrad=False)
+    feats.append(a)
+    a = tape.maxpool(a)
+    for i in range(net.num_stages):
+        for block in getattr(net, f"layer{i + 1}"):
+            inp = a
+            if isinstance(block, BasicBlock):
+                o = tape.conv_bn_act(inp, block.conv1, block.bn1, relu=True)
+                if block.downsample is not None:
+                    a = tape.conv_bn_act(o, block.conv2, block.bn2, relu=True, down=(block.downsample[0], block.downsample[1], inp))
+                else:
+                    a = tape.conv_bn_act(o, block.conv2, block.bn2, relu=True, residual=inp)
+            else:
+                o = tape.conv_bn_act(inp, block.conv1, block.bn1, relu=True)
+                o = tape.conv_bn_act(o, block.conv2, block.bn2, relu=True)
+                if block.downsample is not None:
+                    a = tape.conv_bn_act(o, block.conv3, block.bn3, relu=True, down=(block.downsample[0], block.downsample[1], inp))
+                else:
+                    a = tape.conv_bn_act(o, block.conv3, block.bn3, relu=True, residual=inp)
+        feats.append(a)
+    return feats
+
+
+def decoder_forward(tape: Tape, dec, feats: List[Act]) -> Dict[int, Fp32]:
+    """DepthDecoder._trunk on the tcgen05 path -> {scale: logits (fp32 NHWC buffer, padded channels)}."""
+    logits = {}
+    x = feats[-1]
+    dev = x.planes.t.device
+    for i in range(4, -1, -1):
+        up0 = dec.convs[("upconv", i, 0)]
+        up1 = dec.convs[("upconv", i, 1)]
+        cd = int(dec.num_ch_dec[i])
+        skip = feats[i - 1] if (dec.use_skips and i > 0) else None
+        cs = skip.c if skip is not None else 0
+        cat = Planes(x.n, x.h * 2, x.w * 2, cd + cs, ring=1, device=dev)
+        cat_act = Act(cat, relu=False, grad_ring=1)
+        up_part = Act(cat, 0, cd, relu=True, root=cat_act)
+        tape.conv_bn_act(x, up0.sequence[0], up0.sequence[1], relu=True, up=2, dst=up_part)
+        if skip is not None:
+            tape.copy_skip(skip, Act(cat, cd, cs, relu=False, root=cat_act))
+        x = tape.conv_bn_act(cat_act, up1.sequence[0], up1.sequence[1], relu=True, grad_ring=1)
+        if i in dec.scales:
+            logits[i] = tape.conv_out(x, dec.convs[("dispconv", i)], ("logits", i))
+    return logits
+
+
+def pose_decoder_forward(tape: Tape, dec, last: Act) -> Fp32:
+    """PoseDecoder convolutions (num_input_features = 1) -> fp32 NHWC [N, h, w, pad16(6*n_pred)]."""
+    if dec.num_input_features != 1:
+        raise NotImplementedError("tcgen05 PoseDecoder path handles num_input_features=1 (the only wiring the reference shows)")
+    x = tape.conv_bn_act(last, dec.convs["squeeze"], None, relu=True)
+    x = tape.conv_bn_act(x, dec.convs[("pose", 0)], None, relu=True)
+    x = tape.conv_bn_act(x, dec.convs[("pose", 1)], None, relu=True)
+    return tape.conv_out(x, dec.convs[("pose", 2)], "pose")
+
+
+# ---------------------------------------------------------------------------------------------------
+# autograd wrappers
+# ---------------------------------------------------------------------------------------------------
+def _nhwc_grad(g: torch.Tensor, c_pad: int) -> torch.Tensor:
+    g = g.detach().float().permute(0, 2, 3, 1)
+    if g.shape[-1] != c_pad:
+        out = torch.zeros(*g.shape[:-1], c_pad, device=g.device, dtype=torch.float32)
+        out[..., : g.shape[-1]] = g
+        return out
+    return g.contiguous()
+
+
+def _check_supported(backbone):
+    if backbone.norm_eval or backbone.frozen_stages >= 0:
+        raise NotImplementedError("tcgen05 path: norm_eval=True / frozen_stages are not implemented (no shipped config uses them)")
+
+
+class _DepthNetFn(torch.autograd.Function):
+    """ResNet encoder + U-Net decoder up to the per-scale logits, as ONE autograd node."""
+
+    @staticmethod
+    def forward(ctx, runner, img, *params):
+        need_grad = runner.grad_enabled and any(p.requires_grad for p in params)
+        tape = Tape(runner.states, runner.training, need_grad)
+        feats = resnet_forward(tape, runner.backbone, img, need_grad)
+        logits = decoder_forward(tape, runner.decoder, feats)
+        ctx.tape, ctx.params, ctx.scales = tape, params, list(logits.keys())
+        ctx.c_pad = {s: logits[s].c for s in logits}
+        n = runner.decoder.num_output_channels
+        outs = []
+        for s in ctx.scales:
+            t = logits[s].t.permute(0, 3, 1, 2)         # NCHW view of the NHWC buffer (channels_last strides)
+            if n != logits[s].c:
+                t = t[:, :n].contiguous(memory_format=torch.channels_last)
+            outs.append(t)
+        runner.last_features = feats
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_logits):
+        tape = ctx.tape
+        grads = {("logits", s): _nhwc_grad(g, ctx.c_pad[s]) for s, g in zip(ctx.scales, g_logits) if g is not None}
+        tape.run_backward(grads)
+        return (None, None) + tuple(tape.param_grads.get(id(p)) for p in ctx.params)
+
+
+class _PoseNetFn(torch.autograd.Function):
+    """PoseNet: 6-channel ResNet + PoseDecoder convolutions, as ONE autograd node -> [N, C, h, w] pose map."""
+
+    @staticmethod
+    def forward(ctx, runner, img, *params):
+        need_grad = runner.grad_enabled and any(p.requires_grad for p in params)
+        tape = Tape(runner.states, runner.training, need_grad)
+        feats = resnet_forward(tape, runner.backbone, img, need_grad)
+        out = pose_decoder_forward(tape, runner.decoder, feats[-1])
+        ctx.tape, ctx.params, ctx.c_pad = tape, params, out.c
+        n = 6 * runner.decoder.num_frames_to_predict_for
+        return out.t.permute(0, 3, 1, 2)[:, :n].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        tape = ctx.tape
+        tape.run_backward({"pose": _nhwc_grad(g, ctx.c_pad)})
+        return (None, None) + tuple(tape.param_grads.get(id(p)) for p in ctx.params)
+
+
+class Runner:
+    """Binds a backbone and a decoder module to the persistent per-layer device state."""
+
+    def __init__(self, backbone, decoder):
+        self.backbone, self.decoder = backbone, decoder
+        self.states: Dict[int, LayerState] = {}
+        self.last_features = None
+
+    def params(self):
+        return [p for p in list(self.backbone.parameters()) + list(self.decoder.parameters())]
+
+    def _prep(self):
+        _check_supported(self.backbone)
+        self.training = self.backbone.training
+        self.grad_enabled = torch.is_grad_enabled()
+
+    def depth_logits(self, img):
+        self._prep()
+        outs = _DepthNetFn.apply(self, img, *self.params())
+        return dict(zip([s for s in range(4, -1, -1) if s in self.decoder.scales], outs))
+
+    def pose_map(self, img):
+        self._prep()
+        return _PoseNetFn.apply(self, img, *self.params())

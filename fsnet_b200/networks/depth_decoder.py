@@ -51,6 +51,14 @@ class DepthDecoder(nn.Module):
         return (P2[:, 0, 0] / self.base_fx).float()
 
     def _trunk(self, input_features):
+        from .ops_tc import LazyFeatures, runner_for
+        if isinstance(input_features, LazyFeatures) and not input_features.materialized:
+            # tcgen05 path: encoder + decoder as one autograd node
+            logits = runner_for(self, input_features.backbone).depth_logits(input_features.image)
+            for i in range(4, -1, -1):
+                if i in self.scales:
+                    yield i, logits[i]
+            return
         x = input_features[-1]
         for i in range(4, -1, -1):
             x = self.convs[("upconv", i, 0)](x)

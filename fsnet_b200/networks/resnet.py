@@ -120,6 +120,9 @@ class ResNet(nn.Module):
                 p.requires_grad = False
 
     def forward(self, img_batch):
+        if ops.BACKEND == "tc" and img_batch.is_cuda:
+            from .ops_tc import LazyFeatures
+            return LazyFeatures(self, img_batch)      # executed by the consuming head (fsnet_b200/engine.py)
         outs = []
         x = ops.conv_bn_act(img_batch, self.conv1, self.bn1, relu=True)
         if -1 in self.out_indices:

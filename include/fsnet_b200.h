@@ -193,7 +193,8 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
  *                          dy (bf16 plane) = gamma*invstd*(g - mean g - xhat*mean g*xhat); mean_invstd == NULL
  *                          means "no BatchNorm" (dy = masked g); `up`=2 reads the gradient through the adjoint
  *                          of the nearest x2 up-sampling; res_mode 1/2 writes/accumulates the masked gradient
- *                          into another fp32 view (identity residual)
+ *                          into another fp32 view (identity residual); the ReLU mask is `mask` (activation planes)
+ *                          or, when mask == NULL and mask_scale_shift != NULL, raw*scale+shift > 0
  *   fsnet_fold_ring        adjoint of replicate padding: adds the ring of a ringed fp32 gradient into its border
  *   fsnet_add_slice        dst (+)= channel slice of src (fp32 views)
  *   fsnet_zero_insert      bf16 plane -> zero-stuffed x2 plane (stride-2 data gradient as a stride-1 convolution)
@@ -211,9 +212,9 @@ int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift, int res_mo
 int fsnet_copy_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
 int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
 int fsnet_maxpool_bwd(const fsnet_view* src, const fsnet_view* grad_dst, const fsnet_view* grad_src, int accumulate, void* stream);
-int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_scale_shift, const fsnet_view* raw,
                         const float* mean_invstd, double* sums, void* stream);
-int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const fsnet_view* raw,
+int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_scale_shift, const fsnet_view* raw,
                        const float* mean_invstd, const float* gamma, double* sums, double count,
                        const fsnet_view* dy, int res_mode, const fsnet_view* res, void* stream);
 int fsnet_fold_ring(const fsnet_view* g, void* stream);

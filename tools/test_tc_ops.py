@@ -117,12 +117,12 @@ def test_bn_act(N, C, H, W, up, res_mode):
     act_lowres = tc.Planes(N, H, W, C, ring=1, zero=True)
     _lib.call("fsnet_act_planes", rawb.view(), ss, res_mode, resp.view() if resp else None, None, 1, 1, act_lowres.view())
     sums = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
-    _lib.call("fsnet_bn_bwd_reduce", gbuf.view(), up, act_lowres.view(), rawb.view(), mi, sums)
+    _lib.call("fsnet_bn_bwd_reduce", gbuf.view(), up, act_lowres.view() if up == 1 else None, ss if up == 2 else None, rawb.view(), mi, sums)
     check("bn bwd dbeta " + tag, sums[:C], grads[2], 1e-4)
     check("bn bwd dgamma " + tag, sums[C:], grads[1], 1e-4)
     dy = tc.Planes(N, H, W, C, ring=0, zero=True)
     gres = tc.Fp32(N, H, W, C, zero=True)
-    _lib.call("fsnet_bn_bwd_apply", gbuf.view(), up, act_lowres.view(), rawb.view(), mi, gamma.detach(), sums, tc.c_double(cnt),
+    _lib.call("fsnet_bn_bwd_apply", gbuf.view(), up, act_lowres.view() if up == 1 else None, ss if up == 2 else None, rawb.view(), mi, gamma.detach(), sums, tc.c_double(cnt),
               dy.view(), 1 if res_mode == 1 else 0, gres.view() if res_mode == 1 else None)
     check("bn bwd dy " + tag, dy.t[0].float().permute(0, 3, 1, 2), grads[0], 1e-2)
     if res_mode == 1:
