@@ -404,7 +404,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   p.org = use_ring ? in->ring : 0;
   pick_tile(p.Ho, p.Wo, p.TH, p.TW);
   p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
-  p.BN = Cout <= 128 ? Cout : 128;
+  p.BN = Cout <= 128 ? Cout : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16)));
   FSNET_REQUIRE(Cout % p.BN == 0, "fsnet_conv: cannot tile Cout=%d", Cout);
   p.n_tiles = Cout / p.BN;
   p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
@@ -616,7 +616,7 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   p.BM_real = BMr; p.co_tiles = p.Cout / BMr;
   p.nA = BMr / p.atomA;
   FSNET_REQUIRE(p.nA == 1 || p.nA * p.atomA == 128, "fsnet_conv_wgrad: Cout=%d needs partial atom aliasing (unsupported)", p.Cout);
-  p.BN = p.Cin <= 128 ? p.Cin : 128;
+  p.BN = p.Cin <= 128 ? p.Cin : (p.Cin % 128 == 0 ? 128 : (p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16)));
   FSNET_REQUIRE(p.Cin % p.BN == 0, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
   p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
   int pw = 1;

@@ -86,8 +86,6 @@ class LayerState:
         self.C, self.c_real = C, w.shape[0]
         self.stats = torch.zeros(2 * C, device=dev, dtype=torch.float64)
         self.sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
-        self.ss = torch.zeros(2 * C, device=dev, dtype=torch.float32)
-        self.mi = torch.zeros(2 * C, device=dev, dtype=torch.float32)
         self.kh, self.kw = conv.kernel_size
         self.stride = conv.stride[0]
         self.pad = conv.padding[0]
@@ -102,6 +100,18 @@ class LayerState:
         out = torch.full((self.C,), fill, device=t.device, dtype=torch.float32)
         out[: t.shape[0]] = t.detach()
         return out
+
+
+class Inv:
+    """Per-invocation results of one layer (a network may run several times per step, e.g. the PoseNet):
+    BN scale/shift, mean/invstd and the element count; the backward of THAT invocation reads them."""
+
+    def __init__(self, st: LayerState):
+        dev = st.stats.device
+        self.st = st
+        self.ss = torch.empty(2 * st.C, device=dev, dtype=torch.float32)
+        self.mi = torch.empty(2 * st.C, device=dev, dtype=torch.float32)
+        self.count = 1.0
 
 
 def _sync_world(bn) -> int:
@@ -139,13 +149,14 @@ class Tape:
         bn_train = bn is not None and (self.training and bn.training)
         tc.conv(x.planes, st.w, raw, st.stride, st.pad, use_ring=st.replicate, stats=st.stats if bn_train else None, in_view=x.pview())
         count = float(N * Ho * Wo)
-        self._finalize(st, bn, bn_train, count)
+        inv = Inv(st)
+        self._finalize(inv, bn, bn_train, count)
         res_mode, res_view, res_ss = 0, None, None
         down_state = None
         if down is not None:
             dconv, dbn, x_down = down
             down_state = self._down_forward(x_down, dconv, dbn)
-            res_mode, res_view, res_ss = 2, down_state["raw"].view(), down_state["st"].ss
+            res_mode, res_view, res_ss = 2, down_state["raw"].view(), down_state["inv"].ss
         elif residual is not None:
             res_mode, res_view = 1, residual.pview()
         if dst is None:
@@ -153,7 +164,7 @@ class Tape:
             out = Act(out_planes, relu=relu, grad_ring=grad_ring)
         else:
             out = dst
-        _lib.call("fsnet_act_planes", raw.view(), st.ss, res_mode, res_view, res_ss, int(relu), up, out.pview())
+        _lib.call("fsnet_act_planes", raw.view(), inv.ss, res_mode, res_view, res_ss, int(relu), up, out.pview())
         if self.need_grad:
             if need_dgrad:
                 x.ensure_grad()
@@ -161,26 +172,28 @@ class Tape:
                 residual.ensure_grad()
             if down_state is not None:
                 down_state["x"].ensure_grad()
-            self.backward_ops.append(lambda: self._conv_bn_act_bwd(x, st, bn, bn_train, raw, out, relu, residual, down_state, up, count, need_dgrad))
+            self.backward_ops.append(lambda: self._conv_bn_act_bwd(x, inv, bn, bn_train, raw, out, relu, residual, down_state, up, need_dgrad))
         return out
 
-    def _finalize(self, st: LayerState, bn, bn_train: bool, count: float):
+    def _finalize(self, inv: Inv, bn, bn_train: bool, count: float):
+        st = inv.st
         conv = st.conv
+        inv.count = count
         if bn is None:
             # plain convolution with bias: scale = 1, shift = bias
-            st.ss[: st.C] = 1.0
-            st.ss[st.C:] = 0.0 if conv.bias is None else st.padded(conv.bias)
+            inv.ss[: st.C] = 1.0
+            inv.ss[st.C:] = 0.0 if conv.bias is None else st.padded(conv.bias)
             return
         world = _sync_world(bn) if bn_train else 1
         if world > 1:
             dist.all_reduce(st.stats)
             count = count * world
-        st.count = count
+        inv.count = count
         momentum = MOMENTUM_DEFAULT if bn.momentum is None else bn.momentum
         _lib.call("fsnet_bn_finalize", st.stats, tc.c_double(count), st.padded(bn.weight, 1.0), st.padded(bn.bias),
                   st.padded(conv.bias), self._buf(bn.running_mean, st), self._buf(bn.running_var, st),
                   bn.num_batches_tracked if bn_train else None, float(momentum), float(bn.eps), int(bn_train), st.C,
-                  st.ss, st.mi)
+                  inv.ss, inv.mi)
 
     @staticmethod
     def _buf(t, st):
@@ -196,16 +209,17 @@ class Tape:
         raw = Fp32(x.n, Ho, Wo, st.C, device=x.planes.t.device)
         bn_train = self.training and bn.training
         tc.conv(x.planes, st.w, raw, st.stride, 0, stats=st.stats if bn_train else None, in_view=x.pview())
-        count = float(x.n * Ho * Wo)
-        self._finalize(st, bn, bn_train, count)
-        return dict(st=st, raw=raw, x=x, bn=bn, bn_train=bn_train, count=count)
+        inv = Inv(st)
+        self._finalize(inv, bn, bn_train, float(x.n * Ho * Wo))
+        return dict(st=st, inv=inv, raw=raw, x=x, bn=bn, bn_train=bn_train)
 
     # -------------------------------------------------------------------------------------------
-    def _bn_bwd(self, st: LayerState, bn, bn_train, g_view: View, up, mask_view, mask_ss, raw: Fp32, count, res_mode=0, res_view=None):
+    def _bn_bwd(self, inv: Inv, bn, bn_train, g_view: View, up, mask_view, mask_ss, raw: Fp32, res_mode=0, res_view=None):
         """(ReLU o BatchNorm) backward -> dy plane; fills the BN / bias parameter gradients."""
+        st = inv.st
         st.sums.zero_()
         has_bn = bn is not None and bn_train
-        mi = st.mi if has_bn else None
+        mi = inv.mi if has_bn else None
         _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, st.sums)
         world = _sync_world(bn) if has_bn else 1
         if world > 1:
@@ -215,7 +229,7 @@ class Tape:
         if bn is not None and not bn_train:
             # BatchNorm in eval mode inside a training step (norm_eval=True): a fixed per-channel scale
             raise NotImplementedError("norm_eval=True training is not implemented on the tcgen05 path")
-        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, st.sums, tc.c_double(getattr(st, "count", count)),
+        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, st.sums, tc.c_double(inv.count),
                   dy.view(), res_mode, res_view)
         C = st.c_real
         if bn is not None:
@@ -261,13 +275,14 @@ class Tape:
             _lib.call("fsnet_fold_ring", a.grad.view())
             a.ring_dirty = False
 
-    def _conv_bn_act_bwd(self, x: Act, st, bn, bn_train, raw, out: Act, relu, residual, down_state, up, count, need_dgrad=True):
+    def _conv_bn_act_bwd(self, x: Act, inv: Inv, bn, bn_train, raw, out: Act, relu, residual, down_state, up, need_dgrad=True):
+        st = inv.st
         if out.grad is None or not out.grad_written:
             return                                  # nothing downstream needs this activation's gradient
         self._fold_if_needed(out)
         g_view = out.gview()
         mask_view = out.pview() if (relu and up == 1) else None
-        mask_ss = st.ss if (relu and up == 2) else None
+        mask_ss = inv.ss if (relu and up == 2) else None
         res_mode, res_view = 0, None
         if residual is not None and down_state is None and residual.grad is not None:
             if residual.grad.ring == 1 and not residual.grad_written:
@@ -275,10 +290,10 @@ class Tape:
             res_mode = 2 if residual.grad_written else 1
             res_view = residual.gview()
             residual.grad_written = True
-        dy = self._bn_bwd(st, bn, bn_train, g_view, up, mask_view, mask_ss, raw, count, res_mode, res_view)
+        dy = self._bn_bwd(inv, bn, bn_train, g_view, up, mask_view, mask_ss, raw, res_mode, res_view)
         if down_state is not None:
             ds = down_state
-            dyd = self._bn_bwd(ds["st"], ds["bn"], ds["bn_train"], g_view, 1, out.pview() if relu else None, None, ds["raw"], ds["count"])
+            dyd = self._bn_bwd(ds["inv"], ds["bn"], ds["bn_train"], g_view, 1, out.pview() if relu else None, None, ds["raw"])
             self._conv_bwd(ds["x"], ds["st"], dyd)
         self._conv_bwd(x, st, dy, need_dgrad)
 
@@ -328,7 +343,7 @@ class Tape:
                     return
                 g = Fp32(out.n, out.h, out.w, st.C, device=out.t.device)
                 g.t.copy_(g_out)
-                dy = self._bn_bwd(st, None, False, g.view(), 1, None, None, out, float(out.n * out.h * out.w))
+                dy = self._bn_bwd(Inv(st), None, False, g.view(), 1, None, None, out)
                 self._conv_bwd(x, st, dy)
             self.backward_ops.append(bwd)
         return out
