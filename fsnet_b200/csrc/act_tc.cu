@@ -44,6 +44,64 @@ __device__ __forceinline__ void store_with_ring(const V& d, __nv_bfloat16* hi, _
   if (r && b) split_store(hi, lo, vidx(d, n, d.h, d.w, c), val);
 }
 
+
+// ---- 8-channel vector helpers (all channel counts on this path are multiples of 16) ------------------------
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld_f8(const float* p) {
+  F8 r; float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w; return r;
+}
+__device__ __forceinline__ void st_f8(float* p, const F8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ F8 ld_bf8(const __nv_bfloat16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r; const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { r.v[2 * i] = __uint_as_float(w[i] << 16); r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// splits 8 floats into hi / lo bf16 and stores them (lo may be null)
+__device__ __forceinline__ void st_split8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t i, const F8& x) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    h[k] = pack_bf2(x.v[2 * k], x.v[2 * k + 1]);
+    float h0 = __uint_as_float(h[k] << 16), h1 = __uint_as_float(h[k] & 0xffff0000u);
+    l[k] = pack_bf2(x.v[2 * k] - h0, x.v[2 * k + 1] - h1);
+  }
+  *reinterpret_cast<uint4*>(hi + i) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) *reinterpret_cast<uint4*>(lo + i) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void store_with_ring8(const V& d, __nv_bfloat16* hi, __nv_bfloat16* lo, int n, int y, int x, int c, const F8& val) {
+  st_split8(hi, lo, vidx(d, n, y, x, c), val);
+  if (d.ring == 0) return;
+  const bool l = x == 0, r = x == d.w - 1, t = y == 0, b = y == d.h - 1;
+  if (!(l | r | t | b)) return;
+  if (l) st_split8(hi, lo, vidx(d, n, y, -1, c), val);
+  if (r) st_split8(hi, lo, vidx(d, n, y, d.w, c), val);
+  if (t) st_split8(hi, lo, vidx(d, n, -1, x, c), val);
+  if (b) st_split8(hi, lo, vidx(d, n, d.h, x, c), val);
+  if (l && t) st_split8(hi, lo, vidx(d, n, -1, -1, c), val);
+  if (r && t) st_split8(hi, lo, vidx(d, n, -1, d.w, c), val);
+  if (l && b) st_split8(hi, lo, vidx(d, n, d.h, -1, c), val);
+  if (r && b) st_split8(hi, lo, vidx(d, n, d.h, d.w, c), val);
+}
+// 32-bit decode of a flat (pixel, 8-channel group) index
+struct Px { int n, y, x, c; };
+__device__ __forceinline__ Px decode8(unsigned i, int H, int W, int C) {
+  const unsigned g = (unsigned)C >> 3;
+  Px p; unsigned pix = i / g; p.c = (int)(i - pix * g) << 3;
+  unsigned t = pix / (unsigned)W; p.x = (int)(pix - t * (unsigned)W);
+  unsigned n = t / (unsigned)H; p.y = (int)(t - n * (unsigned)H); p.n = (int)n;
+  return p;
+}
+
 // ---- image (fp32 NCHW) -> planes with zero-filled extra channels ----------------------------------
 __global__ void image_to_planes_kernel(const float* __restrict__ img, int C, V d) {
   size_t total = (size_t)d.n * d.h * d.w * d.c;
@@ -102,103 +160,118 @@ struct ActParams {
   int relu, up;
   V dst;                        // planes
 };
-__global__ void act_planes_kernel(ActParams p) {
+__global__ void __launch_bounds__(256) act_planes_kernel(ActParams p) {
   const V& s = p.raw;
-  size_t total = (size_t)s.n * s.h * s.w * s.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)s.n * s.h * s.w * (s.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % s.c); size_t r = i / s.c;
-  int x = (int)(r % s.w); r /= s.w;
-  int y = (int)(r % s.h); int n = (int)(r / s.h);
-  float v = ((const float*)s.ptr)[vidx(s, n, y, x, c)];
-  if (p.ss) v = fmaf(v, __ldg(p.ss + c), __ldg(p.ss + s.c + c));
+  const Px q = decode8(i, s.h, s.w, s.c);
+  F8 v = ld_f8((const float*)s.ptr + vidx(s, q.n, q.y, q.x, q.c));
+  if (p.ss) {
+    F8 sc = ld_f8(p.ss + q.c), sh = ld_f8(p.ss + s.c + q.c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaf(v.v[k], sc.v[k], sh.v[k]);
+  }
   if (p.res_mode == 1) {
     const __nv_bfloat16* rh = (const __nv_bfloat16*)p.res.ptr;
-    v += plane_load(rh, rh + plane_stride(p.res), vidx(p.res, n, y, x, c));
+    const size_t ri = vidx(p.res, q.n, q.y, q.x, q.c);
+    F8 a = ld_bf8(rh + ri), b = ld_bf8(rh + ri + plane_stride(p.res));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] += a.v[k] + b.v[k];
   } else if (p.res_mode == 2) {
-    float rv = ((const float*)p.res.ptr)[vidx(p.res, n, y, x, c)];
-    v += fmaf(rv, __ldg(p.res_ss + c), __ldg(p.res_ss + s.c + c));
+    F8 rv = ld_f8((const float*)p.res.ptr + vidx(p.res, q.n, q.y, q.x, q.c));
+    F8 sc = ld_f8(p.res_ss + q.c), sh = ld_f8(p.res_ss + s.c + q.c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] += fmaf(rv.v[k], sc.v[k], sh.v[k]);
   }
-  if (p.relu) v = fmaxf(v, 0.f);
+  if (p.relu) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+  }
   __nv_bfloat16* hi = (__nv_bfloat16*)p.dst.ptr;
   __nv_bfloat16* lo = hi + plane_stride(p.dst);
   if (p.up == 1) {
-    store_with_ring(p.dst, hi, lo, n, y, x, c, v);
+    store_with_ring8(p.dst, hi, lo, q.n, q.y, q.x, q.c, v);
   } else {
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) store_with_ring(p.dst, hi, lo, n, 2 * y + dy, 2 * x + dx, c, v);
+      for (int dx = 0; dx < 2; ++dx) store_with_ring8(p.dst, hi, lo, q.n, 2 * q.y + dy, 2 * q.x + dx, q.c, v);
   }
 }
 
 // ---- planes -> planes channel-slice copy (skip connection into the concat buffer), ring included --------
-__global__ void copy_planes_kernel(V s, V d) {
+__global__ void __launch_bounds__(256) copy_planes_kernel(V s, V d) {
   const int ph = s.h + 2 * s.ring, pw = s.w + 2 * s.ring;
-  size_t total = (size_t)s.n * ph * pw * s.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)s.n * ph * pw * (s.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % s.c); size_t r = i / s.c;
-  int x = (int)(r % pw) - s.ring; r /= pw;
-  int y = (int)(r % ph) - s.ring; int n = (int)(r / ph);
+  Px q = decode8(i, ph, pw, s.c);
+  q.y -= s.ring; q.x -= s.ring;
   const __nv_bfloat16* sh = (const __nv_bfloat16*)s.ptr;
   __nv_bfloat16* dh = (__nv_bfloat16*)d.ptr;
-  size_t si = vidx(s, n, y, x, c), di = vidx(d, n, y, x, c);
-  dh[di] = sh[si];
-  dh[di + plane_stride(d)] = sh[si + plane_stride(s)];
+  const size_t si = vidx(s, q.n, q.y, q.x, q.c), di = vidx(d, q.n, q.y, q.x, q.c);
+  *reinterpret_cast<uint4*>(dh + di) = *reinterpret_cast<const uint4*>(sh + si);
+  *reinterpret_cast<uint4*>(dh + di + plane_stride(d)) = *reinterpret_cast<const uint4*>(sh + si + plane_stride(s));
 }
 
 // ---- 3x3 / stride 2 / pad 1 max-pool on planes ---------------------------------------------------------------
-__global__ void maxpool_planes_kernel(V s, V d) {
-  size_t total = (size_t)d.n * d.h * d.w * d.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) maxpool_planes_kernel(V s, V d, uint8_t* __restrict__ argmax) {
+  const unsigned total = (unsigned)d.n * d.h * d.w * (d.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % d.c); size_t r = i / d.c;
-  int x = (int)(r % d.w); r /= d.w;
-  int y = (int)(r % d.h); int n = (int)(r / d.h);
+  const Px q = decode8(i, d.h, d.w, d.c);
   const __nv_bfloat16* sh = (const __nv_bfloat16*)s.ptr;
   const __nv_bfloat16* sl = sh + plane_stride(s);
-  float m = -INFINITY;
+  F8 m; int am[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { m.v[k] = -INFINITY; am[k] = 0; }
   for (int dy = -1; dy <= 1; ++dy)
     for (int dx = -1; dx <= 1; ++dx) {
-      int yy = 2 * y + dy, xx = 2 * x + dx;
+      const int yy = 2 * q.y + dy, xx = 2 * q.x + dx;
       if (yy < 0 || yy >= s.h || xx < 0 || xx >= s.w) continue;
-      m = fmaxf(m, plane_load(sh, sl, vidx(s, n, yy, xx, c)));
+      const size_t si = vidx(s, q.n, yy, xx, q.c);
+      F8 a = ld_bf8(sh + si), b = ld_bf8(sl + si);
+      const int pos = (dy + 1) * 3 + dx + 1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { float v = a.v[k] + b.v[k]; if (v > m.v[k]) { m.v[k] = v; am[k] = pos; } }   // first maximum wins (PyTorch)
     }
   __nv_bfloat16* dh = (__nv_bfloat16*)d.ptr;
-  store_with_ring(d, dh, dh + plane_stride(d), n, y, x, c, m);
+  store_with_ring8(d, dh, dh + plane_stride(d), q.n, q.y, q.x, q.c, m);
+  if (argmax) {
+    uint2 pk = make_uint2(am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24), am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24));
+    *reinterpret_cast<uint2*>(argmax + (((size_t)q.n * d.h + q.y) * d.w + q.x) * d.c + q.c) = pk;
+  }
 }
-// backward: each source pixel gathers from the (up to 4) windows that contain it and whose first maximum
-// (row-major scan order, as PyTorch) it is.  g_src (+)= ...
-__global__ void maxpool_bwd_kernel(V s, V gd, V gs, int accumulate) {
-  size_t total = (size_t)s.n * s.h * s.w * s.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// backward: every source pixel looks at the (up to 4) windows that contain it and takes their gradient where the
+// stored arg-max points at it.  g_src (+)= ...
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(V s, const uint8_t* __restrict__ argmax, V gd, V gs, int accumulate) {
+  const unsigned total = (unsigned)s.n * s.h * s.w * (s.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % s.c); size_t r = i / s.c;
-  int x = (int)(r % s.w); r /= s.w;
-  int y = (int)(r % s.h); int n = (int)(r / s.h);
-  const __nv_bfloat16* sh = (const __nv_bfloat16*)s.ptr;
-  const __nv_bfloat16* sl = sh + plane_stride(s);
-  const float me = plane_load(sh, sl, vidx(s, n, y, x, c));
-  float g = 0.f;
-  for (int oy = (y - 1 + 1) / 2; oy <= (y + 1) / 2; ++oy) {          // windows with 2*oy-1 <= y <= 2*oy+1
-    if (oy < 0 || oy >= gd.h) continue;
-    for (int ox = x / 2; ox <= (x + 1) / 2; ++ox) {
-      if (ox < 0 || ox >= gd.w) continue;
-      bool first = true;                                               // is (y,x) the first maximum of window (oy,ox)?
-      for (int dy = -1; dy <= 1 && first; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          int yy = 2 * oy + dy, xx = 2 * ox + dx;
-          if (yy < 0 || yy >= s.h || xx < 0 || xx >= s.w) continue;
-          float v = plane_load(sh, sl, vidx(s, n, yy, xx, c));
-          bool before = (yy < y) || (yy == y && xx < x);
-          if (v > me || (before && v == me)) { first = false; break; }
-        }
-      if (first) g += ((const float*)gd.ptr)[vidx(gd, n, oy, ox, c)];
+  const Px q = decode8(i, s.h, s.w, s.c);
+  F8 g;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+  for (int oy = q.y / 2; oy <= (q.y + 1) / 2; ++oy) {                 // windows with 2*oy-1 <= y <= 2*oy+1
+    if (oy >= gd.h) continue;
+    for (int ox = q.x / 2; ox <= (q.x + 1) / 2; ++ox) {
+      if (ox >= gd.w) continue;
+      const int pos = (q.y - 2 * oy + 1) * 3 + (q.x - 2 * ox + 1);
+      const uint2 pk = *reinterpret_cast<const uint2*>(argmax + (((size_t)q.n * gd.h + oy) * gd.w + ox) * gd.c + q.c);
+      const F8 gv = ld_f8((const float*)gd.ptr + vidx(gd, q.n, oy, ox, q.c));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int a = ((k < 4 ? pk.x : pk.y) >> (8 * (k & 3))) & 0xff;
+        if (a == pos) g.v[k] += gv.v[k];
+      }
     }
   }
-  float* o = (float*)gs.ptr + vidx(gs, n, y, x, c);
-  *o = accumulate ? *o + g : g;
+  float* o = (float*)gs.ptr + vidx(gs, q.n, q.y, q.x, q.c);
+  if (accumulate) { F8 old = ld_f8(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] += old.v[k]; }
+  st_f8(o, g);
 }
 
 // ---- BatchNorm (+ReLU mask) backward ------------------------------------------------------------------------------
@@ -215,78 +288,100 @@ struct BnBwdParams {
   V dy;                         // out: bf16 plane (hi only), ring zeroed
   V res; int res_mode;          // 0 none, 1 write masked g, 2 accumulate masked g   (identity residual / downsample input)
 };
-__device__ __forceinline__ float read_g(const BnBwdParams& p, int n, int y, int x, int c) {
-  const float* g = (const float*)p.g.ptr;
-  if (p.up == 1) return g[vidx(p.g, n, y, x, c)];
-  return g[vidx(p.g, n, 2 * y, 2 * x, c)] + g[vidx(p.g, n, 2 * y, 2 * x + 1, c)] + g[vidx(p.g, n, 2 * y + 1, 2 * x, c)] +
-         g[vidx(p.g, n, 2 * y + 1, 2 * x + 1, c)];
-}
-__device__ __forceinline__ float masked_g(const BnBwdParams& p, int n, int y, int x, int c) {
-  float g = read_g(p, n, y, x, c);
+__device__ __forceinline__ F8 masked_g8(const BnBwdParams& p, const Px& q, const F8& rawv) {
+  const float* gp = (const float*)p.g.ptr;
+  F8 g;
+  if (p.up == 1) {
+    g = ld_f8(gp + vidx(p.g, q.n, q.y, q.x, q.c));
+  } else {
+    g = ld_f8(gp + vidx(p.g, q.n, 2 * q.y, 2 * q.x, q.c));
+    F8 b = ld_f8(gp + vidx(p.g, q.n, 2 * q.y, 2 * q.x + 1, q.c)), c = ld_f8(gp + vidx(p.g, q.n, 2 * q.y + 1, 2 * q.x, q.c)),
+       d = ld_f8(gp + vidx(p.g, q.n, 2 * q.y + 1, 2 * q.x + 1, q.c));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] += b.v[k] + c.v[k] + d.v[k];
+  }
   if (p.has_mask) {
     const __nv_bfloat16* mh = (const __nv_bfloat16*)p.mask.ptr;
-    size_t mi = vidx(p.mask, n, y, x, c);
-    float a = __bfloat162float(mh[mi]) + __bfloat162float(mh[mi + plane_stride(p.mask)]);
-    g = a > 0.f ? g : 0.f;
+    const size_t mi = vidx(p.mask, q.n, q.y, q.x, q.c);
+    F8 a = ld_bf8(mh + mi), b = ld_bf8(mh + mi + plane_stride(p.mask));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = (a.v[k] + b.v[k]) > 0.f ? g.v[k] : 0.f;
   } else if (p.mask_ss) {
-    float a = fmaf(((const float*)p.raw.ptr)[vidx(p.raw, n, y, x, c)], __ldg(p.mask_ss + c), __ldg(p.mask_ss + p.raw.c + c));
-    g = a > 0.f ? g : 0.f;
+    F8 sc = ld_f8(p.mask_ss + q.c), sh = ld_f8(p.mask_ss + p.raw.c + q.c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(rawv.v[k], sc.v[k], sh.v[k]) > 0.f ? g.v[k] : 0.f;
   }
   return g;
 }
-// grid: (pixel blocks); block 256 threads = 8 pixel-rows x 32 channel lanes; channels looped in chunks of 32
-__global__ void bn_bwd_reduce_kernel(BnBwdParams p) {
+// Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory
+// float atomics, then one fp64 atomic per channel and block.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
+  extern __shared__ float s_acc[];           // [2*C]
   const V& r = p.raw;
-  const int C = r.c;
-  const size_t npix = (size_t)r.n * r.h * r.w;
-  const int lane = threadIdx.x & 31, row = threadIdx.x >> 5;
-  __shared__ float red[2][8][32];
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int c = c0 + lane;
-    float s1 = 0.f, s2 = 0.f;
-    if (c < C) {
-      const float mean = p.mean_invstd ? __ldg(p.mean_invstd + c) : 0.f, inv = p.mean_invstd ? __ldg(p.mean_invstd + C + c) : 0.f;
-      for (size_t pix = (size_t)blockIdx.x * 8 + row; pix < npix; pix += (size_t)gridDim.x * 8) {
-        int x = (int)(pix % r.w); size_t t = pix / r.w;
-        int y = (int)(t % r.h); int n = (int)(t / r.h);
-        float g = masked_g(p, n, y, x, c);
-        float xh = (((const float*)r.ptr)[vidx(r, n, y, x, c)] - mean) * inv;
-        s1 += g; s2 = fmaf(g, xh, s2);
-      }
+  const int C = r.c, groups = C >> 3;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  if ((int)threadIdx.x < threads_used) {
+    const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
+    const int c = cg << 3;
+    const unsigned npix = (unsigned)r.n * r.h * r.w;
+    F8 mean, inv;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mean.v[k] = 0.f; inv.v[k] = 0.f; }
+    if (p.mean_invstd) { mean = ld_f8(p.mean_invstd + c); inv = ld_f8(p.mean_invstd + C + c); }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += gridDim.x * pix_per_iter) {
+      Px q; unsigned t = pix / (unsigned)r.w; q.x = (int)(pix - t * r.w);
+      unsigned n = t / (unsigned)r.h; q.y = (int)(t - n * r.h); q.n = (int)n; q.c = c;
+      const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, c));
+      const F8 g = masked_g8(p, q, rv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], (rv.v[k] - mean.v[k]) * inv.v[k], s2[k]); }
     }
-    red[0][row][lane] = s1; red[1][row][lane] = s2;
-    __syncthreads();
-    if (row < 2 && c < C) {
-      float t = 0.f;
-      for (int k = 0; k < 8; ++k) t += red[row][k][lane];
-      atomicAdd(p.sums + row * C + c, (double)t);
-    }
-    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float v = s_acc[i];
+    if (v != 0.f) atomicAdd(p.sums + i, (double)v);
   }
 }
-__global__ void bn_bwd_apply_kernel(BnBwdParams p) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
   const V& r = p.raw;
   const int C = r.c;
-  size_t total = (size_t)r.n * r.h * r.w * C;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)r.n * r.h * r.w * (C >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % C); size_t t = i / C;
-  int x = (int)(t % r.w); t /= r.w;
-  int y = (int)(t % r.h); int n = (int)(t / r.h);
-  float g = masked_g(p, n, y, x, c);
+  const Px q = decode8(i, r.h, r.w, C);
+  const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, q.c));
+  const F8 g = masked_g8(p, q, rv);
   if (p.res_mode) {
-    float* o = (float*)p.res.ptr + vidx(p.res, n, y, x, c);
-    *o = p.res_mode == 2 ? *o + g : g;
+    float* o = (float*)p.res.ptr + vidx(p.res, q.n, q.y, q.x, q.c);
+    F8 w = g;
+    if (p.res_mode == 2) { F8 old = ld_f8(o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w.v[k] += old.v[k]; }
+    st_f8(o, w);
   }
-  float d = g;
+  F8 d = g;
   if (p.mean_invstd) {
-    const float mean = __ldg(p.mean_invstd + c), inv = __ldg(p.mean_invstd + C + c);
-    const float xh = (((const float*)r.ptr)[vidx(r, n, y, x, c)] - mean) * inv;
-    const float sg = (float)(p.sums[c] / p.count), sgx = (float)(p.sums[C + c] / p.count);
-    d = (p.gamma ? __ldg(p.gamma + c) : 1.f) * inv * (g - sg - xh * sgx);
+    const F8 mean = ld_f8(p.mean_invstd + q.c), inv = ld_f8(p.mean_invstd + C + q.c);
+    F8 gam;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gam.v[k] = 1.f;
+    if (p.gamma) gam = ld_f8(p.gamma + q.c);
+    const float rc = (float)(1.0 / p.count);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (rv.v[k] - mean.v[k]) * inv.v[k];
+      const float sg = (float)p.sums[q.c + k] * rc, sgx = (float)p.sums[C + q.c + k] * rc;
+      d.v[k] = gam.v[k] * inv.v[k] * (g.v[k] - sg - xh * sgx);
+    }
   }
-  __nv_bfloat16* dh = (__nv_bfloat16*)p.dy.ptr;
-  dh[vidx(p.dy, n, y, x, c)] = __float2bfloat16_rn(d);
+  st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, q.n, q.y, q.x, q.c), d);
 }
 
 // ---- ring folding: adjoint of replicate padding on a ringed fp32 gradient ----------------------------------------------
@@ -318,29 +413,29 @@ __global__ void fold_ring_kernel(V g) {
 }
 
 // dst (+)= src channel slice (both fp32 views, same N,H,W,C)
-__global__ void add_slice_kernel(V d, V s, int accumulate) {
-  size_t total = (size_t)d.n * d.h * d.w * d.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) add_slice_kernel(V d, V s, int accumulate) {
+  const unsigned total = (unsigned)d.n * d.h * d.w * (d.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % d.c); size_t t = i / d.c;
-  int x = (int)(t % d.w); t /= d.w;
-  int y = (int)(t % d.h); int n = (int)(t / d.h);
-  float v = ((const float*)s.ptr)[vidx(s, n, y, x, c)];
-  float* o = (float*)d.ptr + vidx(d, n, y, x, c);
-  *o = accumulate ? *o + v : v;
+  const Px q = decode8(i, d.h, d.w, d.c);
+  F8 v = ld_f8((const float*)s.ptr + vidx(s, q.n, q.y, q.x, q.c));
+  float* o = (float*)d.ptr + vidx(d, q.n, q.y, q.x, q.c);
+  if (accumulate) { F8 old = ld_f8(o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] += old.v[k]; }
+  st_f8(o, v);
 }
 
 // zero-insertion x2 of a bf16 plane (transposed stride-2 convolution as a stride-1 convolution)
-__global__ void zero_insert_kernel(V s, V d) {
-  size_t total = (size_t)d.n * d.h * d.w * d.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) zero_insert_kernel(V s, V d) {
+  const unsigned total = (unsigned)d.n * d.h * d.w * (d.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % d.c); size_t t = i / d.c;
-  int x = (int)(t % d.w); t /= d.w;
-  int y = (int)(t % d.h); int n = (int)(t / d.h);
-  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-  if (!(y & 1) && !(x & 1) && (y >> 1) < s.h && (x >> 1) < s.w) v = ((const __nv_bfloat16*)s.ptr)[vidx(s, n, y >> 1, x >> 1, c)];
-  ((__nv_bfloat16*)d.ptr)[vidx(d, n, y, x, c)] = v;
+  const Px q = decode8(i, d.h, d.w, d.c);
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (!(q.y & 1) && !(q.x & 1) && (q.y >> 1) < s.h && (q.x >> 1) < s.w)
+    v = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)s.ptr + vidx(s, q.n, q.y >> 1, q.x >> 1, q.c));
+  *reinterpret_cast<uint4*>((__nv_bfloat16*)d.ptr + vidx(d, q.n, q.y, q.x, q.c)) = v;
 }
 
 // weights fp32 [Cout,Cin,KH,KW] -> forward planes [Cout_pad,KH,KW,Cin_pad] (hi, lo) and, optionally, the
@@ -407,7 +502,8 @@ extern "C" int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift,
   ActParams p = {};
   p.raw = *raw; p.ss = scale_shift; p.res_mode = res_mode; if (res) p.res = *res; p.res_ss = res_scale_shift;
   p.relu = relu; p.up = up; p.dst = *dst;
-  size_t total = (size_t)raw->n * raw->h * raw->w * raw->c;
+  FSNET_REQUIRE(raw->c % 8 == 0 && raw->c_off % 8 == 0 && dst->c_off % 8 == 0 && dst->c_total % 8 == 0, "fsnet_act_planes: channels must be multiples of 8");
+  size_t total = (size_t)raw->n * raw->h * raw->w * (raw->c / 8);
   act_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
@@ -416,25 +512,27 @@ extern "C" int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift,
 extern "C" int fsnet_copy_planes(const fsnet_view* src, const fsnet_view* dst, void* stream) {
   FSNET_REQUIRE(src && dst && src->ptr && dst->ptr && src->ring == dst->ring && src->h == dst->h && src->w == dst->w && src->c == dst->c,
                 "fsnet_copy_planes: bad arguments");
-  size_t total = (size_t)src->n * (src->h + 2 * src->ring) * (src->w + 2 * src->ring) * src->c;
+  FSNET_REQUIRE(src->c % 8 == 0 && src->c_off % 8 == 0 && dst->c_off % 8 == 0 && dst->c_total % 8 == 0 && src->c_total % 8 == 0, "fsnet_copy_planes: channels must be multiples of 8");
+  size_t total = (size_t)src->n * (src->h + 2 * src->ring) * (src->w + 2 * src->ring) * (src->c / 8);
   copy_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *dst);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
 
-extern "C" int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, void* stream) {
-  FSNET_REQUIRE(src && dst && src->ptr && dst->ptr && dst->h == (src->h + 1) / 2 && dst->w == (src->w + 1) / 2 && dst->c == src->c,
+extern "C" int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, uint8_t* argmax, void* stream) {
+  FSNET_REQUIRE(src && dst && src->ptr && dst->ptr && dst->h == (src->h + 1) / 2 && dst->w == (src->w + 1) / 2 && dst->c == src->c && src->c % 8 == 0,
                 "fsnet_maxpool_planes: bad arguments");
-  size_t total = (size_t)dst->n * dst->h * dst->w * dst->c;
-  maxpool_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *dst);
+  size_t total = (size_t)dst->n * dst->h * dst->w * (dst->c / 8);
+  maxpool_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *dst, argmax);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
 
-extern "C" int fsnet_maxpool_bwd(const fsnet_view* src, const fsnet_view* grad_dst, const fsnet_view* grad_src, int accumulate, void* stream) {
-  FSNET_REQUIRE(src && grad_dst && grad_src && src->ptr && grad_dst->ptr && grad_src->ptr, "fsnet_maxpool_bwd: bad arguments");
-  size_t total = (size_t)src->n * src->h * src->w * src->c;
-  maxpool_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *grad_dst, *grad_src, accumulate);
+extern "C" int fsnet_maxpool_bwd(const fsnet_view* src, const uint8_t* argmax, const fsnet_view* grad_dst, const fsnet_view* grad_src,
+                                 int accumulate, void* stream) {
+  FSNET_REQUIRE(src && argmax && grad_dst && grad_src && grad_dst->ptr && grad_src->ptr, "fsnet_maxpool_bwd: bad arguments");
+  size_t total = (size_t)src->n * src->h * src->w * (src->c / 8);
+  maxpool_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, argmax, *grad_dst, *grad_src, accumulate);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -453,11 +551,15 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   BnBwdParams p = {};
   int rc = fill_bn_bwd(p, g, up, mask, mask_ss, raw, mean_invstd, nullptr, sums, 1.0);
   if (rc) return rc;
+  FSNET_REQUIRE(raw->c % 8 == 0 && raw->c <= 2048, "fsnet_bn_bwd_reduce: channels must be a multiple of 8 and <= 2048");
+  const int groups = raw->c / 8;
+  const int pix_per_iter = 256 / groups > 0 ? 256 / groups : 1;
+  const int threads_used = groups * pix_per_iter;
   size_t npix = (size_t)raw->n * raw->h * raw->w;
-  unsigned grid = (unsigned)((npix + 8 * 16 - 1) / (8 * 16));
-  if (grid > 148 * 8) grid = 148 * 8;
+  unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * 16 - 1) / ((size_t)pix_per_iter * 16));
+  if (grid > 148 * 4) grid = 148 * 4;
   if (grid == 0) grid = 1;
-  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -470,7 +572,7 @@ extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view*
   if (rc) return rc;
   FSNET_REQUIRE(dy && dy->ptr && (res_mode == 0 || (res && res->ptr)), "fsnet_bn_bwd_apply: bad arguments");
   p.dy = *dy; p.res_mode = res_mode; if (res) p.res = *res;
-  size_t total = (size_t)raw->n * raw->h * raw->w * raw->c;
+  size_t total = (size_t)raw->n * raw->h * raw->w * (raw->c / 8);
   bn_bwd_apply_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
@@ -487,7 +589,7 @@ extern "C" int fsnet_fold_ring(const fsnet_view* g, void* stream) {
 
 extern "C" int fsnet_add_slice(const fsnet_view* dst, const fsnet_view* src, int accumulate, void* stream) {
   FSNET_REQUIRE(dst && src && dst->ptr && src->ptr && dst->h == src->h && dst->w == src->w && dst->c == src->c, "fsnet_add_slice: bad arguments");
-  size_t total = (size_t)dst->n * dst->h * dst->w * dst->c;
+  size_t total = (size_t)dst->n * dst->h * dst->w * (dst->c / 8);
   add_slice_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*dst, *src, accumulate);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
@@ -495,7 +597,7 @@ extern "C" int fsnet_add_slice(const fsnet_view* dst, const fsnet_view* src, int
 
 extern "C" int fsnet_zero_insert(const fsnet_view* src, const fsnet_view* dst, void* stream) {
   FSNET_REQUIRE(dst && src && dst->ptr && src->ptr && dst->c == src->c, "fsnet_zero_insert: bad arguments");
-  size_t total = (size_t)dst->n * dst->h * dst->w * dst->c;
+  size_t total = (size_t)dst->n * dst->h * dst->w * (dst->c / 8);
   zero_insert_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(*src, *dst);
   FSNET_LAUNCH_OK();
   return FSNET_OK;

@@ -300,14 +300,15 @@ class Tape:
     # -------------------------------------------------------------------------------------------
     def maxpool(self, x: Act) -> Act:
         out = Act(Planes(x.n, (x.h + 1) // 2, (x.w + 1) // 2, x.c, ring=1, device=x.planes.t.device))
-        _lib.call("fsnet_maxpool_planes", x.pview(), out.pview())
+        argmax = torch.empty(out.n, out.h, out.w, x.c, device=x.planes.t.device, dtype=torch.uint8) if self.need_grad else None
+        _lib.call("fsnet_maxpool_planes", x.pview(), out.pview(), argmax)
         if self.need_grad:
             x.ensure_grad()
 
             def bwd():
                 if out.grad is None or not out.grad_written or x.grad is None:
                     return
-                _lib.call("fsnet_maxpool_bwd", x.pview(), out.gview(), x.gview(), int(x.grad_written))
+                _lib.call("fsnet_maxpool_bwd", x.pview(), argmax, out.gview(), x.gview(), int(x.grad_written))
                 x.grad_written = True
             self.backward_ops.append(bwd)
         return out

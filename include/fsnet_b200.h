@@ -188,7 +188,9 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
  *                          channel slice of a concat buffer; residual: 0 none, 1 planes, 2 raw fp32 with its
  *                          own scale_shift (the down-sample branch, resnet.py:138-145)
  *   fsnet_copy_planes      planes -> channel slice of another planes buffer (skip connection, depth_encoder.py:99-101)
- *   fsnet_maxpool_planes / fsnet_maxpool_bwd   nn.MaxPool2d(3, 2, 1) (resnet.py:122) and its gradient
+ *   fsnet_maxpool_planes / fsnet_maxpool_bwd   nn.MaxPool2d(3, 2, 1) (resnet.py:122) and its gradient; `argmax`
+ *                          [N,Ho,Wo,C] uint8 = window position (0..8) of the first maximum, written by the
+ *                          forward (may be NULL there) and read by the backward
  *   fsnet_bn_bwd_reduce / fsnet_bn_bwd_apply   gradient of (ReLU o BatchNorm): sums[2C] = (sum g, sum g*xhat);
  *                          dy (bf16 plane) = gamma*invstd*(g - mean g - xhat*mean g*xhat); mean_invstd == NULL
  *                          means "no BatchNorm" (dy = masked g); `up`=2 reads the gradient through the adjoint
@@ -210,8 +212,9 @@ int fsnet_bn_finalize(double* stats, double count, const float* gamma, const flo
 int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift, int res_mode, const fsnet_view* res,
                      const float* res_scale_shift, int relu, int up, const fsnet_view* dst, void* stream);
 int fsnet_copy_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
-int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);
-int fsnet_maxpool_bwd(const fsnet_view* src, const fsnet_view* grad_dst, const fsnet_view* grad_src, int accumulate, void* stream);
+int fsnet_maxpool_planes(const fsnet_view* src, const fsnet_view* dst, uint8_t* argmax, void* stream);
+int fsnet_maxpool_bwd(const fsnet_view* src, const uint8_t* argmax, const fsnet_view* grad_dst, const fsnet_view* grad_src,
+                      int accumulate, void* stream);
 int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_scale_shift, const fsnet_view* raw,
                         const float* mean_invstd, double* sums, void* stream);
 int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_scale_shift, const fsnet_view* raw,

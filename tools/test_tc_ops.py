@@ -138,11 +138,12 @@ def test_maxpool(N, C, H, W):
     gx_ref, = torch.autograd.grad(y, x, gy)
     xp = planes_from(x.detach())
     yp = tc.Planes(N, y.shape[2], y.shape[3], C, ring=1, zero=True)
-    _lib.call("fsnet_maxpool_planes", xp.view(), yp.view())
+    am = torch.empty(N, y.shape[2], y.shape[3], C, device="cuda", dtype=torch.uint8)
+    _lib.call("fsnet_maxpool_planes", xp.view(), yp.view(), am)
     check(f"maxpool fwd [{N},{C},{H}x{W}]", yp.to_float(), y.detach(), 1e-6)
     gyb = tc.Fp32(N, y.shape[2], y.shape[3], C); gyb.t.copy_(gy.permute(0, 2, 3, 1))
     gxb = tc.Fp32(N, H, W, C, zero=True)
-    _lib.call("fsnet_maxpool_bwd", xp.view(), gyb.view(), gxb.view(), 0)
+    _lib.call("fsnet_maxpool_bwd", xp.view(), am, gyb.view(), gxb.view(), 0)
     check(f"maxpool bwd [{N},{C},{H}x{W}]", gxb.nchw(), gx_ref, 1e-6)
 
 
