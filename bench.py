@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--impl", default="fsnet_b200", choices=["fsnet_b200", "reference"])
     ap.add_argument("--backend", default=os.environ.get("FSNET_CONV_BACKEND", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA graph replay)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -157,7 +158,9 @@ def main():
     model.train()
     from vision_base.networks.optimizers.optimizers import build_optimizer
     optimizer = build_optimizer(model, **cfg.optimizer)
-    hook = build(**cfg.trainer.training_hook)
+    use_graph = world == 1 and ops.BACKEND == "tc" and not args.no_graph
+    hook = build(**dict(cfg.trainer.training_hook, cuda_graph=use_graph))
+    probe_hook = build(**dict(cfg.trainer.training_hook, cuda_graph=False))     # eager steps for per-kernel event timing
 
     host = make_batch(B_PER_GPU, H, W, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
@@ -169,7 +172,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, use_host):
+    def timed(n, use_host, hook=hook):
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
@@ -189,19 +192,24 @@ def main():
             ms = float(t)
         return ms, last
 
-    timed(args.warmup, False)
+    timed(max(args.warmup, 5 if use_graph else 3), False)     # includes the eager warm-up calls and the capture
+    _lib.reset_counters()
+    timed(1, False, probe_hook)                                # one eager step: counts this arm's kernel launches per step
+    launches_per_step = _lib.kernel_launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.reset_counters()
-    _lib.profile_entry("fsnet_warp_ssim_fwd", True)
     ms, _ = timed(args.steps, False)
-    launches = _lib.kernel_launches
-    kern_us = _lib.profile_results("fsnet_warp_ssim_fwd")        # per-launch CUDA-event times (us), scale order
-    _lib.profile_entry("fsnet_warp_ssim_fwd", False)
     clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
+    # roofline leg: the same training steps run eagerly so that the fused warp-SSIM launches can be bracketed
+    # with CUDA events on their stream (events cannot be read back from inside a replayed graph)
+    _lib.profile_entry("fsnet_warp_ssim_fwd", True)
+    timed(min(args.steps, 5), False, probe_hook)
+    kern_us = _lib.profile_results("fsnet_warp_ssim_fwd")        # per-launch CUDA-event times (us), scale order
+    _lib.profile_entry("fsnet_warp_ssim_fwd", False)
 
     if rank != 0:
         if world > 1:
@@ -221,6 +229,7 @@ def main():
         "config": {"workload": "cfg2a kitti_wpose_synthetic: ResNet-18 depth net, 192x640, 4 scales, 16 bins, dataset poses, "
                                "fwd+bwd+clip(35)+Adam", "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
                    "parallelism": f"dp{world}" + (" (DDP + SyncBN over NCCL)" if world > 1 else ""), "conv_backend": ops.BACKEND,
+                   "cuda_graph": use_graph,
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
         "roofline": {"kernel": "loss_fwd_kernel<1> (fused warp-SSIM forward, one launch per scale)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

@@ -1,5 +1,6 @@
 """Training / validation hooks (reference: vision_base/pipeline_hooks/train_val_hooks/
 base_training_hooks.py:9-49 and base_validation_hooks.py:5-28)."""
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -8,29 +9,96 @@ import torch.nn as nn
 
 class BaseTrainingHook(object):
     """One optimisation step: zero_grad, host->device, forward, ``loss.mean().backward()``,
-    ``clip_grad_norm_``, ``optimizer.step()`` -- same order and semantics as the reference."""
+    ``clip_grad_norm_``, ``optimizer.step()`` -- same order and semantics as the reference.
 
-    def __init__(self, tensor_keys: Optional[List[str]] = None, clip_gradients: Optional[float] = None, **kwargs):
+    ``cuda_graph=True`` (or env FSNET_CUDA_GRAPH=1) replays the whole step as ONE CUDA graph: the first
+    ``graph_warmup`` calls run eagerly (each is a normal step), the next call captures
+    zero_grad+forward+backward+clip+step and every call from then on copies its batch into the graph's
+    static inputs and replays it.  One call is still exactly one optimiser step; the returned tensors
+    are the graph's static outputs (valid until the next call)."""
+
+    def __init__(self, tensor_keys: Optional[List[str]] = None, clip_gradients: Optional[float] = None, cuda_graph=None,
+                 graph_warmup: int = 3, **kwargs):
         self.tensor_keys = tensor_keys
         self.clip_gradients = clip_gradients
+        if cuda_graph is None:
+            cuda_graph = os.environ.get("FSNET_CUDA_GRAPH", "0").lower() in ("1", "true")
+        self.cuda_graph = bool(cuda_graph)
+        self.graph_warmup = graph_warmup
+        self._calls = 0
+        self._graph = None
+        self._static_in = None
+        self._static_out = None
+        self._side_stream = None
 
-    def __call__(self, data: Dict, meta_arch: nn.Module, optimizer, writer=None, training_loss_logger=None,
-                 global_step: int = 0, epoch_num: int = 0):
-        optimizer.zero_grad()
+    def _to_device(self, data):
         for key in data:
             if isinstance(data[key], torch.Tensor):
                 if self.tensor_keys is None or key in self.tensor_keys:
                     data[key] = data[key].cuda(non_blocking=True).contiguous()
-        meta = dict(epoch_num=epoch_num, global_step=global_step, is_training=True)
+        return data
+
+    def _step(self, data, meta_arch, optimizer, meta):
+        optimizer.zero_grad()
         output: dict = meta_arch(data, meta)
-        if training_loss_logger is not None:
-            training_loss_logger.update(output["loss_dict"])
-            training_loss_logger.update_hm(output.get("hm", dict()))
         output["loss"].mean().backward()
         if self.clip_gradients is not None:
             torch.nn.utils.clip_grad_norm_(meta_arch.parameters(), self.clip_gradients)
         optimizer.step()
         return output
+
+    def __call__(self, data: Dict, meta_arch: nn.Module, optimizer, writer=None, training_loss_logger=None,
+                 global_step: int = 0, epoch_num: int = 0):
+        meta = dict(epoch_num=epoch_num, global_step=global_step, is_training=True)
+        if self.cuda_graph:
+            output = self._graphed(data, meta_arch, optimizer, meta)
+        else:
+            output = self._step(self._to_device(data), meta_arch, optimizer, meta)
+        if training_loss_logger is not None:
+            training_loss_logger.update(output["loss_dict"])
+            training_loss_logger.update_hm(output.get("hm", dict()))
+        return output
+
+    # ---------------------------------------------------------------------------------------------
+    def _graphed(self, data, meta_arch, optimizer, meta):
+        if self._calls == 0:
+            for group in optimizer.param_groups:          # Adam must keep its step counters on the device
+                if "capturable" in group and not optimizer.state:
+                    group["capturable"] = True
+            self._side_stream = torch.cuda.Stream()
+        self._calls += 1
+        if self._graph is None and self._calls <= self.graph_warmup:
+            # eager warm-up steps on a side stream (allocator, cuDNN/cuBLAS handles, lazily built kernel state)
+            cur = torch.cuda.current_stream()
+            self._side_stream.wait_stream(cur)
+            with torch.cuda.stream(self._side_stream):
+                out = self._step(self._to_device(data), meta_arch, optimizer, meta)
+            cur.wait_stream(self._side_stream)
+            return out
+        if self._graph is None:
+            dev = next(meta_arch.parameters()).device
+            self._static_in = {}
+            for k, v in data.items():
+                if isinstance(v, torch.Tensor) and (self.tensor_keys is None or k in self.tensor_keys):
+                    self._static_in[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                else:
+                    self._static_in[k] = v
+            self._copy_in(data)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self._graph):
+                self._static_out = self._step(dict(self._static_in), meta_arch, optimizer, meta)
+        else:
+            self._copy_in(data)
+        self._graph.replay()
+        return self._static_out
+
+    def _copy_in(self, data):
+        for k, v in data.items():
+            dst = self._static_in.get(k)
+            if isinstance(dst, torch.Tensor) and isinstance(v, torch.Tensor):
+                dst.copy_(v, non_blocking=True)
 
 
 class BaseValidationHook(object):
