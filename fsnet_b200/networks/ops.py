@@ -1,16 +1,22 @@
 """Composite layer operations used by the network modules.
 
 Two back-ends:
-  "tc"     hand-written tcgen05 implicit-GEMM convolutions + fused BN statistics (fsnet_b200/csrc/conv_tc.cu)
-  "torch"  stock PyTorch ops (cuDNN) -- the INTERIM library path for layer types the tcgen05
-           path does not cover yet; DESIGN.md lists which.
-The network modules only hold parameters (reference names / state-dict layout) and call these.
+  "tc"     (default) the whole network runs as hand-written tcgen05 kernels through fsnet_b200/engine.py:
+           ``ResNet.forward`` only returns a deferred handle and the consuming head executes encoder + decoder
+           as one autograd node.  The functions below are then not on the path at all.
+  "torch"  stock PyTorch ops (cuDNN): a comparison / debugging path and the route for the few constructor
+           options the tcgen05 executor rejects (norm_eval=True, frozen_stages, dilation), never a silent
+           fallback: the executor raises NotImplementedError and the user selects this back-end explicitly
+           (``ops.set_backend("torch")`` or FSNET_CONV_BACKEND=torch).
+The network modules only hold parameters (reference names / state-dict layout).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-BACKEND = "torch"
+BACKEND = os.environ.get("FSNET_CONV_BACKEND", "tc")      # "tc" needs CUDA tensors; CPU tensors always take the torch ops
 
 
 def set_backend(name: str) -> None:
@@ -31,15 +37,11 @@ def tc_available() -> bool:
 def precision_note() -> str:
     if BACKEND == "tc":
         return "tcgen05 bf16x3 split operands, fp32 accumulate"
-    return "cuDNN fp32 (interim library path)"
+    return "cuDNN fp32 (comparison path)"
 
 
 def conv_bn_act(x, conv: nn.Conv2d, bn, relu: bool = True, residual=None):
     """conv -> (train-mode) batch-norm -> (+ residual) -> ReLU."""
-    if BACKEND == "tc" and x.is_cuda:
-        from . import ops_tc
-        if ops_tc.supports(conv, x):
-            return ops_tc.conv_bn_act(x, conv, bn, relu, residual)
     y = conv(x)
     if bn is not None:
         y = bn(y)
@@ -49,10 +51,6 @@ def conv_bn_act(x, conv: nn.Conv2d, bn, relu: bool = True, residual=None):
 
 
 def conv_act(x, conv: nn.Conv2d, relu: bool = False):
-    if BACKEND == "tc" and x.is_cuda:
-        from . import ops_tc
-        if ops_tc.supports(conv, x):
-            return ops_tc.conv_bn_act(x, conv, None, relu, None)
     y = conv(x)
     return F.relu(y) if relu else y
 

@@ -32,9 +32,11 @@ class LazyFeatures(list):
             with torch.no_grad():
                 tape = Tape({}, self.backbone.training, False)
                 # statistics must not be updated twice: run on a throw-away copy of the running buffers
-                saved = {k: v.clone() for k, v in self.backbone.state_dict().items() if "running" in k or "num_batches" in k}
+                bufs = [b for _, b in self.backbone.named_buffers()]
+                saved = [b.clone() for b in bufs]
                 acts = resnet_forward(tape, self.backbone, self.image, False)
-                self.backbone.load_state_dict(saved, strict=False)
+                for b, v in zip(bufs, saved):
+                    b.copy_(v)
             super().extend(a.planes.to_float()[:, :a.c].contiguous() for a in acts)
             self.materialized = True
 

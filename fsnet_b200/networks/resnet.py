@@ -93,7 +93,7 @@ class ResNet(nn.Module):
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         # ImageNet 3-channel stem -> N-image stem: tile and rescale (resnet.py:155-160)
-        if self.conv1.weight.shape != state_dict["conv1.weight"].shape:
+        if "conv1.weight" in state_dict and self.conv1.weight.shape != state_dict["conv1.weight"].shape:
             state_dict["conv1.weight"] = torch.cat([state_dict["conv1.weight"]] * self.num_input_images, 1) / self.num_input_images
         return super().load_state_dict(state_dict, *args, **kwargs)
 
