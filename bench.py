@@ -215,9 +215,7 @@ def main():
     _lib.profile_entry("fsnet_warp_ssim_fwd", False)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return _finish(world)
     imgs = B_PER_GPU * world * args.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
@@ -248,8 +246,18 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/, torch CPU fp32)"}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """destroy_process_group() blocks for ever once NCCL collectives live inside a captured CUDA graph (seen on
+    this stack); the step results are already on the host, so synchronise, flush and leave."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

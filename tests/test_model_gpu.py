@@ -105,7 +105,8 @@ def test_graphed_hook_matches_eager_hook():
     for mode in (False, True):
         torch.manual_seed(0)
         model = build_model(topo).cuda()
-        model.head.tie_break_noise = O.tie_break_noise(2, 64, 128, topo.scales, 0)
+        # device-resident noise: a host->device copy cannot be captured into the step graph
+        model.head.tie_break_noise = {s: n.cuda() for s, n in O.tie_break_noise(2, 64, 128, topo.scales, 0).items()}
         hook = build("vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0, cuda_graph=mode)
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)
         seq = []
