@@ -20,6 +20,7 @@
 // epilogue (TMEM lane quadrant = warp_id % 4).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace fsnet {
@@ -36,6 +37,7 @@ struct ConvParams {
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int BN;                      // output channels per tile (multiple of 16, <= 128)
   int KC, cchunks, kiters;     // channels per stage, Cin/KC, taps*cchunks
+  int fold;                    // x-taps folded into K: kiters = KH * cchunks, cchunks = ceil(KW*Cin / 64)
   int stages;
   uint32_t a_bytes, b_bytes, stage_bytes, tx_bytes;
   uint32_t tmem_cols;
@@ -84,6 +86,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -199,17 +206,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int ty = rest % p.tiles_y; int img = rest / p.tiles_y;
         const int x_base = tx * p.TW * p.stride - p.pad + p.org;
         const int y_base = ty * p.TH * p.stride - p.pad + p.org;
+        int tap = 0, cc = 0, r = 0, sx = 0;
         for (int kit = 0; kit < p.kiters; ++kit) {
-          int tap = kit / p.cchunks, cc = kit - tap * p.cchunks;
-          int r = tap / p.KW, s = tap - r * p.KW;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * p.stage_bytes;
           mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-          tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * p.KC, x_base + s * p.dil, y_base + r * p.dil, img);
-          tma_load_2d(st + p.a_bytes, &map_b_hi, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
-          if (NPROD == 3) {
-            tma_load_4d(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * p.KC, x_base + s * p.dil, y_base + r * p.dil, img);
-            tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+          if (p.fold) {
+            // A: 64-element slice cc of the "fat pixel" row (KW taps x Cin channels, contiguous in NHWC) of kernel row r
+            const int xo = tx * p.TW, yo = ty * p.TH + r;
+            tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
+            tma_load_3d(st + p.a_bytes, &map_b_hi, &full_bar[stage], cc * 64, r, nt * p.BN);
+            if (NPROD == 3) {
+              tma_load_4d(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * 64, xo, yo, img);
+              tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], cc * 64, r, nt * p.BN);
+            }
+            if (++cc == p.cchunks) { cc = 0; ++r; }
+          } else {
+            tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+            tma_load_2d(st + p.a_bytes, &map_b_hi, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+            if (NPROD == 3) {
+              tma_load_4d(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+              tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+            }
+            if (++cc == p.cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -409,6 +428,15 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   p.n_tiles = Cout / p.BN;
   p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
   p.KC = pick_kc(Cin); p.cchunks = Cin / p.KC; p.kiters = KH * KW * p.cchunks;
+  // x-tap folding for thin replicate-padded layers: the KW taps x Cin channels of a kernel row are one contiguous
+  // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
+  static int fold_env = -1;
+  if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 1; }
+  p.fold = fold_env && stride == 1 && use_ring && in->ring == 1 && pad == 1 && KH == 3 && KW == 3 && in->c_off == 0 &&
+           in->c == in->c_total && (Cin < 64 || Cin == 96);
+  if (p.fold) {
+    p.KC = 64; p.cchunks = ceil_div(KW * Cin, 64); p.kiters = KH * p.cchunks;
+  }
   p.a_bytes = 128u * p.KC * 2;
   p.b_bytes = ((uint32_t)p.BN * p.KC * 2 + 1023u) & ~1023u;
   p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
@@ -427,20 +455,47 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   p.bias = bias; p.stats = stats; p.relu = relu;
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  int rc = encode_act_map(&ma_hi, in, 0, use_ring, p.KC, p.TW, p.TH, stride, "fsnet_conv");
+  if (p.fold) {
+    const int pw = W + 2, ph = H + 2;
+    const size_t plane_elems = (size_t)N * ph * pw * Cin;
+    cuuint64_t adim[4] = {(cuuint64_t)(64 * p.cchunks), (cuuint64_t)W, (cuuint64_t)ph, (cuuint64_t)N};
+    cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)pw * Cin * 2, (cuuint64_t)ph * pw * Cin * 2};
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t aes[4] = {1, 1, 1, 1};
+    cuuint64_t wdim[3] = {(cuuint64_t)(KW * Cin), (cuuint64_t)KH, (cuuint64_t)Cout};
+    cuuint64_t wstr[2] = {(cuuint64_t)KW * Cin * 2, (cuuint64_t)KH * KW * Cin * 2};
+    cuuint32_t wbox[3] = {64, 1, (cuuint32_t)p.BN};
+    cuuint32_t wes[3] = {1, 1, 1};
+    for (int pl = 0; pl < (nprod == 3 ? 2 : 1); ++pl) {
+      CUresult r = enc(pl ? &ma_lo : &ma_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (char*)in->ptr + plane_elems * pl * 2, adim, astr, abox, aes,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(folded A) failed with %d", (int)r);
+      r = enc(pl ? &mb_lo : &mb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)(pl ? w_lo : w_hi), wdim, wstr, wbox, wes,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(folded B) failed with %d", (int)r);
+    }
+    if (nprod != 3) { ma_lo = ma_hi; mb_lo = mb_hi; }
+  }
+  int rc = 0;
+  if (!p.fold) {
+  rc = encode_act_map(&ma_hi, in, 0, use_ring, p.KC, p.TW, p.TH, stride, "fsnet_conv");
   if (rc) return rc;
   ma_lo = ma_hi;
   if (nprod == 3) { rc = encode_act_map(&ma_lo, in, 1, use_ring, p.KC, p.TW, p.TH, stride, "fsnet_conv"); if (rc) return rc; }
+  }
   const int Ktot = KH * KW * Cin;
   cuuint64_t bdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t bstr[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t bbox[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.BN};
   cuuint32_t bes[2] = {1, 1};
-  CUresult r = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_hi, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
-  mb_lo = mb_hi;
-  if (nprod == 3) {
+  CUresult r = CUDA_SUCCESS;
+  if (!p.fold) {
+    r = enc(&mb_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_hi, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    mb_lo = mb_hi;
+  }
+  if (nprod == 3 && !p.fold) {
     r = enc(&mb_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_lo, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
             swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
@@ -473,7 +528,6 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
 namespace fsnet {
 namespace {
 
-constexpr int kWgPix = 64;          // pixels (K) per pipeline stage
 
 struct WgradParams {
   int N, Ho, Wo, KH, KW, stride, pad, org;
@@ -481,6 +535,7 @@ struct WgradParams {
   int co_tiles, ci_tiles, ksplit, taps;
   int BM_real, BN;                  // real rows (channels of dy) in the tile, ci tile width
   int atomA, atomB, nA, nB;         // channels per swizzle atom, atoms actually loaded
+  int pix;                          // pixels (K) per pipeline stage: 64, 128 or 256
   int PW, PH, chunks_x, chunks_y, total_chunks, chunks_per_split;
   int stages;
   uint32_t a_atom_bytes, b_atom_bytes, a_bytes, b_bytes, stage_bytes, tx_bytes;
@@ -560,7 +615,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        for (int k = 0; k < kWgPix / 16; ++k) {
+        for (int k = 0; k < p.pix / 16; ++k) {
           const uint64_t da = make_desc_mn(st + k * 16 * rowA, lboA, 8 * rowA, p.a_layout);
           const uint64_t db = make_desc_mn(st + p.a_bytes + k * 16 * rowB, p.b_atom_bytes, 8 * rowB, p.b_layout);
           umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
@@ -584,8 +639,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       tmem_ld16(taddr + c0, raw);
       tmem_ld_wait();
       if (valid) {
+        if (p.ksplit == 1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                   __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(raw[j]));
+        }
       }
     }
   }
@@ -619,18 +681,23 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   p.BN = p.Cin <= 128 ? p.Cin : (p.Cin % 128 == 0 ? 128 : (p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16)));
   FSNET_REQUIRE(p.Cin % p.BN == 0, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
   p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
+  // thin layers get more pixels per stage so that one stage moves >= 16 KB
+  p.pix = 64;
+  while (p.pix < 128 && (size_t)(p.pix * 2) * (p.nA * p.atomA + p.BN) * 2 <= 32 * 1024 && (size_t)p.pix * 2 <= (size_t)p.Ho * p.Wo) p.pix *= 2;
   int pw = 1;
-  while (pw * 2 <= p.Wo && pw * 2 <= kWgPix) pw *= 2;
-  p.PW = pw; p.PH = kWgPix / pw;
+  while (pw * 2 <= p.Wo && pw * 2 <= 64) pw *= 2;
+  p.PW = pw; p.PH = p.pix / pw;
   p.chunks_x = ceil_div(p.Wo, p.PW); p.chunks_y = ceil_div(p.Ho, p.PH);
   p.total_chunks = p.N * p.chunks_x * p.chunks_y;
   const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  int ksplit = ceil_div(148 * 3, base_items);
+  // K split: ~3 CTAs per SM hide the TMA latency of thin layers (32-64 byte rows); once the (tap, tile) grid alone
+  // fills half the machine, more splits only add fp32 atomics on large weight tensors
+  int ksplit = base_items >= 74 ? ceil_div(148, base_items) : ceil_div(148 * 3, base_items);
   if (ksplit > p.total_chunks) ksplit = p.total_chunks;
   if (ksplit < 1) ksplit = 1;
   p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
   p.ksplit = ceil_div(p.total_chunks, p.chunks_per_split);
-  p.a_atom_bytes = (uint32_t)kWgPix * p.atomA * 2; p.b_atom_bytes = (uint32_t)kWgPix * p.atomB * 2;
+  p.a_atom_bytes = (uint32_t)p.pix * p.atomA * 2; p.b_atom_bytes = (uint32_t)p.pix * p.atomB * 2;
   p.a_bytes = ((uint32_t)p.nA * p.a_atom_bytes + 1023u) & ~1023u;
   p.b_bytes = ((uint32_t)p.nB * p.b_atom_bytes + 1023u) & ~1023u;
   p.stage_bytes = p.a_bytes + p.b_bytes;

@@ -9,6 +9,7 @@
 // warp shuffles, vertical 3-tap sums are rolling registers, so the 3x3 SSIM window never touches
 // shared memory and no block-level barrier exists.  The halo lanes/rows recompute the warp of the
 // reflected pixel, exactly what ReflectionPad2d(1) on the *warped* image means.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace fsnet {
@@ -20,7 +21,8 @@ constexpr float k81C2 = 81.f * 9e-4f;     // 81 * 0.03^2
 
 struct LossParams {
   const float* depth; int hs, ws;
-  const float* tgt; const float* src0; const float* src1;
+  const float* tgt; const float* src0; const float* src1;   // fp32 NCHW (identity kernel only)
+  const float4* packed; float4* packed_out;                 // [3][B,H,W] RGBX: target, source 0, source 1
   const void* mask; int mask_dtype;
   const float* cam; const float* ident; const float* noise; const float* motion;
   unsigned flags; int B, H, W;
@@ -140,6 +142,104 @@ __device__ __forceinline__ Sample<GRAD> sample_frame(const float* __restrict__ s
   return o;
 }
 
+
+// ---- row-skewed loads (software pipeline) -------------------------------------------------------------
+// The images are read from the RGBX-packed copy written once per step by the identity kernel: one 128-bit
+// load per bilinear corner.  issue_* only computes addresses and issues loads; finish_* consumes them one
+// loop iteration later, so a row's gathers are in flight while the previous row's SSIM arithmetic runs.
+struct DepthLoads { float d00, d01, d10, d11, ly; };
+__device__ __forceinline__ DepthLoads issue_depth(const float* d, int ws, int hs, float sy, int yr, const UpW& wx) {
+  UpW wy = up_weights(yr, sy, hs);
+  const float* r0 = d + (size_t)wy.i0 * ws;
+  const float* r1 = d + (size_t)wy.i1 * ws;
+  DepthLoads o;
+  o.d00 = __ldg(r0 + wx.i0); o.d01 = __ldg(r0 + wx.i1); o.d10 = __ldg(r1 + wx.i0); o.d11 = __ldg(r1 + wx.i1); o.ly = wy.l;
+  return o;
+}
+__device__ __forceinline__ float finish_depth(const DepthLoads& o, float lx) {
+  float top = (1.f - lx) * o.d00 + lx * o.d01, bot = (1.f - lx) * o.d10 + lx * o.d11;
+  return (1.f - o.ly) * top + o.ly * bot;
+}
+
+struct FrameLoads {
+  float4 nw, ne, sw, se;
+  float fx, fy, ix, iy, rz;
+  float ax, ay, az;            // d p / d D (gradient variant only)
+  float mval; bool inb;
+};
+template <int GRAD>
+__device__ __forceinline__ FrameLoads issue_frame(const float4* __restrict__ src, const float* P, const Geo& g,
+                                                  const void* mask, int mask_dtype, bool want_valid, int H, int W) {
+  FrameLoads o;
+  float px = fmaf(P[0], g.c[0], fmaf(P[1], g.c[1], fmaf(P[2], g.c[2], P[3])));
+  float py = fmaf(P[4], g.c[0], fmaf(P[5], g.c[1], fmaf(P[6], g.c[2], P[7])));
+  float pz = fmaf(P[8], g.c[0], fmaf(P[9], g.c[1], fmaf(P[10], g.c[2], P[11])));
+  float rz = __frcp_rn(pz + 1e-7f);
+  float ix = px * rz, iy = py * rz;
+  const float xm = (float)(W - 1), ym = (float)(H - 1);
+  o.inb = true; o.mval = 1.f;
+  if (want_valid) {
+    float xn = rintf(ix), yn = rintf(iy);
+    o.inb = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
+    if (o.inb && mask != nullptr) o.mval = load_mask(mask, mask_dtype, (size_t)(int)yn * W + (int)xn);
+  }
+  float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);
+  float x0f = floorf(ixc), y0f = floorf(iyc);
+  o.fx = ixc - x0f; o.fy = iyc - y0f;
+  int x0 = (int)x0f, y0 = (int)y0f;
+  int dx = x0 < W - 1 ? 1 : 0, dy = y0 < H - 1 ? W : 0;
+  const float4* p00 = src + (size_t)y0 * W + x0;
+  o.nw = __ldg(p00); o.ne = __ldg(p00 + dx); o.sw = __ldg(p00 + dy); o.se = __ldg(p00 + dy + dx);
+  o.ix = ix; o.iy = iy; o.rz = rz;
+  o.ax = o.ay = o.az = 0.f;
+  if (GRAD) {
+    o.ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
+    o.ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
+    o.az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
+  }
+  return o;
+}
+template <int GRAD>
+__device__ __forceinline__ Sample<GRAD> finish_frame(const FrameLoads& o, int H, int W) {
+  Sample<GRAD> s;
+  const float nw[3] = {o.nw.x, o.nw.y, o.nw.z}, ne[3] = {o.ne.x, o.ne.y, o.ne.z};
+  const float sw[3] = {o.sw.x, o.sw.y, o.sw.z}, se[3] = {o.se.x, o.se.y, o.se.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float top = fmaf(o.fx, ne[c] - nw[c], nw[c]), bot = fmaf(o.fx, se[c] - sw[c], sw[c]);
+    s.pred[c] = fmaf(o.fy, bot - top, top);
+    if (GRAD) {
+      float dx_top = ne[c] - nw[c], dx_bot = se[c] - sw[c];
+      s.dix[c] = fmaf(o.fy, dx_bot - dx_top, dx_top);
+      s.diy[c] = bot - top;
+    }
+  }
+  s.valid = o.inb && (o.mval == 1.f);
+  s.px = o.ix; s.py = o.iy; s.rz = o.rz;
+  s.du = 0.f; s.dv = 0.f;
+  if (GRAD) {
+    bool mx = (o.ix > 0.f) && (o.ix < (float)(W - 1)), my = (o.iy > 0.f) && (o.iy < (float)(H - 1));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.dix[c] = mx ? s.dix[c] : 0.f; s.diy[c] = my ? s.diy[c] : 0.f; }
+    s.du = (o.ax - o.ix * o.az) * o.rz;
+    s.dv = (o.ay - o.iy * o.az) * o.rz;
+  }
+  return s;
+}
+struct RowLoads { float4 t; FrameLoads f0, f1; float D; };
+template <int GRAD>
+__device__ __forceinline__ RowLoads issue_row(const LossParams& p, const float4* tg, const float4* s0, const float4* s1,
+                                              const float* ik, const float* P0, const float* P1, const void* mask_b,
+                                              bool overlap, int yr, int xr, float D) {
+  RowLoads r;
+  r.t = __ldg(tg + (size_t)yr * p.W + xr);
+  Geo g = geometry(ik, (float)xr, (float)yr, D);
+  r.f0 = issue_frame<GRAD>(s0, P0, g, mask_b, p.mask_dtype, overlap, p.H, p.W);
+  r.f1 = issue_frame<GRAD>(s1, P1, g, mask_b, p.mask_dtype, overlap, p.H, p.W);
+  r.D = D;
+  return r;
+}
+
 // SSIM loss value of (x = pred, t = target) from the 3x3 SUMS (not means).
 __device__ __forceinline__ float ssim_sums(float Sx, float Sxx, float Sxt, float St, float Stt) {
   float sxst = Sx * St;
@@ -210,8 +310,8 @@ __device__ __forceinline__ bool decode_item(const LossParams& p, Item& it) {
 //           MODE 1: reprojection loss (pred_f := warped src_f, result reduced into accum).
 // Columns per warp: 30 (lanes 0 and 31 are the reflect / neighbour halo).
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
+template <int MODE, int PIPE>
+__global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(LossParams p) {
   __shared__ float s_cam[kWarps][42];
   Item it;
   if (!decode_item(p, it)) return;
@@ -222,24 +322,9 @@ __global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
   const int x = it.strip * 30 + lane - 1;
   const int xr = reflect_idx(x, W);
   const bool out_lane = lane >= 1 && lane <= 30 && x < W;
-  const float* tgt = p.tgt + (size_t)b * 3 * HW;
-  const float* src0 = p.src0 + (size_t)b * 3 * HW;
-  const float* src1 = p.src1 + (size_t)b * 3 * HW;
   const void* mask = p.mask;
   const bool overlap = (p.flags & FSNET_FLAG_OVERLAP_MASK) != 0;
   const bool use_ident = (p.flags & FSNET_FLAG_MOTION_MASK) == 0;
-
-  const float* ik = s_cam[warp];
-  UpW wx = {0, 0, 0.f};
-  const float* depth = nullptr;
-  if (MODE == 1) {
-    for (int i = lane; i < 42; i += 32) s_cam[warp][i] = __ldg(p.cam + (size_t)b * 42 + i);
-    __syncwarp();
-    wx = up_weights(xr, p.sx, p.ws);
-    depth = p.depth + (size_t)b * p.hs * p.ws;
-  }
-  const float* P0 = s_cam[warp] + 9;        // frame 0: inv(K) at [0,9), P at [9,21)
-  const float* P1 = s_cam[warp] + 21 + 9;   // frame 1: inv(K) at [21,30), P at [30,42)
   const void* mask_b = mask ? mask_dtype_ptr_add(mask, p.mask_dtype, (size_t)b * HW) : nullptr;
 
   float A1[24], A2[24];
@@ -248,26 +333,87 @@ __global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
   float l1_prev[2] = {0.f, 0.f};
   bool valid_prev[2] = {true, true};
   float acc_num = 0.f, acc_den = 0.f;
+  const int y_first = it.y_begin - 1, y_last = it.y_end;
 
-  for (int yy = it.y_begin - 1; yy <= it.y_end; ++yy) {
+  // ---- MODE 0 state: plain NCHW loads -------------------------------------------------------------
+  const float* tgt = MODE == 0 ? p.tgt + (size_t)b * 3 * HW : nullptr;
+  const float* src0 = MODE == 0 ? p.src0 + (size_t)b * 3 * HW : nullptr;
+  const float* src1 = MODE == 0 ? p.src1 + (size_t)b * 3 * HW : nullptr;
+  // ---- MODE 1 state: packed images + software pipeline ----------------------------------------------
+  const float* ik = s_cam[warp];
+  const float* P0 = s_cam[warp] + 9;        // frame 0: inv(K) at [0,9), P at [9,21)
+  const float* P1 = s_cam[warp] + 21 + 9;   // frame 1: inv(K) at [21,30), P at [30,42)
+  UpW wx = {0, 0, 0.f};
+  const float* depth = nullptr;
+  const float4 *tg4 = nullptr, *s04 = nullptr, *s14 = nullptr;
+  RowLoads rl_next;
+  DepthLoads dl_next;
+  if (MODE == 1) {
+    for (int i = lane; i < 42; i += 32) s_cam[warp][i] = __ldg(p.cam + (size_t)b * 42 + i);
+    __syncwarp();
+    wx = up_weights(xr, p.sx, p.ws);
+    depth = p.depth + (size_t)b * p.hs * p.ws;
+    tg4 = p.packed + ((size_t)0 * p.B + b) * HW;
+    s04 = p.packed + ((size_t)1 * p.B + b) * HW;
+    s14 = p.packed + ((size_t)2 * p.B + b) * HW;
+    if (PIPE == 1) {
+      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
+      rl_next = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(y_first, H), xr, finish_depth(dl_next, wx.l));
+      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(y_first + 1, y_last), H), wx);
+    } else {
+      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
+    }
+  }
+
+#pragma unroll 1
+  for (int yy = y_first; yy <= y_last; ++yy) {
     const int yr = reflect_idx(yy, H);
     float raw[9];
     float l1[2];
     bool valid[2] = {true, true};
-#pragma unroll
-    for (int c = 0; c < 3; ++c) raw[c] = __ldg(tgt + c * HW + (size_t)yr * W + xr);
+    // centre-pixel inputs (row yy-1) depend on nothing computed here: issue their loads first
+    float c_i0 = 0.f, c_i1 = 0.f, c_n0 = 0.f, c_n1 = 0.f, c_m = 1.f;
+    if (MODE == 1 && out_lane && yy >= it.y_begin + 1) {
+      const size_t pix = (size_t)(yy - 1) * W + x;
+      if (use_ident) {
+        c_i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
+        c_i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
+        if (p.noise) {
+          c_n0 = __ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix);
+          c_n1 = __ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix);
+        }
+      }
+      if (mask) c_m = load_mask(mask_b, p.mask_dtype, pix);
+    }
     if (MODE == 0) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
+        raw[c] = __ldg(tgt + c * HW + (size_t)yr * W + xr);
         raw[3 + c] = __ldg(src0 + c * HW + (size_t)yr * W + xr);
         raw[6 + c] = __ldg(src1 + c * HW + (size_t)yr * W + xr);
       }
+      if (p.packed_out != nullptr && out_lane && yy >= it.y_begin && yy < it.y_end) {
+        const size_t pix = (size_t)yy * W + x;
+        p.packed_out[((size_t)0 * p.B + b) * HW + pix] = make_float4(raw[0], raw[1], raw[2], 0.f);
+        p.packed_out[((size_t)1 * p.B + b) * HW + pix] = make_float4(raw[3], raw[4], raw[5], 0.f);
+        p.packed_out[((size_t)2 * p.B + b) * HW + pix] = make_float4(raw[6], raw[7], raw[8], 0.f);
+      }
     } else {
-      UpW wy = up_weights(yr, p.sy, p.hs);
-      float D = depth_at(depth, p.ws, wy, wx);
-      Geo g = geometry(ik, (float)xr, (float)yr, D);
-      Sample<0> s0 = sample_frame<0>(src0, P0, g, mask_b, p.mask_dtype, overlap, H, W);
-      Sample<0> s1 = sample_frame<0>(src1, P1, g, mask_b, p.mask_dtype, overlap, H, W);
+      RowLoads rl;
+      if (PIPE == 1) {
+        rl = rl_next;
+        if (yy < y_last) {           // next row: its depth arrived during the previous iteration
+          rl_next = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy + 1, H), xr, finish_depth(dl_next, wx.l));
+          dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 2, y_last), H), wx);
+        }
+      } else {
+        // this row's depth was requested one iteration ago: the gathers can go out immediately
+        rl = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, yr, xr, finish_depth(dl_next, wx.l));
+        dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx);
+      }
+      Sample<0> s0 = finish_frame<0>(rl.f0, H, W);
+      Sample<0> s1 = finish_frame<0>(rl.f1, H, W);
+      raw[0] = rl.t.x; raw[1] = rl.t.y; raw[2] = rl.t.z;
 #pragma unroll
       for (int c = 0; c < 3; ++c) { raw[3 + c] = s0.pred[c]; raw[6 + c] = s1.pred[c]; }
       valid[0] = s0.valid; valid[1] = s1.valid;
@@ -310,12 +456,7 @@ __global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
           float best;
           int arg;
           if (use_ident) {
-            float i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
-            float i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
-            if (p.noise) {
-              i0 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix), 1e-5f, i0);
-              i1 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix), 1e-5f, i1);
-            }
+            const float i0 = fmaf(c_n0, 1e-5f, c_i0), i1 = fmaf(c_n1, 1e-5f, c_i1);
             best = i0; arg = 0;
             if (i1 < best) { best = i1; arg = 1; }
             if (ph[0] < best) { best = ph[0]; arg = 2; }
@@ -324,9 +465,8 @@ __global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
             best = ph[0]; arg = 0;
             if (ph[1] < best) { best = ph[1]; arg = 1; }
           }
-          float m = mask ? load_mask(mask_b, p.mask_dtype, pix) : 1.f;
-          acc_num = fmaf(best, m, acc_num);
-          acc_den += m;
+          acc_num = fmaf(best, c_m, acc_num);
+          acc_den += c_m;
           if (p.sel) p.sel[(size_t)b * HW + pix] = (uint8_t)arg;
         }
       }
@@ -351,8 +491,8 @@ __global__ void __launch_bounds__(kWarps * 32) loss_fwd_kernel(LossParams p) {
 // yc = yy-1  C) adjoint box filter -> d pred, chain to depth (and pose) at yq = yy-2.
 // POSE=1 additionally reduces d loss / d P (12 numbers per frame).
 // ------------------------------------------------------------------------------------------------
-template <int POSE>
-__global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
+template <int POSE, int PIPE>
+__global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 3) loss_bwd_kernel(LossParams p) {
   constexpr int NV = POSE ? 22 : 15;        // delayed values per pixel
   __shared__ float s_cam[kWarps][42];
   __shared__ float s_delay[kWarps][3][NV][32];
@@ -366,9 +506,9 @@ __global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
   const int xr = reflect_idx(x, W);
   const bool x_in = x >= 0 && x < W;
   const bool out_lane = lane >= 2 && lane <= 29 && x < W;
-  const float* tgt = p.tgt + (size_t)b * 3 * HW;
-  const float* src0 = p.src0 + (size_t)b * 3 * HW;
-  const float* src1 = p.src1 + (size_t)b * 3 * HW;
+  const float4* tg4 = p.packed + ((size_t)0 * p.B + b) * HW;
+  const float4* s04 = p.packed + ((size_t)1 * p.B + b) * HW;
+  const float4* s14 = p.packed + ((size_t)2 * p.B + b) * HW;
   const bool overlap = (p.flags & FSNET_FLAG_OVERLAP_MASK) != 0;
   const bool use_ident = (p.flags & FSNET_FLAG_MOTION_MASK) == 0;
   const void* mask_b = p.mask ? mask_dtype_ptr_add(p.mask, p.mask_dtype, (size_t)b * HW) : nullptr;
@@ -396,20 +536,56 @@ __global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
 #pragma unroll
   for (int i = 0; i < (POSE ? 24 : 1); ++i) gP[i] = 0.f;
 
-  for (int yy = it.y_begin - 2; yy <= it.y_end + 1; ++yy) {
-    // ---- A: raw values at row yy (reflected / clamped) -------------------------------------------
-    const int yr = reflect_idx(yy, H);
+  const int y_first = it.y_begin - 2, y_last = it.y_end + 1;
+  DepthLoads dl_next;
+  RowLoads rl_next;
+  if (PIPE == 1) {
+    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
+    rl_next = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(y_first, H), xr, finish_depth(dl_next, wx.l));
+    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first + 1, H), wx);
+  } else {
+    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
+  }
+
+#pragma unroll 1
+  for (int yy = y_first; yy <= y_last; ++yy) {
+    // centre-pixel inputs (row yy-1) depend on nothing computed here: issue their loads first
+    const bool centre_live = yy >= it.y_begin && (yy - 1) >= 0 && (yy - 1) < H && x_in && lane >= 1 && lane <= 30;
+    float c_i0 = 0.f, c_i1 = 0.f, c_n0 = 0.f, c_n1 = 0.f, c_m = 1.f, c_gate = 1.f;
+    if (centre_live) {
+      const size_t pix = (size_t)(yy - 1) * W + x;
+      if (use_ident) {
+        c_i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
+        c_i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
+        if (p.noise) {
+          c_n0 = __ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix);
+          c_n1 = __ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix);
+        }
+      } else {
+        c_gate = 1.f - __ldg(p.motion + (size_t)b * HW + pix);
+      }
+      if (p.mask) c_m = load_mask(mask_b, p.mask_dtype, pix);
+    }
+    // ---- A: raw values at row yy (reflected / clamped) ------------------------------------------------
     float raw[9];
     float l1[2];
     bool valid[2];
     {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) raw[c] = __ldg(tgt + c * HW + (size_t)yr * W + xr);
-      UpW wy = up_weights(yr, p.sy, p.hs);
-      float D = depth_at(depth, p.ws, wy, wx);
-      Geo g = geometry(ik, (float)xr, (float)yr, D);
-      Sample<1> s0 = sample_frame<1>(src0, P0, g, mask_b, p.mask_dtype, overlap, H, W);
-      Sample<1> s1 = sample_frame<1>(src1, P1, g, mask_b, p.mask_dtype, overlap, H, W);
+      RowLoads rl;
+      if (PIPE == 1) {
+        rl = rl_next;
+        if (yy < y_last) {
+          rl_next = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy + 1, H), xr, finish_depth(dl_next, wx.l));
+          dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 2, y_last), H), wx);
+        }
+      } else {
+        rl = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy, H), xr, finish_depth(dl_next, wx.l));
+        dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx);
+      }
+      const float D = rl.D;
+      Sample<1> s0 = finish_frame<1>(rl.f0, H, W);
+      Sample<1> s1 = finish_frame<1>(rl.f1, H, W);
+      raw[0] = rl.t.x; raw[1] = rl.t.y; raw[2] = rl.t.z;
 #pragma unroll
       for (int c = 0; c < 3; ++c) { raw[3 + c] = s0.pred[c]; raw[6 + c] = s1.pred[c]; }
       valid[0] = s0.valid; valid[1] = s1.valid;
@@ -442,7 +618,7 @@ __global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
 #pragma unroll
     for (int i = 0; i < 18; ++i) w[i] = 0.f;
     float gf[2] = {0.f, 0.f};
-    if (yy >= it.y_begin && yc >= 0 && yc < H && x_in && lane >= 1 && lane <= 30) {
+    if (centre_live) {
       float ph[2], da[2][3], db[2][3], dc[2][3];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
@@ -456,27 +632,19 @@ __global__ void __launch_bounds__(kWarps * 32) loss_bwd_kernel(LossParams p) {
         ph[k] = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_prev[k]);
         if (overlap && !valid_prev[k]) ph[k] = 100.f;
       }
-      const size_t pix = (size_t)yc * W + x;
       int win;                               // 0 / 1 = reprojection frame that wins, -1 = none
-      float gate = 1.f;
+      const float gate = c_gate;
       if (use_ident) {
-        float i0 = __ldg(p.ident + ((size_t)b * 2 + 0) * HW + pix);
-        float i1 = __ldg(p.ident + ((size_t)b * 2 + 1) * HW + pix);
-        if (p.noise) {
-          i0 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 0) * HW + pix), 1e-5f, i0);
-          i1 = fmaf(__ldg(p.noise + ((size_t)b * 2 + 1) * HW + pix), 1e-5f, i1);
-        }
+        const float i0 = fmaf(c_n0, 1e-5f, c_i0), i1 = fmaf(c_n1, 1e-5f, c_i1);
         float best = fminf(i0, i1);
         win = -1;
         if (ph[0] < best) { best = ph[0]; win = 0; }
         if (ph[1] < best) { win = 1; }
       } else {
         win = ph[1] < ph[0] ? 1 : 0;
-        gate = 1.f - __ldg(p.motion + (size_t)b * HW + pix);
       }
       if (win >= 0 && (!overlap || valid_prev[win])) {
-        float m = p.mask ? load_mask(mask_b, p.mask_dtype, pix) : 1.f;
-        float gv = gbase * m * gate;
+        float gv = gbase * c_m * gate;
         float ws_ = (0.85f / 3.f) * gv;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -618,12 +786,28 @@ __global__ void camera_setup_kernel(const float* __restrict__ P2, const float* _
     }
 }
 
-int plan(LossParams& p, int cols_per_warp) {
+int loss_pipe() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FSNET_LOSS_PIPE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+// Rows per warp-item: minimise (number of waves) x (rows + halo rows) given how many warps are resident
+// (148 SMs x warps/SM allowed by the kernel's registers), so that no second, mostly empty wave is left.
+int plan(LossParams& p, int cols_per_warp, int halo_rows, int warps_per_sm) {
   p.n_strips = ceil_div(p.W, cols_per_warp);
-  int rows = 32;
-  while (rows > 8 && (long)p.B * p.n_strips * ceil_div(p.H, rows) < 148L * 16) rows >>= 1;
-  p.rows_per_item = rows;
-  p.n_chunks = ceil_div(p.H, rows);
+  const long cap = 148L * warps_per_sm;
+  int best_rows = 8;
+  double best_cost = 1e30;
+  for (int rows = 8; rows <= 64; ++rows) {
+    const long items = (long)p.B * p.n_strips * ceil_div(p.H, rows);
+    const long waves = (items + cap - 1) / cap;
+    // rows actually walked by the longest item, plus a small bias towards more (smaller) items for balance
+    const double cost = (double)waves * (rows + halo_rows) * (1.0 + 0.002 * rows) * ((double)ceil_div(p.H, rows) * rows / p.H);
+    if (cost < best_cost) { best_cost = cost; best_rows = rows; }
+  }
+  p.rows_per_item = best_rows;
+  p.n_chunks = ceil_div(p.H, best_rows);
   p.sy = p.H > 1 ? (float)(p.hs - 1) / (float)(p.H - 1) : 0.f;
   p.sx = p.W > 1 ? (float)(p.ws - 1) / (float)(p.W - 1) : 0.f;
   return ceil_div(p.B * p.n_strips * p.n_chunks, kWarps);
@@ -642,22 +826,24 @@ extern "C" int fsnet_camera_setup(const float* P2, const float* T0, const float*
 }
 
 extern "C" int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
-                                          int B, int H, int W, float* ident, void* stream) {
+                                          int B, int H, int W, float* ident, float* packed, void* stream) {
   FSNET_REQUIRE(tgt && src0 && src1 && ident, "fsnet_identity_photometric: null pointer");
+  FSNET_REQUIRE(packed == nullptr || ((uintptr_t)packed & 15) == 0, "fsnet_identity_photometric: packed buffer must be 16-byte aligned");
   FSNET_REQUIRE(B > 0 && H >= 3 && W >= 3, "fsnet_identity_photometric: need B>0, H>=3, W>=3 (got %d,%d,%d)", B, H, W);
   LossParams p = {};
   p.tgt = tgt; p.src0 = src0; p.src1 = src1; p.B = B; p.H = H; p.W = W; p.hs = H; p.ws = W;
-  p.ident_out = ident;
-  int blocks = plan(p, 30);
-  loss_fwd_kernel<0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  p.ident_out = ident; p.packed_out = reinterpret_cast<float4*>(packed);
+  int blocks = plan(p, 30, 2, 16);
+  loss_fwd_kernel<0, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
 
-static int check_common(const float* depth_s, int hs, int ws, const float* tgt, const float* src0, const float* src1,
+static int check_common(const float* depth_s, int hs, int ws, const float* packed,
                         const void* mask, int mask_dtype, const float* cam, const float* ident, const float* motion,
                         unsigned flags, int B, int H, int W) {
-  FSNET_REQUIRE(depth_s && tgt && src0 && src1 && cam, "fsnet_warp_ssim: null pointer");
+  FSNET_REQUIRE(depth_s && packed && cam, "fsnet_warp_ssim: null pointer");
+  FSNET_REQUIRE(((uintptr_t)packed & 15) == 0, "fsnet_warp_ssim: packed images must be 16-byte aligned");
   FSNET_REQUIRE(B > 0 && H >= 3 && W >= 3 && hs >= 1 && ws >= 1 && hs <= H && ws <= W,
                 "fsnet_warp_ssim: bad shape B=%d H=%d W=%d hs=%d ws=%d", B, H, W, hs, ws);
   FSNET_REQUIRE((mask == nullptr) == (mask_dtype == FSNET_MASK_NONE), "fsnet_warp_ssim: mask pointer / dtype mismatch");
@@ -667,39 +853,41 @@ static int check_common(const float* depth_s, int hs, int ws, const float* tgt, 
   return FSNET_OK;
 }
 
-extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* tgt, const float* src0,
-                                   const float* src1, const void* mask, int mask_dtype, const float* cam,
+extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* packed,
+                                   const void* mask, int mask_dtype, const float* cam,
                                    const float* ident, const float* noise, const float* motion, unsigned flags,
                                    int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
-  int rc = check_common(depth_s, hs, ws, tgt, src0, src1, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
+  int rc = check_common(depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
   if (rc) return rc;
   FSNET_REQUIRE(accum, "fsnet_warp_ssim_fwd: null accumulator");
   LossParams p = {};
-  p.depth = depth_s; p.hs = hs; p.ws = ws; p.tgt = tgt; p.src0 = src0; p.src1 = src1;
+  p.depth = depth_s; p.hs = hs; p.ws = ws; p.packed = reinterpret_cast<const float4*>(packed);
   p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum = accum; p.sel = sel; p.pred0 = pred0;
-  int blocks = plan(p, 30);
-  loss_fwd_kernel<1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  int blocks = plan(p, 30, 2, loss_pipe() ? 8 : 16);
+  if (loss_pipe()) loss_fwd_kernel<1, 1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  else loss_fwd_kernel<1, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
 
-extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* tgt, const float* src0,
-                                   const float* src1, const void* mask, int mask_dtype, const float* cam,
+extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packed,
+                                   const void* mask, int mask_dtype, const float* cam,
                                    const float* ident, const float* noise, const float* motion, unsigned flags,
                                    int B, int H, int W, const double* accum, const float* gout,
                                    float* grad_depth, float* grad_P, void* stream) {
-  int rc = check_common(depth_s, hs, ws, tgt, src0, src1, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
+  int rc = check_common(depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
   if (rc) return rc;
   FSNET_REQUIRE(accum && gout && grad_depth, "fsnet_warp_ssim_bwd: null pointer");
   LossParams p = {};
-  p.depth = depth_s; p.hs = hs; p.ws = ws; p.tgt = tgt; p.src0 = src0; p.src1 = src1;
+  p.depth = depth_s; p.hs = hs; p.ws = ws; p.packed = reinterpret_cast<const float4*>(packed);
   p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
   p.grad_depth = grad_depth; p.grad_P = grad_P;
-  int blocks = plan(p, 28);
-  if (grad_P) loss_bwd_kernel<1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  else loss_bwd_kernel<0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  int blocks = plan(p, 28, 4, (loss_pipe() && !grad_P) ? 8 : 12);
+  if (grad_P) loss_bwd_kernel<1, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  else if (loss_pipe()) loss_bwd_kernel<0, 1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  else loss_bwd_kernel<0, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

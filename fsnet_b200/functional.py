@@ -58,10 +58,12 @@ class _ReprojectionLoss(torch.autograd.Function):
 
         cam = torch.empty(B, 2, 21, device=dev, dtype=torch.float32)
         _lib.call("fsnet_camera_setup", P2c, T0c, T1c, B, cam)
-        ident = None
-        if motion is None:
-            ident = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
-            _lib.call("fsnet_identity_photometric", tgt, src0, src1, B, H, W, ident)
+        # identity terms (needed unless the motion-mask branch is on) + the RGBX-packed images for the gathers
+        ident = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
+        packed = torch.empty(3, B, H, W, 4, device=dev, dtype=torch.float32)
+        _lib.call("fsnet_identity_photometric", tgt, src0, src1, B, H, W, ident, packed)
+        if motion is not None:
+            ident = None
         acc = torch.zeros(S, 4, device=dev, dtype=torch.float64)
         sums = torch.zeros(S, B, 3, device=dev, dtype=torch.float64)
         sel = pred0 = None
@@ -71,7 +73,7 @@ class _ReprojectionLoss(torch.autograd.Function):
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
-            _lib.call("fsnet_warp_ssim_fwd", depths[i], hs, ws, tgt, src0, src1, mask_c, mdt, cam, ident, noise_c[i],
+            _lib.call("fsnet_warp_ssim_fwd", depths[i], hs, ws, packed, mask_c, mdt, cam, ident, noise_c[i],
                       motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
                       pred0 if want_log else None)
             h, w = disps[i].shape[-2:]
@@ -81,7 +83,7 @@ class _ReprojectionLoss(torch.autograd.Function):
         ctx.S, ctx.cfg, ctx.flags, ctx.mdt = S, cfg, flags, mdt
         ctx.shapes = (B, H, W)
         ctx.need_pose = any(ctx.needs_input_grad[2 + 2 * S + j] for j in range(2))
-        ctx.save_for_backward(*depths, *disps, tgt, src0, src1, cam, P2c, acc, sums,
+        ctx.save_for_backward(*depths, *disps, tgt, packed, cam, P2c, acc, sums,
                               *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
                               *( [motion_c] if motion_c is not None else []), *[n for n in noise_c if n is not None])
         ctx.has = (ident is not None, mask_c is not None, motion_c is not None, noise_c[0] is not None)
@@ -99,8 +101,8 @@ class _ReprojectionLoss(torch.autograd.Function):
         B, H, W = ctx.shapes
         sv = list(ctx.saved_tensors)
         depths, disps = sv[:S], sv[S:2 * S]
-        tgt, src0, src1, cam, P2c, acc, sums = sv[2 * S:2 * S + 7]
-        rest = sv[2 * S + 7:]
+        tgt, packed, cam, P2c, acc, sums = sv[2 * S:2 * S + 6]
+        rest = sv[2 * S + 6:]
         has_ident, has_mask, has_motion, has_noise = ctx.has
         ident = rest.pop(0) if has_ident else None
         mask_c = rest.pop(0) if has_mask else None
@@ -114,7 +116,7 @@ class _ReprojectionLoss(torch.autograd.Function):
             hs, ws = depths[i].shape[-2:]
             full = (hs == H and ws == W)
             gd = (torch.empty if full else torch.zeros)(depths[i].shape, device=dev, dtype=torch.float32)
-            _lib.call("fsnet_warp_ssim_bwd", depths[i], hs, ws, tgt, src0, src1, mask_c, ctx.mdt, cam, ident, noise_c[i],
+            _lib.call("fsnet_warp_ssim_bwd", depths[i], hs, ws, packed, mask_c, ctx.mdt, cam, ident, noise_c[i],
                       motion_c, _lib.ctypes.c_uint(ctx.flags), B, H, W, acc[i], gout, gd, gP)
             g_depths.append(gd)
             h, w = disps[i].shape[-2:]

@@ -25,8 +25,15 @@ class _Buf:
 
 
 class Planes(_Buf):
+    SLACK = 256      # zeroed elements behind the lo plane: the folded-tap TMA windows of the last pixels run past the end
+
     def __init__(self, n, h, w, c, ring=1, device="cuda", zero=False):
-        t = (torch.zeros if zero else torch.empty)(2, n, h + 2 * ring, w + 2 * ring, c, device=device, dtype=torch.bfloat16)
+        numel = 2 * n * (h + 2 * ring) * (w + 2 * ring) * c
+        flat = (torch.zeros if zero else torch.empty)(numel + self.SLACK, device=device, dtype=torch.bfloat16)
+        if not zero:
+            flat[numel:].zero_()
+        self._flat = flat
+        t = flat[:numel].view(2, n, h + 2 * ring, w + 2 * ring, c)
         super().__init__(t, n, h, w, c, ring)
 
     def to_float(self):

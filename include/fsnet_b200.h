@@ -58,11 +58,14 @@ int fsnet_camera_setup(const float* P2, const float* T0, const float* T1, int B,
 /* ---------------------------------------------------------------------------------------------
  * identity photometric terms: 0.85*mean_c SSIM(src_f, tgt) + 0.15*mean_c |tgt - src_f| for both
  * source frames.  monodepth2_decoder.py:248-254 (+ :118-128, monodepth_utils.py:184-215).  They do
- * not depend on the scale, so they are computed once per step.
+ * not depend on the scale, so they are computed once per step.  The same pass also emits the
+ * RGBX-packed copy of the three images that the per-scale kernels gather from (one 128-bit load per
+ * bilinear corner instead of three scalar ones).
  *   tgt, src0, src1 [B,3,H,W] fp32        ident [B,2,H,W] fp32 out
+ *   packed [3,B,H,W,4] fp32 out (target, source 0, source 1; 16-byte aligned) or NULL
  * ------------------------------------------------------------------------------------------- */
 int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
-                               int B, int H, int W, float* ident, void* stream);
+                               int B, int H, int W, float* ident, float* packed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * fused per-scale reprojection loss, forward.  One launch replaces, for one scale,
@@ -70,7 +73,7 @@ int fsnet_identity_photometric(const float* tgt, const float* src0, const float*
  * Project3D, two F.grid_sample per frame), compute_reprojection_loss for both frames (:118-128),
  * the 100.0 overwrite (:231-235), the tie-break noise and 4-way min (:257-263), the patched-mask
  * product and the two sums of :292.
- *   depth_s [B,1,hs,ws]   tgt/src0/src1 [B,3,H,W]   mask [B,H,W] (mask_dtype) or NULL
+ *   depth_s [B,1,hs,ws]   packed [3,B,H,W,4] from fsnet_identity_photometric   mask [B,H,W] (mask_dtype) or NULL
  *   cam     [B,2,21] from fsnet_camera_setup
  *   ident   [B,2,H,W] from fsnet_identity_photometric (ignored with FSNET_FLAG_MOTION_MASK)
  *   noise   [B,2,H,W] fp32 standard-normal draws (scaled by 1e-5 in the kernel) or NULL
@@ -79,8 +82,7 @@ int fsnet_identity_photometric(const float* tgt, const float* src0, const float*
  *   sel     [B,H,W] uint8 arg-min index (0,1 identity; 2,3 reprojection) or NULL
  *   pred0   [2,3,H,W] fp32 warped sources of batch sample 0 (the reference's `hm` images) or NULL
  * ------------------------------------------------------------------------------------------- */
-int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws,
-                        const float* tgt, const float* src0, const float* src1,
+int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* packed,
                         const void* mask, int mask_dtype, const float* cam,
                         const float* ident, const float* noise, const float* motion,
                         unsigned flags, int B, int H, int W,
@@ -96,8 +98,7 @@ int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws,
  *   grad_depth [B,1,hs,ws] fp32, must be zeroed by the caller when hs != H (scatter-add)
  *   grad_P     [B,2,12] fp32, zeroed by the caller, or NULL
  * ------------------------------------------------------------------------------------------- */
-int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws,
-                        const float* tgt, const float* src0, const float* src1,
+int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packed,
                         const void* mask, int mask_dtype, const float* cam,
                         const float* ident, const float* noise, const float* motion,
                         unsigned flags, int B, int H, int W,

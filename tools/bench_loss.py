@@ -20,6 +20,7 @@ def main(B=12, H=192, W=640, iters=20):
     cam = torch.empty(B, 2, 21, device=dev)
     _lib.call("fsnet_camera_setup", data["P2"].to(dev), data[("relative_pose", 1)].to(dev), data[("relative_pose", -1)].to(dev), B, cam)
     ident = torch.empty(B, 2, H, W, device=dev)
+    packed = torch.empty(3, B, H, W, 4, device=dev)
     noise = torch.randn(B, 2, H, W, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     gout = torch.full((1,), 0.25, device=dev)
@@ -35,15 +36,15 @@ def main(B=12, H=192, W=640, iters=20):
         ts.sort()
         return ts[len(ts) // 2]
 
-    res["identity_us"] = timeit(lambda: _lib.call("fsnet_identity_photometric", tgt, s0, s1, B, H, W, ident))
+    res["identity_us"] = timeit(lambda: _lib.call("fsnet_identity_photometric", tgt, s0, s1, B, H, W, ident, packed))
     for s in range(4):
         d = outs[("depth", s, s)].to(dev)
         hs, ws = d.shape[-2:]
         acc = torch.zeros(4, dtype=torch.float64, device=dev)
         gd = torch.zeros_like(d)
-        f = lambda: _lib.call("fsnet_warp_ssim_fwd", d, hs, ws, tgt, s0, s1, mask, 1, cam, ident, noise, None,
+        f = lambda: _lib.call("fsnet_warp_ssim_fwd", d, hs, ws, packed, mask, 1, cam, ident, noise, None,
                               _lib.ctypes.c_uint(1), B, H, W, acc, None, None)
-        bwd = lambda: _lib.call("fsnet_warp_ssim_bwd", d, hs, ws, tgt, s0, s1, mask, 1, cam, ident, noise, None,
+        bwd = lambda: _lib.call("fsnet_warp_ssim_bwd", d, hs, ws, packed, mask, 1, cam, ident, noise, None,
                                 _lib.ctypes.c_uint(1), B, H, W, acc, gout, gd, None)
         tf, tb = timeit(f), timeit(bwd)
         bytes_f = B * H * W * (40 + 8 / 4 ** s)

@@ -147,6 +147,44 @@ def test_maxpool(N, C, H, W):
     check(f"maxpool bwd [{N},{C},{H}x{W}]", gxb.nchw(), gx_ref, 1e-6)
 
 
+def perf():
+    """Forward / dgrad / wgrad times of the hot cfg2 layer shapes (B=12)."""
+    shapes = [("(1,1) 96->32 @96x320 rep", 96, 32, 96, 320, 3, 1, 1, True), ("(0,1) 16->16 @192x640 rep", 16, 16, 192, 640, 3, 1, 1, True),
+              ("disp1 32->16 @96x320 rep", 32, 16, 96, 320, 3, 1, 1, True), ("(0,0) 32->16 @96x320 zero", 32, 16, 96, 320, 3, 1, 1, False),
+              ("layer1 64->64 @48x160", 64, 64, 48, 160, 3, 1, 1, False), ("layer4 512->512 @6x20", 512, 512, 6, 20, 3, 1, 1, False),
+              ("stem 3->64 @192x640 s2", 3, 64, 192, 640, 7, 2, 3, False)]
+    N = 12
+    for name, Cin, Cout, H, W, k, stride, pad, rep in shapes:
+        x = torch.randn(N, Cin, H, W, device="cuda")
+        w = torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5
+        xp = planes_from(x)
+        cw = tc.ConvWeights(w); cw.refresh(w)
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        out = tc.Fp32(N, Ho, Wo, cw.co_pad)
+        stats = torch.zeros(2 * cw.co_pad, device="cuda", dtype=torch.float64)
+        dy = tc.Planes(N, Ho, Wo, cw.co_pad, ring=0, zero=True)
+        gx = tc.Fp32(N, H, W, cw.ci_pad, ring=1)
+        full = tc.View(gx.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
+
+        def t(fn, n=10):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) * 1e3 / n
+        tf = t(lambda: tc.conv(xp, cw, out, stride, pad, use_ring=rep, stats=stats))
+        tw = t(lambda: tc.conv_wgrad(xp.view(), rep, dy.view(), cw, stride, pad))
+        td = float("nan")
+        if stride == 1:
+            td = t(lambda: tc.conv_dgrad(dy, cw, full if rep else gx.view(), pad=(k - 1) if rep else (k - 1 - pad)))
+        print(f"PERF {name:32s} fwd {tf:7.1f} us  dgrad {td:7.1f} us  wgrad {tw:7.1f} us", flush=True)
+
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["conv", "bn", "pool"]
     if "conv" in which:
@@ -167,5 +205,9 @@ if __name__ == "__main__":
     if "pool" in which:
         test_maxpool(2, 64, 24, 40)
         test_maxpool(2, 16, 13, 21)
+    if "perf" in which:
+        perf()
     print("ALL OK" if OK else "SOME FAILED")
     sys.exit(0 if OK else 1)
+
+
