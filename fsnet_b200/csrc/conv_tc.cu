@@ -432,7 +432,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
   static int fold_env = -1;
   if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 1; }
-  p.fold = fold_env && stride == 1 && use_ring && in->ring == 1 && pad == 1 && KH == 3 && KW == 3 && in->c_off == 0 &&
+  p.fold = fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
            in->c == in->c_total && (Cin < 64 || Cin == 96);
   if (p.fold) {
     p.KC = 64; p.cchunks = ceil_div(KW * Cin, 64); p.kiters = KH * p.cchunks;
@@ -456,9 +456,9 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (p.fold) {
-    const int pw = W + 2, ph = H + 2;
+    const int pw = W + 2 * in->ring, ph = H + 2 * in->ring;
     const size_t plane_elems = (size_t)N * ph * pw * Cin;
-    cuuint64_t adim[4] = {(cuuint64_t)(64 * p.cchunks), (cuuint64_t)W, (cuuint64_t)ph, (cuuint64_t)N};
+    cuuint64_t adim[4] = {(cuuint64_t)(64 * p.cchunks), (cuuint64_t)p.Wo, (cuuint64_t)ph, (cuuint64_t)N};
     cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)pw * Cin * 2, (cuuint64_t)ph * pw * Cin * 2};
     cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
     cuuint32_t aes[4] = {1, 1, 1, 1};
@@ -683,7 +683,7 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
   // thin layers get more pixels per stage so that one stage moves >= 16 KB
   p.pix = 64;
-  while (p.pix < 128 && (size_t)(p.pix * 2) * (p.nA * p.atomA + p.BN) * 2 <= 32 * 1024 && (size_t)p.pix * 2 <= (size_t)p.Ho * p.Wo) p.pix *= 2;
+  while (false && p.pix < 128 && (size_t)(p.pix * 2) * (p.nA * p.atomA + p.BN) * 2 <= 32 * 1024 && (size_t)p.pix * 2 <= (size_t)p.Ho * p.Wo) p.pix *= 2;
   int pw = 1;
   while (pw * 2 <= p.Wo && pw * 2 <= 64) pw *= 2;
   p.PW = pw; p.PH = p.pix / pw;

@@ -224,7 +224,8 @@ class Tape:
         world = _sync_world(bn) if has_bn else 1
         if world > 1:
             dist.all_reduce(st.sums)
-        dy = Planes(raw.n, raw.h, raw.w, st.C, ring=0, device=raw.t.device)
+        fold_dgrad = st.replicate and st.kh == 3 and st.C < 64          # see fsnet_conv: folded x-taps need ring == pad
+        dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device, zero=fold_dgrad)
         gamma = st.padded(bn.weight, 1.0) if bn is not None else None
         if bn is not None and not bn_train:
             # BatchNorm in eval mode inside a training step (norm_eval=True): a fixed per-channel scale
@@ -256,7 +257,7 @@ class Tape:
         if st.replicate:
             # x_pad = replicate_pad(x): gradient of the padded tensor (pad k-1 correlation), then fold the ring
             assert x.grad.ring == 1, "replicate consumers need a ringed gradient buffer"
-            tc.conv_dgrad(dy, st.w, x.gview_full_ring(), pad=k - 1, accumulate=x.grad_written)
+            tc.conv_dgrad(dy, st.w, x.gview_full_ring(), pad=k - 1, accumulate=x.grad_written, use_ring=(dy.ring == k - 1))
             x.grad_written = True
             x.ring_dirty = True
             return

@@ -84,9 +84,10 @@ def conv(inp: Planes, w: ConvWeights, out: Fp32, stride=1, pad=1, use_ring=False
               bias, int(relu), out_view or out.view(), int(accumulate), stats)
 
 
-def conv_dgrad(dy: Planes, w: ConvWeights, out_view: View, pad, accumulate=False, dy_view=None):
-    """Data gradient of a stride-1 convolution = convolution of dy with the flipped, transposed weights."""
-    _lib.call("fsnet_conv", dy_view or dy.view(), 0, w.dgrad, None, w.ci_pad, w.kh, w.kw, 1, pad, 1, None, 0, out_view,
+def conv_dgrad(dy: Planes, w: ConvWeights, out_view: View, pad, accumulate=False, dy_view=None, use_ring=False):
+    """Data gradient of a stride-1 convolution = convolution of dy with the flipped, transposed weights.
+    ``use_ring``: dy carries a materialised zero ring of width ``pad`` (enables the folded-tap path for thin layers)."""
+    _lib.call("fsnet_conv", dy_view or dy.view(), int(use_ring), w.dgrad, None, w.ci_pad, w.kh, w.kw, 1, pad, 1, None, 0, out_view,
               int(accumulate), None)
 
 
