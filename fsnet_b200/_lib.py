@@ -13,6 +13,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfsnet_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fsnet_b200.h")
 
+class WeightDesc(ctypes.Structure):
+    """fsnet_weight_desc of include/fsnet_b200.h."""
+    _fields_ = [("w", ctypes.c_void_p), ("fwd_hi", ctypes.c_void_p), ("fwd_lo", ctypes.c_void_p), ("dgrad_hi", ctypes.c_void_p),
+                ("cout", ctypes.c_int), ("cin", ctypes.c_int), ("kh", ctypes.c_int), ("kw", ctypes.c_int),
+                ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
+
+
 _lock = threading.Lock()
 _lib = None
 launch_count = 0          # entry-point calls issued through this binding

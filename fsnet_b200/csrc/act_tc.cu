@@ -287,6 +287,7 @@ struct BnBwdParams {
   double count;
   V dy;                         // out: bf16 plane (hi only), ring zeroed
   V res; int res_mode;          // 0 none, 1 write masked g, 2 accumulate masked g   (identity residual / downsample input)
+  float* dgamma; float* dbeta; int c_real;   // optional fp32 parameter gradients (= sums[C..], sums[..C]) written by block 0
 };
 __device__ __forceinline__ F8 masked_g8(const BnBwdParams& p, const Px& q, const F8& rawv) {
   const float* gp = (const float*)p.g.ptr;
@@ -354,6 +355,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
   const int C = r.c;
   const unsigned total = (unsigned)r.n * r.h * r.w * (C >> 3);
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < p.c_real; c += blockDim.x) {
+      if (p.dbeta) p.dbeta[c] = (float)p.sums[c];
+      if (p.dgamma) p.dgamma[c] = (float)p.sums[C + c];
+    }
+  }
   if (i >= total) return;
   const Px q = decode8(i, r.h, r.w, C);
   const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, q.c));
@@ -454,6 +461,23 @@ __global__ void weight_planes_kernel(const float* __restrict__ w, int Cout, int 
   fwd_hi[i] = h;
   if (fwd_lo) fwd_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
   if (dg_hi) dg_hi[(((size_t)ci * KH + (KH - 1 - r)) * KW + (KW - 1 - s)) * Cout_pad + co] = h;
+}
+
+// all layers of a network in one launch: blockIdx.y selects the layer descriptor
+__global__ void weight_planes_batched_kernel(const fsnet_weight_desc* __restrict__ table) {
+  const fsnet_weight_desc d = table[blockIdx.y];
+  const size_t total = (size_t)d.cout_pad * d.kh * d.kw * d.cin_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int ci = (int)(i % d.cin_pad); size_t t = i / d.cin_pad;
+    int s = (int)(t % d.kw); t /= d.kw;
+    int r = (int)(t % d.kh); int co = (int)(t / d.kh);
+    float v = (co < d.cout && ci < d.cin) ? __ldg(d.w + (((size_t)co * d.cin + ci) * d.kh + r) * d.kw + s) : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16* fh = (__nv_bfloat16*)d.fwd_hi;
+    fh[i] = h;
+    if (d.fwd_lo) ((__nv_bfloat16*)d.fwd_lo)[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (d.dgrad_hi) ((__nv_bfloat16*)d.dgrad_hi)[(((size_t)ci * d.kh + (d.kh - 1 - r)) * d.kw + (d.kw - 1 - s)) * d.cout_pad + co] = h;
+  }
 }
 
 // wgrad accumulator fp32 [Cout_pad,KH,KW,Cin_pad] -> parameter gradient [Cout,Cin,KH,KW] (+=)
@@ -566,12 +590,14 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
 
 extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_ss, const fsnet_view* raw,
                                   const float* mean_invstd, const float* gamma, double* sums, double count,
-                                  const fsnet_view* dy, int res_mode, const fsnet_view* res, void* stream) {
+                                  const fsnet_view* dy, int res_mode, const fsnet_view* res, float* dgamma, float* dbeta, int c_real,
+                                  void* stream) {
   BnBwdParams p = {};
   int rc = fill_bn_bwd(p, g, up, mask, mask_ss, raw, mean_invstd, gamma, sums, count);
   if (rc) return rc;
   FSNET_REQUIRE(dy && dy->ptr && (res_mode == 0 || (res && res->ptr)), "fsnet_bn_bwd_apply: bad arguments");
   p.dy = *dy; p.res_mode = res_mode; if (res) p.res = *res;
+  p.dgamma = dgamma; p.dbeta = dbeta; p.c_real = c_real;
   size_t total = (size_t)raw->n * raw->h * raw->w * (raw->c / 8);
   bn_bwd_apply_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
@@ -609,6 +635,14 @@ extern "C" int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, in
   size_t total = (size_t)Cout_pad * KH * KW * Cin_pad;
   weight_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, KH, KW, Cout_pad, Cin_pad, (__nv_bfloat16*)fwd_hi,
                                                                           (__nv_bfloat16*)fwd_lo, (__nv_bfloat16*)dgrad_hi);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device, int n_layers, void* stream) {
+  FSNET_REQUIRE(table_device && n_layers > 0, "fsnet_weight_planes_batched: bad arguments");
+  dim3 grid(64, n_layers);
+  weight_planes_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_device);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

@@ -85,7 +85,6 @@ class LayerState:
         dev = w.device
         self.C, self.c_real = C, w.shape[0]
         self.stats = torch.zeros(2 * C, device=dev, dtype=torch.float64)
-        self.sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
         self.kh, self.kw = conv.kernel_size
         self.stride = conv.stride[0]
         self.pad = conv.padding[0]
@@ -123,10 +122,36 @@ def _sync_world(bn) -> int:
 class Tape:
     """Forward executor + backward tape for one network invocation."""
 
-    def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool):
+    def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool, weights_fresh=False):
         self.states, self.training, self.need_grad = states, training, need_grad
         self.backward_ops: List = []
         self.param_grads: Dict[int, torch.Tensor] = {}      # id(parameter) -> gradient tensor
+        self.weights_fresh = weights_fresh                    # operand planes already refreshed by one batched launch
+        self._pools = None
+
+    def _make_pools(self):
+        """One zeroed workspace per backward pass instead of one fill kernel per layer: BN-backward sums (fp64),
+        wgrad accumulators (fp32) and the all-zero gradients of BN-cancelled conv biases."""
+        dev = next(iter(self.states.values())).stats.device
+        n_sums = sum(2 * st.C for st in self.states.values())
+        n_acc = sum(st.w.acc_numel for st in self.states.values())
+        n_zero = sum(st.c_real for st in self.states.values())
+        self._pools = dict(sums=torch.zeros(n_sums, device=dev, dtype=torch.float64), acc=torch.zeros(n_acc, device=dev, dtype=torch.float32),
+                           zero=torch.zeros(n_zero, device=dev, dtype=torch.float32), off={})
+        o_s = o_a = o_z = 0
+        for key, st in self.states.items():
+            self._pools["off"][key] = (o_s, o_a, o_z)
+            o_s += 2 * st.C; o_a += st.w.acc_numel; o_z += st.c_real
+
+    def _pool(self, st: LayerState, which: str):
+        if self._pools is None:
+            self._make_pools()
+        o_s, o_a, o_z = self._pools["off"][id(st.conv)]
+        if which == "sums":
+            return self._pools["sums"][o_s:o_s + 2 * st.C]
+        if which == "acc":
+            return self._pools["acc"][o_a:o_a + st.w.acc_numel]
+        return self._pools["zero"][o_z:o_z + st.c_real]
 
     def state(self, conv, bn, need_dgrad=True) -> LayerState:
         st = self.states.get(id(conv))
@@ -141,7 +166,8 @@ class Tape:
         """conv -> BatchNorm (batch statistics when training) -> (+ residual | + BN(down conv)) -> ReLU -> planes.
         ``down`` = (conv, bn) of the 1x1 down-sample branch applied to ``residual``'s source ``x_down``."""
         st = self.state(conv, bn, need_dgrad)
-        st.w.refresh(conv.weight)
+        if not self.weights_fresh:
+            st.w.refresh(conv.weight)
         N = x.n
         Ho = (x.h + 2 * st.pad - st.kh) // st.stride + 1
         Wo = (x.w + 2 * st.pad - st.kw) // st.stride + 1
@@ -203,7 +229,8 @@ class Tape:
 
     def _down_forward(self, x: Act, conv, bn):
         st = self.state(conv, bn)
-        st.w.refresh(conv.weight)
+        if not self.weights_fresh:
+            st.w.refresh(conv.weight)
         Ho = (x.h - 1) // st.stride + 1
         Wo = (x.w - 1) // st.stride + 1
         raw = Fp32(x.n, Ho, Wo, st.C, device=x.planes.t.device)
@@ -217,37 +244,42 @@ class Tape:
     def _bn_bwd(self, inv: Inv, bn, bn_train, g_view: View, up, mask_view, mask_ss, raw: Fp32, res_mode=0, res_view=None):
         """(ReLU o BatchNorm) backward -> dy plane; fills the BN / bias parameter gradients."""
         st = inv.st
-        st.sums.zero_()
+        sums = self._pool(st, "sums")                      # zeroed slice of the pass-wide workspace
         has_bn = bn is not None and bn_train
         mi = inv.mi if has_bn else None
-        _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, st.sums)
+        _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, sums)
         world = _sync_world(bn) if has_bn else 1
         if world > 1:
-            dist.all_reduce(st.sums)
+            dist.all_reduce(sums)
         fold_dgrad = st.replicate and st.kh == 3 and st.C < 64          # see fsnet_conv: folded x-taps need ring == pad
         dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device, zero=fold_dgrad)
         gamma = st.padded(bn.weight, 1.0) if bn is not None else None
         if bn is not None and not bn_train:
             # BatchNorm in eval mode inside a training step (norm_eval=True): a fixed per-channel scale
             raise NotImplementedError("norm_eval=True training is not implemented on the tcgen05 path")
-        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, st.sums, tc.c_double(inv.count),
-                  dy.view(), res_mode, res_view)
         C = st.c_real
+        dgamma = dbeta = None
+        dev = raw.t.device
         if bn is not None:
             if bn.weight is not None and bn.weight.requires_grad:
-                self.param_grads[id(bn.weight)] = st.sums[st.C:st.C + C].float()
-                self.param_grads[id(bn.bias)] = st.sums[:C].float()
+                dgamma = torch.empty(C, device=dev, dtype=torch.float32)
+                dbeta = torch.empty(C, device=dev, dtype=torch.float32)
+                self.param_grads[id(bn.weight)] = dgamma
+                self.param_grads[id(bn.bias)] = dbeta
             if st.conv.bias is not None and st.conv.bias.requires_grad:
-                self.param_grads[id(st.conv.bias)] = torch.zeros_like(st.conv.bias)     # cancelled by the batch mean
+                self.param_grads[id(st.conv.bias)] = self._pool(st, "zero")      # cancelled by the batch mean
         elif st.conv.bias is not None and st.conv.bias.requires_grad:
-            self.param_grads[id(st.conv.bias)] = st.sums[:C].float()
+            dbeta = torch.empty(C, device=dev, dtype=torch.float32)
+            self.param_grads[id(st.conv.bias)] = dbeta
+        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, sums, tc.c_double(inv.count),
+                  dy.view(), res_mode, res_view, dgamma, dbeta, C)
         return dy
 
     def _conv_bwd(self, x: Act, st: LayerState, dy: Planes, need_dgrad=True):
         """Weight gradient and (accumulated) data gradient of one convolution."""
         conv = st.conv
         if conv.weight.requires_grad:
-            acc = tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad)
+            acc = tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
             gw = torch.empty_like(conv.weight)
             _lib.call("fsnet_wgrad_to_param", acc, st.w.co, st.w.ci, st.kh, st.kw, st.w.co_pad, st.w.ci_pad, gw, 0)
             self.param_grads[id(conv.weight)] = gw
@@ -331,7 +363,8 @@ class Tape:
         """Plain convolution + bias whose fp32 result leaves the tcgen05 graph (dispconv logits, pose output).
         Its incoming gradient is looked up as ``self.out_grads[key]`` (fp32 NHWC, padded channels) at backward time."""
         st = self.state(conv, None)
-        st.w.refresh(conv.weight)
+        if not self.weights_fresh:
+            st.w.refresh(conv.weight)
         Ho = (x.h + 2 * st.pad - st.kh) // st.stride + 1
         Wo = (x.w + 2 * st.pad - st.kw) // st.stride + 1
         out = Fp32(x.n, Ho, Wo, st.C, device=x.planes.t.device)
@@ -343,8 +376,7 @@ class Tape:
                 g_out = self.out_grads.get(key)
                 if g_out is None:
                     return
-                g = Fp32(out.n, out.h, out.w, st.C, device=out.t.device)
-                g.t.copy_(g_out)
+                g = Fp32.wrap(g_out)
                 dy = self._bn_bwd(Inv(st), None, False, g.view(), 1, None, None, out)
                 self._conv_bwd(x, st, dy)
             self.backward_ops.append(bwd)
@@ -450,7 +482,7 @@ class _DepthNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, img, *params):
         need_grad = runner.grad_enabled and any(p.requires_grad for p in params)
-        tape = Tape(runner.states, runner.training, need_grad)
+        tape = Tape(runner.states, runner.training, need_grad, runner.weights_fresh)
         feats = resnet_forward(tape, runner.backbone, img, need_grad)
         logits = decoder_forward(tape, runner.decoder, feats)
         ctx.tape, ctx.params, ctx.scales = tape, params, list(logits.keys())
@@ -479,7 +511,7 @@ class _PoseNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, img, *params):
         need_grad = runner.grad_enabled and any(p.requires_grad for p in params)
-        tape = Tape(runner.states, runner.training, need_grad)
+        tape = Tape(runner.states, runner.training, need_grad, runner.weights_fresh)
         feats = resnet_forward(tape, runner.backbone, img, need_grad)
         out = pose_decoder_forward(tape, runner.decoder, feats[-1])
         ctx.tape, ctx.params, ctx.c_pad = tape, params, out.c
@@ -508,6 +540,22 @@ class Runner:
         _check_supported(self.backbone)
         self.training = self.backbone.training
         self.grad_enabled = torch.is_grad_enabled()
+        self.weights_fresh = self._refresh_all()
+
+    def _refresh_all(self) -> bool:
+        """From the second invocation on (all LayerStates exist) every convolution's bf16 operand planes are rebuilt
+        from the fp32 parameters by ONE launch over a device-resident descriptor table."""
+        if not self.states:
+            return False
+        sig = tuple(st.conv.weight.data_ptr() for st in self.states.values())
+        if getattr(self, "_table_sig", None) != sig:
+            descs = (_lib.WeightDesc * len(self.states))(*[st.w.desc(st.conv.weight) for st in self.states.values()])
+            raw = bytes(descs)
+            dev = next(iter(self.states.values())).stats.device
+            self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            self._table_sig = sig
+        _lib.call("fsnet_weight_planes_batched", self._table, len(self.states))
+        return True
 
     def depth_logits(self, img):
         self._prep()

@@ -48,6 +48,13 @@ class Fp32(_Buf):
         t = (torch.zeros if zero else torch.empty)(n, h + 2 * ring, w + 2 * ring, c, device=device, dtype=torch.float32)
         super().__init__(t, n, h, w, c, ring)
 
+    @classmethod
+    def wrap(cls, t: torch.Tensor):
+        """View an existing contiguous fp32 [N,H,W,C] tensor (no ring) as a buffer."""
+        obj = cls.__new__(cls)
+        _Buf.__init__(obj, t, t.shape[0], t.shape[1], t.shape[2], t.shape[3], 0)
+        return obj
+
     def interior(self):
         r = self.ring
         return self.t[:, r:r + self.h, r:r + self.w, :]
@@ -72,10 +79,16 @@ class ConvWeights:
         _lib.call("fsnet_weight_planes", weight.detach(), self.co, self.ci, self.kh, self.kw, self.co_pad, self.ci_pad,
                   self.fwd[0], self.fwd[1], self.dgrad)
 
-    def wgrad_acc(self):
-        if self.acc is None:
-            self.acc = torch.empty(self.co_pad, self.kh, self.kw, self.ci_pad, device=self.fwd.device, dtype=torch.float32)
-        return self.acc
+    @property
+    def acc_numel(self):
+        return self.co_pad * self.kh * self.kw * self.ci_pad
+
+    def desc(self, weight):
+        d = _lib.WeightDesc()
+        d.w = weight.data_ptr(); d.fwd_hi = self.fwd[0].data_ptr(); d.fwd_lo = self.fwd[1].data_ptr()
+        d.dgrad_hi = 0 if self.dgrad is None else self.dgrad.data_ptr()
+        d.cout, d.cin, d.kh, d.kw, d.cout_pad, d.cin_pad = self.co, self.ci, self.kh, self.kw, self.co_pad, self.ci_pad
+        return d
 
 
 def conv(inp: Planes, w: ConvWeights, out: Fp32, stride=1, pad=1, use_ring=False, nprod=3, bias=None, relu=False, stats=None,
@@ -91,9 +104,10 @@ def conv_dgrad(dy: Planes, w: ConvWeights, out_view: View, pad, accumulate=False
               int(accumulate), None)
 
 
-def conv_wgrad(x_view: View, use_ring, dy_view: View, w: ConvWeights, stride, pad):
-    acc = w.wgrad_acc()
-    acc.zero_()
+def conv_wgrad(x_view: View, use_ring, dy_view: View, w: ConvWeights, stride, pad, acc=None):
+    """acc: zeroed fp32 [co_pad, kh, kw, ci_pad] accumulator (a slice of the tape's pool) or None (allocated here)."""
+    if acc is None:
+        acc = torch.zeros(w.acc_numel, device=w.fwd.device, dtype=torch.float32)
     _lib.call("fsnet_conv_wgrad", x_view, int(use_ring), dy_view, w.kh, w.kw, stride, pad, acc)
     return acc
 

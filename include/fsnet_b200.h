@@ -196,7 +196,8 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
  *                          dy (bf16 plane) = gamma*invstd*(g - mean g - xhat*mean g*xhat); mean_invstd == NULL
  *                          means "no BatchNorm" (dy = masked g); `up`=2 reads the gradient through the adjoint
  *                          of the nearest x2 up-sampling; res_mode 1/2 writes/accumulates the masked gradient
- *                          into another fp32 view (identity residual); the ReLU mask is `mask` (activation planes)
+ *                          into another fp32 view (identity residual); dgamma / dbeta (fp32 [c_real], may be NULL) receive
+ *                          the BatchNorm parameter gradients; the ReLU mask is `mask` (activation planes)
  *                          or, when mask == NULL and mask_scale_shift != NULL, raw*scale+shift > 0
  *   fsnet_fold_ring        adjoint of replicate padding: adds the ring of a ringed fp32 gradient into its border
  *   fsnet_add_slice        dst (+)= channel slice of src (fp32 views)
@@ -205,6 +206,13 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
 int fsnet_image_to_planes(const float* img, int C, const fsnet_view* dst, void* stream);
 int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad,
                         void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* stream);
+/* one launch for every convolution of a network: `table_device` is a DEVICE array of n_layers descriptors */
+typedef struct {
+  const float* w;            /* fp32 [cout, cin, kh, kw] parameter */
+  void* fwd_hi; void* fwd_lo; void* dgrad_hi;   /* outputs as in fsnet_weight_planes (fwd_lo / dgrad_hi may be NULL) */
+  int cout, cin, kh, kw, cout_pad, cin_pad;
+} fsnet_weight_desc;
+int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device, int n_layers, void* stream);
 int fsnet_wgrad_to_param(const float* acc, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad, float* grad,
                          int accumulate, void* stream);
 int fsnet_bn_finalize(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,
@@ -220,7 +228,8 @@ int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view* mask, con
                         const float* mean_invstd, double* sums, void* stream);
 int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view* mask, const float* mask_scale_shift, const fsnet_view* raw,
                        const float* mean_invstd, const float* gamma, double* sums, double count,
-                       const fsnet_view* dy, int res_mode, const fsnet_view* res, void* stream);
+                       const fsnet_view* dy, int res_mode, const fsnet_view* res, float* dgamma, float* dbeta, int c_real,
+                       void* stream);
 int fsnet_fold_ring(const fsnet_view* g, void* stream);
 int fsnet_add_slice(const fsnet_view* dst, const fsnet_view* src, int accumulate, void* stream);
 int fsnet_zero_insert(const fsnet_view* src, const fsnet_view* dst, void* stream);

@@ -123,7 +123,7 @@ def test_bn_act(N, C, H, W, up, res_mode):
     dy = tc.Planes(N, H, W, C, ring=0, zero=True)
     gres = tc.Fp32(N, H, W, C, zero=True)
     _lib.call("fsnet_bn_bwd_apply", gbuf.view(), up, act_lowres.view() if up == 1 else None, ss if up == 2 else None, rawb.view(), mi, gamma.detach(), sums, tc.c_double(cnt),
-              dy.view(), 1 if res_mode == 1 else 0, gres.view() if res_mode == 1 else None)
+              dy.view(), 1 if res_mode == 1 else 0, gres.view() if res_mode == 1 else None, None, None, C)
     check("bn bwd dy " + tag, dy.t[0].float().permute(0, 3, 1, 2), grads[0], 1e-2)
     if res_mode == 1:
         check("bn bwd residual grad " + tag, gres.nchw(), grads[3], 1e-5)
