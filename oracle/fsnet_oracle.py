@@ -44,6 +44,7 @@ class Topology:
     width: int = 640
     overlapped_mask: bool = True
     frame_ids: Tuple[int, ...] = (0, 1, -1)
+    fisheye: bool = False                # FishEyeDecoder: MEI camera, the network output is the ray norm
 
     @property
     def bottleneck(self) -> bool:
@@ -380,6 +381,130 @@ def warp_sources(depth_full: Tensor, data: Dict, cam_T: Dict[int, Tensor], topo:
     return warped, overlap
 
 
+# --------------------------------------------------------------------------------------------
+# MEI (unified omnidirectional) camera -- FishEyeDecoder (monodepth2_decoder.py:350-420)
+# --------------------------------------------------------------------------------------------
+def _mei_radial(k1: float, k2: float, r1: np.ndarray, r0: np.ndarray) -> np.ndarray:
+    """radial_distort_func (mei_fisheye_utils.py:66-68), fp64."""
+    r2 = r0 * r0
+    return r0 - r1 / (1 + k1 * r2 + k2 * (r2 * r2))
+
+
+def _mei_mirror(r0: np.ndarray, xi: float, Z) -> np.ndarray:
+    """mirror_backtrack_func (mei_fisheye_utils.py:81-83), fp64."""
+    return r0 * r0 - (1 - Z * Z) / ((xi + Z) * (xi + Z))
+
+
+def mei_lut(H: int, W: int, gamma1: float, gamma2: float, u0: float, v0: float, k1: float, k2: float, xi: float,
+            tol: float = 1e-6, max_iter: int = 100):
+    """The per-calibration look-up table of MeiCameraProjection.image2cam (mei_fisheye_utils.py:139-170):
+    returns fp32 ``X, Y, Z, mask`` of shape [H, W].  The per-pixel Newton solve (:70-79, finite-difference
+    derivative with step ``tol``) and bisection (:85-101) are restated vectorised with per-element
+    early exit, in fp64 like numba evaluates them (fp32 ``r1`` promoted by the fp64 calibration scalars)."""
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H), indexing="xy")
+    X = ((xs.astype(np.float32) - u0) / gamma1).astype(np.float32)
+    Y = ((ys.astype(np.float32) - v0) / gamma2).astype(np.float32)
+    r1 = np.sqrt(X ** 2 + Y ** 2).astype(np.float32).astype(np.float64)
+    # Newton (:70-79)
+    x = r1.copy()
+    done = np.zeros(r1.shape, bool)
+    with np.errstate(all="ignore"):
+        for _ in range(max_iter):
+            f = _mei_radial(k1, k2, r1, x)
+            done |= np.abs(f) < tol
+            if done.all():
+                break
+            df = (_mei_radial(k1, k2, r1, x + tol) - f) / tol
+            x = np.where(done, x, x - f / df)
+        r0 = x
+        # bisection on Z in [0, 1] (:85-101)
+        y0 = _mei_mirror(r0, xi, 0.0)
+        y1 = _mei_mirror(r0, xi, 1.0)
+        flag = ~(y0 * y1 > 0)
+        lo = np.zeros(r1.shape)
+        hi = np.ones(r1.shape)
+        z = np.where(flag, 0.0, -1.0)
+        done = ~flag
+        for _ in range(max_iter):
+            mid = (lo + hi) / 2
+            f = _mei_mirror(r0, xi, mid)
+            z = np.where(done, z, mid)
+            done |= np.abs(f) < tol
+            if done.all():
+                break
+            left = f * _mei_mirror(r0, xi, lo) < 0
+            hi = np.where(~done & left, mid, hi)
+            lo = np.where(~done & ~left, mid, lo)
+    Z = z.astype(np.float32)
+    mask = flag.astype(np.float32)
+    mask[Z < 0.05] = 0                                   # :161
+    dead = mask == 0
+    Z[dead] = -1
+    X[dead] = -1
+    Y[dead] = -1
+    X = (X * (Z + np.float32(xi))).astype(np.float32)    # :167-168 (no r0/r1 un-distortion factor: follow the code)
+    Y = (Y * (Z + np.float32(xi))).astype(np.float32)
+    return X, Y, Z, mask
+
+
+def mei_lut_batch(P2: Tensor, calib: Sequence[dict], H: int, W: int) -> Tensor:
+    """[B, 4, H, W] (X, Y, Z, mask) -- one table per sample, cached per distinct calibration."""
+    cache, out = {}, []
+    for b in range(P2.shape[0]):
+        key = (P2[b, 0, 0].item(), P2[b, 1, 1].item(), P2[b, 0, 2].item(), P2[b, 1, 2].item(),
+               calib[b]["distortion_parameters"]["k1"], calib[b]["distortion_parameters"]["k2"], calib[b]["mirror_parameters"]["xi"])
+        if key not in cache:
+            cache[key] = torch.from_numpy(np.stack(mei_lut(H, W, *key), 0))
+        out.append(cache[key])
+    return torch.stack(out, 0)
+
+
+def mei_cam2image(points: Tensor, P: Tensor, calib: dict) -> Tuple[Tensor, Tensor]:
+    """_cam2image (mei_fisheye_utils.py:23-51) for points [..., 3] of one sample -> pixel (u, v)."""
+    eps = 1e-6
+    norm = torch.norm(points, dim=-1)
+    x = points[..., 0] / (norm + eps)
+    y = points[..., 1] / (norm + eps)
+    z = points[..., 2] / (norm + eps)
+    xi = calib["mirror_parameters"]["xi"]
+    x = x / (z + xi + eps)
+    y = y / (z + xi + eps)
+    k1, k2 = calib["distortion_parameters"]["k1"], calib["distortion_parameters"]["k2"]
+    ro2 = x * x + y * y
+    x = x * (1 + k1 * ro2 + k2 * ro2 * ro2)
+    y = y * (1 + k1 * ro2 + k2 * ro2 * ro2)
+    return P[0, 0] * x + P[0, 2], P[1, 1] * y + P[1, 2]
+
+
+def warp_sources_fisheye(norm_full: Tensor, data: Dict, cam_T: Dict[int, Tensor], topo: Topology):
+    """FishEyeDecoder._generate_images_pred inner loop (monodepth2_decoder.py:367-413) for one scale."""
+    B, _, H, W = norm_full.shape
+    lut = mei_lut_batch(data["P2"], data["calib_meta"], H, W)
+    points = torch.stack([lut[:, 0:1] * norm_full, lut[:, 1:2] * norm_full, lut[:, 2:3] * norm_full], -1)   # [B,1,H,W,3]
+    homo = torch.cat([points, torch.ones_like(points[..., :1])], -1).squeeze(1)[..., None]
+    warped, overlap = {}, {}
+    for f in topo.frame_ids[1:]:
+        tp = torch.matmul(cam_T[f][:, None, None], homo)[..., 0]
+        grids = []
+        for b in range(B):
+            u, v = mei_cam2image(tp[b, ..., 0:3], data["P2"][b], data["calib_meta"][b])
+            grids.append(torch.stack([u / max(W - 1, 1) * 2 - 1, v / max(H - 1, 1) * 2 - 1], -1))
+        grid = torch.stack(grids, 0)
+        warped[f] = F.grid_sample(data[("original_image", f)], grid, padding_mode="border", align_corners=True)
+        if topo.overlapped_mask:
+            pm = (data["patched_mask"] if "patched_mask" in data else torch.ones(B, H, W)) * lut[:, 3]
+            rp = F.grid_sample(pm.unsqueeze(1).float(), grid, align_corners=True, mode="nearest")
+            overlap[f] = (rp == 1).squeeze(1)
+    return warped, overlap
+
+
+def fisheye_prediction(norm: Tensor, data: Dict) -> Dict:
+    """FishEyeDecoder.get_prediction (monodepth2_decoder.py:415-420): z of the back-projected ray + the norm."""
+    H, W = norm.shape[-2:]
+    lut = mei_lut_batch(data["P2"], data["calib_meta"], H, W)
+    return {"depth": lut[:, 2:3] * norm, "norm": norm}
+
+
 def loss_chain(outputs: Dict, data: Dict, cam_T: Dict[int, Tensor], topo: Topology,
                noise: Optional[Dict[int, Tensor]] = None, keep: bool = False) -> Dict:
     """compute_total_reprojection_loss + loss (monodepth2_decoder.py:205-347), pinhole, default weights.
@@ -393,7 +518,7 @@ def loss_chain(outputs: Dict, data: Dict, cam_T: Dict[int, Tensor], topo: Topolo
     total = 0
     for s in topo.scales:
         depth_full = F.interpolate(outputs[("depth", s, s)], [H, W], mode="bilinear", align_corners=True)
-        warped, overlap = warp_sources(depth_full, data, cam_T, topo)
+        warped, overlap = (warp_sources_fisheye if topo.fisheye else warp_sources)(depth_full, data, cam_T, topo)
         disp = outputs[("disp", s)]
         color = target if s == 0 else F.adaptive_avg_pool2d(target, disp.shape[-2:])
         reproj = []
@@ -458,6 +583,8 @@ def forward_test(sd, data: Dict, topo: Topology) -> Dict:
     """forward_test (monodepth2_model.py:132-136); BN uses running statistics in eval mode."""
     feats = resnet_forward(sd, "depth_backbone.", data[("image", 0)], topo.depth, training=False)
     outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, None if topo.posenet else data["P2"], training=False)
+    if topo.fisheye:
+        return fisheye_prediction(outputs[("depth", 0, 0)], data)
     return {"depth": outputs[("depth", 0, 0)]}
 
 
@@ -535,6 +662,36 @@ def synthetic_batch(B: int, H: int, W: int, seed: int = 1234, frame_ids=(0, 1, -
         else:
             mask[b, :, W - wstrip:] = 0
     data["patched_mask"] = mask
+    return data
+
+
+MEI_KITTI360 = dict(xi=2.2134, k1=0.016798, k2=1.6548, gamma=1336.3, u0=716.94, v0=705.76, size=1400.0)
+
+
+def synthetic_fisheye_batch(B: int, H: int, W: int, seed: int = 1234, frame_ids=(0, 1, -1), mask_dtype=torch.float64,
+                            two_calibrations: bool = False) -> Dict:
+    """``synthetic_batch`` with a KITTI-360-like MEI calibration scaled to the crop, lateral
+    motion, ``calib_meta`` as the dataset delivers it (fisheye_dataset.py:45-58,254)."""
+    data = synthetic_batch(B, H, W, seed, frame_ids, mask_dtype)
+    g = torch.Generator().manual_seed(seed + 77)
+    m = MEI_KITTI360
+    P2 = torch.zeros(B, 3, 4)
+    calib = []
+    for b in range(B):
+        k = 1.0 if not (two_calibrations and b % 2) else 0.97
+        P2[b, 0, 0] = m["gamma"] * W / m["size"] * k
+        P2[b, 1, 1] = m["gamma"] * H / m["size"] * k
+        P2[b, 0, 2] = m["u0"] * W / m["size"]
+        P2[b, 1, 2] = m["v0"] * H / m["size"]
+        P2[b, 2, 2] = 1.0
+        calib.append(dict(mirror_parameters=dict(xi=m["xi"]), distortion_parameters=dict(k1=m["k1"], k2=m["k2"] * k)))
+    data["P2"] = P2
+    data["calib_meta"] = calib
+    for f in frame_ids[1:]:
+        T = data[("relative_pose", f)]
+        tx = (0.8 + 0.2 * (torch.rand(B, generator=g) * 2 - 1)) * (-1.0 if f > 0 else 1.0)
+        T[:, 0, 3] = tx                      # side-looking fisheye: the vehicle's forward motion is lateral
+        T[:, 2, 3] = 0.1 * (torch.rand(B, generator=g) * 2 - 1)
     return data
 
 

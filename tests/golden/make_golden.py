@@ -35,7 +35,7 @@ from oracle import fsnet_oracle as O  # noqa: E402
 
 def ref_meta_arch(topo: O.Topology):
     head = edict(
-        name="monodepth.networks.models.heads.monodepth2_decoder.MonoDepth2Decoder",
+        name="monodepth.networks.models.heads.monodepth2_decoder." + ("FishEyeDecoder" if topo.fisheye else "MonoDepth2Decoder"),
         scales=list(topo.scales), height=topo.height, width=topo.width,
         min_depth=topo.min_depth, max_depth=topo.max_depth, overlapped_mask=topo.overlapped_mask, is_log_image=False,
         depth_decoder_cfg=edict(
@@ -60,12 +60,12 @@ def ref_meta_arch(topo: O.Topology):
 
 
 def input_checksum(data):
-    return np.array([float(v.double().sum()) for k, v in sorted(data.items(), key=lambda kv: str(kv[0]))])
+    return np.array([float(v.double().sum()) for k, v in sorted(data.items(), key=lambda kv: str(kv[0])) if torch.is_tensor(v)])
 
 
 def run_full(name, topo: O.Topology, B, seed=1234, noise_seed=0, store_disp=True, grads_of=()):
     model, sd = ref_meta_arch(topo)
-    data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids)
+    data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, seed, topo.frame_ids)
     out = {"input_checksum": input_checksum(data)}
     # full call through the reference's public entry, seeded so that its randn tie-break draws are known
     torch.manual_seed(noise_seed)
@@ -105,6 +105,8 @@ def run_full(name, topo: O.Topology, B, seed=1234, noise_seed=0, store_disp=True
     with torch.no_grad():
         pred = model2(dict(data), dict(is_training=False))
     out["test_depth"] = pred["depth"].numpy().copy()
+    if "norm" in pred:
+        out["test_norm"] = pred["norm"].numpy().copy()
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     print(name, "loss", float(out["loss"]), "fp64" if out["loss_is_fp64"] else "fp32", os.path.getsize(path) // 1024, "KiB")
@@ -114,13 +116,16 @@ def run_loss_only(name, topo: O.Topology, B, seed, noise_seed=0, mask_dtype=torc
                   motion_mask=False, depth_lo=2.0, depth_hi=40.0):
     """The reference's MonoDepth2Decoder.loss on given depth / disparity maps (no network): pins the
     fused loss kernels, including d loss / d depth and d loss / d disp."""
-    from monodepth.networks.models.heads.monodepth2_decoder import MonoDepth2Decoder
-    head = MonoDepth2Decoder(
+    from monodepth.networks.models.heads.monodepth2_decoder import MonoDepth2Decoder, FishEyeDecoder
+    head = (FishEyeDecoder if topo.fisheye else MonoDepth2Decoder)(
         scales=list(topo.scales), height=topo.height, width=topo.width, frame_ids=list(topo.frame_ids),
         depth_decoder_cfg=edict(name="monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoder",
                                 num_ch_enc=np.array([64, 64, 128, 256, 512]), num_output_channels=4, scales=list(topo.scales)),
         overlapped_mask=topo.overlapped_mask, is_log_image=True)
-    data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype)
+    if topo.fisheye:
+        data = O.synthetic_fisheye_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype, two_calibrations=True)
+    else:
+        data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype)
     if not with_mask:
         del data["patched_mask"]
     outputs = O.synthetic_depth_outputs(B, topo.height, topo.width, topo.scales, seed + 1, depth_lo, depth_hi, topo.min_depth, topo.max_depth)
@@ -164,6 +169,11 @@ if __name__ == "__main__":
                       depth_lo=0.6, depth_hi=6.0)     # near depths: large flow, many out-of-view pixels
     if want("loss_mm"):
         run_loss_only("loss_mm", O.Topology(height=64, width=96, overlapped_mask=True, scales=(0, 1)), B=2, seed=14, motion_mask=True)
+    if want("loss_fe"):      # MEI fisheye camera, two distinct calibrations in the batch, overlap mask x LUT mask
+        run_loss_only("loss_fe", O.Topology(height=96, width=128, overlapped_mask=True, fisheye=True, max_depth=150.0), B=3, seed=15)
+    if want("loss_fe_nomask"):
+        run_loss_only("loss_fe_nomask", O.Topology(height=64, width=64, overlapped_mask=True, fisheye=True, scales=(0, 1)), B=2, seed=16,
+                      with_mask=False, depth_lo=1.0, depth_hi=10.0)
     # full step
     if want("tiny4"):
         run_full("tiny4", O.Topology(height=64, width=128), B=2,
@@ -175,5 +185,7 @@ if __name__ == "__main__":
                  grads_of=("head.pose_decoder.net.3.weight", "pose_backbone.conv1.weight"))
     if want("tiny_sigmoid"):
         run_full("tiny_sigmoid", O.Topology(height=64, width=96, multi_channel=False, n_bins=1, min_depth=0.1, scales=(0, 1, 2, 3)), B=2)
+    if want("tiny_fe"):
+        run_full("tiny_fe", O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0), B=2)
     if want("tiny_r50"):
         run_full("tiny_r50", O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2, store_disp=True)

@@ -20,7 +20,7 @@ def load(golden_dir, name):
 
 
 def checksum(data):
-    return np.array([float(v.double().sum()) for k, v in sorted(data.items(), key=lambda kv: str(kv[0]))])
+    return np.array([float(v.double().sum()) for k, v in sorted(data.items(), key=lambda kv: str(kv[0])) if torch.is_tensor(v)])
 
 
 def rel(a, b):
@@ -35,11 +35,18 @@ LOSS_CASES = {
     "loss_c": dict(topo=O.Topology(height=64, width=128, overlapped_mask=True), B=2, seed=13, mask_dtype=torch.float32,
                    depth_lo=0.6, depth_hi=6.0),
     "loss_mm": dict(topo=O.Topology(height=64, width=96, overlapped_mask=True, scales=(0, 1)), B=2, seed=14, motion_mask=True),
+    # FishEyeDecoder (MEI camera, LUT back-projection), two distinct calibrations in one batch
+    "loss_fe": dict(topo=O.Topology(height=96, width=128, overlapped_mask=True, fisheye=True, max_depth=150.0), B=3, seed=15),
+    "loss_fe_nomask": dict(topo=O.Topology(height=64, width=64, overlapped_mask=True, fisheye=True, scales=(0, 1)), B=2, seed=16,
+                           with_mask=False, depth_lo=1.0, depth_hi=10.0),
 }
 
 
 def build_loss_case(topo, B, seed, mask_dtype=torch.float64, with_mask=True, motion_mask=False, depth_lo=2.0, depth_hi=40.0):
-    data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype)
+    if topo.fisheye:
+        data = O.synthetic_fisheye_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype, two_calibrations=True)
+    else:
+        data = O.synthetic_batch(B, topo.height, topo.width, seed, topo.frame_ids, mask_dtype=mask_dtype)
     if not with_mask:
         del data["patched_mask"]
     outputs = O.synthetic_depth_outputs(B, topo.height, topo.width, topo.scales, seed + 1, depth_lo, depth_hi,
@@ -81,6 +88,7 @@ FULL_CASES = {
     "tiny_pose": dict(topo=O.Topology(height=64, width=128, posenet=True, overlapped_mask=False), B=2),
     "tiny_sigmoid": dict(topo=O.Topology(height=64, width=96, multi_channel=False, n_bins=1, min_depth=0.1, scales=(0, 1, 2, 3)), B=2),
     "tiny_r50": dict(topo=O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2),
+    "tiny_fe": dict(topo=O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0), B=2),
 }
 
 
@@ -88,7 +96,7 @@ FULL_CASES = {
 def test_full_step_matches_reference(golden_dir, name):
     g = load(golden_dir, name)
     topo, B = FULL_CASES[name]["topo"], FULL_CASES[name]["B"]
-    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1234, topo.frame_ids)
     np.testing.assert_allclose(checksum(data), g["input_checksum"], rtol=1e-12)
     sd = O.make_state_dict(topo)
     names = O.trainable(sd)
@@ -122,3 +130,5 @@ def test_full_step_matches_reference(golden_dir, name):
         pred = O.forward_test(sd2, data, topo)
     # the reference ran its train-mode forward on model2's backbone + decoder only (no PoseNet influence)
     assert rel(pred["depth"], g["test_depth"]) < 1e-4
+    if topo.fisheye:
+        assert rel(pred["norm"], g["test_norm"]) < 1e-4
