@@ -30,6 +30,7 @@ struct LossParams {
   const double* accum_in; const float* gout; float* grad_depth; float* grad_P;
   int rows_per_item, n_strips, n_chunks;
   float sy, sx;                           // (hs-1)/(H-1), (ws-1)/(W-1): align_corners=True scales
+  const float4* lut; const int* lut_idx;  // MEI camera: per-pixel ray table (X, Y, Z, mask) and sample -> table index
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -73,6 +74,56 @@ __device__ __forceinline__ Geo geometry(const float* ik, float x, float y, float
     g.c[i] = g.r[i] * D;
   }
   return g;
+}
+
+// ---- MEI (unified omnidirectional) camera: FishEyeDecoder, mei_fisheye_utils.py:14-51 ---------------------
+// cam block of a frame in MEI mode: [0..6] = gamma1, gamma2, u0, v0, xi, k1, k2; [9..20] = T[:3, :4].
+// The ray of a pixel comes from the calibration's look-up table (X, Y, Z) instead of inv(K)(x, y, 1).
+__device__ __forceinline__ Geo geometry_lut(const float4& L, float D) {
+  Geo g;
+  g.r[0] = L.x; g.r[1] = L.y; g.r[2] = L.z;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g.c[i] = g.r[i] * D;
+  return g;
+}
+struct Mei { float inv_n, n, mx, my, inv_d, ro2, dd; };
+// _cam2image (mei_fisheye_utils.py:23-51): unit sphere -> shifted plane -> radial distortion -> pixel
+__device__ __forceinline__ Mei mei_project(const float* in, float px, float py, float pz, float& u, float& v) {
+  Mei m;
+  m.n = sqrtf(fmaf(px, px, fmaf(py, py, pz * pz)));
+  m.inv_n = __frcp_rn(m.n + 1e-6f);
+  const float qx = px * m.inv_n, qy = py * m.inv_n, qz = pz * m.inv_n;
+  m.inv_d = __frcp_rn((qz + in[4]) + 1e-6f);
+  m.mx = qx * m.inv_d; m.my = qy * m.inv_d;
+  m.ro2 = fmaf(m.mx, m.mx, m.my * m.my);
+  m.dd = 1.f + in[5] * m.ro2 + in[6] * m.ro2 * m.ro2;
+  u = fmaf(in[0], m.mx * m.dd, in[2]);
+  v = fmaf(in[1], m.my * m.dd, in[3]);
+  return m;
+}
+// forward-mode derivative of (u, v) along a = d p / d D
+__device__ __forceinline__ void mei_jvp(const float* in, const Mei& m, float px, float py, float pz,
+                                        float ax, float ay, float az, float& du, float& dv) {
+  const float dn = (px * ax + py * ay + pz * az) * __frcp_rn(fmaxf(m.n, 1e-30f));
+  const float dinv = -dn * m.inv_n * m.inv_n;
+  const float dqx = fmaf(ax, m.inv_n, px * dinv), dqy = fmaf(ay, m.inv_n, py * dinv), dqz = fmaf(az, m.inv_n, pz * dinv);
+  const float dmx = (dqx - m.mx * dqz) * m.inv_d, dmy = (dqy - m.my * dqz) * m.inv_d;
+  const float ddd = (in[5] + 2.f * in[6] * m.ro2) * 2.f * (m.mx * dmx + m.my * dmy);
+  du = in[0] * fmaf(dmx, m.dd, m.mx * ddd);
+  dv = in[1] * fmaf(dmy, m.dd, m.my * ddd);
+}
+// reverse mode: (gu, gv) -> d loss / d p
+__device__ __forceinline__ void mei_vjp(const float* in, const Mei& m, float px, float py, float pz,
+                                        float gu, float gv, float (&gp)[3]) {
+  const float gdx = in[0] * gu, gdy = in[1] * gv;
+  const float gro2 = (gdx * m.mx + gdy * m.my) * (in[5] + 2.f * in[6] * m.ro2);
+  const float gmx = fmaf(gdx, m.dd, 2.f * m.mx * gro2), gmy = fmaf(gdy, m.dd, 2.f * m.my * gro2);
+  const float gqx = gmx * m.inv_d, gqy = gmy * m.inv_d, gqz = -(gmx * m.mx + gmy * m.my) * m.inv_d;
+  const float ginv = gqx * px + gqy * py + gqz * pz;
+  const float gn_over_n = -ginv * m.inv_n * m.inv_n * __frcp_rn(fmaxf(m.n, 1e-30f));
+  gp[0] = fmaf(gqx, m.inv_n, px * gn_over_n);
+  gp[1] = fmaf(gqy, m.inv_n, py * gn_over_n);
+  gp[2] = fmaf(gqz, m.inv_n, pz * gn_over_n);
 }
 
 // One source frame at one pixel.  GRAD=0: colour + validity.  GRAD=1: also d pred/d ix, d pred/d iy
@@ -147,13 +198,16 @@ __device__ __forceinline__ Sample<GRAD> sample_frame(const float* __restrict__ s
 // The images are read from the RGBX-packed copy written once per step by the identity kernel: one 128-bit
 // load per bilinear corner.  issue_* only computes addresses and issues loads; finish_* consumes them one
 // loop iteration later, so a row's gathers are in flight while the previous row's SSIM arithmetic runs.
-struct DepthLoads { float d00, d01, d10, d11, ly; };
-__device__ __forceinline__ DepthLoads issue_depth(const float* d, int ws, int hs, float sy, int yr, const UpW& wx) {
+struct DepthLoads { float d00, d01, d10, d11, ly; float4 L; };
+// lut_row: this sample's ray table at column xr (MEI camera) or nullptr (pinhole)
+__device__ __forceinline__ DepthLoads issue_depth(const float* d, int ws, int hs, float sy, int yr, const UpW& wx,
+                                                  const float4* lut_col = nullptr, int W = 0) {
   UpW wy = up_weights(yr, sy, hs);
   const float* r0 = d + (size_t)wy.i0 * ws;
   const float* r1 = d + (size_t)wy.i1 * ws;
   DepthLoads o;
   o.d00 = __ldg(r0 + wx.i0); o.d01 = __ldg(r0 + wx.i1); o.d10 = __ldg(r1 + wx.i0); o.d11 = __ldg(r1 + wx.i1); o.ly = wy.l;
+  o.L = lut_col ? __ldg(lut_col + (size_t)yr * W) : make_float4(0.f, 0.f, 0.f, 0.f);
   return o;
 }
 __device__ __forceinline__ float finish_depth(const DepthLoads& o, float lx) {
@@ -163,25 +217,36 @@ __device__ __forceinline__ float finish_depth(const DepthLoads& o, float lx) {
 
 struct FrameLoads {
   float4 nw, ne, sw, se;
-  float fx, fy, ix, iy, rz;
-  float ax, ay, az;            // d p / d D (gradient variant only)
+  float fx, fy, ix, iy;
+  float du, dv;                // d(u, v) / d D (gradient variant only)
   float mval; bool inb;
 };
-template <int GRAD>
-__device__ __forceinline__ FrameLoads issue_frame(const float4* __restrict__ src, const float* P, const Geo& g,
-                                                  const void* mask, int mask_dtype, bool want_valid, int H, int W) {
+// `in` = the 9 leading floats of the frame's camera block (inv(K) for the pinhole camera, MEI intrinsics otherwise);
+// lut_b = this sample's ray table (its .w = validity of the source pixel, folded into the overlap mask,
+// monodepth2_decoder.py:409) or nullptr.
+template <int GRAD, int CAM>
+__device__ __forceinline__ FrameLoads issue_frame(const float4* __restrict__ src, const float* in, const float* P, const Geo& g,
+                                                  const void* mask, int mask_dtype, bool want_valid, int H, int W,
+                                                  const float4* lut_b) {
   FrameLoads o;
   float px = fmaf(P[0], g.c[0], fmaf(P[1], g.c[1], fmaf(P[2], g.c[2], P[3])));
   float py = fmaf(P[4], g.c[0], fmaf(P[5], g.c[1], fmaf(P[6], g.c[2], P[7])));
   float pz = fmaf(P[8], g.c[0], fmaf(P[9], g.c[1], fmaf(P[10], g.c[2], P[11])));
-  float rz = __frcp_rn(pz + 1e-7f);
-  float ix = px * rz, iy = py * rz;
+  float ix, iy, rz = 0.f;
+  Mei mei;
+  if (CAM == 0) {
+    rz = __frcp_rn(pz + 1e-7f);
+    ix = px * rz; iy = py * rz;
+  } else {
+    mei = mei_project(in, px, py, pz, ix, iy);
+  }
   const float xm = (float)(W - 1), ym = (float)(H - 1);
   o.inb = true; o.mval = 1.f;
   if (want_valid) {
     float xn = rintf(ix), yn = rintf(iy);
     o.inb = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
     if (o.inb && mask != nullptr) o.mval = load_mask(mask, mask_dtype, (size_t)(int)yn * W + (int)xn);
+    if (CAM == 1 && o.inb) o.mval *= __ldg(reinterpret_cast<const float*>(lut_b + (size_t)(int)yn * W + (int)xn) + 3);
   }
   float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);
   float x0f = floorf(ixc), y0f = floorf(iyc);
@@ -190,12 +255,18 @@ __device__ __forceinline__ FrameLoads issue_frame(const float4* __restrict__ src
   int dx = x0 < W - 1 ? 1 : 0, dy = y0 < H - 1 ? W : 0;
   const float4* p00 = src + (size_t)y0 * W + x0;
   o.nw = __ldg(p00); o.ne = __ldg(p00 + dx); o.sw = __ldg(p00 + dy); o.se = __ldg(p00 + dy + dx);
-  o.ix = ix; o.iy = iy; o.rz = rz;
-  o.ax = o.ay = o.az = 0.f;
+  o.ix = ix; o.iy = iy;
+  o.du = o.dv = 0.f;
   if (GRAD) {
-    o.ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
-    o.ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
-    o.az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
+    const float ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
+    const float ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
+    const float az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
+    if (CAM == 0) {
+      o.du = (ax - ix * az) * rz;          // (ax*z - px*az)/z^2
+      o.dv = (ay - iy * az) * rz;
+    } else {
+      mei_jvp(in, mei, px, py, pz, ax, ay, az, o.du, o.dv);
+    }
   }
   return o;
 }
@@ -215,27 +286,28 @@ __device__ __forceinline__ Sample<GRAD> finish_frame(const FrameLoads& o, int H,
     }
   }
   s.valid = o.inb && (o.mval == 1.f);
-  s.px = o.ix; s.py = o.iy; s.rz = o.rz;
+  s.px = o.ix; s.py = o.iy; s.rz = 0.f;
   s.du = 0.f; s.dv = 0.f;
   if (GRAD) {
     bool mx = (o.ix > 0.f) && (o.ix < (float)(W - 1)), my = (o.iy > 0.f) && (o.iy < (float)(H - 1));
 #pragma unroll
     for (int c = 0; c < 3; ++c) { s.dix[c] = mx ? s.dix[c] : 0.f; s.diy[c] = my ? s.diy[c] : 0.f; }
-    s.du = (o.ax - o.ix * o.az) * o.rz;
-    s.dv = (o.ay - o.iy * o.az) * o.rz;
+    s.du = o.du;
+    s.dv = o.dv;
   }
   return s;
 }
 struct RowLoads { float4 t; FrameLoads f0, f1; float D; };
-template <int GRAD>
+template <int GRAD, int CAM>
 __device__ __forceinline__ RowLoads issue_row(const LossParams& p, const float4* tg, const float4* s0, const float4* s1,
                                               const float* ik, const float* P0, const float* P1, const void* mask_b,
-                                              bool overlap, int yr, int xr, float D) {
+                                              bool overlap, int yr, int xr, const DepthLoads& dl, float lx, const float4* lut_b) {
   RowLoads r;
+  const float D = finish_depth(dl, lx);
   r.t = __ldg(tg + (size_t)yr * p.W + xr);
-  Geo g = geometry(ik, (float)xr, (float)yr, D);
-  r.f0 = issue_frame<GRAD>(s0, P0, g, mask_b, p.mask_dtype, overlap, p.H, p.W);
-  r.f1 = issue_frame<GRAD>(s1, P1, g, mask_b, p.mask_dtype, overlap, p.H, p.W);
+  Geo g = CAM == 0 ? geometry(ik, (float)xr, (float)yr, D) : geometry_lut(dl.L, D);
+  r.f0 = issue_frame<GRAD, CAM>(s0, ik, P0, g, mask_b, p.mask_dtype, overlap, p.H, p.W, lut_b);
+  r.f1 = issue_frame<GRAD, CAM>(s1, ik, P1, g, mask_b, p.mask_dtype, overlap, p.H, p.W, lut_b);
   r.D = D;
   return r;
 }
@@ -310,8 +382,8 @@ __device__ __forceinline__ bool decode_item(const LossParams& p, Item& it) {
 //           MODE 1: reprojection loss (pred_f := warped src_f, result reduced into accum).
 // Columns per warp: 30 (lanes 0 and 31 are the reflect / neighbour halo).
 // ------------------------------------------------------------------------------------------------
-template <int MODE, int PIPE>
-__global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(LossParams p) {
+template <int MODE, int CAM>
+__global__ void __launch_bounds__(kWarps * 32, 4) loss_fwd_kernel(LossParams p) {
   __shared__ float s_cam[kWarps][42];
   Item it;
   if (!decode_item(p, it)) return;
@@ -346,8 +418,9 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(Los
   UpW wx = {0, 0, 0.f};
   const float* depth = nullptr;
   const float4 *tg4 = nullptr, *s04 = nullptr, *s14 = nullptr;
-  RowLoads rl_next;
   DepthLoads dl_next;
+  const float4* lut_b = nullptr;            // MEI camera: this sample's ray table
+  const float4* lut_col = nullptr;
   if (MODE == 1) {
     for (int i = lane; i < 42; i += 32) s_cam[warp][i] = __ldg(p.cam + (size_t)b * 42 + i);
     __syncwarp();
@@ -356,13 +429,11 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(Los
     tg4 = p.packed + ((size_t)0 * p.B + b) * HW;
     s04 = p.packed + ((size_t)1 * p.B + b) * HW;
     s14 = p.packed + ((size_t)2 * p.B + b) * HW;
-    if (PIPE == 1) {
-      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
-      rl_next = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(y_first, H), xr, finish_depth(dl_next, wx.l));
-      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(y_first + 1, y_last), H), wx);
-    } else {
-      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
+    if (CAM == 1) {
+      lut_b = p.lut + (size_t)(p.lut_idx ? __ldg(p.lut_idx + b) : 0) * HW;
+      lut_col = lut_b + xr;
     }
+    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx, lut_col, W);
   }
 
 #pragma unroll 1
@@ -399,18 +470,9 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(Los
         p.packed_out[((size_t)2 * p.B + b) * HW + pix] = make_float4(raw[6], raw[7], raw[8], 0.f);
       }
     } else {
-      RowLoads rl;
-      if (PIPE == 1) {
-        rl = rl_next;
-        if (yy < y_last) {           // next row: its depth arrived during the previous iteration
-          rl_next = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy + 1, H), xr, finish_depth(dl_next, wx.l));
-          dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 2, y_last), H), wx);
-        }
-      } else {
-        // this row's depth was requested one iteration ago: the gathers can go out immediately
-        rl = issue_row<0>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, yr, xr, finish_depth(dl_next, wx.l));
-        dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx);
-      }
+      // this row's depth (and ray) was requested one iteration ago: the gathers can go out immediately
+      RowLoads rl = issue_row<0, CAM>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, yr, xr, dl_next, wx.l, lut_b);
+      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx, lut_col, W);
       Sample<0> s0 = finish_frame<0>(rl.f0, H, W);
       Sample<0> s1 = finish_frame<0>(rl.f1, H, W);
       raw[0] = rl.t.x; raw[1] = rl.t.y; raw[2] = rl.t.z;
@@ -491,8 +553,8 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 4) loss_fwd_kernel(Los
 // yc = yy-1  C) adjoint box filter -> d pred, chain to depth (and pose) at yq = yy-2.
 // POSE=1 additionally reduces d loss / d P (12 numbers per frame).
 // ------------------------------------------------------------------------------------------------
-template <int POSE, int PIPE>
-__global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 3) loss_bwd_kernel(LossParams p) {
+template <int POSE, int CAM>
+__global__ void __launch_bounds__(kWarps * 32, 3) loss_bwd_kernel(LossParams p) {
   constexpr int NV = POSE ? 22 : 15;        // delayed values per pixel
   __shared__ float s_cam[kWarps][42];
   __shared__ float s_delay[kWarps][3][NV][32];
@@ -537,15 +599,9 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 3) loss_bwd_kernel(Los
   for (int i = 0; i < (POSE ? 24 : 1); ++i) gP[i] = 0.f;
 
   const int y_first = it.y_begin - 2, y_last = it.y_end + 1;
-  DepthLoads dl_next;
-  RowLoads rl_next;
-  if (PIPE == 1) {
-    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
-    rl_next = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(y_first, H), xr, finish_depth(dl_next, wx.l));
-    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first + 1, H), wx);
-  } else {
-    dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx);
-  }
+  const float4* lut_b = CAM == 1 ? p.lut + (size_t)(p.lut_idx ? __ldg(p.lut_idx + b) : 0) * HW : nullptr;
+  const float4* lut_col = CAM == 1 ? lut_b + xr : nullptr;
+  DepthLoads dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(y_first, H), wx, lut_col, W);
 
 #pragma unroll 1
   for (int yy = y_first; yy <= y_last; ++yy) {
@@ -571,17 +627,8 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 3) loss_bwd_kernel(Los
     float l1[2];
     bool valid[2];
     {
-      RowLoads rl;
-      if (PIPE == 1) {
-        rl = rl_next;
-        if (yy < y_last) {
-          rl_next = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy + 1, H), xr, finish_depth(dl_next, wx.l));
-          dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 2, y_last), H), wx);
-        }
-      } else {
-        rl = issue_row<1>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy, H), xr, finish_depth(dl_next, wx.l));
-        dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx);
-      }
+      RowLoads rl = issue_row<1, CAM>(p, tg4, s04, s14, ik, P0, P1, mask_b, overlap, reflect_idx(yy, H), xr, dl_next, wx.l, lut_b);
+      dl_next = issue_depth(depth, p.ws, p.hs, p.sy, reflect_idx(min(yy + 1, y_last), H), wx, lut_col, W);
       const float D = rl.D;
       Sample<1> s0 = finish_frame<1>(rl.f0, H, W);
       Sample<1> s1 = finish_frame<1>(rl.f1, H, W);
@@ -702,26 +749,33 @@ __global__ void __launch_bounds__(kWarps * 32, PIPE ? 2 : 3) loss_bwd_kernel(Los
       }
       if (POSE) {
         float D = slot[21][lane];
-        Geo g = geometry(ik, (float)x, (float)yq, D);
+        Geo g = CAM == 0 ? geometry(ik, (float)x, (float)yq, D) : geometry_lut(__ldg(lut_b + (size_t)yq * W + x), D);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float* P = k == 0 ? P0 : P1;
           float px = fmaf(P[0], g.c[0], fmaf(P[1], g.c[1], fmaf(P[2], g.c[2], P[3])));
           float py = fmaf(P[4], g.c[0], fmaf(P[5], g.c[1], fmaf(P[6], g.c[2], P[7])));
           float pz = fmaf(P[8], g.c[0], fmaf(P[9], g.c[1], fmaf(P[10], g.c[2], P[11])));
-          float rz = __frcp_rn(pz + 1e-7f);
-          float u = px * rz, v = py * rz;
           float ax = fmaf(P[0], g.r[0], fmaf(P[1], g.r[1], P[2] * g.r[2]));
           float ay = fmaf(P[4], g.r[0], fmaf(P[5], g.r[1], P[6] * g.r[2]));
           float az = fmaf(P[8], g.r[0], fmaf(P[9], g.r[1], P[10] * g.r[2]));
-          gD = fmaf(gu[k], (ax - u * az) * rz, fmaf(gv2[k], (ay - v * az) * rz, gD));
-          float r0 = gu[k] * rz, r1 = gv2[k] * rz, r2 = -(gu[k] * u + gv2[k] * v) * rz;
+          float gp[3];                       // d loss / d p (projected camera point)
+          if (CAM == 0) {
+            float rz = __frcp_rn(pz + 1e-7f);
+            float u = px * rz, v = py * rz;
+            gp[0] = gu[k] * rz; gp[1] = gv2[k] * rz; gp[2] = -(gu[k] * u + gv2[k] * v) * rz;
+          } else {
+            float u, v;
+            Mei mei = mei_project(ik, px, py, pz, u, v);
+            mei_vjp(ik, mei, px, py, pz, gu[k], gv2[k], gp);
+          }
+          gD = fmaf(gp[0], ax, fmaf(gp[1], ay, fmaf(gp[2], az, gD)));
           float hh[4] = {g.c[0], g.c[1], g.c[2], 1.f};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            gP[12 * k + j] = fmaf(r0, hh[j], gP[12 * k + j]);
-            gP[12 * k + 4 + j] = fmaf(r1, hh[j], gP[12 * k + 4 + j]);
-            gP[12 * k + 8 + j] = fmaf(r2, hh[j], gP[12 * k + 8 + j]);
+            gP[12 * k + j] = fmaf(gp[0], hh[j], gP[12 * k + j]);
+            gP[12 * k + 4 + j] = fmaf(gp[1], hh[j], gP[12 * k + 4 + j]);
+            gP[12 * k + 8 + j] = fmaf(gp[2], hh[j], gP[12 * k + 8 + j]);
           }
         }
       }
@@ -786,10 +840,112 @@ __global__ void camera_setup_kernel(const float* __restrict__ P2, const float* _
     }
 }
 
-int loss_pipe() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("FSNET_LOSS_PIPE"); v = e ? atoi(e) : 0; }
-  return v;
+// MEI camera block: [0..6] = gamma1, gamma2, u0, v0, xi, k1, k2 (P2 and calib_meta), [9..20] = T[:3, :4]
+// (FishEyeDecoder multiplies the back-projected point by cam_T_cam directly, monodepth2_decoder.py:379-381).
+__global__ void camera_setup_mei_kernel(const float* __restrict__ P2, const double* __restrict__ calib,
+                                        const float* __restrict__ T0, const float* __restrict__ T1, int B,
+                                        float* __restrict__ cam) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 2) return;
+  int b = i >> 1, f = i & 1;
+  const float* K = P2 + (size_t)b * 12;
+  const float* T = (f == 0 ? T0 : T1) + (size_t)b * 16;
+  float* o = cam + (size_t)i * 21;
+  o[0] = K[0]; o[1] = K[5]; o[2] = K[2]; o[3] = K[6];
+  o[4] = (float)calib[b * 3 + 0]; o[5] = (float)calib[b * 3 + 1]; o[6] = (float)calib[b * 3 + 2];
+  o[7] = 0.f; o[8] = 0.f;
+  for (int j = 0; j < 12; ++j) o[9 + j] = T[j];
+}
+
+// ---- MEI ray table: MeiCameraProjection.image2cam's cached LUT (mei_fisheye_utils.py:139-170) -------------
+// header [B,8] = the calibration a table slot was last built for (gamma1, gamma2, u0, v0, xi, k1, k2, dirty).
+// plan: sample b shares the table of the first sample with an identical calibration (lut_idx[b]); a slot is
+// rebuilt only when its calibration changed, so the steady-state cost per step is this one tiny launch plus
+// an early-exit build launch -- no host synchronisation (the reference calls .item() per sample, :151-154).
+__global__ void mei_lut_plan_kernel(const float* __restrict__ P2, const double* __restrict__ calib, int B,
+                                    double* __restrict__ header, int* __restrict__ lut_idx) {
+  __shared__ double s_cal[256][7];
+  const int b = threadIdx.x;
+  if (b < B) {
+    const float* K = P2 + (size_t)b * 12;
+    s_cal[b][0] = K[0]; s_cal[b][1] = K[5]; s_cal[b][2] = K[2]; s_cal[b][3] = K[6];
+    s_cal[b][4] = calib[b * 3 + 0]; s_cal[b][5] = calib[b * 3 + 1]; s_cal[b][6] = calib[b * 3 + 2];
+  }
+  __syncthreads();
+  if (b >= B) return;
+  int first = b;
+  for (int j = 0; j < b; ++j) {
+    bool same = true;
+    for (int k = 0; k < 7; ++k) same = same && (s_cal[j][k] == s_cal[b][k]);
+    if (same) { first = j; break; }
+  }
+  lut_idx[b] = first;
+  double* h = header + (size_t)b * 8;
+  bool dirty = false;
+  if (first == b) {
+    for (int k = 0; k < 7; ++k) dirty = dirty || !(h[k] == s_cal[b][k]);
+    for (int k = 0; k < 7; ++k) h[k] = s_cal[b][k];
+  }
+  h[7] = dirty ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ double mei_radial(double k1, double k2, double r1, double r0) {
+  const double r2 = r0 * r0;
+  return r0 - r1 / (1.0 + k1 * r2 + k2 * (r2 * r2));
+}
+__device__ __forceinline__ double mei_mirror(double r0, double xi, double Z) {
+  return r0 * r0 - (1.0 - Z * Z) / ((xi + Z) * (xi + Z));
+}
+__global__ void mei_lut_build_kernel(const double* __restrict__ header, const int* __restrict__ lut_idx, int H, int W,
+                                     float4* __restrict__ lut) {
+  const int b = blockIdx.y;
+  const double* h = header + (size_t)b * 8;
+  if (lut_idx[b] != b || h[7] == 0.0) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const int yy = i / W, xx = i % W;
+  const double k1 = h[5], k2 = h[6], xi = h[4];
+  float X = __fdiv_rn((float)xx - (float)h[2], (float)h[0]);      // gamma / principal point are fp32 P2 entries
+  float Y = __fdiv_rn((float)yy - (float)h[3], (float)h[1]);
+  const double r1 = (double)__fsqrt_rn(__fadd_rn(__fmul_rn(X, X), __fmul_rn(Y, Y)));
+  const double tol = 1e-6;
+  // Newton with a finite-difference derivative (mei_fisheye_utils.py:70-79)
+  double r0 = r1;
+  for (int it = 0; it < 100; ++it) {
+    const double f = mei_radial(k1, k2, r1, r0);
+    if (fabs(f) < tol) break;
+    const double df = (mei_radial(k1, k2, r1, r0 + tol) - f) / tol;
+    r0 = r0 - f / df;
+  }
+  // bisection on Z in [0, 1] (:85-101)
+  const double y0 = mei_mirror(r0, xi, 0.0), y1 = mei_mirror(r0, xi, 1.0);
+  bool flag = !(y0 * y1 > 0.0);
+  double z = -1.0;
+  if (flag) {
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      z = (lo + hi) / 2;
+      const double f = mei_mirror(r0, xi, z);
+      if (fabs(f) < tol) break;
+      if (f * mei_mirror(r0, xi, lo) < 0.0) hi = z; else lo = z;
+    }
+  }
+  float Z = (float)z;
+  float m = flag ? 1.f : 0.f;
+  if (Z < 0.05f) m = 0.f;
+  if (m == 0.f) { X = -1.f; Y = -1.f; Z = -1.f; }
+  const float zx = __fadd_rn(Z, (float)xi);
+  lut[(size_t)b * H * W + i] = make_float4(__fmul_rn(X, zx), __fmul_rn(Y, zx), Z, m);
+}
+
+// FishEyeDecoder.get_prediction (monodepth2_decoder.py:415-420): depth = z of the back-projected ray
+__global__ void mei_depth_kernel(const float* __restrict__ norm, const float4* __restrict__ lut, const int* __restrict__ lut_idx,
+                                 int B, int HW, float* __restrict__ depth) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)B * HW) return;
+  const int b = (int)(i / HW), px = (int)(i % HW);
+  const int t = lut_idx ? lut_idx[b] : 0;
+  depth[i] = __ldg(reinterpret_cast<const float*>(lut + (size_t)t * HW + px) + 2) * norm[i];
 }
 
 // Rows per warp-item: minimise (number of waves) x (rows + halo rows) given how many warps are resident
@@ -853,10 +1009,11 @@ static int check_common(const float* depth_s, int hs, int ws, const float* packe
   return FSNET_OK;
 }
 
-extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* packed,
-                                   const void* mask, int mask_dtype, const float* cam,
-                                   const float* ident, const float* noise, const float* motion, unsigned flags,
-                                   int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
+static int launch_fwd(int cam_model, const float* lut, const int* lut_idx,
+                      const float* depth_s, int hs, int ws, const float* packed,
+                      const void* mask, int mask_dtype, const float* cam,
+                      const float* ident, const float* noise, const float* motion, unsigned flags,
+                      int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
   int rc = check_common(depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
   if (rc) return rc;
   FSNET_REQUIRE(accum, "fsnet_warp_ssim_fwd: null accumulator");
@@ -864,18 +1021,20 @@ extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const f
   p.depth = depth_s; p.hs = hs; p.ws = ws; p.packed = reinterpret_cast<const float4*>(packed);
   p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum = accum; p.sel = sel; p.pred0 = pred0;
-  int blocks = plan(p, 30, 2, loss_pipe() ? 8 : 16);
-  if (loss_pipe()) loss_fwd_kernel<1, 1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  else loss_fwd_kernel<1, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  p.lut = reinterpret_cast<const float4*>(lut); p.lut_idx = lut_idx;
+  int blocks = plan(p, 30, 2, 16);
+  if (cam_model == 0) loss_fwd_kernel<1, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  else loss_fwd_kernel<1, 1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
 
-extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packed,
-                                   const void* mask, int mask_dtype, const float* cam,
-                                   const float* ident, const float* noise, const float* motion, unsigned flags,
-                                   int B, int H, int W, const double* accum, const float* gout,
-                                   float* grad_depth, float* grad_P, void* stream) {
+static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
+                      const float* depth_s, int hs, int ws, const float* packed,
+                      const void* mask, int mask_dtype, const float* cam,
+                      const float* ident, const float* noise, const float* motion, unsigned flags,
+                      int B, int H, int W, const double* accum, const float* gout,
+                      float* grad_depth, float* grad_P, void* stream) {
   int rc = check_common(depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
   if (rc) return rc;
   FSNET_REQUIRE(accum && gout && grad_depth, "fsnet_warp_ssim_bwd: null pointer");
@@ -884,10 +1043,85 @@ extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const f
   p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
   p.grad_depth = grad_depth; p.grad_P = grad_P;
-  int blocks = plan(p, 28, 4, (loss_pipe() && !grad_P) ? 8 : 12);
-  if (grad_P) loss_bwd_kernel<1, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  else if (loss_pipe()) loss_bwd_kernel<0, 1><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
-  else loss_bwd_kernel<0, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  p.lut = reinterpret_cast<const float4*>(lut); p.lut_idx = lut_idx;
+  int blocks = plan(p, 28, 4, 12);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cam_model == 0) {
+    if (grad_P) loss_bwd_kernel<1, 0><<<blocks, kWarps * 32, 0, st>>>(p);
+    else loss_bwd_kernel<0, 0><<<blocks, kWarps * 32, 0, st>>>(p);
+  } else {
+    if (grad_P) loss_bwd_kernel<1, 1><<<blocks, kWarps * 32, 0, st>>>(p);
+    else loss_bwd_kernel<0, 1><<<blocks, kWarps * 32, 0, st>>>(p);
+  }
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_warp_ssim_fwd(const float* depth_s, int hs, int ws, const float* packed,
+                                   const void* mask, int mask_dtype, const float* cam,
+                                   const float* ident, const float* noise, const float* motion, unsigned flags,
+                                   int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
+  return launch_fwd(0, nullptr, nullptr, depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, noise, motion, flags,
+                    B, H, W, accum, sel, pred0, stream);
+}
+
+extern "C" int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packed,
+                                   const void* mask, int mask_dtype, const float* cam,
+                                   const float* ident, const float* noise, const float* motion, unsigned flags,
+                                   int B, int H, int W, const double* accum, const float* gout,
+                                   float* grad_depth, float* grad_P, void* stream) {
+  return launch_bwd(0, nullptr, nullptr, depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, noise, motion, flags,
+                    B, H, W, accum, gout, grad_depth, grad_P, stream);
+}
+
+extern "C" int fsnet_warp_ssim_mei_fwd(const float* lut, const int* lut_idx,
+                                       const float* norm_s, int hs, int ws, const float* packed,
+                                       const void* mask, int mask_dtype, const float* cam,
+                                       const float* ident, const float* noise, const float* motion, unsigned flags,
+                                       int B, int H, int W, double* accum, uint8_t* sel, float* pred0, void* stream) {
+  FSNET_REQUIRE(lut && ((uintptr_t)lut & 15) == 0, "fsnet_warp_ssim_mei_fwd: ray table must be non-null and 16-byte aligned");
+  return launch_fwd(1, lut, lut_idx, norm_s, hs, ws, packed, mask, mask_dtype, cam, ident, noise, motion, flags,
+                    B, H, W, accum, sel, pred0, stream);
+}
+
+extern "C" int fsnet_warp_ssim_mei_bwd(const float* lut, const int* lut_idx,
+                                       const float* norm_s, int hs, int ws, const float* packed,
+                                       const void* mask, int mask_dtype, const float* cam,
+                                       const float* ident, const float* noise, const float* motion, unsigned flags,
+                                       int B, int H, int W, const double* accum, const float* gout,
+                                       float* grad_norm, float* grad_T, void* stream) {
+  FSNET_REQUIRE(lut && ((uintptr_t)lut & 15) == 0, "fsnet_warp_ssim_mei_bwd: ray table must be non-null and 16-byte aligned");
+  return launch_bwd(1, lut, lut_idx, norm_s, hs, ws, packed, mask, mask_dtype, cam, ident, noise, motion, flags,
+                    B, H, W, accum, gout, grad_norm, grad_T, stream);
+}
+
+extern "C" int fsnet_camera_setup_mei(const float* P2, const double* calib, const float* T0, const float* T1, int B,
+                                      float* cam, void* stream) {
+  FSNET_REQUIRE(P2 && calib && T0 && T1 && cam && B > 0, "fsnet_camera_setup_mei: bad arguments");
+  camera_setup_mei_kernel<<<ceil_div(B * 2, 64), 64, 0, (cudaStream_t)stream>>>(P2, calib, T0, T1, B, cam);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_mei_lut(const float* P2, const double* calib, int B, int H, int W,
+                             double* header, int* lut_idx, float* lut, void* stream) {
+  FSNET_REQUIRE(P2 && calib && header && lut_idx && lut, "fsnet_mei_lut: null pointer");
+  FSNET_REQUIRE(B > 0 && B <= 256 && H > 0 && W > 0, "fsnet_mei_lut: bad shape (B <= 256) B=%d H=%d W=%d", B, H, W);
+  FSNET_REQUIRE(((uintptr_t)lut & 15) == 0, "fsnet_mei_lut: ray table must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  mei_lut_plan_kernel<<<1, 256, 0, st>>>(P2, calib, B, header, lut_idx);
+  FSNET_LAUNCH_OK();
+  dim3 grid(ceil_div(H * W, 128), B);
+  mei_lut_build_kernel<<<grid, 128, 0, st>>>(header, lut_idx, H, W, reinterpret_cast<float4*>(lut));
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_mei_depth(const float* norm, const float* lut, const int* lut_idx, int B, int H, int W,
+                               float* depth, void* stream) {
+  FSNET_REQUIRE(norm && lut && depth && B > 0 && H > 0 && W > 0, "fsnet_mei_depth: bad arguments");
+  const long n = (long)B * H * W;
+  mei_depth_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(norm, reinterpret_cast<const float4*>(lut), lut_idx, B, H * W, depth);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

@@ -57,7 +57,13 @@ class _ReprojectionLoss(torch.autograd.Function):
         noise_c = [None] * S if len(noise) == 0 else [_f32c(n) for n in noise]
 
         cam = torch.empty(B, 2, 21, device=dev, dtype=torch.float32)
-        _lib.call("fsnet_camera_setup", P2c, T0c, T1c, B, cam)
+        mei = cfg.get("mei")            # MEI fisheye camera: dict(calib [B,3], lut [B,H,W,4], lut_idx [B]) from mei_ray_table
+        if mei is None:
+            _lib.call("fsnet_camera_setup", P2c, T0c, T1c, B, cam)
+            warp_fwd, lut_args = "fsnet_warp_ssim_fwd", ()
+        else:
+            _lib.call("fsnet_camera_setup_mei", P2c, mei["calib"], T0c, T1c, B, cam)
+            warp_fwd, lut_args = "fsnet_warp_ssim_mei_fwd", (mei["lut"], mei["lut_idx"])
         # identity terms (needed unless the motion-mask branch is on) + the RGBX-packed images for the gathers
         ident = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
         packed = torch.empty(3, B, H, W, 4, device=dev, dtype=torch.float32)
@@ -73,7 +79,7 @@ class _ReprojectionLoss(torch.autograd.Function):
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
-            _lib.call("fsnet_warp_ssim_fwd", depths[i], hs, ws, packed, mask_c, mdt, cam, ident, noise_c[i],
+            _lib.call(warp_fwd, *lut_args, depths[i], hs, ws, packed, mask_c, mdt, cam, ident, noise_c[i],
                       motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
                       pred0 if want_log else None)
             h, w = disps[i].shape[-2:]
@@ -112,11 +118,13 @@ class _ReprojectionLoss(torch.autograd.Function):
         gout = (g_total.detach().to(torch.float32) / S).reshape(1).contiguous()
         g_depths, g_disps = [], []
         gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
+        mei = cfg.get("mei")
+        warp_bwd, lut_args = ("fsnet_warp_ssim_bwd", ()) if mei is None else ("fsnet_warp_ssim_mei_bwd", (mei["lut"], mei["lut_idx"]))
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             full = (hs == H and ws == W)
             gd = (torch.empty if full else torch.zeros)(depths[i].shape, device=dev, dtype=torch.float32)
-            _lib.call("fsnet_warp_ssim_bwd", depths[i], hs, ws, packed, mask_c, ctx.mdt, cam, ident, noise_c[i],
+            _lib.call(warp_bwd, *lut_args, depths[i], hs, ws, packed, mask_c, ctx.mdt, cam, ident, noise_c[i],
                       motion_c, _lib.ctypes.c_uint(ctx.flags), B, H, W, acc[i], gout, gd, gP)
             g_depths.append(gd)
             h, w = disps[i].shape[-2:]
@@ -124,7 +132,12 @@ class _ReprojectionLoss(torch.autograd.Function):
             _lib.call("fsnet_smooth_bwd", disps[i], tgt, B, h, w, H, W, float(cfg["smooth_weight"] / (2 ** s)), sums[i], gout, gs)
             g_disps.append(gs)
         gT = [None, None]
-        if gP is not None:
+        if gP is not None and mei is not None:
+            # the kernel's 3x4 block IS cam_T_cam[:, :3, :4] (monodepth2_decoder.py:379-381); the last row gets no gradient
+            for f in range(2):
+                if ctx.needs_input_grad[2 + 2 * S + f]:
+                    gT[f] = torch.nn.functional.pad(gP[:, f].reshape(B, 3, 4), (0, 0, 0, 1))
+        elif gP is not None:
             # P = (K4 @ T)[:3]  =>  dL/dT = K4[:3,:]^T @ dL/dP      (Project3D, monodepth_utils.py:155)
             K3 = torch.zeros(B, 3, 4, device=dev, dtype=torch.float32)
             K3[:, :, :3] = P2c[:, :3, :3]
@@ -137,13 +150,61 @@ class _ReprojectionLoss(torch.autograd.Function):
 
 def reprojection_loss(depths: Sequence[torch.Tensor], disps: Sequence[torch.Tensor], T0, T1, P2, tgt, src0, src1,
                       mask=None, motion=None, noise: Optional[Sequence[torch.Tensor]] = None, *, scales, overlapped_mask: bool,
-                      smooth_weight: float = 1e-5, log_image: bool = False):
+                      smooth_weight: float = 1e-5, log_image: bool = False, mei: Optional[dict] = None):
     """Returns (total, stats, sel, pred0) -- see _ReprojectionLoss; sel / pred0 are empty unless log_image.  ``noise[i]`` are standard-normal draws
     of shape [B,2,H,W] for scale i (monodepth2_decoder.py:258); None => no tie-break noise."""
     S = len(scales)
-    cfg = dict(scales=list(scales), overlapped_mask=bool(overlapped_mask), smooth_weight=float(smooth_weight), log_image=log_image)
+    cfg = dict(scales=list(scales), overlapped_mask=bool(overlapped_mask), smooth_weight=float(smooth_weight), log_image=log_image,
+               mei=mei)
     extra = [] if noise is None else list(noise)
     return _ReprojectionLoss.apply(S, cfg, *depths, *disps, T0, T1, P2, tgt, src0, src1, mask, motion, *extra)
+
+
+class MeiRayTable:
+    """Device-resident cache of MeiCameraProjection.image2cam's look-up tables (mei_fisheye_utils.py:139-170).
+
+    One ``[B,H,W,4]`` (X, Y, Z, mask) buffer whose slots remember the calibration they were built for;
+    ``update`` launches ``fsnet_mei_lut`` (a plan kernel + an early-exit build kernel), so a calibration
+    change is picked up on the device without the reference's per-sample ``.item()`` synchronisation and
+    the call can sit inside a captured CUDA graph."""
+
+    def __init__(self):
+        self.key = None
+        self.state = None
+        self._calib_cache = {}
+
+    def calib_tensor(self, calib_meta, device):
+        """[B,3] fp64 (xi, k1, k2) of the dataset's ``calib_meta`` dicts (fisheye_dataset.py:45-58,254)."""
+        vals = tuple((float(c["mirror_parameters"]["xi"]), float(c["distortion_parameters"]["k1"]),
+                      float(c["distortion_parameters"]["k2"])) for c in calib_meta)
+        key = (vals, str(device))
+        t = self._calib_cache.get(key)
+        if t is None:
+            if len(self._calib_cache) > 64:
+                self._calib_cache.clear()
+            t = torch.tensor(vals, dtype=torch.float64).to(device)
+            self._calib_cache[key] = t
+        return t
+
+    def update(self, P2: torch.Tensor, calib: torch.Tensor, H: int, W: int) -> dict:
+        B, dev = P2.shape[0], P2.device
+        key = (B, H, W, str(dev))
+        if self.key != key:
+            self.key = key
+            self.state = dict(header=torch.zeros(B, 8, device=dev, dtype=torch.float64),
+                              lut_idx=torch.zeros(B, device=dev, dtype=torch.int32),
+                              lut=torch.empty(B, H, W, 4, device=dev, dtype=torch.float32))
+        st = self.state
+        _lib.call("fsnet_mei_lut", _f32c(P2), calib, B, H, W, st["header"], st["lut_idx"], st["lut"])
+        return dict(calib=calib, lut=st["lut"], lut_idx=st["lut_idx"])
+
+
+def mei_depth(norm: torch.Tensor, mei: dict) -> torch.Tensor:
+    """FishEyeDecoder.get_prediction (monodepth2_decoder.py:415-420): z of the back-projected ray."""
+    B, _, H, W = norm.shape
+    out = torch.empty_like(norm, dtype=torch.float32)
+    _lib.call("fsnet_mei_depth", _f32c(norm), mei["lut"], mei["lut_idx"], B, H, W, out)
+    return out
 
 
 class _DepthHead(torch.autograd.Function):

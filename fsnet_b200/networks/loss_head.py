@@ -47,6 +47,10 @@ class MonoDepth2Decoder(nn.Module):
             loss = loss + torch.abs(input_dict[("relative_pose", f)] - output_dict[("cam_T_cam", f)]).mean()
         return loss
 
+    def _mei_camera(self, input_dict, H, W):
+        """None for the pinhole camera; FishEyeDecoder returns the MEI ray table + calibration."""
+        return None
+
     def _unsupported(self):
         for flag in ("is_residual_flow", "is_light_compensate", "learnable_photometric_uncertain", "is_ssim_weight"):
             if getattr(self, flag, False):
@@ -72,10 +76,11 @@ class MonoDepth2Decoder(nn.Module):
             else:   # the reference draws on the CPU and uploads (:258-259); same distribution, drawn on the device
                 noise = list(torch.randn(self.num_scales, B, 2, H, W, device=tgt.device).unbind(0))
         log_image = getattr(self, "is_log_image", True)
+        mei = self._mei_camera(input_dict, H, W)
         total, stats, sel, pred0 = Fn.reprojection_loss(
             depths, disps, output_dict[("cam_T_cam", f1)], output_dict[("cam_T_cam", f2)], input_dict["P2"], tgt,
             input_dict[("original_image", f1)], input_dict[("original_image", f2)], input_dict.get("patched_mask"), motion,
-            noise, scales=self.scales, overlapped_mask=getattr(self, "overlapped_mask", False), log_image=log_image)
+            noise, scales=self.scales, overlapped_mask=getattr(self, "overlapped_mask", False), log_image=log_image, mei=mei)
         S = self.num_scales
         losses = {}
         for i, s in enumerate(self.scales):
@@ -102,3 +107,27 @@ class MonoDepth2Decoder(nn.Module):
         if not getattr(self, "is_log_image", True):
             hm = {}
         return {"loss": total, "loss_dict": losses, "hm": hm}
+
+
+class FishEyeDecoder(MonoDepth2Decoder):
+    """MonoDepth2Decoder for the KITTI-360 fisheye cameras (monodepth2_decoder.py:350-420): the decoder
+    output is the NORM of the camera ray, back-projection goes through the MEI model's cached ray table
+    (``inputs['calib_meta']`` + ``inputs['P2']``) and projection through ``cam2image`` with radial
+    distortion; the overlap mask is additionally multiplied by the table's validity mask.  Same fused
+    kernels as the pinhole head, instantiated for the MEI camera (csrc/warp_ssim.cu)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.mei_projection = Fn.MeiRayTable()
+
+    def _mei_camera(self, input_dict, H, W):
+        P2 = input_dict["P2"]
+        calib = input_dict.get("calib_mei")          # optional pre-packed [B,3] fp64 (xi, k1, k2) device tensor
+        if calib is None:
+            calib = self.mei_projection.calib_tensor(input_dict["calib_meta"], P2.device)
+        return self.mei_projection.update(P2, calib.double().contiguous(), H, W)
+
+    def get_prediction(self, input_dict, output_dict):
+        norm = output_dict[("depth", 0, 0)]
+        mei = self._mei_camera(input_dict, norm.shape[-2], norm.shape[-1])
+        return dict(depth=Fn.mei_depth(norm, mei), norm=norm)

@@ -106,6 +106,48 @@ int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packe
                         float* grad_depth, float* grad_P, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * MEI (unified omnidirectional) fisheye camera -- FishEyeDecoder (monodepth2_decoder.py:350-420)
+ * with MeiCameraProjection (monodepth/networks/utils/mei_fisheye_utils.py).
+ *
+ * fsnet_mei_lut: the cached per-calibration ray table of image2cam (mei_fisheye_utils.py:139-170:
+ * X=(u-u0)/gamma1, Y=(v-v0)/gamma2, Newton solve of the radial distortion :70-79, bisection of the
+ * mirror equation :85-101, mask := 0 where no root or Z < 0.05, masked entries := -1, X,Y *= Z+xi),
+ * built on the device in fp64 like numba evaluates it.  The reference keys its cache with values
+ * pulled to the host by .item() (:151-154); here the table slots carry the calibration they were
+ * built for, and a slot is rebuilt only when its calibration changed (no host synchronisation).
+ *   P2      [B,3,4] fp32 (gamma1, gamma2, u0, v0 = P2[0,0], P2[1,1], P2[0,2], P2[1,2])
+ *   calib   [B,3]   fp64 (xi, k1, k2 of calib_meta[b]; fp64 because numba solves with the Python doubles)
+ *   header  [B,8]   fp64 persistent state, zero-initialised by the caller once
+ *   lut_idx [B]     int32 out: table slot of sample b (first sample with the same calibration)
+ *   lut     [B,H,W,4] fp32 persistent (X, Y, Z, mask), 16-byte aligned
+ * fsnet_camera_setup_mei: cam [B,2,21] = {gamma1, gamma2, u0, v0, xi, k1, k2, 0, 0, T[:3,:4]} per frame.
+ * fsnet_warp_ssim_mei_fwd / _bwd: the fused per-scale loss with points = LUT * norm, p = T [points;1],
+ * (u,v) = cam2image(p) (:23-51, :379-387) and the overlap mask additionally multiplied by the LUT mask
+ * (:409).  Arguments as fsnet_warp_ssim_fwd / _bwd; `norm_s` is the decoder output (the ray norm);
+ * grad_T [B,2,12] is d loss / d cam_T_cam[:, :3, :4] per frame (or NULL).
+ * fsnet_mei_depth: FishEyeDecoder.get_prediction (:415-420), depth = Z_lut * norm.
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_mei_lut(const float* P2, const double* calib, int B, int H, int W,
+                  double* header, int* lut_idx, float* lut, void* stream);
+int fsnet_camera_setup_mei(const float* P2, const double* calib, const float* T0, const float* T1, int B,
+                           float* cam, void* stream);
+int fsnet_warp_ssim_mei_fwd(const float* lut, const int* lut_idx,
+                            const float* norm_s, int hs, int ws, const float* packed,
+                            const void* mask, int mask_dtype, const float* cam,
+                            const float* ident, const float* noise, const float* motion,
+                            unsigned flags, int B, int H, int W,
+                            double* accum, uint8_t* sel, float* pred0, void* stream);
+int fsnet_warp_ssim_mei_bwd(const float* lut, const int* lut_idx,
+                            const float* norm_s, int hs, int ws, const float* packed,
+                            const void* mask, int mask_dtype, const float* cam,
+                            const float* ident, const float* noise, const float* motion,
+                            unsigned flags, int B, int H, int W,
+                            const double* accum, const float* gout,
+                            float* grad_norm, float* grad_T, void* stream);
+int fsnet_mei_depth(const float* norm, const float* lut, const int* lut_idx, int B, int H, int W,
+                    float* depth, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * edge-aware smoothness on mean-normalised disparity (monodepth2_decoder.py:214-219,294-296,
  * monodepth_utils.py:168-181), forward and backward.  `img` is original_image_0 at full resolution;
  * the 2^s x 2^s box average (adaptive_avg_pool2d) is taken inside the kernel.

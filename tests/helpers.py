@@ -7,7 +7,7 @@ from oracle import fsnet_oracle as O
 
 def meta_arch_cfg(topo: O.Topology, is_log_image=False):
     head = edict(
-        name="monodepth.networks.models.heads.monodepth2_decoder.MonoDepth2Decoder",
+        name="monodepth.networks.models.heads.monodepth2_decoder." + ("FishEyeDecoder" if topo.fisheye else "MonoDepth2Decoder"),
         scales=list(topo.scales), height=topo.height, width=topo.width, min_depth=topo.min_depth, max_depth=topo.max_depth,
         overlapped_mask=topo.overlapped_mask, is_log_image=is_log_image,
         depth_decoder_cfg=edict(

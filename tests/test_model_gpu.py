@@ -23,14 +23,14 @@ def _tc_backend():
 
 
 def to_cuda(data):
-    return {k: v.cuda() for k, v in data.items()}
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
 
 
 @pytest.mark.parametrize("name", sorted(FULL_CASES))
 def test_training_forward_backward_matches_reference(golden_dir, name):
     g = load(golden_dir, name)
     topo, B = FULL_CASES[name]["topo"], FULL_CASES[name]["B"]
-    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1234, topo.frame_ids)
     model = build_model(topo).cuda()
     model.head.tie_break_noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
     # piecewise, to see the maps (same orchestration as forward_train); on the tcgen05 path `feats` is a deferred
@@ -63,6 +63,8 @@ def test_training_forward_backward_matches_reference(golden_dir, name):
     with torch.no_grad():
         pred = model(to_cuda(data), dict(is_training=False))
     assert rel(pred["depth"].cpu(), g["test_depth"]) < 2e-3
+    if topo.fisheye:       # FishEyeDecoder.get_prediction: depth = z of the ray, plus the norm
+        assert rel(pred["norm"].cpu(), g["test_norm"]) < 2e-3
 
 
 def test_training_hook_steps_and_loss_decreases():
