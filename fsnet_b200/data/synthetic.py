@@ -54,16 +54,42 @@ def make_batch(B, H, W, seed=1234, frame_ids=(0, 1, -1), mask_dtype=torch.float6
     return data
 
 
+MEI_KITTI360 = dict(xi=2.2134, k1=0.016798, k2=1.6548, gamma=1336.3, u0=716.94, v0=705.76, size=1400.0)
+
+
+def make_fisheye_batch(B, H, W, seed=1234, frame_ids=(0, 1, -1), mask_dtype=torch.float64, device="cpu"):
+    """``make_batch`` with a KITTI-360-like MEI calibration scaled to the crop, lateral (side-looking camera)
+    motion and ``calib_meta`` dicts as fisheye_dataset.py:45-58,254 delivers them."""
+    data = make_batch(B, H, W, seed, frame_ids, mask_dtype)
+    g = torch.Generator().manual_seed(seed + 77)
+    m = MEI_KITTI360
+    P2 = torch.zeros(B, 3, 4)
+    P2[:, 0, 0], P2[:, 1, 1] = m["gamma"] * W / m["size"], m["gamma"] * H / m["size"]
+    P2[:, 0, 2], P2[:, 1, 2] = m["u0"] * W / m["size"], m["v0"] * H / m["size"]
+    P2[:, 2, 2] = 1.0
+    data["P2"], data["original_P2"] = P2, P2.double()
+    for f in frame_ids[1:]:
+        T = data[("relative_pose", f)]
+        T[:, 0, 3] = (0.8 + 0.2 * (torch.rand(B, generator=g) * 2 - 1)) * (-1.0 if f > 0 else 1.0)
+        T[:, 2, 3] = 0.1 * (torch.rand(B, generator=g) * 2 - 1)
+    if device != "cpu":
+        data = {k: v.to(device) for k, v in data.items()}
+    data["calib_meta"] = [dict(mirror_parameters=dict(xi=m["xi"]), distortion_parameters=dict(k1=m["k1"], k2=m["k2"]))
+                          for _ in range(B)]
+    return data
+
+
 class SyntheticTripletDataset(torch.utils.data.Dataset):
     """``length`` samples of size (height, width); sample i is reproducible from (seed, i)."""
 
-    def __init__(self, length=256, height=192, width=640, frame_idxs=(0, 1, -1), seed=1234, **kwargs):
+    def __init__(self, length=256, height=192, width=640, frame_idxs=(0, 1, -1), seed=1234, fisheye=False, **kwargs):
         self.length, self.height, self.width = int(length), int(height), int(width)
-        self.frame_idxs, self.seed = tuple(frame_idxs), int(seed)
+        self.frame_idxs, self.seed, self.fisheye = tuple(frame_idxs), int(seed), bool(fisheye)
 
     def __len__(self):
         return self.length
 
     def __getitem__(self, index):
-        batch = make_batch(1, self.height, self.width, seed=self.seed + int(index), frame_ids=self.frame_idxs)
+        make = make_fisheye_batch if self.fisheye else make_batch
+        batch = make(1, self.height, self.width, seed=self.seed + int(index), frame_ids=self.frame_idxs)
         return {k: v[0] for k, v in batch.items()}

@@ -16,6 +16,7 @@ DOTTED = [
     "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthMeta",
     "vision_base.networks.models.backbone.resnet.resnet",
     "monodepth.networks.models.heads.monodepth2_decoder.MonoDepth2Decoder",
+    "monodepth.networks.models.heads.monodepth2_decoder.FishEyeDecoder",
     "monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoder",
     "monodepth.networks.models.heads.depth_encoder.DepthDecoder",
     "monodepth.networks.models.heads.pose_decoder.PoseDecoder",
@@ -147,3 +148,14 @@ def test_synthetic_dataset_schema():
     mine, ref = make_batch(2, 32, 64, seed=7), O.synthetic_batch(2, 32, 64, seed=7)
     for k in ref:
         assert torch.equal(mine[k], ref[k]), k
+    # fisheye variant: calib_meta dicts survive the reference-style collate as a list (dataset_utils.py:24-25)
+    from fsnet_b200.data.synthetic import make_fisheye_batch
+    from vision_base.data.datasets.dataset_utils import collate_fn
+    fe = SyntheticTripletDataset(length=4, height=32, width=32, fisheye=True)
+    batch = collate_fn([fe[0], fe[1]])
+    assert isinstance(batch["calib_meta"], list) and batch["calib_meta"][1]["mirror_parameters"]["xi"] > 2
+    mine, ref = make_fisheye_batch(2, 32, 32, seed=7), O.synthetic_fisheye_batch(2, 32, 32, seed=7)
+    for k in ref:
+        if torch.is_tensor(ref[k]):
+            assert torch.equal(mine[k], ref[k]), k
+    assert mine["calib_meta"] == ref["calib_meta"]

@@ -118,3 +118,26 @@ def test_graphed_hook_matches_eager_hook():
         losses[mode] = seq
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
+
+
+def test_fisheye_graphed_hook_matches_eager_hook():
+    """FishEyeDecoder through BaseTrainingHook: the MEI ray table is (re)built on the device, so the step --
+    table refresh included -- captures into one CUDA graph and replays the eager trajectory; `hm` images are
+    produced because is_log_image is unset (=> True) in the shipped fisheye config."""
+    from vision_base.utils.builder import build
+    topo = O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0)
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        model = build_model(topo, is_log_image=True).cuda()
+        model.head.tie_break_noise = {s: n.cuda() for s, n in O.tie_break_noise(2, 64, 64, topo.scales, 0).items()}
+        hook = build("vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=1.0, cuda_graph=mode)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        seq = []
+        for step in range(7):
+            out = hook(O.synthetic_fisheye_batch(2, 64, 64, 1234 + step), model, opt, None, None, step, 0)
+            seq.append(float(out["loss"].detach()))
+        assert out["hm"]["predicted_image_1"].shape == (1, 3, 64, 64) and out["hm"]["loss_mask_0"]["data"].dtype == torch.bool
+        losses[mode] = seq
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses[False], losses[True])
