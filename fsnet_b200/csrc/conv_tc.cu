@@ -37,7 +37,9 @@ struct ConvParams {
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int BN;                      // output channels per tile (multiple of 16, <= 128)
   int KC, cchunks, kiters;     // channels per stage, Cin/KC, taps*cchunks
-  int fold;                    // x-taps folded into K: kiters = KH * cchunks, cchunks = ceil(KW*Cin / 64)
+  int fold;                    // x-taps folded into K (cchunks = ceil(KW*Cin / 64)).  1: one stage per (kernel row, chunk);
+                               // 2: one stage per chunk holding the (TH+KH-1)-row halo tile once, kernel rows = smem row offsets
+  uint32_t b_each, tap_bytes;  // fold 2: bytes of one kernel row's weight box, smem offset between kernel rows of A (TW * 128)
   int stages;
   uint32_t a_bytes, b_bytes, stage_bytes, tx_bytes;
   uint32_t tmem_cols;
@@ -166,6 +168,75 @@ __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
   return v[0];      // column index = ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
 }
 
+// Epilogue of both convolution kernels, run by four warps (TMEM lane quadrant = warp % 4): accumulator ->
+// (+bias, ReLU) -> fp32 NHWC store (optionally accumulating) + per-channel sum / sum-of-squares of the tile.
+// `first_tid` = threadIdx.x of the first epilogue thread (for the final statistics flush).
+__device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, int lane, uint32_t tmem_base,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, float* s_stats, int first_tid) {
+  const int q = warp & 3;                         // TMEM lane quadrant of this warp
+  const int m = q * 32 + lane;                    // row of the tile = pixel
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const int acc = it & 1;
+    int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    int tx = mt % p.tiles_x; int rest = mt / p.tiles_x;
+    int ty = rest % p.tiles_y; int img = rest / p.tiles_y;
+    const int py = m / p.TW, px = m - py * p.TW;
+    const int oy = ty * p.TH + py, ox = tx * p.TW + px;
+    const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo;
+    float* orow = p.out + (((size_t)img * p.out_ph + oy + p.out_ring) * p.out_pw + ox + p.out_ring) * p.out_ct + p.out_coff + nt * p.BN;
+    mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      uint32_t raw[16];
+      tmem_ld16(taddr + c0, raw);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + nt * p.BN + c0 + j);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *dst = o;
+        }
+      }
+      if (p.stats) {
+        float sq[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
+        float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
+        if ((lane & 1) == 0) {
+          int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          atomicAdd(&s_stats[nt * p.BN + c0 + col], s1);
+          atomicAdd(&s_stats[p.Cout + nt * p.BN + c0 + col], s2);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+  }
+  if (p.stats) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+    for (int i = threadIdx.x - first_tid; i < 2 * p.Cout; i += 128) {
+      float s = s_stats[i];
+      if (s != 0.f) atomicAdd(p.stats + i, (double)s);
+    }
+  }
+}
+
 template <int NPROD>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -211,7 +282,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * p.stage_bytes;
           mbar_expect_tx(&full_bar[stage], p.tx_bytes);
-          if (p.fold) {
+          if (p.fold == 2) {
+            // A: the whole (TH+KH-1) x TW halo tile of 64-element fat-pixel slice cc, loaded ONCE for all kernel rows
+            const int xo = tx * p.TW, yo = ty * p.TH;
+            tma_load_4d(st, &map_a_hi, &full_bar[stage], kit * 64, xo, yo, img);
+            for (int rr = 0; rr < p.KH; ++rr)
+              tma_load_3d(st + p.a_bytes + rr * p.b_each, &map_b_hi, &full_bar[stage], kit * 64, rr, nt * p.BN);
+            if (NPROD == 3) {
+              uint8_t* lo = st + p.a_bytes + p.b_bytes;
+              tma_load_4d(lo, &map_a_lo, &full_bar[stage], kit * 64, xo, yo, img);
+              for (int rr = 0; rr < p.KH; ++rr)
+                tma_load_3d(lo + p.a_bytes + rr * p.b_each, &map_b_lo, &full_bar[stage], kit * 64, rr, nt * p.BN);
+            }
+          } else if (p.fold) {
             // A: 64-element slice cc of the "fat pixel" row (KW taps x Cin channels, contiguous in NHWC) of kernel row r
             const int xo = tx * p.TW, yo = ty * p.TH + r;
             tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
@@ -250,6 +333,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          if (p.fold == 2) {
+            // kernel row rr reads the halo tile rr*TW rows further down (a whole number of 1024-byte swizzle atoms)
+            for (int rr = 0; rr < p.KH; ++rr) {
+              const uint64_t a_hi = make_desc(st + rr * p.tap_bytes, p.sbo, p.layout_type);
+              const uint64_t b_hi = make_desc(st + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (kit | rr | k) != 0);
+              if (NPROD == 3) {
+                const uint32_t lo = st + p.a_bytes + p.b_bytes;
+                const uint64_t a_lo = make_desc(lo + rr * p.tap_bytes, p.sbo, p.layout_type);
+                const uint64_t b_lo = make_desc(lo + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
+                for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
+                for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint64_t a_hi = make_desc(st, p.sbo, p.layout_type);
           const uint64_t b_hi = make_desc(st + p.a_bytes, p.sbo, p.layout_type);
           for (int k = 0; k < ksteps; ++k)
@@ -268,68 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                         // TMEM lane quadrant of this warp
-    const int m = q * 32 + lane;                    // row of the tile = pixel
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-      int tx = mt % p.tiles_x; int rest = mt / p.tiles_x;
-      int ty = rest % p.tiles_y; int img = rest / p.tiles_y;
-      const int py = m / p.TW, px = m - py * p.TW;
-      const int oy = ty * p.TH + py, ox = tx * p.TW + px;
-      const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo;
-      float* orow = p.out + (((size_t)img * p.out_ph + oy + p.out_ring) * p.out_pw + ox + p.out_ring) * p.out_ct + p.out_coff + nt * p.BN;
-      mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c0, raw);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(raw[j]) : 0.f;
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + nt * p.BN + c0 + j);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-            *dst = o;
-          }
-        }
-        if (p.stats) {
-          float sq[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
-          float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
-          if ((lane & 1) == 0) {
-            int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            atomicAdd(&s_stats[nt * p.BN + c0 + col], s1);
-            atomicAdd(&s_stats[p.Cout + nt * p.BN + c0 + col], s2);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-    }
-    if (p.stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-      for (int i = threadIdx.x - 64; i < 2 * p.Cout; i += 128) {
-        float s = s_stats[i];
-        if (s != 0.f) atomicAdd(p.stats + i, (double)s);
-      }
-    }
+    epilogue_warps(p, warp, lane, tmem_base, tmem_full, tmem_empty, s_stats, 64);
   }
   tc_fence_before();
   __syncthreads();
@@ -431,16 +472,33 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   // x-tap folding for thin replicate-padded layers: the KW taps x Cin channels of a kernel row are one contiguous
   // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
   static int fold_env = -1;
-  if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 1; }
+  if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 2; }
   p.fold = fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
            in->c == in->c_total && (Cin < 64 || Cin == 96);
+
   if (p.fold) {
     p.KC = 64; p.cchunks = ceil_div(KW * Cin, 64); p.kiters = KH * p.cchunks;
+    // halo variant: an 8 x 16 output tile whose 10 x 16 fat-pixel halo is loaded once; needs full 16-wide tiles in smem
+    // (rows of the box are TW pixels apart, so the kernel-row offset TW*128 B must be a multiple of the 1024 B atom)
+    if (fold_env >= 2 && p.Ho >= 8 && p.Wo >= 16) {
+      p.fold = 2; p.TH = 8; p.TW = 16;
+      p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
+      p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
+      p.kiters = p.cchunks;
+    }
   }
   p.a_bytes = 128u * p.KC * 2;
   p.b_bytes = ((uint32_t)p.BN * p.KC * 2 + 1023u) & ~1023u;
-  p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
   p.tx_bytes = (nprod == 3 ? 2u : 1u) * ((uint32_t)p.TH * p.TW * p.KC * 2 + (uint32_t)p.BN * p.KC * 2);
+  if (p.fold == 2) {
+    const uint32_t rows = (uint32_t)(p.TH + KH - 1) * p.TW;
+    p.a_bytes = rows * 128u;
+    p.b_each = p.b_bytes;
+    p.b_bytes = (uint32_t)KH * p.b_each;
+    p.tap_bytes = (uint32_t)p.TW * 128u;
+    p.tx_bytes = (nprod == 3 ? 2u : 1u) * (rows * 128u + (uint32_t)KH * p.BN * 128u);
+  }
+  p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
   const uint32_t stats_bytes = stats ? 2u * Cout * 4u : 0u;
   int stages = (int)((200u * 1024u - stats_bytes) / p.stage_bytes);
   p.stages = stages > kMaxStages ? kMaxStages : stages;
@@ -460,7 +518,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     const size_t plane_elems = (size_t)N * ph * pw * Cin;
     cuuint64_t adim[4] = {(cuuint64_t)(64 * p.cchunks), (cuuint64_t)p.Wo, (cuuint64_t)ph, (cuuint64_t)N};
     cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)pw * Cin * 2, (cuuint64_t)ph * pw * Cin * 2};
-    cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.fold == 2 ? p.TH + KH - 1 : p.TH), 1};
     cuuint32_t aes[4] = {1, 1, 1, 1};
     cuuint64_t wdim[3] = {(cuuint64_t)(KW * Cin), (cuuint64_t)KH, (cuuint64_t)Cout};
     cuuint64_t wstr[2] = {(cuuint64_t)KW * Cin * 2, (cuuint64_t)KH * KW * Cin * 2};

@@ -8,13 +8,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from fsnet_b200 import _lib
-from oracle import fsnet_oracle as O
+from fsnet_b200.data.synthetic import make_batch
 
 
 def main(B=12, H=192, W=640, iters=20):
     dev = "cuda"
-    data = O.synthetic_batch(B, H, W)
-    outs = O.synthetic_depth_outputs(B, H, W, (0, 1, 2, 3), 5)
+    data = make_batch(B, H, W)
+    g = torch.Generator().manual_seed(5)
+    outs = {}
+    for s in range(4):       # smooth random depth pyramid, 2..40 m
+        h, w = H >> s, W >> s
+        f = torch.nn.functional.interpolate(torch.rand(B, 1, max(h // 8, 2), max(w // 8, 2), generator=g), size=(h, w), mode="bilinear", align_corners=True)
+        outs[("depth", s, s)] = (2.0 * torch.exp(f * 3.0)).contiguous()
     tgt, s0, s1 = (data[("original_image", f)].to(dev) for f in (0, 1, -1))
     mask = data["patched_mask"].float().to(dev)
     cam = torch.empty(B, 2, 21, device=dev)
