@@ -103,16 +103,26 @@ __device__ __forceinline__ Px decode8(unsigned i, int H, int W, int C) {
 }
 
 // ---- image (fp32 NCHW) -> planes with zero-filled extra channels ----------------------------------
-__global__ void image_to_planes_kernel(const float* __restrict__ img, int C, V d) {
-  size_t total = (size_t)d.n * d.h * d.w * d.c;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per (PADDED pixel, 8-channel group): coalesced reads along x, one 128-bit store per plane.  The ring
+// (any width) is either the replicate copy of the border or zeros (zero_ring: the zero padding of the 7x7 stem,
+// materialised so that the stem can run on the folded-tap convolution path).
+__global__ void image_to_planes_kernel(const float* __restrict__ img, int C, V d, int zero_ring) {
+  const int ph = d.h + 2 * d.ring, pw = d.w + 2 * d.ring;
+  const unsigned total = (unsigned)d.n * ph * pw * (d.c >> 3);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  int c = (int)(i % d.c); size_t r = i / d.c;
-  int x = (int)(r % d.w); r /= d.w;
-  int y = (int)(r % d.h); int n = (int)(r / d.h);
-  float v = c < C ? __ldg(img + (((size_t)n * C + c) * d.h + y) * d.w + x) : 0.f;
+  Px q = decode8(i, ph, pw, d.c);
+  int y = q.y - d.ring, x = q.x - d.ring;
+  const bool outside = y < 0 || y >= d.h || x < 0 || x >= d.w;
+  y = min(max(y, 0), d.h - 1); x = min(max(x, 0), d.w - 1);
+  F8 v;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = q.c + k;
+    v.v[k] = (c < C && !(outside && zero_ring)) ? __ldg(img + (((size_t)q.n * C + c) * d.h + y) * d.w + x) : 0.f;
+  }
   __nv_bfloat16* hi = (__nv_bfloat16*)d.ptr;
-  store_with_ring(d, hi, hi + plane_stride(d), n, y, x, c, v);
+  st_split8(hi, hi + plane_stride(d), vidx(d, q.n, q.y - d.ring, q.x - d.ring, q.c), v);
 }
 
 // ---- BatchNorm finalisation -------------------------------------------------------------------------
@@ -500,12 +510,18 @@ inline unsigned blocks_for(size_t total, int threads = 256) { return (unsigned)(
 
 using namespace fsnet;
 
-extern "C" int fsnet_image_to_planes(const float* img, int C, const fsnet_view* dst, void* stream) {
+extern "C" int fsnet_image_to_planes_ring(const float* img, int C, const fsnet_view* dst, int zero_ring, void* stream) {
   FSNET_REQUIRE(img && dst && dst->ptr && C <= dst->c, "fsnet_image_to_planes: bad arguments");
-  size_t total = (size_t)dst->n * dst->h * dst->w * dst->c;
-  image_to_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(img, C, *dst);
+  FSNET_REQUIRE(dst->c % 8 == 0 && dst->c_off == 0 && dst->c == dst->c_total, "fsnet_image_to_planes: destination must be a whole buffer with channels % 8 == 0");
+  size_t total = (size_t)dst->n * (dst->h + 2 * dst->ring) * (dst->w + 2 * dst->ring) * (dst->c / 8);
+  FSNET_REQUIRE(total < (1ull << 32), "fsnet_image_to_planes: tensor too large for 32-bit indexing");
+  image_to_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(img, C, *dst, zero_ring);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
+}
+
+extern "C" int fsnet_image_to_planes(const float* img, int C, const fsnet_view* dst, void* stream) {
+  return fsnet_image_to_planes_ring(img, C, dst, 0, stream);
 }
 
 extern "C" int fsnet_bn_finalize(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,

@@ -296,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           } else if (p.fold) {
             // A: 64-element slice cc of the "fat pixel" row (KW taps x Cin channels, contiguous in NHWC) of kernel row r
-            const int xo = tx * p.TW, yo = ty * p.TH + r;
+            const int xo = tx * p.TW, yo = ty * p.TH * p.stride + r;
             tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
             tma_load_3d(st + p.a_bytes, &map_b_hi, &full_bar[stage], cc * 64, r, nt * p.BN);
             if (NPROD == 3) {
@@ -475,12 +475,17 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 2; }
   p.fold = fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
            in->c == in->c_total && (Cin < 64 || Cin == 96);
+  // the 7x7 / stride-2 stem on 16-channel (3 real) image planes with a materialised zero ring: 7 taps x 16 channels = 112 -> two
+  // 64-element slices per kernel row instead of 49 separate 4 KB tap loads
+  const bool stem_fold = fold_env && stride == 2 && use_ring && in->ring == pad && pad == 3 && KH == 7 && KW == 7 && in->c_off == 0 &&
+                         in->c == in->c_total && Cin == 16;
+  if (stem_fold) p.fold = 1;
 
   if (p.fold) {
     p.KC = 64; p.cchunks = ceil_div(KW * Cin, 64); p.kiters = KH * p.cchunks;
     // halo variant: an 8 x 16 output tile whose 10 x 16 fat-pixel halo is loaded once; needs full 16-wide tiles in smem
     // (rows of the box are TW pixels apart, so the kernel-row offset TW*128 B must be a multiple of the 1024 B atom)
-    if (fold_env >= 2 && p.Ho >= 8 && p.Wo >= 16) {
+    if (fold_env >= 2 && stride == 1 && p.Ho >= 8 && p.Wo >= 16) {
       p.fold = 2; p.TH = 8; p.TW = 16;
       p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
       p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
@@ -517,9 +522,9 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     const int pw = W + 2 * in->ring, ph = H + 2 * in->ring;
     const size_t plane_elems = (size_t)N * ph * pw * Cin;
     cuuint64_t adim[4] = {(cuuint64_t)(64 * p.cchunks), (cuuint64_t)p.Wo, (cuuint64_t)ph, (cuuint64_t)N};
-    cuuint64_t astr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)pw * Cin * 2, (cuuint64_t)ph * pw * Cin * 2};
-    cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.fold == 2 ? p.TH + KH - 1 : p.TH), 1};
-    cuuint32_t aes[4] = {1, 1, 1, 1};
+    cuuint64_t astr[3] = {(cuuint64_t)stride * Cin * 2, (cuuint64_t)pw * Cin * 2, (cuuint64_t)ph * pw * Cin * 2};
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.TW, (cuuint32_t)(p.fold == 2 ? p.TH + KH - 1 : p.TH * stride), 1};
+    cuuint32_t aes[4] = {1, 1, (cuuint32_t)stride, 1};
     cuuint64_t wdim[3] = {(cuuint64_t)(KW * Cin), (cuuint64_t)KH, (cuuint64_t)Cout};
     cuuint64_t wstr[2] = {(cuuint64_t)KW * Cin * 2, (cuuint64_t)KH * KW * Cin * 2};
     cuuint32_t wbox[3] = {64, 1, (cuuint32_t)p.BN};

@@ -33,6 +33,7 @@ class Act:
         self._grad_ring = grad_ring
         self._written = False
         self._dirty = False
+        self.zero_ring = False          # the ring holds materialised ZERO padding (network input for the 7x7 stem)
 
     n = property(lambda self: self.planes.n)
     h = property(lambda self: self.planes.h)
@@ -173,7 +174,8 @@ class Tape:
         Wo = (x.w + 2 * st.pad - st.kw) // st.stride + 1
         raw = Fp32(N, Ho, Wo, st.C, device=x.planes.t.device)
         bn_train = bn is not None and (self.training and bn.training)
-        tc.conv(x.planes, st.w, raw, st.stride, st.pad, use_ring=st.replicate, stats=st.stats if bn_train else None, in_view=x.pview())
+        use_ring = st.replicate or (x.zero_ring and x.planes.ring == st.pad)     # zero ring == zero padding, read as data
+        tc.conv(x.planes, st.w, raw, st.stride, st.pad, use_ring=use_ring, stats=st.stats if bn_train else None, in_view=x.pview())
         count = float(N * Ho * Wo)
         inv = Inv(st)
         self._finalize(inv, bn, bn_train, count)
@@ -393,9 +395,12 @@ class Tape:
 # ---------------------------------------------------------------------------------------------------
 def _image_act(img: torch.Tensor) -> Act:
     n, c, h, w = img.shape
-    p = Planes(n, h, w, pad16(c), ring=1, device=img.device)
-    _lib.call("fsnet_image_to_planes", img.detach().float().contiguous(), c, p.view())
-    return Act(p, relu=False)
+    # ring 3 = the stem's zero padding, materialised (the 7x7/2 stem then runs on the folded-tap convolution path)
+    p = Planes(n, h, w, pad16(c), ring=3, device=img.device)
+    _lib.call("fsnet_image_to_planes_ring", img.detach().float().contiguous(), c, p.view(), 1)
+    a = Act(p, relu=False)
+    a.zero_ring = True
+    return a
 
 
 def resnet_forward(tape: Tape, net, img: torch.Tensor, want_grads: bool) -> List[Act]:

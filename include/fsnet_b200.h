@@ -246,6 +246,9 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
  *   fsnet_zero_insert      bf16 plane -> zero-stuffed x2 plane (stride-2 data gradient as a stride-1 convolution)
  * ------------------------------------------------------------------------------------------- */
 int fsnet_image_to_planes(const float* img, int C, const fsnet_view* dst, void* stream);
+/* same, choosing what the ring (any width) holds: zero_ring = 0 replicate copies of the border, 1 zeros
+ * (the 7x7 stem's zero padding, materialised for the folded-tap convolution path) */
+int fsnet_image_to_planes_ring(const float* img, int C, const fsnet_view* dst, int zero_ring, void* stream);
 int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad,
                         void* fwd_hi, void* fwd_lo, void* dgrad_hi, void* stream);
 /* one launch for every convolution of a network: `table_device` is a DEVICE array of n_layers descriptors */
