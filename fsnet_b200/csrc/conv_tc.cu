@@ -709,7 +709,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                                                                    __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(raw[j]));
+          for (int j = 0; j < 16; j += 4)       // one 128-bit reduction per four accumulators (the L2 atomic units are the limit)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(raw[j])),
+                         "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3])) : "memory");
         }
       }
     }
@@ -755,7 +757,14 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   const int base_items = p.taps * p.co_tiles * p.ci_tiles;
   // K split: ~3 CTAs per SM hide the TMA latency of thin layers (32-64 byte rows); once the (tap, tile) grid alone
   // fills half the machine, more splits only add fp32 atomics on large weight tensors
-  int ksplit = base_items >= 74 ? ceil_div(148, base_items) : ceil_div(148 * 3, base_items);
+  // every K-split CTA adds a full [Cout, taps, Cin] tile through L2 reductions: with many outputs one wave of CTAs is
+  // enough (measured: the reductions, not the MMAs, bound the 128..512-channel layers), with few outputs three
+  static int occ_env = -1, big_env = -1;
+  if (occ_env < 0) { const char* e = getenv("FSNET_WGRAD_OCC"); occ_env = e ? atoi(e) : 0; }
+  if (big_env < 0) { const char* e = getenv("FSNET_WGRAD_BIG"); big_env = e ? atoi(e) : 64; }
+  const long outputs = (long)p.Cout * p.taps * p.Cin;
+  const int occ = occ_env ? occ_env : (outputs <= (long)big_env * 1024 ? 3 : 1);
+  int ksplit = base_items >= 148 ? 1 : (occ == 1 ? (148 / base_items > 0 ? 148 / base_items : 1) : ceil_div(148 * occ, base_items));
   if (ksplit > p.total_chunks) ksplit = p.total_chunks;
   if (ksplit < 1) ksplit = 1;
   p.chunks_per_split = ceil_div(p.total_chunks, ksplit);
