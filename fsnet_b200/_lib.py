@@ -24,7 +24,7 @@ _lock = threading.Lock()
 _lib = None
 launch_count = 0          # entry-point calls issued through this binding
 kernel_launches = 0       # CUDA kernels those calls launched (bench.py reports it as gpu_launches)
-KERNELS_PER_ENTRY = {"fsnet_smooth_fwd": 2, "fsnet_mei_lut": 2}          # everything else launches exactly one kernel
+KERNELS_PER_ENTRY = {"fsnet_smooth_fwd": 2, "fsnet_mei_lut": 2, "fsnet_adam_step": 2}          # everything else launches exactly one kernel
 _profiled = {}            # entry name -> list of (start_event, end_event) while profiling is on
 
 

@@ -596,7 +596,11 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   const int pix_per_iter = 256 / groups > 0 ? 256 / groups : 1;
   const int threads_used = groups * pix_per_iter;
   size_t npix = (size_t)raw->n * raw->h * raw->w;
-  unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * 16 - 1) / ((size_t)pix_per_iter * 16));
+  // at most 16 pixels per thread, but never fewer than ~2 blocks per SM: the small deep layers were latency bound
+  // with a few dozen blocks walking their pixels serially
+  size_t per_thread = npix / ((size_t)pix_per_iter * 296);
+  per_thread = per_thread < 1 ? 1 : (per_thread > 16 ? 16 : per_thread);
+  unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * per_thread - 1) / ((size_t)pix_per_iter * per_thread));
   if (grid > 148 * 4) grid = 148 * 4;
   if (grid == 0) grid = 1;
   bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);

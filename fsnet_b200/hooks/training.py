@@ -61,9 +61,12 @@ class BaseTrainingHook(object):
         output: dict = meta_arch(data, meta)
         output["loss"].mean().backward()
         self.sync_gradients(meta_arch)
-        if self.clip_gradients is not None:
-            torch.nn.utils.clip_grad_norm_(meta_arch.parameters(), self.clip_gradients)
-        optimizer.step()
+        if getattr(optimizer, "sync_hyperparams", None) is not None and len(optimizer.param_groups) == 1:
+            optimizer.step(max_norm=self.clip_gradients)      # FusedAdam: clip_grad_norm_ folded into the update (2 launches)
+        else:
+            if self.clip_gradients is not None:
+                torch.nn.utils.clip_grad_norm_(meta_arch.parameters(), self.clip_gradients)
+            optimizer.step()
         return output
 
     def __call__(self, data: Dict, meta_arch: nn.Module, optimizer, writer=None, training_loss_logger=None,
@@ -110,6 +113,8 @@ class BaseTrainingHook(object):
                 self._static_out = self._step(dict(self._static_in), meta_arch, optimizer, meta)
         else:
             self._copy_in(data)
+        if getattr(optimizer, "sync_hyperparams", None) is not None:
+            optimizer.sync_hyperparams()                  # scheduler changes of lr reach the captured step through device memory
         self._graph.replay()
         return self._static_out
 

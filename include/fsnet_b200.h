@@ -279,6 +279,27 @@ int fsnet_fold_ring(const fsnet_view* g, void* stream);
 int fsnet_add_slice(const fsnet_view* dst, const fsnet_view* src, int accumulate, void* stream);
 int fsnet_zero_insert(const fsnet_view* src, const fsnet_view* dst, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fused multi-tensor clip_grad_norm_ + Adam (base_training_hooks.py:46-49: torch.nn.utils.clip_grad_norm_
+ * then optimizer.step(); optimizers.py:8: torch.optim.Adam).  SURVEY.md 8(f) N1.
+ *   table  device array of fsnet_adam_tensor: parameter, gradient, exp_avg, exp_avg_sq (fp32, n elements) and
+ *          chunk_start = index of the tensor's first 4096-element chunk (prefix sum, n_chunks in total)
+ *   sumsq  [1] fp64, zeroed by the caller; fsnet_grad_sumsq adds sum(g^2) over all tensors
+ *   hyper  [8] fp64 device: lr, beta1, beta2, eps, weight_decay, max_norm (<= 0: no clipping), step, unused;
+ *          fsnet_adam_step increments `step`, scales the gradients by min(1, max_norm / (sqrt(sumsq) + 1e-6)) on the
+ *          fly and applies torch.optim.Adam's update (bias correction, L2 weight decay, no amsgrad)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  long long n;
+  long long chunk_start;
+} fsnet_adam_tensor;
+int fsnet_grad_sumsq(const fsnet_adam_tensor* table, int n_tensors, long long n_chunks, double* sumsq, void* stream);
+int fsnet_adam_step(const fsnet_adam_tensor* table, int n_tensors, long long n_chunks, const double* sumsq, double* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

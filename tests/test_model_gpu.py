@@ -110,7 +110,8 @@ def test_graphed_hook_matches_eager_hook():
         # device-resident noise: a host->device copy cannot be captured into the step graph
         model.head.tie_break_noise = {s: n.cuda() for s, n in O.tie_break_noise(2, 64, 128, topo.scales, 0).items()}
         hook = build("vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0, cuda_graph=mode)
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        from vision_base.networks.optimizers.optimizers import build_optimizer
+        opt = build_optimizer(model, name="adam", lr=1e-4) if mode else torch.optim.Adam(model.parameters(), lr=1e-4)   # FusedAdam vs stock
         seq = []
         for step in range(7):
             out = hook(O.synthetic_batch(2, 64, 128, 1234 + step), model, opt, None, None, step, 0)
