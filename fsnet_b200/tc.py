@@ -27,10 +27,12 @@ class _Buf:
 class Planes(_Buf):
     SLACK = 256      # zeroed elements behind the lo plane: the folded-tap TMA windows of the last pixels run past the end
 
-    def __init__(self, n, h, w, c, ring=1, device="cuda", zero=False):
+    def __init__(self, n, h, w, c, ring=1, device="cuda", zero=False, slack=None):
         numel = 2 * n * (h + 2 * ring) * (w + 2 * ring) * c
-        flat = (torch.zeros if zero else torch.empty)(numel + self.SLACK, device=device, dtype=torch.bfloat16)
-        if not zero:
+        if slack is None:            # only the folded-tap convolution path (thin layers, 96-channel concat) over-reads
+            slack = c < 64 or c == 96
+        flat = (torch.zeros if zero else torch.empty)(numel + (self.SLACK if slack else 0), device=device, dtype=torch.bfloat16)
+        if slack and not zero:
             flat[numel:].zero_()
         self._flat = flat
         t = flat[:numel].view(2, n, h + 2 * ring, w + 2 * ring, c)
