@@ -20,6 +20,12 @@ class WeightDesc(ctypes.Structure):
                 ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
 
 
+class WgradDesc(ctypes.Structure):
+    """fsnet_wgrad_desc of include/fsnet_b200.h."""
+    _fields_ = [("acc_off", ctypes.c_longlong), ("grad_off", ctypes.c_longlong), ("cout", ctypes.c_int), ("cin", ctypes.c_int),
+                ("kh", ctypes.c_int), ("kw", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
+
+
 _lock = threading.Lock()
 _lib = None
 launch_count = 0          # entry-point calls issued through this binding

@@ -522,6 +522,39 @@ __global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_
     }
   }
 }
+// All layers' accumulators -> parameter-gradient layout in one launch (blockIdx.y = layer): a [co tile][tap][ci tile]
+// brick of the padded fp32 accumulator [Cout_pad, KH, KW, Cin_pad] goes through shared memory and comes out as the
+// contiguous [co][ci][tap] run of the nn.Conv2d weight gradient.  Offsets are relative to the two base pointers, so the
+// table is static across steps.
+__global__ void __launch_bounds__(256) wgrad_to_param_batched_kernel(const fsnet_wgrad_desc* __restrict__ table,
+                                                                     const float* __restrict__ acc_base, float* __restrict__ grad_base) {
+  __shared__ float s_w[kWpTile];
+  const fsnet_wgrad_desc d = table[blockIdx.y];
+  const int T = d.kh * d.kw;
+  const int CI_T = d.cin_pad < 32 ? d.cin_pad : 32;
+  int CO_T = kWpTile / (CI_T * T);
+  CO_T = CO_T > 16 ? 16 : (CO_T < 1 ? 1 : CO_T);
+  if (CI_T * T > kWpTile) return;
+  const int ci_tiles = (d.cin + CI_T - 1) / CI_T, co_tiles = (d.cout + CO_T - 1) / CO_T;
+  const int brick = CO_T * CI_T * T, run = CI_T * T;
+  const float* acc = acc_base + d.acc_off;
+  float* grad = grad_base + d.grad_off;
+  for (int tile = blockIdx.x; tile < ci_tiles * co_tiles; tile += gridDim.x) {
+    const int co0 = (tile / ci_tiles) * CO_T, ci0 = (tile % ci_tiles) * CI_T;
+    __syncthreads();
+    for (int i = threadIdx.x; i < brick; i += 256) {         // accumulator layout: ci fastest
+      const int ci_l = i % CI_T, t2 = i / CI_T, tap = t2 % T, co_l = t2 / T;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      s_w[(co_l * CI_T + ci_l) * T + tap] = (co < d.cout && ci < d.cin) ? acc[((size_t)co * T + tap) * d.cin_pad + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < brick; i += 256) {         // parameter layout: (ci, tap) contiguous
+      const int co_l = i / run, rem = i - co_l * run, ci_l = rem / T;
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (co < d.cout && ci < d.cin) grad[((size_t)co * d.cin + ci0) * T + rem] = s_w[i];
+    }
+  }
+}
 __global__ void wgrad_to_param_kernel(const float* __restrict__ acc, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad,
                                       float* __restrict__ grad, int accumulate) {
   size_t total = (size_t)Cout * Cin * KH * KW;
@@ -692,8 +725,17 @@ extern "C" int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, in
 
 extern "C" int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device, int n_layers, void* stream) {
   FSNET_REQUIRE(table_device && n_layers > 0, "fsnet_weight_planes_batched: bad arguments");
-  dim3 grid(64, n_layers);
+  dim3 grid(148, n_layers);
   weight_planes_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_device);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_wgrad_to_param_batched(const fsnet_wgrad_desc* table_device, int n_layers, const float* acc_base, float* grad_base,
+                                            void* stream) {
+  FSNET_REQUIRE(table_device && n_layers > 0 && acc_base && grad_base, "fsnet_wgrad_to_param_batched: bad arguments");
+  dim3 grid(148, n_layers);
+  wgrad_to_param_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_device, acc_base, grad_base);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

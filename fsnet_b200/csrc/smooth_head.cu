@@ -227,12 +227,71 @@ extern "C" int fsnet_smooth_bwd(const float* disp, const float* img, int B, int 
   return FSNET_OK;
 }
 
+// ---- channels-last softmax head, n in {4, 8, 16, 32, 64, 128}: L = n/4 lanes per pixel, one float4 of logits per lane, the two
+// sums over bins by xor-shuffles inside the lane group -> every global access is a fully coalesced 128-bit transaction
+// (the thread-per-pixel kernel above strides 4-byte accesses by n*4 bytes across the warp).
+template <int BWD>
+__global__ void __launch_bounds__(256) depth_head_cl_kernel(const float* __restrict__ logits, const float* __restrict__ bins,
+                                                            const float* __restrict__ scale, int B, int n, int hw, int L,
+                                                            float min_depth, float max_depth, float* __restrict__ depth,
+                                                            float* __restrict__ disp, const float* __restrict__ gdepth,
+                                                            const float* __restrict__ gdisp, float* __restrict__ glogits) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t i = t / L;                       // pixel
+  const int sub = (int)(t % L);                 // float4 index inside the pixel's bin vector
+  const bool live_px = i < (size_t)B * hw;
+  const size_t ic = live_px ? i : 0;
+  const float4 lr = __ldg(reinterpret_cast<const float4*>(logits + ic * n) + sub);
+  const float4 bn = __ldg(reinterpret_cast<const float4*>(bins) + sub);
+  const float l[4] = {lr.x, lr.y, lr.z, lr.w}, bv[4] = {bn.x, bn.y, bn.z, bn.w};
+  float e[4], se = 0.f, sb = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e[k] = __expf(fminf(fmaxf(l[k], -10.f), 10.f));
+    se += e[k];
+    sb = fmaf(e[k], bv[k], sb);
+  }
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  const float sc = scale ? __ldg(scale + ic / hw) : 1.f;
+  const float raw = sb / se, d = raw * sc;
+  const float mn = min_depth * sc, mx = max_depth * sc;
+  if (!BWD) {
+    if (live_px && sub == 0) {
+      depth[i] = d;
+      disp[i] = (1.f / d - 1.f / mx) / (1.f / mn - 1.f / mx);
+    }
+  } else {
+    const float gd = gdepth ? __ldg(gdepth + ic) : 0.f, gs = gdisp ? __ldg(gdisp + ic) : 0.f;
+    const float g = (gd + gs * (-1.f / (d * d)) / (1.f / mn - 1.f / mx)) * sc;     // d L / d raw
+    const float rse = 1.f / se;
+    float o4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o4[k] = (l[k] >= -10.f && l[k] <= 10.f) ? g * (e[k] * rse) * (bv[k] - raw) : 0.f;
+    if (live_px) reinterpret_cast<float4*>(glogits + i * n)[sub] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
+static bool head_cl_ok(int n, int channels_last, int sigmoid_head, const void* logits, const void* bins, const void* out) {
+  const int L = n / 4;
+  return channels_last && !sigmoid_head && n % 4 == 0 && L >= 1 && L <= 32 && (L & (L - 1)) == 0 &&
+         ((uintptr_t)logits & 15) == 0 && ((uintptr_t)bins & 15) == 0 && ((uintptr_t)out & 15) == 0;
+}
+
 extern "C" int fsnet_depth_head_fwd(const float* logits, const float* bins, const float* scale, int B, int n, int h, int w,
                                     int channels_last, int sigmoid_head, float min_depth, float max_depth,
                                     float* depth, float* disp, void* stream) {
   FSNET_REQUIRE(logits && depth && disp && (sigmoid_head || bins), "fsnet_depth_head_fwd: null pointer");
   FSNET_REQUIRE(B > 0 && n > 0 && h > 0 && w > 0 && (!sigmoid_head || n == 1), "fsnet_depth_head_fwd: bad shape");
   size_t total = (size_t)B * h * w;
+  if (head_cl_ok(n, channels_last, sigmoid_head, logits, bins, nullptr)) {
+    const int L = n / 4;
+    depth_head_cl_kernel<0><<<(unsigned)((total * L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        logits, bins, scale, B, n, h * w, L, min_depth, max_depth, depth, disp, nullptr, nullptr, nullptr);
+    FSNET_LAUNCH_OK();
+    return FSNET_OK;
+  }
   depth_head_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       logits, bins, scale, B, n, h * w, channels_last, sigmoid_head, min_depth, max_depth, depth, disp);
   FSNET_LAUNCH_OK();
@@ -245,6 +304,13 @@ extern "C" int fsnet_depth_head_bwd(const float* logits, const float* bins, cons
   FSNET_REQUIRE(logits && grad_logits && (sigmoid_head || bins), "fsnet_depth_head_bwd: null pointer");
   FSNET_REQUIRE(B > 0 && n > 0 && h > 0 && w > 0 && (!sigmoid_head || n == 1), "fsnet_depth_head_bwd: bad shape");
   size_t total = (size_t)B * h * w;
+  if (head_cl_ok(n, channels_last, sigmoid_head, logits, bins, grad_logits)) {
+    const int L = n / 4;
+    depth_head_cl_kernel<1><<<(unsigned)((total * L + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        logits, bins, scale, B, n, h * w, L, min_depth, max_depth, nullptr, nullptr, grad_depth, grad_disp, grad_logits);
+    FSNET_LAUNCH_OK();
+    return FSNET_OK;
+  }
   depth_head_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       logits, bins, scale, B, n, h * w, channels_last, sigmoid_head, min_depth, max_depth, grad_depth, grad_disp, grad_logits);
   FSNET_LAUNCH_OK();

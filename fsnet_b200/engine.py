@@ -122,6 +122,7 @@ def _sync_world(bn) -> int:
 
 class Tape:
     """Forward executor + backward tape for one network invocation."""
+    _wgrad_tables: Dict = {}
 
     def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool, weights_fresh=False):
         self.states, self.training, self.need_grad = states, training, need_grad
@@ -137,12 +138,27 @@ class Tape:
         n_sums = sum(2 * st.C for st in self.states.values())
         n_acc = sum(st.w.acc_numel for st in self.states.values())
         n_zero = sum(st.c_real for st in self.states.values())
+        n_w = sum(st.conv.weight.numel() for st in self.states.values())
         self._pools = dict(sums=torch.zeros(n_sums, device=dev, dtype=torch.float64), acc=torch.zeros(n_acc, device=dev, dtype=torch.float32),
-                           zero=torch.zeros(n_zero, device=dev, dtype=torch.float32), off={})
-        o_s = o_a = o_z = 0
+                           zero=torch.zeros(n_zero, device=dev, dtype=torch.float32), off={},
+                           gw=torch.empty(n_w, device=dev, dtype=torch.float32), gw_off={}, gw_used=False)
+        o_s = o_a = o_z = o_w = 0
+        descs = []
         for key, st in self.states.items():
             self._pools["off"][key] = (o_s, o_a, o_z)
-            o_s += 2 * st.C; o_a += st.w.acc_numel; o_z += st.c_real
+            self._pools["gw_off"][key] = o_w
+            d = _lib.WgradDesc()
+            d.acc_off, d.grad_off = o_a, o_w
+            d.cout, d.cin, d.kh, d.kw, d.cout_pad, d.cin_pad = st.w.co, st.w.ci, st.kh, st.kw, st.w.co_pad, st.w.ci_pad
+            descs.append(d)
+            o_s += 2 * st.C; o_a += st.w.acc_numel; o_z += st.c_real; o_w += st.conv.weight.numel()
+        # the offsets only depend on the layer list: one device table per network, built on the first (eager) backward
+        sig = (id(self.states), len(self.states), n_acc, n_w)
+        if Tape._wgrad_tables.get("sig:%d" % id(self.states)) != sig:
+            raw = bytes((_lib.WgradDesc * len(descs))(*descs))
+            Tape._wgrad_tables[id(self.states)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            Tape._wgrad_tables["sig:%d" % id(self.states)] = sig
+        self._pools["gw_table"] = Tape._wgrad_tables[id(self.states)]
 
     def _pool(self, st: LayerState, which: str):
         if self._pools is None:
@@ -281,10 +297,12 @@ class Tape:
         """Weight gradient and (accumulated) data gradient of one convolution."""
         conv = st.conv
         if conv.weight.requires_grad:
-            acc = tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
-            gw = torch.empty_like(conv.weight)
-            _lib.call("fsnet_wgrad_to_param", acc, st.w.co, st.w.ci, st.kh, st.kw, st.w.co_pad, st.w.ci_pad, gw, 0)
-            self.param_grads[id(conv.weight)] = gw
+            tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
+            # the accumulator is re-laid out into this slice of the flat gradient buffer by ONE batched launch at the end
+            # of the backward pass (run_backward)
+            o_w = self._pools["gw_off"][id(st.conv)]
+            self.param_grads[id(conv.weight)] = self._pools["gw"][o_w:o_w + conv.weight.numel()].view_as(conv.weight)
+            self._pools["gw_used"] = True
         if not need_dgrad or x.grad is None:
             return
         k = st.kh
@@ -318,6 +336,10 @@ class Tape:
         g_view = out.gview()
         mask_view = out.pview() if (relu and up == 1) else None
         mask_ss = inv.ss if (relu and up == 2) else None
+        if relu and up == 1 and bn is not None and residual is None and down_state is None:
+            # no residual: the ReLU mask is sign(raw*scale+shift), recomputed from the raw output the kernels read anyway
+            # (saves the 4 bytes/element read of the activation planes in both BatchNorm-backward passes)
+            mask_view, mask_ss = None, inv.ss
         res_mode, res_view = 0, None
         if residual is not None and down_state is None and residual.grad is not None:
             if residual.grad.ring == 1 and not residual.grad_written:
@@ -388,6 +410,8 @@ class Tape:
         self.out_grads = out_grads
         for op in reversed(self.backward_ops):
             op()
+        if self._pools is not None and self._pools["gw_used"]:
+            _lib.call("fsnet_wgrad_to_param_batched", self._pools["gw_table"], len(self.states), self._pools["acc"], self._pools["gw"])
 
 
 # ---------------------------------------------------------------------------------------------------

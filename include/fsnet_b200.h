@@ -260,6 +260,14 @@ typedef struct {
 int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device, int n_layers, void* stream);
 int fsnet_wgrad_to_param(const float* acc, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad, float* grad,
                          int accumulate, void* stream);
+/* all layers of one backward pass in one launch: accumulator / gradient positions are element offsets from the two
+ * base pointers (the executor's pooled accumulator and its flat gradient buffer), so the device table is static */
+typedef struct {
+  long long acc_off, grad_off;
+  int cout, cin, kh, kw, cout_pad, cin_pad;
+} fsnet_wgrad_desc;
+int fsnet_wgrad_to_param_batched(const fsnet_wgrad_desc* table_device, int n_layers, const float* acc_base, float* grad_base,
+                                 void* stream);
 int fsnet_bn_finalize(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,
                       float* running_mean, float* running_var, long long* num_batches, float momentum, float eps,
                       int training, int C, float* scale_shift, float* mean_invstd, void* stream);

@@ -12,7 +12,8 @@ from vision_base.utils.utils import cfg_from_file, set_random_seed
 cfg = cfg_from_file(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "kitti_wpose_synthetic.py"))
 set_random_seed(123)
 model = build(**cfg.meta_arch).cuda().train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+from vision_base.networks.optimizers.optimizers import build_optimizer
+opt = build_optimizer(model, **cfg.optimizer)
 hook = build(**cfg.trainer.training_hook)
 data = make_batch(int(os.environ.get("B", 12)), 192, 640, device="cuda")
 for i in range(int(os.environ.get("STEPS", 3))):
