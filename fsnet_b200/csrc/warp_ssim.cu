@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) loss_bwd_kernel(LossParams p) 
   float gP[POSE ? 24 : 1];
 #pragma unroll
   for (int i = 0; i < (POSE ? 24 : 1); ++i) gP[i] = 0.f;
+  float acc_num = 0.f;                       // forward value of the owned pixels (fused forward+backward launches, p.accum != null)
 
   const int y_first = it.y_begin - 2, y_last = it.y_end + 1;
   const float4* lut_b = CAM == 1 ? p.lut + (size_t)(p.lut_idx ? __ldg(p.lut_idx + b) : 0) * HW : nullptr;
@@ -681,15 +682,19 @@ __global__ void __launch_bounds__(kWarps * 32, 3) loss_bwd_kernel(LossParams p) 
       }
       int win;                               // 0 / 1 = reprojection frame that wins, -1 = none
       const float gate = c_gate;
+      float best;
       if (use_ident) {
         const float i0 = fmaf(c_n0, 1e-5f, c_i0), i1 = fmaf(c_n1, 1e-5f, c_i1);
-        float best = fminf(i0, i1);
+        best = fminf(i0, i1);
         win = -1;
         if (ph[0] < best) { best = ph[0]; win = 0; }
-        if (ph[1] < best) { win = 1; }
+        if (ph[1] < best) { best = ph[1]; win = 1; }
       } else {
         win = ph[1] < ph[0] ? 1 : 0;
+        best = fminf(ph[0], ph[1]);
       }
+      // the forward sum counts every pixel once: the rows and columns this warp owns
+      if (p.accum != nullptr && out_lane && yc >= it.y_begin && yc < it.y_end) acc_num = fmaf(best, c_m, acc_num);
       if (win >= 0 && (!overlap || valid_prev[win])) {
         float gv = gbase * c_m * gate;
         float ws_ = (0.85f / 3.f) * gv;
@@ -804,6 +809,10 @@ __global__ void __launch_bounds__(kWarps * 32, 3) loss_bwd_kernel(LossParams p) 
       float v = warp_sum(gP[i]);
       if (lane == 0) atomicAdd(p.grad_P + (size_t)b * 24 + i, v);
     }
+  }
+  if (p.accum != nullptr) {
+    const double n = warp_sum((double)acc_num);
+    if (lane == 0) atomicAdd(p.accum, n);
   }
 }
 
@@ -948,6 +957,22 @@ __global__ void mei_depth_kernel(const float* __restrict__ norm, const float4* _
   depth[i] = __ldg(reinterpret_cast<const float*>(lut + (size_t)t * HW + px) + 2) * norm[i];
 }
 
+// sum of the patched mask (the normaliser of monodepth2_decoder.py:292); it does not depend on the depth, so the fused
+// forward+backward launches get it up front.  out[1] = sum(mask) (or `count` when there is no mask); out[0] is left alone.
+__global__ void __launch_bounds__(256) mask_sum_kernel(const void* __restrict__ mask, int mask_dtype, size_t n, double count,
+                                                       double* __restrict__ out, int n_out, int out_stride) {
+  double acc = 0.0;
+  if (mask != nullptr) {
+    float a = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a += load_mask(mask, mask_dtype, i);
+    acc = warp_sum((double)a);
+  } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+    acc = count;
+  }
+  if ((threadIdx.x & 31) == 0 && acc != 0.0)
+    for (int k = 0; k < n_out; ++k) atomicAdd(out + (size_t)k * out_stride + 1, acc);
+}
+
 // Rows per warp-item: minimise (number of waves) x (rows + halo rows) given how many warps are resident
 // (148 SMs x warps/SM allowed by the kernel's registers), so that no second, mostly empty wave is left.
 int plan(LossParams& p, int cols_per_warp, int halo_rows, int warps_per_sm) {
@@ -1034,7 +1059,7 @@ static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
                       const void* mask, int mask_dtype, const float* cam,
                       const float* ident, const float* noise, const float* motion, unsigned flags,
                       int B, int H, int W, const double* accum, const float* gout,
-                      float* grad_depth, float* grad_P, void* stream) {
+                      float* grad_depth, float* grad_P, void* stream, double* accum_out = nullptr) {
   int rc = check_common(depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, motion, flags, B, H, W);
   if (rc) return rc;
   FSNET_REQUIRE(accum && gout && grad_depth, "fsnet_warp_ssim_bwd: null pointer");
@@ -1042,7 +1067,7 @@ static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
   p.depth = depth_s; p.hs = hs; p.ws = ws; p.packed = reinterpret_cast<const float4*>(packed);
   p.mask = mask; p.mask_dtype = mask_dtype; p.cam = cam; p.ident = ident; p.noise = noise; p.motion = motion;
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
-  p.grad_depth = grad_depth; p.grad_P = grad_P;
+  p.grad_depth = grad_depth; p.grad_P = grad_P; p.accum = accum_out;
   p.lut = reinterpret_cast<const float4*>(lut); p.lut_idx = lut_idx;
   int blocks = plan(p, 28, 4, 12);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1124,4 +1149,24 @@ extern "C" int fsnet_mei_depth(const float* norm, const float* lut, const int* l
   mei_depth_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(norm, reinterpret_cast<const float4*>(lut), lut_idx, B, H * W, depth);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
+}
+
+extern "C" int fsnet_mask_sum(const void* mask, int mask_dtype, long long n, double* out, int n_out, int out_stride, void* stream) {
+  FSNET_REQUIRE(out && n > 0 && n_out > 0 && out_stride >= 2, "fsnet_mask_sum: bad arguments");
+  FSNET_REQUIRE((mask == nullptr) == (mask_dtype == FSNET_MASK_NONE) && mask_dtype >= 0 && mask_dtype <= 2, "fsnet_mask_sum: mask pointer / dtype mismatch");
+  const int grid = mask ? (int)((n + 256 * 16 - 1) / (256 * 16) < 148 * 8 ? (n + 256 * 16 - 1) / (256 * 16) : 148 * 8) : 1;
+  mask_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, mask_dtype, (size_t)n, (double)n, out, n_out, out_stride);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_warp_ssim_fwdbwd(const float* lut, const int* lut_idx,
+                                      const float* depth_s, int hs, int ws, const float* packed,
+                                      const void* mask, int mask_dtype, const float* cam,
+                                      const float* ident, const float* noise, const float* motion, unsigned flags,
+                                      int B, int H, int W, double* accum, const float* gout,
+                                      float* grad_depth, float* grad_P, void* stream) {
+  FSNET_REQUIRE(lut == nullptr || ((uintptr_t)lut & 15) == 0, "fsnet_warp_ssim_fwdbwd: ray table must be 16-byte aligned");
+  return launch_bwd(lut ? 1 : 0, lut, lut_idx, depth_s, hs, ws, packed, mask, mask_dtype, cam, ident, noise, motion, flags,
+                    B, H, W, accum, gout, grad_depth, grad_P, stream, accum);
 }

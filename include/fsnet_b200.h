@@ -106,6 +106,26 @@ int fsnet_warp_ssim_bwd(const float* depth_s, int hs, int ws, const float* packe
                         float* grad_depth, float* grad_P, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * fused forward + backward of the per-scale reprojection loss for training steps: ONE pass computes the masked sum of
+ * the per-pixel minimum (the forward value) and, by the same recomputation-free walk, d loss / d depth_s (and d loss /
+ * d P).  The normaliser sum(patched_mask) of monodepth2_decoder.py:292 does not depend on the depth, so it is produced
+ * up front by fsnet_mask_sum; the upstream gradient enters as `gout` (d total / d this scale's term -- the executor
+ * runs the kernel with the unit gradient 1/num_scales during the forward and rescales in backward, which is exact
+ * because the loss is linear in it).  Saves the separate forward launch (~100 us per scale at cfg2).
+ *   fsnet_mask_sum: out[k*out_stride + 1] += sum(mask) for k < n_out (mask == NULL: += n); `out` zeroed by the caller
+ *   fsnet_warp_ssim_fwdbwd: arguments as fsnet_warp_ssim_bwd (+ the MEI ray table, NULL for the pinhole camera);
+ *   accum [2] fp64: accum[1] = sum(mask) on entry (read), accum[0] += sum(min * mask)
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_mask_sum(const void* mask, int mask_dtype, long long n, double* out, int n_out, int out_stride, void* stream);
+int fsnet_warp_ssim_fwdbwd(const float* lut, const int* lut_idx,
+                           const float* depth_s, int hs, int ws, const float* packed,
+                           const void* mask, int mask_dtype, const float* cam,
+                           const float* ident, const float* noise, const float* motion,
+                           unsigned flags, int B, int H, int W,
+                           double* accum, const float* gout,
+                           float* grad_depth, float* grad_P, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * MEI (unified omnidirectional) fisheye camera -- FishEyeDecoder (monodepth2_decoder.py:350-420)
  * with MeiCameraProjection (monodepth/networks/utils/mei_fisheye_utils.py).
  *
