@@ -207,12 +207,17 @@ def main():
     launches = launches_per_step * args.steps
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
-    # roofline leg: the same training steps run eagerly so that the fused warp-SSIM launches can be bracketed
-    # with CUDA events on their stream (events cannot be read back from inside a replayed graph)
-    _lib.profile_entry("fsnet_warp_ssim_fwd", True)
+    # roofline leg: the same training steps run eagerly so that the kernels can be bracketed with CUDA events on their
+    # stream (events cannot be read back from inside a replayed graph)
+    LOSS_ENTRY = "fsnet_warp_ssim_fwdbwd"
+    _lib.profile_entry(LOSS_ENTRY, True)
+    _lib.profile_entry("fsnet_conv", True, tag=lambda a: a[9])       # a[9] = number of tensor-core products (3 = forward)
     timed(min(args.steps, 5), False, probe_hook)
-    kern_us = _lib.profile_results("fsnet_warp_ssim_fwd")        # per-launch CUDA-event times (us), scale order
-    _lib.profile_entry("fsnet_warp_ssim_fwd", False)
+    kern_us = _lib.profile_results(LOSS_ENTRY)                       # per-launch CUDA-event times (us), scale order
+    conv_rows = _lib.profile_results("fsnet_conv", with_tags=True)
+    _lib.profile_entry(LOSS_ENTRY, False)
+    _lib.profile_entry("fsnet_conv", False)
+    probe_steps = min(args.steps, 5)
 
     if rank != 0:
         return _finish(world)
@@ -220,9 +225,24 @@ def main():
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
     peak, peak_src = peaks()
-    bytes_per_launch = sum(B_PER_GPU * H * W * (40 + 8 / 4 ** s) for s in SCALES) / len(SCALES)
+    # backward-by-recomputation bytes B*HW*(40 + 16/4^s); the fused launch also produces the forward sums
+    bytes_per_launch = sum(B_PER_GPU * H * W * (40 + 16 / 4 ** s) for s in SCALES) / len(SCALES)
     avg_us = sum(kern_us) / max(len(kern_us), 1) if kern_us else float("nan")
     achieved = bytes_per_launch / (avg_us * 1e-6) / 1e9 if kern_us else None
+    traffic = None
+    prof = os.path.join(REPO, "profiles", "r1_loss_fwdbwd_ncu.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    # tensor-bound leg: all forward convolutions of one step (34 launches), SURVEY.md 8(d): 17.02 GFLOP per image at cfg2
+    fwd_us = sum(t for t, tag in conv_rows if tag == 3) / max(probe_steps, 1)
+    conv_flops = 17.02e9 * B_PER_GPU
+    tf_peak = 1364.9
+    pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            tf_peak = float(json.load(f).get("bf16_tflops_sustained", tf_peak))
+    conv_tf = conv_flops / (fwd_us * 1e-6) / 1e12 if fwd_us > 0 else None
     line = {
         "metric": "images/sec (640x192 triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -233,10 +253,16 @@ def main():
                    "conv_backend": ops.BACKEND,
                    "cuda_graph": use_graph,
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
-        "roofline": {"kernel": "loss_fwd_kernel<1> (fused warp-SSIM forward, one launch per scale)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
+        "roofline": {"kernel": "loss_bwd_kernel<0,0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": traffic, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
+        "roofline_conv": {"kernel": "conv_tc_kernel<3> (all 34 forward convolutions of the depth net, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
+                          "bound": "tensor", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
+                          "frac": (conv_tf / tf_peak) if conv_tf else None, "us_per_step": fwd_us,
+                          "algorithmic_flops_per_step": conv_flops,
+                          "note": "useful fp32-equivalent FLOPs; the tensor pipe executes 3x as many (bf16x3 split)",
+                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
         "gpu_launches": launches, "clocks": clocks,

@@ -40,18 +40,28 @@ def reset_counters():
     kernel_launches = 0
 
 
-def profile_entry(name, on=True):
-    """Bracket every call of `name` with CUDA events on the launching stream (bench.py's roofline leg)."""
+_profile_tags = {}         # entry name -> function(args) -> tag stored with each timed launch
+
+
+def profile_entry(name, on=True, tag=None):
+    """Bracket every call of `name` with CUDA events on the launching stream (bench.py's roofline leg).
+    ``tag(args)`` (optional) labels each launch, e.g. with the number of tensor-core products of fsnet_conv."""
     if on:
         _profiled[name] = []
+        if tag is not None:
+            _profile_tags[name] = tag
     else:
         _profiled.pop(name, None)
+        _profile_tags.pop(name, None)
 
 
-def profile_results(name):
+def profile_results(name, with_tags=False):
     """Per-launch durations in microseconds (synchronises)."""
     torch.cuda.synchronize()
-    return [a.elapsed_time(b) * 1e3 for a, b in _profiled.get(name, [])]
+    rows = _profiled.get(name, [])
+    if with_tags:
+        return [(r[0].elapsed_time(r[1]) * 1e3, r[2]) for r in rows]
+    return [r[0].elapsed_time(r[1]) * 1e3 for r in rows]
 
 
 class FsnetError(RuntimeError):
@@ -137,7 +147,8 @@ def call(name, *args):
         ev0.record()
         rc = fn(*cargs)
         ev1.record()
-        rec.append((ev0, ev1))
+        tagger = _profile_tags.get(name)
+        rec.append((ev0, ev1, tagger(args) if tagger else None))
     else:
         rc = fn(*cargs)
     launch_count += 1
