@@ -605,6 +605,10 @@ struct WgradParams {
   uint32_t tmem_cols;
   uint32_t a_layout, b_layout;
   float* acc;
+  // folded mode (thin 3x3 layers, the 7x7 stem): the N operand is a 64-element slice of the "fat pixel" (KW taps x Cin
+  // channels, contiguous in NHWC, read through an overlapping-stride tensor map), one work item per KERNEL ROW:
+  // KW x fewer MMAs and dy re-reads than one item per tap.  taps = KH, ci_tiles = slices, row_elems = KW * Cin.
+  int fold, row_elems;
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -660,9 +664,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         mbar_expect_tx(&full_bar[stage], p.tx_bytes);
         for (int a = 0; a < p.nA; ++a)
           tma_load_4d(st + a * p.a_atom_bytes, &map_dy, &full_bar[stage], cot * 128 + a * p.atomA, xo, yo, img);
-        for (int b = 0; b < p.nB; ++b)
-          tma_load_4d(st + p.a_bytes + b * p.b_atom_bytes, &map_x, &full_bar[stage], cit * p.BN + b * p.atomB,
-                      xo * p.stride + s - p.pad + p.org, yo * p.stride + r - p.pad + p.org, img);
+        if (p.fold) {
+          tma_load_4d(st + p.a_bytes, &map_x, &full_bar[stage], cit * 64, xo, yo * p.stride + tap, img);
+        } else {
+          for (int b = 0; b < p.nB; ++b)
+            tma_load_4d(st + p.a_bytes + b * p.b_atom_bytes, &map_x, &full_bar[stage], cit * p.BN + b * p.atomB,
+                        xo * p.stride + s - p.pad + p.org, yo * p.stride + r - p.pad + p.org, img);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -696,8 +704,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int co = cot * 128 + m;
     const bool valid = m < p.BM_real && co < p.Cout;
-    float* dst = p.acc + ((size_t)co * p.taps + tap) * p.Cin + cit * p.BN;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    float* dst = p.acc + ((size_t)co * p.taps + tap) * p.row_elems + cit * p.BN;
+    const int n_cols = min(p.BN, p.row_elems - cit * p.BN);       // folded mode: the last slice is partly padding
+    for (int c0 = 0; c0 < n_cols; c0 += 16) {
       uint32_t raw[16];
       tmem_ld16(taddr + c0, raw);
       tmem_ld_wait();
@@ -746,6 +755,17 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   p.BN = p.Cin <= 128 ? p.Cin : (p.Cin % 128 == 0 ? 128 : (p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16)));
   FSNET_REQUIRE(p.Cin % p.BN == 0, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
   p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
+  p.row_elems = p.Cin;
+  static int wfold_env = -1;
+  if (wfold_env < 0) { const char* e = getenv("FSNET_WGRAD_FOLD"); wfold_env = e ? atoi(e) : 1; }
+  p.fold = wfold_env && use_ring && x->ring == pad && x->c_off == 0 && x->c == x->c_total &&
+           ((stride == 1 && KH == 3 && KW == 3 && pad == 1 && p.Cin < 64) || (stride == 2 && KH == 7 && KW == 7 && pad == 3 && p.Cin == 16));
+  if (p.fold) {
+    p.row_elems = KW * p.Cin;
+    p.taps = KH;
+    p.BN = 64; p.atomB = 64; p.nB = 1;
+    p.ci_tiles = ceil_div(p.row_elems, 64);
+  }
   // thin layers get more pixels per stage so that one stage moves >= 16 KB
   p.pix = 64;
   while (false && p.pix < 128 && (size_t)(p.pix * 2) * (p.nA * p.atomA + p.BN) * 2 <= 32 * 1024 && (size_t)p.pix * 2 <= (size_t)p.Ho * p.Wo) p.pix *= 2;
@@ -784,8 +804,21 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   CUtensorMap mdy, mx;
   int rc = encode_act_map(&mdy, dy, 0, 0, p.atomA, p.PW, p.PH, 1, "fsnet_conv_wgrad");
   if (rc) return rc;
-  rc = encode_act_map(&mx, x, 0, use_ring, p.atomB, p.PW, p.PH, stride, "fsnet_conv_wgrad");
-  if (rc) return rc;
+  if (p.fold) {
+    EncodeTiledFn enc = encode_fn();
+    FSNET_REQUIRE(enc != nullptr, "fsnet_conv_wgrad: cuTensorMapEncodeTiled not available from the driver");
+    const int pw = x->w + 2 * x->ring, ph = x->h + 2 * x->ring;
+    cuuint64_t adim[4] = {(cuuint64_t)(64 * p.ci_tiles), (cuuint64_t)p.Wo, (cuuint64_t)ph, (cuuint64_t)p.N};
+    cuuint64_t astr[3] = {(cuuint64_t)stride * p.Cin * 2, (cuuint64_t)pw * p.Cin * 2, (cuuint64_t)ph * pw * p.Cin * 2};
+    cuuint32_t abox[4] = {64, (cuuint32_t)p.PW, (cuuint32_t)(p.PH * stride), 1};
+    cuuint32_t aes[4] = {1, 1, (cuuint32_t)stride, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, adim, astr, abox, aes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv_wgrad: cuTensorMapEncodeTiled(folded x) failed with %d", (int)r);
+  } else {
+    rc = encode_act_map(&mx, x, 0, use_ring, p.atomB, p.PW, p.PH, stride, "fsnet_conv_wgrad");
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     FSNET_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

@@ -297,7 +297,8 @@ class Tape:
         """Weight gradient and (accumulated) data gradient of one convolution."""
         conv = st.conv
         if conv.weight.requires_grad:
-            tc.conv_wgrad(x.pview(), st.replicate, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
+            use_ring = st.replicate or (x.zero_ring and x.planes.ring == st.pad)
+            tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
             # the accumulator is re-laid out into this slice of the flat gradient buffer by ONE batched launch at the end
             # of the backward pass (run_backward)
             o_w = self._pools["gw_off"][id(st.conv)]

@@ -1,0 +1,74 @@
+"""tcgen05 convolution kernels (forward bf16x3, data gradient, weight gradient) against torch.nn.functional.conv2d in fp32,
+layer shapes of the in-scope networks incl. the folded-tap paths (thin replicate layers, the 7x7/2 stem on a zero ring)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+CASES = [
+    # N, Cin, Cout, H, W, k, stride, pad, mode      mode: "zero" (TMA OOB fill), "rep" (replicate ring), "zring" (materialised zero ring)
+    (2, 64, 64, 24, 40, 3, 1, 1, "zero"),
+    (2, 16, 16, 48, 80, 3, 1, 1, "rep"),
+    (2, 32, 16, 24, 48, 3, 1, 1, "rep"),
+    (2, 96, 32, 24, 48, 3, 1, 1, "rep"),
+    (2, 3, 64, 48, 80, 7, 2, 3, "zring"),
+    (3, 6, 64, 64, 96, 7, 2, 3, "zring"),
+    (2, 3, 64, 48, 80, 7, 2, 3, "zero"),
+    (2, 64, 128, 24, 40, 3, 2, 1, "zero"),
+    (2, 256, 512, 6, 10, 3, 1, 1, "zero"),
+    (2, 128, 256, 12, 20, 1, 2, 0, "zero"),
+]
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,k,stride,pad,mode", CASES)
+def test_conv_forward_and_gradients(N, Cin, Cout, H, W, k, stride, pad, mode):
+    from fsnet_b200 import _lib, tc
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).requires_grad_(True)
+    rep = mode == "rep"
+    xin = F.pad(x, (pad,) * 4, mode="replicate") if rep else x
+    y = F.conv2d(xin, w, stride=stride, padding=0 if rep else pad)
+    gy = torch.randn(y.shape, device="cuda", generator=g)
+    gx_ref, gw_ref = torch.autograd.grad(y, (x, w), gy)
+    ring = pad if mode == "zring" else 1
+    xp = tc.Planes(N, H, W, tc.pad16(Cin), ring, zero=True)
+    _lib.call("fsnet_image_to_planes_ring", x.detach().contiguous(), Cin, xp.view(), int(mode == "zring"))
+    use_ring = mode in ("rep", "zring")
+    cw = tc.ConvWeights(w)
+    cw.refresh(w)
+    Ho, Wo = y.shape[-2:]
+    out = tc.Fp32(N, Ho, Wo, cw.co_pad)
+    stats = torch.zeros(2 * cw.co_pad, device="cuda", dtype=torch.float64)
+    tc.conv(xp, cw, out, stride, pad, use_ring=use_ring, stats=stats)
+    assert rel(out.nchw()[:, :Cout], y.detach()) < 2e-5                      # bf16x3 split operands: fp32-class accuracy
+    assert rel(stats[:Cout], y.detach().double().sum((0, 2, 3))) < 1e-4       # fused BatchNorm statistics
+    assert rel(stats[cw.co_pad:cw.co_pad + Cout], (y.detach().double() ** 2).sum((0, 2, 3))) < 1e-4
+    # weight gradient (single bf16 product)
+    dy = tc.Planes(N, Ho, Wo, cw.co_pad, ring=0, zero=True)
+    dy.t[0, :, :, :, :Cout] = gy.permute(0, 2, 3, 1).bfloat16()
+    acc = tc.conv_wgrad(xp.view(), use_ring, dy.view(), cw, stride, pad)
+    gw = torch.zeros_like(w)
+    _lib.call("fsnet_wgrad_to_param", acc, Cout, Cin, k, k, cw.co_pad, cw.ci_pad, gw, 0)
+    assert rel(gw, gw_ref) < 1e-2, rel(gw, gw_ref)
+    # per-tap check: a permutation of taps would keep the norm but not this
+    assert rel(gw[:, :, 0, k - 1], gw_ref[:, :, 0, k - 1]) < 2e-2 and rel(gw[:, :, k - 1, 0], gw_ref[:, :, k - 1, 0]) < 2e-2
+    # data gradient of the stride-1 layers
+    if stride == 1:
+        if rep:
+            gx = tc.Fp32(N, H, W, cw.ci_pad, ring=1)
+            full = tc.View(gx.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
+            tc.conv_dgrad(dy, cw, full, pad=k - 1)
+            _lib.call("fsnet_fold_ring", gx.view())
+        else:
+            gx = tc.Fp32(N, H, W, cw.ci_pad)
+            tc.conv_dgrad(dy, cw, gx.view(), pad=k - 1 - pad)
+        assert rel(gx.nchw()[:, :Cin], gx_ref) < 1e-2
