@@ -335,17 +335,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
           if (p.fold == 2) {
             // kernel row rr reads the halo tile rr*TW rows further down (a whole number of 1024-byte swizzle atoms)
+            // the last 64-element slice of a fat pixel is partly padding (zero weights): skip its dead K-steps
+            const int ks2 = min(ksteps, (p.KW * p.Cin - kit * 64 + 15) >> 4);
             for (int rr = 0; rr < p.KH; ++rr) {
               const uint64_t a_hi = make_desc(st + rr * p.tap_bytes, p.sbo, p.layout_type);
               const uint64_t b_hi = make_desc(st + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
-              for (int k = 0; k < ksteps; ++k)
+              for (int k = 0; k < ks2; ++k)
                 umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (kit | rr | k) != 0);
               if (NPROD == 3) {
                 const uint32_t lo = st + p.a_bytes + p.b_bytes;
                 const uint64_t a_lo = make_desc(lo + rr * p.tap_bytes, p.sbo, p.layout_type);
                 const uint64_t b_lo = make_desc(lo + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
-                for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
-                for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
+                for (int k = 0; k < ks2; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
+                for (int k = 0; k < ks2; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
               }
             }
             umma_commit(&empty_bar[stage]);
@@ -354,13 +356,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           const uint64_t a_hi = make_desc(st, p.sbo, p.layout_type);
           const uint64_t b_hi = make_desc(st + p.a_bytes, p.sbo, p.layout_type);
-          for (int k = 0; k < ksteps; ++k)
+          // folded rows: stage kit holds slice (kit % cchunks) of a fat pixel; its padding K-steps are skipped
+          const int ks1 = p.fold ? min(ksteps, (p.KW * p.Cin - (kit % p.cchunks) * 64 + 15) >> 4) : ksteps;
+          for (int k = 0; k < ks1; ++k)
             umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (kit | k) != 0);
           if (NPROD == 3) {
             const uint64_t a_lo = make_desc(st + p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
             const uint64_t b_lo = make_desc(st + 2 * p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
-            for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
-            for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
+            for (int k = 0; k < ks1; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
+            for (int k = 0; k < ks1; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
           }
           umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
