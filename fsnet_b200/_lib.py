@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfsnet_b200.so")
+LIB_PATH = os.environ.get("FSNET_B200_LIB") or os.path.join(_HERE, "lib", "libfsnet_b200.so")   # override: kernel-variant experiments
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fsnet_b200.h")
 
 class WeightDesc(ctypes.Structure):

@@ -15,6 +15,9 @@
 namespace fsnet {
 namespace {
 
+#ifndef LOSS_BWD_OCC
+#define LOSS_BWD_OCC 3
+#endif
 constexpr int kWarps = 4;                 // warps per block
 constexpr float k81C1 = 81.f * 1e-4f;     // 81 * 0.01^2   (sums instead of means: everything scaled by 9^2)
 constexpr float k81C2 = 81.f * 9e-4f;     // 81 * 0.03^2
@@ -554,7 +557,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) loss_fwd_kernel(LossParams p) 
 // POSE=1 additionally reduces d loss / d P (12 numbers per frame).
 // ------------------------------------------------------------------------------------------------
 template <int POSE, int CAM>
-__global__ void __launch_bounds__(kWarps * 32, 3) loss_bwd_kernel(LossParams p) {
+__global__ void __launch_bounds__(kWarps * 32, LOSS_BWD_OCC) loss_bwd_kernel(LossParams p) {
   constexpr int NV = POSE ? 22 : 15;        // delayed values per pixel
   __shared__ float s_cam[kWarps][42];
   __shared__ float s_delay[kWarps][3][NV][32];
@@ -1069,7 +1072,7 @@ static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
   p.grad_depth = grad_depth; p.grad_P = grad_P; p.accum = accum_out;
   p.lut = reinterpret_cast<const float4*>(lut); p.lut_idx = lut_idx;
-  int blocks = plan(p, 28, 4, 12);
+  int blocks = plan(p, 28, 4, 4 * LOSS_BWD_OCC);
   cudaStream_t st = (cudaStream_t)stream;
   if (cam_model == 0) {
     if (grad_P) loss_bwd_kernel<1, 0><<<blocks, kWarps * 32, 0, st>>>(p);
