@@ -28,6 +28,17 @@ import torch.distributed as dist  # noqa: E402
 B_PER_GPU, H, W = 12, 192, 640
 SCALES = (0, 1, 2, 3)
 CONFIG = os.path.join(REPO, "configs", "kitti_wpose_synthetic.py")
+# --workload: the default is BASELINE.json's configs[1] (what the driver runs); the others are extra, informational lines
+WORKLOADS = {
+    "cfg2a": dict(config="kitti_wpose_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02,
+                  text="cfg2a kitti_wpose_synthetic: ResNet-18 depth net, 192x640, 4 scales, 16 bins, dataset poses, fwd+bwd+clip(35)+Adam"),
+    "cfg2b": dict(config="kitti_posenet_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02 + 2 * 9.776,
+                  text="cfg2b kitti_posenet_synthetic: MonoDepthMeta, ResNet-18 depth net + ResNet-18 PoseNet (2 pairs), 192x640, 4 scales, "
+                       "fwd+bwd+clip(35)+Adam"),
+    "cfg5": dict(config="kitti360_fisheye_synthetic.py", B=4, H=512, W=512, fisheye=True, gflop_per_image=18.95 + 24.16,
+                 text="cfg5 kitti360_fisheye_synthetic: FishEyeDecoder (MEI camera), ResNet-18, 512x512, 4 scales, 64 bins, dataset poses, "
+                      "is_log_image (default True), fwd+bwd+clip(1)+Adam"),
+}
 
 
 def peaks():
@@ -121,7 +132,11 @@ def main():
     ap.add_argument("--backend", default=os.environ.get("FSNET_CONV_BACKEND", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA graph replay)")
+    ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS), help="cfg2a = BASELINE.json configs[1] (default)")
     args = ap.parse_args()
+    global B_PER_GPU, H, W, CONFIG
+    wl = WORKLOADS[args.workload]
+    B_PER_GPU, H, W, CONFIG = wl["B"], wl["H"], wl["W"], os.path.join(REPO, "configs", wl["config"])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -137,7 +152,7 @@ def main():
 
     from fsnet_b200 import _lib
     from fsnet_b200.networks import ops
-    from fsnet_b200.data.synthetic import make_batch
+    from fsnet_b200.data.synthetic import make_batch, make_fisheye_batch
     from vision_base.utils.builder import build
     from vision_base.utils.utils import cfg_from_file, set_random_seed
 
@@ -165,10 +180,10 @@ def main():
     hook = build(**dict(cfg.trainer.training_hook, cuda_graph=use_graph))
     probe_hook = build(**dict(cfg.trainer.training_hook, cuda_graph=False))     # eager steps for per-kernel event timing
 
-    host = make_batch(B_PER_GPU, H, W, seed=1234 + rank)
-    pinned = {k: v.pin_memory() for k, v in host.items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    host = (make_fisheye_batch if wl["fisheye"] else make_batch)(B_PER_GPU, H, W, seed=1234 + rank)
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
 
     def barrier():
         if world > 1:
@@ -209,7 +224,8 @@ def main():
     ms_e2e, last_loss = timed(args.steps, True)
     # roofline leg: the same training steps run eagerly so that the kernels can be bracketed with CUDA events on their
     # stream (events cannot be read back from inside a replayed graph)
-    LOSS_ENTRY = "fsnet_warp_ssim_fwdbwd"
+    # (is_log_image heads need the forward-only kernel for their hm outputs: forward and backward are separate launches)
+    LOSS_ENTRY = "fsnet_warp_ssim_fwdbwd" if not wl["fisheye"] else "fsnet_warp_ssim_mei_bwd"
     _lib.profile_entry(LOSS_ENTRY, True)
     _lib.profile_entry("fsnet_conv", True, tag=lambda a: a[9])       # a[9] = number of tensor-core products (3 = forward)
     timed(min(args.steps, 5), False, probe_hook)
@@ -236,7 +252,7 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     # tensor-bound leg: all forward convolutions of one step (34 launches), SURVEY.md 8(d): 17.02 GFLOP per image at cfg2
     fwd_us = sum(t for t, tag in conv_rows if tag == 3) / max(probe_steps, 1)
-    conv_flops = 17.02e9 * B_PER_GPU
+    conv_flops = wl["gflop_per_image"] * 1e9 * B_PER_GPU
     tf_peak = 1364.9
     pk = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -247,8 +263,7 @@ def main():
         "metric": "images/sec (640x192 triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (convs: " + ops.precision_note() + ")", "data": "synthetic",
-        "config": {"workload": "cfg2a kitti_wpose_synthetic: ResNet-18 depth net, 192x640, 4 scales, 16 bins, dataset poses, "
-                               "fwd+bwd+clip(35)+Adam", "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
+        "config": {"workload": wl["text"], "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
                    "parallelism": f"dp{world}" + (" (SyncBN statistics + flat gradient all-reduce over NCCL, inside the step graph)" if world > 1 else ""),
                    "conv_backend": ops.BACKEND,
                    "cuda_graph": use_graph,
@@ -257,7 +272,7 @@ def main():
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
-        "roofline_conv": {"kernel": "conv_tc_kernel<3> (all 34 forward convolutions of the depth net, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
+        "roofline_conv": {"kernel": "conv_tc_kernel<3> (all forward convolutions of one step, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
                           "bound": "tensor", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
                           "frac": (conv_tf / tf_peak) if conv_tf else None, "us_per_step": fwd_us,
                           "algorithmic_flops_per_step": conv_flops,
@@ -267,7 +282,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
         "gpu_launches": launches, "clocks": clocks,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2a":
         rate, sec = oracle_step_rate(4, 2, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/, torch CPU fp32)"}
