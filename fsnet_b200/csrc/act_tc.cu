@@ -663,9 +663,12 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   // at most 16 pixels per thread, but never fewer than ~2 blocks per SM: the small deep layers were latency bound
   // with a few dozen blocks walking their pixels serially
   size_t per_thread = npix / ((size_t)pix_per_iter * 296);
-  per_thread = per_thread < 1 ? 1 : (per_thread > 16 ? 16 : per_thread);
+  per_thread = per_thread < 4 ? 4 : (per_thread > 16 ? 16 : per_thread);
   unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * per_thread - 1) / ((size_t)pix_per_iter * per_thread));
   if (grid > 148 * 4) grid = 148 * 4;
+  // every block ends with 2C fp64 atomics on the same 2C addresses: wide layers get fewer blocks
+  const unsigned cap = (unsigned)(49152 / raw->c) > 24u ? (unsigned)(49152 / raw->c) : 24u;
+  if (grid > cap) grid = cap;
   if (grid == 0) grid = 1;
   bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();

@@ -79,21 +79,24 @@ class _ReprojectionLoss(torch.autograd.Function):
         ctx.need_pose = any(ctx.needs_input_grad[2 + 2 * S + j] for j in range(2))
         # Training steps: ONE launch per scale computes the forward sums AND d loss / d depth (for the unit upstream gradient
         # 1/S; backward() rescales -- the loss is linear in it).  The log-image outputs need the forward-only kernel.
-        fused = sel is None and (any(ctx.needs_input_grad[2 + i] for i in range(S)) or ctx.need_pose)
-        ctx.fused = fused
+        need_grad = any(ctx.needs_input_grad[2 + i] for i in range(S)) or ctx.need_pose
+        # per scale: only the scale that feeds the log images (scale 0 of a log-image head) keeps separate launches
+        fused_s = [need_grad and not (sel is not None and s == 0) for s in cfg["scales"]]
+        fused = any(fused_s)
+        ctx.fused = fused_s
+        unit_gd, unit_gP = [None] * S, None
         if fused:
             _lib.call("fsnet_mask_sum", mask_c, mdt, _lib.ctypes.c_longlong(B * H * W), acc, S, 4)
             unit = torch.full((1,), 1.0 / S, device=dev, dtype=torch.float32)
             unit_gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
-            unit_gd = []
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
-            if fused:
+            if fused_s[i]:
                 gd = (torch.empty if (hs == H and ws == W) else torch.zeros)(depths[i].shape, device=dev, dtype=torch.float32)
                 _lib.call("fsnet_warp_ssim_fwdbwd", *(lut_args if lut_args else (None, None)), depths[i], hs, ws, packed, mask_c, mdt, cam,
                           ident, noise_c[i], motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], unit, gd, unit_gP)
-                unit_gd.append(gd)
+                unit_gd[i] = gd
             else:
                 _lib.call(warp_fwd, *lut_args, depths[i], hs, ws, packed, mask_c, mdt, cam, ident, noise_c[i],
                           motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
@@ -104,7 +107,7 @@ class _ReprojectionLoss(torch.autograd.Function):
         _lib.call("fsnet_loss_finalize", acc, S, stats)
         ctx.S, ctx.cfg, ctx.flags, ctx.mdt = S, cfg, flags, mdt
         ctx.shapes = (B, H, W)
-        ctx.unit_grads = (unit_gd, unit_gP) if fused else None
+        ctx.unit_grads = (unit_gd, unit_gP)
         ctx.save_for_backward(*depths, *disps, tgt, packed, cam, P2c, acc, sums,
                               *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
                               *( [motion_c] if motion_c is not None else []), *[n for n in noise_c if n is not None])
@@ -136,14 +139,13 @@ class _ReprojectionLoss(torch.autograd.Function):
         gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
         mei = cfg.get("mei")
         warp_bwd, lut_args = ("fsnet_warp_ssim_bwd", ()) if mei is None else ("fsnet_warp_ssim_mei_bwd", (mei["lut"], mei["lut_idx"]))
-        if ctx.fused:
-            unit_gd, unit_gP = ctx.unit_grads
-            gscale = g_total.detach().to(torch.float32)          # gradients were computed for d total / d loss = 1
-            if gP is not None:
-                gP = unit_gP * gscale
+        unit_gd, unit_gP = ctx.unit_grads
+        gscale = g_total.detach().to(torch.float32)              # fused launches computed their gradients for d total / d loss = 1
+        if gP is not None and unit_gP is not None:
+            gP = unit_gP * gscale                                # the non-fused scales below accumulate into it
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
-            if ctx.fused:
+            if ctx.fused[i]:
                 g_depths.append(unit_gd[i] * gscale)
             else:
                 full = (hs == H and ws == W)
