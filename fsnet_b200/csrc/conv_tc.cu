@@ -26,7 +26,7 @@
 namespace fsnet {
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // warp 0 TMA producer, 1 MMA issuer, 2-5 epilogue
 constexpr int kMaxStages = 8;
 
 struct ConvParams {
@@ -94,6 +94,28 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// elected (warp-converged) variants, see umma_bf16_elect
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -114,6 +136,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Warp-converged variants: the whole (converged) warp executes the statement, one elected lane issues the instruction.
+// Keeping the issuing code free of thread-dependent control flow lets the compiler hold descriptors in uniform
+// registers instead of the ELECT / R2UR.BROADCAST / BRA.U.ANY sequence it emits inside `if (lane == 0)`.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe, pa;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "setp.ne.b32 pa, %4, 0;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -250,7 +292,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* s_stats = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -268,8 +311,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -281,35 +324,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kit = 0; kit < p.kiters; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-          mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+          mbar_expect_tx_elect(&full_bar[stage], p.tx_bytes);
           if (p.fold == 2) {
             // A: the whole (TH+KH-1) x TW halo tile of 64-element fat-pixel slice cc, loaded ONCE for all kernel rows
             const int xo = tx * p.TW, yo = ty * p.TH;
-            tma_load_4d(st, &map_a_hi, &full_bar[stage], kit * 64, xo, yo, img);
+            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], kit * 64, xo, yo, img);
             for (int rr = 0; rr < p.KH; ++rr)
-              tma_load_3d(st + p.a_bytes + rr * p.b_each, &map_b_hi, &full_bar[stage], kit * 64, rr, nt * p.BN);
+              tma_load_3d_elect(st + p.a_bytes + rr * p.b_each, &map_b_hi, &full_bar[stage], kit * 64, rr, nt * p.BN);
             if (NPROD == 3) {
               uint8_t* lo = st + p.a_bytes + p.b_bytes;
-              tma_load_4d(lo, &map_a_lo, &full_bar[stage], kit * 64, xo, yo, img);
+              tma_load_4d_elect(lo, &map_a_lo, &full_bar[stage], kit * 64, xo, yo, img);
               for (int rr = 0; rr < p.KH; ++rr)
-                tma_load_3d(lo + p.a_bytes + rr * p.b_each, &map_b_lo, &full_bar[stage], kit * 64, rr, nt * p.BN);
+                tma_load_3d_elect(lo + p.a_bytes + rr * p.b_each, &map_b_lo, &full_bar[stage], kit * 64, rr, nt * p.BN);
             }
           } else if (p.fold) {
             // A: 64-element slice cc of the "fat pixel" row (KW taps x Cin channels, contiguous in NHWC) of kernel row r
             const int xo = tx * p.TW, yo = ty * p.TH * p.stride + r;
-            tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
-            tma_load_3d(st + p.a_bytes, &map_b_hi, &full_bar[stage], cc * 64, r, nt * p.BN);
+            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
+            tma_load_3d_elect(st + p.a_bytes, &map_b_hi, &full_bar[stage], cc * 64, r, nt * p.BN);
             if (NPROD == 3) {
-              tma_load_4d(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * 64, xo, yo, img);
-              tma_load_3d(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], cc * 64, r, nt * p.BN);
+              tma_load_4d_elect(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * 64, xo, yo, img);
+              tma_load_3d_elect(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], cc * 64, r, nt * p.BN);
             }
             if (++cc == p.cchunks) { cc = 0; ++r; }
           } else {
-            tma_load_4d(st, &map_a_hi, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
-            tma_load_2d(st + p.a_bytes, &map_b_hi, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+            tma_load_2d_elect(st + p.a_bytes, &map_b_hi, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
             if (NPROD == 3) {
-              tma_load_4d(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
-              tma_load_2d(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+              tma_load_4d_elect(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+              tma_load_2d_elect(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
             }
             if (++cc == p.cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
           }
@@ -319,10 +362,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged and one elected lane issues: with the loop inside `if (lane == 0)` the compiler
+    // wrapped every tcgen05.mma in an ELECT / 7x R2UR.BROADCAST / BRA.U.ANY sequence and this single thread, at ~128 cycles
+    // per MMA, was the critical path of every convolution.
+    {
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const int ksteps = p.KC / 16;
+      // one (A, B) operand pair, K-steps [0, ks); `zero` = first MMA of the tile (literal accumulate predicates otherwise)
+      auto group = [&](uint32_t d, uint64_t a, uint64_t b, int ks, bool zero) {
+        if (zero) umma_bf16_elect(d, a, b, idesc, 0); else umma_bf16_elect(d, a, b, idesc, 1);
+        if (ks > 1) umma_bf16_elect(d, a + 2, b + 2, idesc, 1);
+        if (ks > 2) umma_bf16_elect(d, a + 4, b + 4, idesc, 1);
+        if (ks > 3) umma_bf16_elect(d, a + 6, b + 6, idesc, 1);
+      };
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -334,42 +387,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
           if (p.fold == 2) {
-            // kernel row rr reads the halo tile rr*TW rows further down (a whole number of 1024-byte swizzle atoms)
             // the last 64-element slice of a fat pixel is partly padding (zero weights): skip its dead K-steps
             const int ks2 = min(ksteps, (p.KW * p.Cin - kit * 64 + 15) >> 4);
+            const uint32_t lo = st + p.a_bytes + p.b_bytes;
             for (int rr = 0; rr < p.KH; ++rr) {
+              // kernel row rr reads the halo tile rr*TW rows further down (a whole number of 1024-byte swizzle atoms)
               const uint64_t a_hi = make_desc(st + rr * p.tap_bytes, p.sbo, p.layout_type);
               const uint64_t b_hi = make_desc(st + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
-              for (int k = 0; k < ks2; ++k)
-                umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (kit | rr | k) != 0);
+              group(d_tmem, a_hi, b_hi, ks2, (kit | rr) == 0);
               if (NPROD == 3) {
-                const uint32_t lo = st + p.a_bytes + p.b_bytes;
                 const uint64_t a_lo = make_desc(lo + rr * p.tap_bytes, p.sbo, p.layout_type);
                 const uint64_t b_lo = make_desc(lo + p.a_bytes + rr * p.b_each, p.sbo, p.layout_type);
-                for (int k = 0; k < ks2; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
-                for (int k = 0; k < ks2; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
+                group(d_tmem, a_lo, b_hi, ks2, false);
+                group(d_tmem, a_hi, b_lo, ks2, false);
               }
             }
-            umma_commit(&empty_bar[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            continue;
+          } else {
+            // folded rows: stage kit holds slice (kit % cchunks) of a fat pixel; its padding K-steps are skipped
+            const int ks1 = p.fold ? min(ksteps, (p.KW * p.Cin - (kit % p.cchunks) * 64 + 15) >> 4) : ksteps;
+            const uint64_t a_hi = make_desc(st, p.sbo, p.layout_type);
+            const uint64_t b_hi = make_desc(st + p.a_bytes, p.sbo, p.layout_type);
+            group(d_tmem, a_hi, b_hi, ks1, kit == 0);
+            if (NPROD == 3) {
+              const uint64_t a_lo = make_desc(st + p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
+              const uint64_t b_lo = make_desc(st + 2 * p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
+              group(d_tmem, a_lo, b_hi, ks1, false);
+              group(d_tmem, a_hi, b_lo, ks1, false);
+            }
           }
-          const uint64_t a_hi = make_desc(st, p.sbo, p.layout_type);
-          const uint64_t b_hi = make_desc(st + p.a_bytes, p.sbo, p.layout_type);
-          // folded rows: stage kit holds slice (kit % cchunks) of a fat pixel; its padding K-steps are skipped
-          const int ks1 = p.fold ? min(ksteps, (p.KW * p.Cin - (kit % p.cchunks) * 64 + 15) >> 4) : ksteps;
-          for (int k = 0; k < ks1; ++k)
-            umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, (kit | k) != 0);
-          if (NPROD == 3) {
-            const uint64_t a_lo = make_desc(st + p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
-            const uint64_t b_lo = make_desc(st + 2 * p.a_bytes + p.b_bytes, p.sbo, p.layout_type);
-            for (int k = 0; k < ks1; ++k) umma_bf16(d_tmem, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1);
-            for (int k = 0; k < ks1; ++k) umma_bf16(d_tmem, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, 1);
-          }
-          umma_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs retire
+          umma_commit_elect(&empty_bar[stage]);     // frees the smem stage when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);               // accumulator complete
+        umma_commit_elect(&tmem_full[acc]);         // accumulator complete
       }
     }
   } else {
@@ -625,13 +674,15 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, uint32_t lb
   return d;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kWgradThreads = 192;     // warp 0 TMA producer, 1 MMA issuer, 2-5 epilogue
+__global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], done_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
 
   // work item
   int item = blockIdx.x;
@@ -657,7 +708,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // whole warp converged, one elected lane issues (see conv_tc_kernel)
       int stage = 0; uint32_t phase = 0;
       for (int ch = chunk_begin; ch < chunk_end; ++ch) {
         int cx = ch % p.chunks_x; int rest = ch / p.chunks_x;
@@ -665,21 +716,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const int xo = cx * p.PW, yo = cy * p.PH;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-        mbar_expect_tx(&full_bar[stage], p.tx_bytes);
+        mbar_expect_tx_elect(&full_bar[stage], p.tx_bytes);
         for (int a = 0; a < p.nA; ++a)
-          tma_load_4d(st + a * p.a_atom_bytes, &map_dy, &full_bar[stage], cot * 128 + a * p.atomA, xo, yo, img);
+          tma_load_4d_elect(st + a * p.a_atom_bytes, &map_dy, &full_bar[stage], cot * 128 + a * p.atomA, xo, yo, img);
         if (p.fold) {
-          tma_load_4d(st + p.a_bytes, &map_x, &full_bar[stage], cit * 64, xo, yo * p.stride + tap, img);
+          tma_load_4d_elect(st + p.a_bytes, &map_x, &full_bar[stage], cit * 64, xo, yo * p.stride + tap, img);
         } else {
           for (int b = 0; b < p.nB; ++b)
-            tma_load_4d(st + p.a_bytes + b * p.b_atom_bytes, &map_x, &full_bar[stage], cit * p.BN + b * p.atomB,
+            tma_load_4d_elect(st + p.a_bytes + b * p.b_atom_bytes, &map_x, &full_bar[stage], cit * p.BN + b * p.atomB,
                         xo * p.stride + s - p.pad + p.org, yo * p.stride + r - p.pad + p.org, img);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // D=f32, A=B=bf16, both MN-major (bits 15, 16), N = BN, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t rowA = (uint32_t)p.atomA * 2, rowB = (uint32_t)p.atomB * 2;
@@ -693,12 +744,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         for (int k = 0; k < p.pix / 16; ++k) {
           const uint64_t da = make_desc_mn(st + k * 16 * rowA, lboA, 8 * rowA, p.a_layout);
           const uint64_t db = make_desc_mn(st + p.a_bytes + k * 16 * rowB, p.b_atom_bytes, 8 * rowB, p.b_layout);
-          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+          umma_bf16_elect(tmem_base, da, db, idesc, (i | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&done_bar);
+      umma_commit_elect(&done_bar);
     }
   } else if (nchunks > 0) {
     const int q = warp & 3;
@@ -830,7 +881,7 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   }
   const int grid = base_items * p.ksplit;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  wgrad_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(mdy, mx, p);
+  wgrad_tc_kernel<<<grid, kWgradThreads, smem, (cudaStream_t)stream>>>(mdy, mx, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

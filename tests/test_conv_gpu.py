@@ -17,6 +17,7 @@ CASES = [
     # N, Cin, Cout, H, W, k, stride, pad, mode      mode: "zero" (TMA OOB fill), "rep" (replicate ring), "zring" (materialised zero ring)
     (2, 64, 64, 24, 40, 3, 1, 1, "zero"),
     (2, 16, 16, 48, 80, 3, 1, 1, "rep"),
+    (3, 16, 16, 38, 70, 3, 1, 1, "rep"),        # partial tiles in both directions
     (2, 32, 16, 24, 48, 3, 1, 1, "rep"),
     (2, 96, 32, 24, 48, 3, 1, 1, "rep"),
     (2, 3, 64, 48, 80, 7, 2, 3, "zring"),
@@ -68,6 +69,14 @@ def test_conv_forward_and_gradients(N, Cin, Cout, H, W, k, stride, pad, mode):
             full = tc.View(gx.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
             tc.conv_dgrad(dy, cw, full, pad=k - 1)
             _lib.call("fsnet_fold_ring", gx.view())
+            # the executor's variant: dy with a materialised zero ring of k-1 pixels read as data (folded-tap / TMEM-operand paths)
+            dyr = tc.Planes(N, Ho, Wo, cw.co_pad, ring=k - 1, zero=True)
+            dyr.t[0, :, k - 1:k - 1 + Ho, k - 1:k - 1 + Wo, :Cout] = gy.permute(0, 2, 3, 1).bfloat16()
+            gx2 = tc.Fp32(N, H, W, cw.ci_pad, ring=1)
+            full2 = tc.View(gx2.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
+            tc.conv_dgrad(dyr, cw, full2, pad=k - 1, use_ring=True)
+            _lib.call("fsnet_fold_ring", gx2.view())
+            assert rel(gx2.nchw()[:, :Cin], gx_ref) < 1e-2
         else:
             gx = tc.Fp32(N, H, W, cw.ci_pad)
             tc.conv_dgrad(dy, cw, gx.view(), pad=k - 1 - pad)
