@@ -159,3 +159,25 @@ def test_synthetic_dataset_schema():
         if torch.is_tensor(ref[k]):
             assert torch.equal(mine[k], ref[k]), k
     assert mine["calib_meta"] == ref["calib_meta"]
+
+
+def test_fused_adam_cpu_parameters_use_stock_adam():
+    """FusedAdam has no CPU kernels: parameters that are not CUDA tensors take torch.optim.Adam's own step (incl. the
+    clip_grad_norm_ the hook folds into step(max_norm=...)), so build_optimizer(name='adam') stays usable in CPU tests."""
+    from vision_base.networks.optimizers.optimizers import build_optimizer
+    torch.manual_seed(0)
+    m1, m2 = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    m2.load_state_dict(m1.state_dict())
+    o1 = build_optimizer(m1, name="adam", lr=1e-2)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-2)
+    x = torch.randn(4, 5)
+    for _ in range(3):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            (m(x) ** 2).sum().backward()
+        o1.step(max_norm=0.5)
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), 0.5)
+        o2.step()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(a, b, atol=1e-7)
+    assert set(o1.state_dict()["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
