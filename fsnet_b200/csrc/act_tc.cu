@@ -343,13 +343,27 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int p
     float s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += gridDim.x * pix_per_iter) {
+    // two pixels per iteration: their loads are independent, which doubles the bytes in flight per thread
+    const unsigned step = gridDim.x * pix_per_iter;
+    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += 2 * step) {
+      const unsigned pix2 = pix + step;
+      const bool has2 = pix2 < npix;
       Px q; unsigned t = pix / (unsigned)r.w; q.x = (int)(pix - t * r.w);
       unsigned n = t / (unsigned)r.h; q.y = (int)(t - n * r.h); q.n = (int)n; q.c = c;
+      Px q2 = q;
+      if (has2) { unsigned t2 = pix2 / (unsigned)r.w; q2.x = (int)(pix2 - t2 * r.w);
+                  unsigned n2 = t2 / (unsigned)r.h; q2.y = (int)(t2 - n2 * r.h); q2.n = (int)n2; }
       const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, c));
+      const F8 rv2 = ld_f8((const float*)r.ptr + vidx(r, q2.n, q2.y, q2.x, c));
       const F8 g = masked_g8(p, q, rv);
+      const F8 g2 = masked_g8(p, q2, rv2);
+      const float w2 = has2 ? 1.f : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], (rv.v[k] - mean.v[k]) * inv.v[k], s2[k]); }
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], (rv.v[k] - mean.v[k]) * inv.v[k], s2[k]);
+        const float gg = g2.v[k] * w2;
+        s1[k] += gg; s2[k] = fmaf(gg, (rv2.v[k] - mean.v[k]) * inv.v[k], s2[k]);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
