@@ -61,7 +61,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -218,10 +218,10 @@ def main():
     if rank == 0:
         sampler.start()
     ms, _ = timed(args.steps, False)
-    clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * args.steps
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
+    clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions (value and e2e)
     # roofline leg: the same training steps run eagerly so that the kernels can be bracketed with CUDA events on their
     # stream (events cannot be read back from inside a replayed graph)
     # (is_log_image heads need the forward-only kernel for their hm outputs: forward and backward are separate launches)
