@@ -491,6 +491,14 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   FSNET_REQUIRE(Cout % p.BN == 0, "fsnet_conv: cannot tile Cout=%d", Cout);
   p.n_tiles = Cout / p.BN;
   p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
+  // the 6x20 / 12x40 layers have only 12..48 pixel tiles: narrower channel tiles put more of the 148 SMs to work
+  // (every CTA re-reads its A tile, which is tiny there; the MMA time of a tile scales with BN)
+  static int split_env = -1;
+  if (split_env < 0) { const char* e = getenv("FSNET_CONV_NSPLIT"); split_env = e ? atoi(e) : 1; }
+  while (split_env && p.BN >= 64 && p.total_tiles * 2 <= 148 && Cout % (p.BN / 2) == 0) {
+    p.BN /= 2; p.n_tiles = Cout / p.BN;
+    p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
+  }
   p.KC = pick_kc(Cin); p.cchunks = Cin / p.KC; p.kiters = KH * KW * p.cchunks;
   // x-tap folding for thin replicate-padded layers: the KW taps x Cin channels of a kernel row are one contiguous
   // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
