@@ -365,8 +365,24 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int p
         s1[k] += gg; s2[k] = fmaf(gg, (rv2.v[k] - mean.v[k]) * inv.v[k], s2[k]);
       }
     }
+    // lanes of a warp that own the same channel group (lane % groups, when groups divides 32) combine by shuffles first:
+    // for the 16..64-channel full-resolution layers the shared-memory atomics were 128-way contended
+    if (groups < 32 && (groups & (groups - 1)) == 0 && threads_used == 256) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+      for (int k = 0; k < 8; ++k) {
+        for (int o = 16; o >= groups; o >>= 1) {
+          s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], o);
+          s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], o);
+        }
+      }
+      if ((int)(threadIdx.x & 31) < groups) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
