@@ -827,8 +827,13 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   p.b_bytes = ((uint32_t)p.nB * p.b_atom_bytes + 1023u) & ~1023u;
   p.stage_bytes = p.a_bytes + p.b_bytes;
   p.tx_bytes = (uint32_t)p.nA * p.a_atom_bytes + (uint32_t)p.nB * p.b_atom_bytes;
-  int stages = (int)(200u * 1024u / p.stage_bytes);
-  p.stages = stages > kMaxStages ? kMaxStages : stages;
+  // K-split layers run `occ` CTAs per SM: size the pipeline so that they actually fit next to each other (their fixed
+  // costs -- barrier / TMEM set-up, pipeline ramp, reduction epilogue -- then overlap)
+  static int share_env = -1;
+  if (share_env < 0) { const char* e = getenv("FSNET_WGRAD_SHARE"); share_env = e ? atoi(e) : 1; }
+  const uint32_t budget = (share_env && occ > 1 && p.ksplit > 1) ? 200u * 1024u / (uint32_t)occ : 200u * 1024u;
+  int stages = (int)(budget / p.stage_bytes);
+  p.stages = stages > kMaxStages ? kMaxStages : (stages < 2 ? 2 : stages);
   uint32_t cols = 32;
   while (cols < (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
