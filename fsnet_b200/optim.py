@@ -22,7 +22,7 @@ class FusedAdam(optim.Adam):
     def _fusable(self, group):
         ps = [p for p in group["params"] if p.grad is not None]
         return (bool(ps) and all(p.is_cuda and p.dtype == torch.float32 and p.grad.dtype == torch.float32 and not p.grad.is_sparse
-                                 and p.is_contiguous() for p in ps)
+                                 and p.is_contiguous() and p.grad.is_contiguous() for p in ps)
                 and not group.get("amsgrad", False) and not group.get("maximize", False))
 
     def _group_state(self, gi, group, dev):
