@@ -181,3 +181,14 @@ def test_fused_adam_cpu_parameters_use_stock_adam():
     for a, b in zip(m1.parameters(), m2.parameters()):
         assert torch.allclose(a, b, atol=1e-7)
     assert set(o1.state_dict()["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_lazy_batch_is_a_transparent_dict():
+    """The graphed hook hands the model a _LazyBatch: without copy events it must behave exactly like the dict the
+    reference's models index with tuple keys (getitem / get / in / items / dict())."""
+    from fsnet_b200.hooks.training import _LazyBatch
+    base = {("image", 0): 1, "P2": 2, "calib_meta": [dict(a=1)]}
+    d = _LazyBatch(base, {})
+    assert d[("image", 0)] == 1 and d.get("missing", 7) == 7 and d.get("P2") == 2 and "P2" in d and "x" not in d
+    assert dict(d) == base and sorted(map(str, d.keys())) == sorted(map(str, base.keys())) and len(list(d.items())) == 3
+    assert d.copy() == base
