@@ -1,0 +1,39 @@
+"""Golden vectors for the host-side augmentation pipeline, produced by RUNNING THE REFERENCE's classes
+(vision_base/data/augmentations/augmentations.py) through its own builder with the train / val augmentation lists of
+configs/kitti_wpose_example.  Build container only:   python tests/golden/make_golden_aug.py
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path = [REF] + [p for p in sys.path if os.path.abspath(p or ".") not in (REPO, HERE)] + [REPO]
+
+import numpy as np  # noqa: E402
+
+np.int = int                       # the reference's Resize uses the alias numpy 2 removed (SURVEY.md 8(c) caveat iv)
+from easydict import EasyDict as edict  # noqa: E402
+from vision_base.utils.builder import build  # noqa: E402  (reference)
+import vision_base  # noqa: E402
+
+assert vision_base.__path__[0].startswith(REF)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+from aug_cases import raw_sample, train_cfg, val_cfg, summarize  # noqa: E402
+
+
+def run(name, cfg, seed):
+    np.random.seed(seed)
+    pipe = build(**cfg)
+    outs = {}
+    for i in range(3):                         # three consecutive samples: exercises the generators' state
+        out = pipe(raw_sample(100 + i))
+        for k, v in summarize(out).items():
+            outs[f"{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **outs)
+    print(name, len(outs), "entries", os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    run("aug_train", train_cfg(), 7)
+    run("aug_val", val_cfg(), 8)

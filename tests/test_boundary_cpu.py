@@ -30,7 +30,9 @@ DOTTED = [
     "vision_base.networks.blocks.blocks.ConvBnReLU", "vision_base.networks.models.meta_archs.base_meta.BaseMetaArch",
     "vision_base.utils.utils.cfg_from_file", "vision_base.utils.utils.update_cfg", "vision_base.utils.logger.LossLogger",
     "vision_base.utils.timer.Timer",
-]
+] + [f"vision_base.data.augmentations.augmentations.{n}" for n in (
+    "ConvertToFloat", "RandomWarpAffine", "RandomMirror", "RandomBrightness", "RandomContrast", "ConvertColor", "RandomSaturation",
+    "Normalize", "ConvertToTensor", "Resize", "Copy")]
 
 
 @pytest.mark.parametrize("name", DOTTED)
