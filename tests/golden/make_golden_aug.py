@@ -37,3 +37,27 @@ def run(name, cfg, seed):
 if __name__ == "__main__":
     run("aug_train", train_cfg(), 7)
     run("aug_val", val_cfg(), 8)
+
+
+def run_metrics():
+    """compute_errors / compute_depth_errors / disp<->depth of the reference and KittiEigenEvaluator._single_loss."""
+    import torch
+    from monodepth.networks.utils import monodepth_utils as U
+    from monodepth.evaluation.kitti_unsupervised_eval import KittiEigenEvaluator
+    g = np.random.default_rng(21)
+    gt = g.uniform(1.0, 70.0, size=5000)
+    pred = gt * g.uniform(0.7, 1.4, size=5000)
+    out = {"errors": np.array(U.compute_errors(gt, pred)),
+           "torch_errors": np.array([float(v) for v in U.compute_depth_errors(torch.tensor(gt), torch.tensor(pred))]),
+           "depth": U.disp_to_depth(np.linspace(0, 1, 11), 0.1, 100.0)[1], "disp": U.depth_to_disp(np.linspace(0.5, 90, 11), 0.1, 100.0)}
+    gt_map = np.where(g.uniform(size=(94, 310)) < 0.2, g.uniform(0.5, 90.0, size=(94, 310)), 0.0).astype(np.float32)
+    pred_map = g.uniform(2.0, 60.0, size=(48, 160)).astype(np.float32)
+    ev = KittiEigenEvaluator.__new__(KittiEigenEvaluator)          # the constructor wants KITTI on disk; the protocol does not
+    res = ev._single_loss(pred_map.copy(), gt_map.copy())
+    out["eigen_ratio"] = np.array(res["ratio"]); out["eigen_error"] = np.array(res["error"]); out["eigen_abs_error"] = np.array(res["abs_error"])
+    np.savez_compressed(os.path.join(HERE, "metrics.npz"), **out)
+    print("metrics", out["errors"])
+
+
+if __name__ == "__main__":
+    run_metrics()

@@ -42,3 +42,24 @@ def test_flip_relative_pose_is_an_involution_and_mirrors_translation():
     np.testing.assert_allclose(flip_relative_pose(F.copy(), 0), T, atol=1e-6)
     assert np.isclose(F[0, 3], -T[0, 3]) and np.allclose(F[1:3, 3], T[1:3, 3])
     np.testing.assert_allclose(F[:3, :3] @ F[:3, :3].T, np.eye(3), atol=1e-5)
+
+
+def test_depth_metrics_match_reference(golden_dir):
+    """compute_errors / compute_depth_errors / disp<->depth and the Eigen crop + median-scaling protocol against values
+    computed by the reference's own functions (tests/golden/make_golden_aug.py::run_metrics)."""
+    from monodepth.networks.utils import monodepth_utils as U
+    from fsnet_b200.utils.metrics import eigen_median_scaled_errors
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    r = np.random.default_rng(21)
+    gt = r.uniform(1.0, 70.0, size=5000)
+    pred = gt * r.uniform(0.7, 1.4, size=5000)
+    np.testing.assert_allclose(np.array(U.compute_errors(gt, pred)), g["errors"], rtol=1e-12)
+    np.testing.assert_allclose([float(v) for v in U.compute_depth_errors(torch.tensor(gt), torch.tensor(pred))], g["torch_errors"], rtol=1e-10)
+    np.testing.assert_allclose(U.disp_to_depth(np.linspace(0, 1, 11), 0.1, 100.0)[1], g["depth"], rtol=1e-12)
+    np.testing.assert_allclose(U.depth_to_disp(np.linspace(0.5, 90, 11), 0.1, 100.0), g["disp"], rtol=1e-12)
+    gt_map = np.where(r.uniform(size=(94, 310)) < 0.2, r.uniform(0.5, 90.0, size=(94, 310)), 0.0).astype(np.float32)
+    pred_map = r.uniform(2.0, 60.0, size=(48, 160)).astype(np.float32)
+    res = eigen_median_scaled_errors(pred_map, gt_map)
+    np.testing.assert_allclose(res["ratio"], g["eigen_ratio"], rtol=1e-6)
+    np.testing.assert_allclose(np.array(res["error"]), g["eigen_error"], rtol=1e-5)
+    np.testing.assert_allclose(np.array(res["abs_error"]), g["eigen_abs_error"], rtol=1e-5)
