@@ -61,3 +61,37 @@ def run_metrics():
 
 if __name__ == "__main__":
     run_metrics()
+
+
+def run_kitti():
+    """The reference's KITTI readers on the miniature tree of tests/kitti_fixture.py."""
+    import tempfile
+    from kitti_fixture import build_tree
+    with tempfile.TemporaryDirectory() as root:
+        raw, split = build_tree(root)
+        out = {}
+        np.random.seed(11)
+        train = build(name="monodepth.data.datasets.mono_dataset.KittiDepthMonoDataset", raw_path=raw, split_file=split,
+                      frame_idxs=[0, 1, -1], is_filter_static=True, augmentation=train_cfg())
+        out["train_len"] = np.array(len(train))
+        for i in (0, 3, len(train) - 1):
+            for k, v in summarize(train[i]).items():
+                out[f"train/{i}/{k}"] = v
+        np.random.seed(12)
+        cfg = val_cfg()
+        cfg.image_keys = [("image", 0), ("image", -1), ("original_image", 0)]
+        cfg.cfg_list[2].image_keys = [("image", 0), ("image", -1)]
+        cfg.cfg_list[3].image_keys = [("original_image", 0)]
+        cfg.gt_image_keys = []
+        test = build(name="monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset", raw_path=raw, split_file=split,
+                     depth_path=raw, augmentation=cfg)
+        out["test_len"] = np.array(len(test))
+        for i in (0, 5):
+            for k, v in summarize(test[i]).items():
+                out[f"test/{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "kitti_reader.npz"), **out)
+    print("kitti", int(out["train_len"]), int(out["test_len"]), len(out), "entries")
+
+
+if __name__ == "__main__":
+    run_kitti()

@@ -1,0 +1,67 @@
+"""A miniature KITTI-raw directory tree (two drives, both cameras, calibration files, devkit poses, an Eigen-style split
+file, 16-bit depth maps) written deterministically into a temporary directory: lets the dataset readers be exercised --
+by the reference (golden generation) and by this repo (tests) -- without KITTI on disk."""
+import os
+
+import cv2
+import numpy as np
+import scipy.io as sio
+from PIL import Image
+
+DATE = "2011_09_26"
+DRIVES = ["2011_09_26_drive_0001_sync", "2011_09_26_drive_0002_sync"]
+H, W, N = 120, 400, 8
+
+
+def _rigid(g, scale):
+    ang = g.uniform(-0.02, 0.02, size=3)
+    cx, cy, cz = np.cos(ang)
+    sx, sy, sz = np.sin(ang)
+    R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+         @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    return R, g.uniform(-scale, scale, size=3)
+
+
+def build_tree(root, seed=5):
+    g = np.random.default_rng(seed)
+    d = os.path.join(root, "raw", DATE)
+    os.makedirs(d, exist_ok=True)
+    P2 = np.array([[0.58 * W, 0, 0.5 * W, 4.4], [0, 1.92 * H, 0.5 * H, 0.2], [0, 0, 1, 0.003]])
+    P3 = P2.copy(); P3[0, 3] = -33.0
+    with open(os.path.join(d, "calib_cam_to_cam.txt"), "w") as f:
+        f.write("calib_time: 09-Jan-2012 13:57:47\n")
+        f.write("P_rect_02: " + " ".join(f"{v:.9e}" for v in P2.reshape(-1)) + "\n")
+        f.write("P_rect_03: " + " ".join(f"{v:.9e}" for v in P3.reshape(-1)) + "\n")
+    for name, rt in (("calib_velo_to_cam.txt", _rigid(g, 0.3)), ("calib_imu_to_velo.txt", _rigid(g, 0.8))):
+        with open(os.path.join(d, name), "w") as f:
+            f.write("calib_time: 25-May-2012 16:47:16\n")
+            f.write("R: " + " ".join(f"{v:.9e}" for v in rt[0].reshape(-1)) + "\n")
+            f.write("T: " + " ".join(f"{v:.9e}" for v in rt[1]) + "\n")
+    lines = []
+    for di, drive in enumerate(DRIVES):
+        for cam in ("image_02", "image_03"):
+            os.makedirs(os.path.join(d, drive, cam, "data"), exist_ok=True)
+        os.makedirs(os.path.join(d, drive, "oxts"), exist_ok=True)
+        os.makedirs(os.path.join(d, drive, "depth"), exist_ok=True)
+        poses = np.tile(np.eye(4), (N, 1, 1))
+        for k in range(1, N):
+            R, t = _rigid(g, 0.0)
+            step = np.eye(4)
+            step[:3, :3] = R
+            # drive 0002 stands still between frames 3 and 4 (the static filter must drop the samples around them)
+            step[:3, 3] = [0.0 if (di == 1 and k == 4) else 0.9, 0.01, 0.0]
+            poses[k] = poses[k - 1] @ step
+        sio.savemat(os.path.join(d, drive, "oxts", "pose.mat"), {"pose_mat": poses})
+        for k in range(N):
+            for cam in ("image_02", "image_03"):
+                lo = g.integers(0, 256, size=(H // 8, W // 8, 3)).astype(np.uint8)
+                img = np.kron(lo, np.ones((8, 8, 1), dtype=np.uint8)) // 2 + g.integers(0, 128, size=(H, W, 3)).astype(np.uint8)
+                Image.fromarray(img).save(os.path.join(d, drive, cam, "data", "%010d.png" % k))
+            depth = (g.uniform(0, 80, size=(H, W)) * (g.uniform(size=(H, W)) < 0.1) * 256).astype(np.uint16)
+            cv2.imwrite(os.path.join(d, drive, "depth", "%010d.png" % k), depth)
+        for k in range(1, N - 1):
+            lines.append(f"{DATE}/{drive} {k} {'l' if (k + di) % 2 == 0 else 'r'}")
+    split = os.path.join(root, "split.txt")
+    with open(split, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return os.path.join(root, "raw"), split

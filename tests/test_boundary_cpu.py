@@ -32,7 +32,9 @@ DOTTED = [
     "vision_base.utils.timer.Timer",
 ] + [f"vision_base.data.augmentations.augmentations.{n}" for n in (
     "ConvertToFloat", "RandomWarpAffine", "RandomMirror", "RandomBrightness", "RandomContrast", "ConvertColor", "RandomSaturation",
-    "Normalize", "ConvertToTensor", "Resize", "Copy")]
+    "Normalize", "ConvertToTensor", "Resize", "Copy")] + [
+    "monodepth.data.datasets.mono_dataset.KittiDepthMonoDataset", "monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset",
+    "monodepth.data.datasets.utils.cam_relative_pose", "monodepth.networks.utils.monodepth_utils.compute_errors"]
 
 
 @pytest.mark.parametrize("name", DOTTED)

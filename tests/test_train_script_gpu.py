@@ -30,3 +30,18 @@ def test_train_script_runs(tmp_path, config, extra):
                        map_location="cpu")
     assert "model_state_dict" in state and "optimizer_state_dict" in state
     assert all(torch.isfinite(v).all() for v in state["model_state_dict"].values() if v.is_floating_point())
+
+
+def test_train_script_on_kitti_files(tmp_path):
+    """The KITTI recipe end to end on FILES: miniature KITTI tree -> reference-named readers -> augmentation lists ->
+    dataloader workers -> tcgen05 / fused-loss training step -> checkpoint."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from kitti_fixture import build_tree
+    raw, split = build_tree(str(tmp_path / "kitti"))
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO, FSNET_KITTI_PATH=raw, FSNET_KITTI_SPLIT=split,
+               FSNET_SHIFT_BORDER="32")
+    cmd = [sys.executable, os.path.join(REPO, "scripts", "train.py"), f"--config={os.path.join(REPO, 'configs', 'kitti_wpose_files.py')}",
+           "--experiment_name=pytest", "--trainer.max_steps=3", "--trainer.max_epochs=2", "--data.batch_size=2", "--data.num_workers=2"]
+    out = subprocess.run(cmd, env=env, cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "finished 3 steps" in out.stdout
