@@ -50,7 +50,11 @@ class _ReprojectionLoss(torch.autograd.Function):
         B, _, H, W = tgt.shape
         tgt, src0, src1 = _f32c(tgt), _f32c(src0), _f32c(src1)
         P2c, T0c, T1c = _f32c(P2), _f32c(T0), _f32c(T1)
-        mask_c = None if mask is None else mask.detach().contiguous()
+        mask_c = None if mask is None else mask.detach()
+        if mask_c is not None and not mask_c.is_floating_point():
+            mask_c = mask_c.float()           # e.g. the uint8 fisheye validity image: the reference's products promote it to fp32
+        if mask_c is not None:
+            mask_c = mask_c.contiguous()
         mdt = _mask_dtype(mask_c)
         flags = (FLAG_OVERLAP if cfg["overlapped_mask"] else 0) | (FLAG_MOTION if motion is not None else 0)
         motion_c = None if motion is None else _f32c(motion)

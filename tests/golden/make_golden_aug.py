@@ -95,3 +95,29 @@ def run_kitti():
 
 if __name__ == "__main__":
     run_kitti()
+
+
+def run_fisheye():
+    """The reference's KITTI-360 fisheye reader on the miniature tree (its hard-coded mask path is not used: no mask key)."""
+    import tempfile
+    from kitti_fixture import build_kitti360_tree
+    from aug_cases import fisheye_train_cfg
+    with tempfile.TemporaryDirectory() as root:
+        raw, meta, _ = build_kitti360_tree(root)
+        np.random.seed(13)
+        ds = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta,
+                   frame_ids=[0, 1, -1], is_filter_static=True, use_right_image=True, augmentation=fisheye_train_cfg())
+        out = {"len": np.array(len(ds))}
+        for i in range(len(ds)):
+            s = ds[i]
+            meta_d = s.pop("calib_meta")
+            out[f"{i}/xi"] = np.array(meta_d["mirror_parameters"]["xi"])
+            out[f"{i}/u0"] = np.array(meta_d["projection_parameters"]["u0"])
+            for k, v in summarize(s).items():
+                out[f"{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "kitti360_fisheye_reader.npz"), **out)
+    print("fisheye reader", int(out["len"]), len(out), "entries")
+
+
+if __name__ == "__main__":
+    run_fisheye()

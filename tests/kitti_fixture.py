@@ -65,3 +65,55 @@ def build_tree(root, seed=5):
     with open(split, "w") as f:
         f.write("\n".join(lines) + "\n")
     return os.path.join(root, "raw"), split
+
+
+# --------------------------------------------------------------------------------------------------
+# miniature KITTI-360 (fisheye cameras)
+# --------------------------------------------------------------------------------------------------
+SEQ360 = "2013_05_28_drive_0000_sync"
+FH = FW = 96
+
+
+def build_kitti360_tree(root, seed=9):
+    g = np.random.default_rng(seed)
+    raw = os.path.join(root, "kitti360")
+    calib = os.path.join(raw, "calibration")
+    os.makedirs(calib, exist_ok=True)
+    for cam, u0 in (("image_02", 0.512), ("image_03", 0.498)):
+        with open(os.path.join(calib, cam + ".yaml"), "w") as f:
+            f.write("%YAML:1.0\n---\nmodel_type: MEI\ncamera_name: " + cam + f"\nimage_width: {FW}\nimage_height: {FH}\n"
+                    "mirror_parameters:\n   xi: 2.2134047507854890e+00\n"
+                    "distortion_parameters:\n   k1: 1.6798235660113681e-02\n   k2: 1.6548773243373522e+00\n   p1: 4.2e-04\n   p2: 4.2e-04\n"
+                    f"projection_parameters:\n   gamma1: {1336.3 * FW / 1400:.6f}\n   gamma2: {1335.8 * FH / 1400:.6f}\n"
+                    f"   u0: {u0 * FW:.6f}\n   v0: {0.504 * FH:.6f}\n")
+    with open(os.path.join(calib, "calib_cam_to_pose.txt"), "w") as f:
+        for k in range(4):
+            R, t = _rigid(g, 0.6)
+            T = np.concatenate([R, t[:, None]], 1)
+            f.write(f"image_0{k}: " + " ".join(f"{v:.9e}" for v in T.reshape(-1)) + "\n")
+    os.makedirs(os.path.join(raw, "data_poses", SEQ360), exist_ok=True)
+    pose = np.eye(4)
+    with open(os.path.join(raw, "data_poses", SEQ360, "poses.txt"), "w") as f:
+        for k in range(10):
+            R, _ = _rigid(g, 0.0)
+            step = np.eye(4)
+            step[:3, :3] = R
+            step[:3, 3] = [0.0 if k == 5 else (5.0 if k == 8 else 0.8), 0.02, 0.0]       # one standing pair, one 5 m jump
+            pose = pose @ step
+            f.write(f"{k * 3} " + " ".join(f"{v:.9e}" for v in pose[:3].reshape(-1)) + "\n")
+    for cam in ("image_02", "image_03"):
+        d = os.path.join(raw, "data_2d_raw", SEQ360, cam, "data_rgb")
+        os.makedirs(d, exist_ok=True)
+        for k in range(0, 30, 3):
+            lo = g.integers(0, 256, size=(FH // 8, FW // 8, 3)).astype(np.uint8)
+            img = np.kron(lo, np.ones((8, 8, 1), dtype=np.uint8)) // 2 + g.integers(0, 128, size=(FH, FW, 3)).astype(np.uint8)
+            Image.fromarray(img).save(os.path.join(d, "%010d.png" % k))
+    meta = os.path.join(root, "kitti360_meta.txt")
+    with open(meta, "w") as f:
+        for p in range(1, 9):
+            f.write(f"{SEQ360},{p},{p * 3},{p * 3 - 3},{p * 3 + 3}\n")
+    yy, xx = np.mgrid[0:FH, 0:FW]
+    mask = (((yy - FH / 2) ** 2 + (xx - FW / 2) ** 2) < (0.48 * FW) ** 2).astype(np.uint8)
+    mask_path = os.path.join(root, "fisheye_mask.png")
+    cv2.imwrite(mask_path, mask)
+    return raw, meta, mask_path

@@ -34,7 +34,8 @@ DOTTED = [
     "ConvertToFloat", "RandomWarpAffine", "RandomMirror", "RandomBrightness", "RandomContrast", "ConvertColor", "RandomSaturation",
     "Normalize", "ConvertToTensor", "Resize", "Copy")] + [
     "monodepth.data.datasets.mono_dataset.KittiDepthMonoDataset", "monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset",
-    "monodepth.data.datasets.utils.cam_relative_pose", "monodepth.networks.utils.monodepth_utils.compute_errors"]
+    "monodepth.data.datasets.utils.cam_relative_pose", "monodepth.networks.utils.monodepth_utils.compute_errors",
+    "monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", "monodepth.data.datasets.utils.cam_relative_pose_nusc"]
 
 
 @pytest.mark.parametrize("name", DOTTED)

@@ -62,3 +62,35 @@ def test_kitti_dataset_feeds_the_dataloader(tmp_path):
     assert batch[("image", 0)].shape == (4, 3, 48, 160) and batch[("original_image", -1)].shape == (4, 3, 48, 160)
     assert batch["P2"].shape == (4, 3, 4) and batch[("relative_pose", 1)].shape == (4, 4, 4) and batch["patched_mask"].shape == (4, 48, 160)
     assert batch["patched_mask"].dtype == torch.float64 and float(batch[("original_image", 0)].max()) <= 1.0
+
+
+def test_kitti360_fisheye_reader_matches_reference(golden_dir, tmp_path):
+    """KITTI360FisheyeDataset on a miniature KITTI-360 tree against the reference's reader: MEI yaml calibration -> P2 and
+    calib_meta, camera-frame poses, the static / jump filter, random left / right camera, the fisheye augmentation list."""
+    from vision_base.utils.builder import build
+    from aug_cases import fisheye_train_cfg
+    from kitti_fixture import build_kitti360_tree
+    g = np.load(os.path.join(golden_dir, "kitti360_fisheye_reader.npz"))
+    raw, meta, mask_path = build_kitti360_tree(str(tmp_path))
+    np.random.seed(13)
+    ds = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta,
+               frame_ids=[0, 1, -1], is_filter_static=True, use_right_image=True, augmentation=fisheye_train_cfg())
+    assert len(ds) == int(g["len"]) == 4                   # of 8 listed samples: two touch the standing pair, two the 5 m jump
+    for i in range(len(ds)):
+        s = ds[i]
+        meta_d = s.pop("calib_meta")
+        assert np.isclose(meta_d["mirror_parameters"]["xi"], float(g[f"{i}/xi"])) and np.isclose(meta_d["projection_parameters"]["u0"], float(g[f"{i}/u0"]))
+        got = summarize(s)
+        keys = [k[len(f"{i}/"):] for k in g.files if k.startswith(f"{i}/") and k[len(f"{i}/"):] not in ("xi", "u0")]
+        assert sorted(keys) == sorted(got.keys())
+        for k in keys:
+            if k.startswith("dtype/"):
+                assert str(g[f"{i}/{k}"]) == str(got[k]), k
+            else:
+                np.testing.assert_allclose(got[k], g[f"{i}/{k}"], rtol=1e-6, atol=3e-6, err_msg=k)
+    # the validity mask (honoured from its configured path) ends up as the fp64 patched_mask
+    ds2 = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta,
+                frame_ids=[0, 1, -1], is_filter_static=False, use_right_image=False, fisheye_mask=mask_path, augmentation=fisheye_train_cfg())
+    s = ds2[0]
+    assert s["patched_mask"].shape == (64, 64) and 0.5 < float(s["patched_mask"].float().mean()) < 0.9
+    assert s["P2"].shape == (3, 4) and float(s["P2"][0, 3]) == 0.0 and isinstance(s["calib_meta"], dict)

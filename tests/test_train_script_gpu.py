@@ -45,3 +45,17 @@ def test_train_script_on_kitti_files(tmp_path):
     out = subprocess.run(cmd, env=env, cwd=REPO, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "finished 3 steps" in out.stdout
+
+
+def test_train_script_on_kitti360_fisheye_files(tmp_path):
+    """The KITTI-360 fisheye recipe end to end on FILES: MEI yaml calibration -> calib_meta -> device-built ray table -> FishEyeDecoder."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from kitti_fixture import build_kitti360_tree
+    raw, meta, mask = build_kitti360_tree(str(tmp_path / "k360"))
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO, FSNET_KITTI360_PATH=raw, FSNET_KITTI360_SPLIT=meta,
+               FSNET_FISHEYE_MASK=mask, FSNET_FISHEYE_SIZE="64")
+    cmd = [sys.executable, os.path.join(REPO, "scripts", "train.py"), f"--config={os.path.join(REPO, 'configs', 'kitti360_fisheye_files.py')}",
+           "--experiment_name=pytest", "--trainer.max_steps=3", "--trainer.max_epochs=3", "--data.batch_size=2", "--data.num_workers=0"]
+    out = subprocess.run(cmd, env=env, cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "finished 3 steps" in out.stdout
