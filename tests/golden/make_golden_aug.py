@@ -121,3 +121,26 @@ def run_fisheye():
 
 if __name__ == "__main__":
     run_fisheye()
+
+
+def run_kitti360():
+    """The reference's KITTI-360 perspective reader on the miniature tree."""
+    import tempfile
+    from kitti_fixture import build_kitti360_tree
+    with tempfile.TemporaryDirectory() as root:
+        raw, meta, _ = build_kitti360_tree(root)
+        np.random.seed(14)
+        cfg = train_cfg()
+        cfg.cfg_list[1].shift_border = 16
+        ds = build(name="monodepth.data.datasets.kitti360_dataset.KITTI360MonoDataset", raw_path=raw, split_file=meta,
+                   frame_ids=[0, 1, -1], is_filter_static=True, use_right_image=True, augmentation=cfg)
+        out = {"len": np.array(len(ds))}
+        for i in range(len(ds)):
+            for k, v in summarize(ds[i]).items():
+                out[f"{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "kitti360_reader.npz"), **out)
+    print("kitti360 reader", int(out["len"]), len(out), "entries")
+
+
+if __name__ == "__main__":
+    run_kitti360()

@@ -108,6 +108,21 @@ def build_kitti360_tree(root, seed=9):
             lo = g.integers(0, 256, size=(FH // 8, FW // 8, 3)).astype(np.uint8)
             img = np.kron(lo, np.ones((8, 8, 1), dtype=np.uint8)) // 2 + g.integers(0, 128, size=(FH, FW, 3)).astype(np.uint8)
             Image.fromarray(img).save(os.path.join(d, "%010d.png" % k))
+    # perspective cameras: rectified intrinsics / rotations and rectified frames
+    PH, PW = 64, 208
+    with open(os.path.join(calib, "perspective.txt"), "w") as f:
+        for k in (0, 1):
+            P = np.array([[0.78 * PW, 0, 0.49 * PW, -50.0 * k], [0, 2.1 * PH, 0.51 * PH, 0], [0, 0, 1, 0]])
+            R, _ = _rigid(g, 0.0)
+            f.write(f"P_rect_0{k}: " + " ".join(f"{v:.9e}" for v in P.reshape(-1)) + "\n")
+            f.write(f"R_rect_0{k}: " + " ".join(f"{v:.9e}" for v in R.reshape(-1)) + "\n")
+    for cam in ("image_00", "image_01"):
+        d = os.path.join(raw, "data_2d_raw", SEQ360, cam, "data_rect")
+        os.makedirs(d, exist_ok=True)
+        for k in range(0, 30, 3):
+            lo = g.integers(0, 256, size=(PH // 8, PW // 8, 3)).astype(np.uint8)
+            img = np.kron(lo, np.ones((8, 8, 1), dtype=np.uint8)) // 2 + g.integers(0, 128, size=(PH, PW, 3)).astype(np.uint8)
+            Image.fromarray(img).save(os.path.join(d, "%010d.png" % k))
     meta = os.path.join(root, "kitti360_meta.txt")
     with open(meta, "w") as f:
         for p in range(1, 9):

@@ -94,3 +94,23 @@ def test_kitti360_fisheye_reader_matches_reference(golden_dir, tmp_path):
     s = ds2[0]
     assert s["patched_mask"].shape == (64, 64) and 0.5 < float(s["patched_mask"].float().mean()) < 0.9
     assert s["P2"].shape == (3, 4) and float(s["P2"][0, 3]) == 0.0 and isinstance(s["calib_meta"], dict)
+
+
+def test_kitti360_perspective_reader_matches_reference(golden_dir, tmp_path):
+    """KITTI360MonoDataset (rectified perspective cameras) against the reference's reader on the miniature KITTI-360 tree:
+    perspective.txt parsing, R_rect @ cam_to_pose extrinsics, filter, random camera, the KITTI augmentation list."""
+    from vision_base.utils.builder import build
+    from kitti_fixture import build_kitti360_tree
+    g = np.load(os.path.join(golden_dir, "kitti360_reader.npz"))
+    raw, meta, _ = build_kitti360_tree(str(tmp_path))
+    np.random.seed(14)
+    cfg = train_cfg()
+    cfg.cfg_list[1].shift_border = 16
+    ds = build(name="monodepth.data.datasets.kitti360_dataset.KITTI360MonoDataset", raw_path=raw, split_file=meta,
+               frame_ids=[0, 1, -1], is_filter_static=True, use_right_image=True, augmentation=cfg)
+    assert len(ds) == int(g["len"]) == 4
+    for i in range(len(ds)):
+        _check(f"{i}/", summarize(ds[i]), g)
+    from monodepth.data.datasets.kitti360_dataset import read_extrinsic_from_sequence
+    T0, T1 = read_extrinsic_from_sequence(os.path.join(raw, "calibration", "calib_cam_to_pose.txt"))
+    assert T0.shape == (4, 4) and not np.allclose(T0, T1)
