@@ -115,3 +115,28 @@ def fisheye_train_cfg(size=(64, 64)):
         edict(name=f"{AUG}.Normalize", mean=np.array([0, 0, 0]), stds=np.array([1, 1, 1]), image_keys=original_keys),
         edict(name=f"{AUG}.ConvertToTensor", image_keys=image_keys + original_keys),
     ], image_keys=image_keys, calib_keys=["P2"], gt_image_keys=["patched_mask"])
+
+
+def nusc_train_cfg(size=(64, 128)):
+    """The augmentation list of configs/nusc_wpose_example:123-151 (aspect-preserving Resize + pad, colour, mirror)."""
+    frames = [0, 1, -1]
+    image_keys = [("image", i) for i in frames]
+    original_keys = [("original_image", i) for i in frames]
+    poses = [(("relative_pose", i), 0) for i in frames[1:]]
+    return edict(name="vision_base.utils.builder.Sequential", cfg_list=[
+        edict(name=f"{AUG}.ConvertToFloat"),
+        edict(name=f"{AUG}.Resize", size=size, preserve_aspect_ratio=True, force_pad=True),
+        edict(name="vision_base.utils.builder.Shuffle", image_keys=image_keys, cfg_list=[
+            edict(name=f"{AUG}.RandomBrightness", distort_prob=1.0),
+            edict(name=f"{AUG}.RandomContrast", distort_prob=1.0, lower=0.6, upper=1.4),
+            edict(name="vision_base.utils.builder.Sequential", cfg_list=[
+                edict(name=f"{AUG}.ConvertColor", transform="HSV"),
+                edict(name=f"{AUG}.RandomSaturation", distort_prob=1.0, lower=0.6, upper=1.4),
+                edict(name=f"{AUG}.ConvertColor", current="HSV", transform="RGB"),
+            ]),
+        ]),
+        edict(name=f"{AUG}.RandomMirror", mirror_prob=0.5, pose_axis_pairs=poses),
+        edict(name=f"{AUG}.Normalize", mean=np.array([0.485, 0.456, 0.406]), stds=np.array([0.229, 0.224, 0.225]), image_keys=image_keys),
+        edict(name=f"{AUG}.Normalize", mean=np.array([0, 0, 0]), stds=np.array([1, 1, 1]), image_keys=original_keys),
+        edict(name=f"{AUG}.ConvertToTensor"),
+    ], image_keys=image_keys + original_keys, calib_keys=["P2"], gt_image_keys=["patched_mask"])

@@ -19,7 +19,7 @@ import vision_base  # noqa: E402
 
 assert vision_base.__path__[0].startswith(REF)
 sys.path.insert(0, os.path.join(REPO, "tests"))
-from aug_cases import raw_sample, train_cfg, val_cfg, summarize  # noqa: E402
+from aug_cases import raw_sample, train_cfg, val_cfg, summarize, nusc_train_cfg  # noqa: E402
 
 
 def run(name, cfg, seed):
@@ -144,3 +144,26 @@ def run_kitti360():
 
 if __name__ == "__main__":
     run_kitti360()
+
+
+def run_nusc():
+    """The reference's NusceneJsonDataset on the miniature JSON export."""
+    import tempfile
+    from kitti_fixture import build_nusc_json
+    with tempfile.TemporaryDirectory() as root:
+        path = build_nusc_json(root)
+        np.random.seed(15)
+        ds = build(name="monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset", json_path=path, frame_ids=[0, 1, -1],
+                   augmentation=nusc_train_cfg())
+        out = {"len": np.array(len(ds))}
+        for i in range(len(ds)):
+            s = ds[i]
+            out[f"{i}/meta"] = np.array([s.pop("camera_type"), str(s.pop("camera_type_index")), s.pop(("filename", 0))])
+            for k, v in summarize(s).items():
+                out[f"{i}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "nusc_reader.npz"), **out)
+    print("nusc reader", int(out["len"]), len(out), "entries")
+
+
+if __name__ == "__main__":
+    run_nusc()

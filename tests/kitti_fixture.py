@@ -132,3 +132,38 @@ def build_kitti360_tree(root, seed=9):
     mask_path = os.path.join(root, "fisheye_mask.png")
     cv2.imwrite(mask_path, mask)
     return raw, meta, mask_path
+
+
+# --------------------------------------------------------------------------------------------------
+# miniature nuScenes JSON export
+# --------------------------------------------------------------------------------------------------
+def build_nusc_json(root, seed=17, n=5, h0=96, w=160):
+    import json
+    g = np.random.default_rng(seed)
+    cams = ["CAM_FRONT", "CAM_BACK", "CAM_FRONT_LEFT"]
+    samples = []
+    for i in range(n):
+        cam = cams[i % len(cams)]
+        d = os.path.join(root, "nusc", "samples", cam)
+        os.makedirs(d, exist_ok=True)
+        paths = {}
+        h = 720 if cam == "CAM_BACK" else h0           # tall enough for the ego-car rows (700..) of the rear camera
+        for key in ("frame0", "frame1", "frame-1"):
+            lo = g.integers(0, 256, size=(h // 8, w // 8, 3)).astype(np.uint8)
+            img = np.kron(lo, np.ones((8, 8, 1), dtype=np.uint8)) // 2 + g.integers(0, 128, size=(h, w, 3)).astype(np.uint8)
+            p = os.path.join(d, f"n{i:03d}_{key.replace('-', 'm')}.png")
+            Image.fromarray(img).save(p)
+            paths[key] = p
+        poses = {}
+        for key, sign in (("pose01", -1.0), ("pose0-1", 1.0)):
+            R, _ = _rigid(g, 0.0)
+            T = np.eye(4)
+            T[:3, :3] = R
+            T[:3, 3] = [0.02, 0.01, sign * 0.6]
+            poses[key] = [float(v) for v in T.reshape(-1)]
+        K = [0.79 * w, 0.0, 0.5 * w, 0.0, 0.79 * w, 0.5 * h, 0.0, 0.0, 1.0]
+        samples.append(dict(camera_type=cam, camera_type_indexes=cams.index(cam), P2=K, **paths, **poses))
+    path = os.path.join(root, "nusc.json")
+    with open(path, "w") as f:
+        json.dump(dict(samples=samples), f)
+    return path

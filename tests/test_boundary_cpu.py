@@ -36,7 +36,8 @@ DOTTED = [
     "monodepth.data.datasets.mono_dataset.KittiDepthMonoDataset", "monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset",
     "monodepth.data.datasets.utils.cam_relative_pose", "monodepth.networks.utils.monodepth_utils.compute_errors",
     "monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", "monodepth.data.datasets.utils.cam_relative_pose_nusc",
-    "monodepth.data.datasets.kitti360_dataset.KITTI360MonoDataset"]
+    "monodepth.data.datasets.kitti360_dataset.KITTI360MonoDataset",
+    "monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset"]
 
 
 @pytest.mark.parametrize("name", DOTTED)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import torch
 
-from aug_cases import summarize, train_cfg, val_cfg
+from aug_cases import nusc_train_cfg, summarize, train_cfg, val_cfg
 from kitti_fixture import build_tree
 
 
@@ -114,3 +114,56 @@ def test_kitti360_perspective_reader_matches_reference(golden_dir, tmp_path):
     from monodepth.data.datasets.kitti360_dataset import read_extrinsic_from_sequence
     T0, T1 = read_extrinsic_from_sequence(os.path.join(raw, "calibration", "calib_cam_to_pose.txt"))
     assert T0.shape == (4, 4) and not np.allclose(T0, T1)
+
+
+def test_nuscenes_json_reader_matches_reference(golden_dir, tmp_path):
+    """NusceneJsonDataset against the reference's reader on a miniature JSON export (incl. the CAM_BACK ego-car rows)."""
+    from vision_base.utils.builder import build
+    from kitti_fixture import build_nusc_json
+    g = np.load(os.path.join(golden_dir, "nusc_reader.npz"))
+    path = build_nusc_json(str(tmp_path))
+    np.random.seed(15)
+    ds = build(name="monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset", json_path=path, frame_ids=[0, 1, -1],
+               augmentation=nusc_train_cfg())
+    assert len(ds) == int(g["len"]) == 5
+    for i in range(len(ds)):
+        s = ds[i]
+        meta = [s.pop("camera_type"), str(s.pop("camera_type_index")), s.pop(("filename", 0))]
+        want = g[f"{i}/meta"].tolist()
+        assert meta[:2] == want[:2] and meta[2].split(os.sep)[-1] == want[2].split(os.sep)[-1]
+        got = summarize(s)
+        keys = [k[len(f"{i}/"):] for k in g.files if k.startswith(f"{i}/") and not k.endswith("/meta")]
+        assert sorted(keys) == sorted(got.keys())
+        for k in keys:
+            if k.startswith("dtype/"):
+                assert str(g[f"{i}/{k}"]) == str(got[k]), k
+            else:
+                np.testing.assert_allclose(got[k], g[f"{i}/{k}"], rtol=1e-6, atol=3e-6, err_msg=k)
+
+
+def test_nuscenes_config_feeds_the_dataloader(tmp_path, monkeypatch):
+    """configs/nusc_wpose_files.py: both JSON exports concatenated, the recipe's pad-resize, one collated training batch and
+    one single-frame evaluation sample."""
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file
+    from vision_base.data.dataloader import build_dataloader
+    from vision_base.data.datasets.dataset_utils import collate_fn
+    from kitti_fixture import build_nusc_json
+    a = build_nusc_json(str(tmp_path / "a"), seed=3, n=3)
+    b = build_nusc_json(str(tmp_path / "b"), seed=4, n=4)
+    monkeypatch.setenv("FSNET_NUSC_JSON", f"{a},{b}")
+    monkeypatch.setenv("FSNET_NUSC_SIZE", "64x128")
+    monkeypatch.setenv("FSNET_WORKDIR", str(tmp_path / "work"))
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = cfg_from_file(os.path.join(repo, "configs", "nusc_wpose_files.py"))
+    train = build(**cfg.train_dataset)
+    assert len(train) == 7
+    loader = build_dataloader(train, num_workers=0, batch_size=4, collate_fn=collate_fn)
+    batch = next(iter(loader))
+    assert batch[("image", 0)].shape == (4, 3, 64, 128) and batch[("original_image", -1)].shape == (4, 3, 64, 128)
+    assert batch["P2"].shape == (4, 3, 4) and batch[("relative_pose", -1)].shape == (4, 4, 4) and batch["patched_mask"].shape == (4, 64, 128)
+    assert len(batch["camera_type"]) == 4 and len(batch[("filename", 0)]) == 4
+    val = build(**cfg.val_dataset)
+    s = val[1]
+    assert s[("image", 0)].shape == (3, 64, 128) and ("image", 1) not in s and s["camera_type"] == "CAM_BACK"
+    assert cfg.meta_arch.head_cfg.depth_decoder_cfg.base_fx == 369 and cfg.meta_arch.head_cfg.overlapped_mask is False
