@@ -3,6 +3,9 @@ through the reference's dotted names); only the path entries differ: they come f
     FSNET_KITTI_PATH   KITTI raw root (dates / drives / image_02, image_03, oxts/pose.mat, calibration files)
     FSNET_KITTI_SPLIT  training split file (default <repo>/meta_data/eigen_zhou/train_files.txt)
     FSNET_KITTI_VAL_SPLIT  evaluation split file (default = training split)
+    FSNET_KITTI_GT     ground-truth export (npz) of the evaluation split: when set, the reference's evaluate_hook
+                       (KittiEvaluationHook + KittiEigenEvaluator) is configured and runs every FSNET_TEST_ITER (5) epochs;
+                       the file is written from the split's Velodyne scans on first use
 """
 import os
 
@@ -24,6 +27,15 @@ cfg.trainer = edict(
     gpu=0, max_epochs=20, disp_iter=50, save_iter=5, test_iter=0,
     training_hook=edict(name="vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0),
 )
+_val_split = os.environ.get("FSNET_KITTI_VAL_SPLIT", os.environ.get("FSNET_KITTI_SPLIT", os.path.join(path.base_path, "meta_data", "eigen", "test_files.txt")))
+if os.environ.get("FSNET_KITTI_GT"):
+    cfg.trainer.test_iter = int(os.environ.get("FSNET_TEST_ITER", 5))
+    cfg.trainer.evaluate_hook = edict(
+        name="monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.KittiEvaluationHook",
+        test_run_hook_cfg=edict(name="vision_base.pipeline_hooks.train_val_hooks.base_validation_hooks.BaseValidationHook"),
+        dataset_eval_cfg=edict(name="monodepth.evaluation.kitti_unsupervised_eval.KittiEigenEvaluator", data_path=path.kitti_path,
+                               split_file=_val_split, gt_saved_file=os.environ["FSNET_KITTI_GT"]),
+    )
 cfg.optimizer = edict(name="adam", lr=1e-4, weight_decay=0)
 cfg.scheduler = edict(name="StepLR", step_size=15)
 

@@ -68,6 +68,15 @@ def read_poses_file(path):
     return frames, np.array(poses)
 
 
+def read_cam_to_velo(path):
+    """calib_cam_to_velo.txt: one line of 12 numbers -> 4x4 (kitti360_dataset.py:73-83, there ``read_T_from_sequence``)."""
+    with open(path) as f:
+        vals = f.readline().strip().split(" ")
+    T = np.eye(4)
+    T[:3, :] = np.array([float(x) for x in vals[:12]]).reshape(3, 4)
+    return T
+
+
 def read_P01_from_sequence(path):
     """perspective.txt -> P_rect_00, P_rect_01 (3x4) and R_rect_00, R_rect_01 embedded in 4x4."""
     P, R = {}, {0: np.eye(4), 1: np.eye(4)}

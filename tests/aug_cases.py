@@ -140,3 +140,13 @@ def nusc_train_cfg(size=(64, 128)):
         edict(name=f"{AUG}.Normalize", mean=np.array([0, 0, 0]), stds=np.array([1, 1, 1]), image_keys=original_keys),
         edict(name=f"{AUG}.ConvertToTensor"),
     ], image_keys=image_keys + original_keys, calib_keys=["P2"], gt_image_keys=["patched_mask"])
+
+
+def eval_cfg(size=(OUT_H, OUT_W), preserve_aspect_ratio=False):
+    """The single-frame evaluation list of the reference configs (configs/kitti_wpose_example:160-171)."""
+    return edict(name="vision_base.utils.builder.Sequential", cfg_list=[
+        edict(name=f"{AUG}.ConvertToFloat"),
+        edict(name=f"{AUG}.Resize", size=size, preserve_aspect_ratio=preserve_aspect_ratio, force_pad=True),
+        edict(name=f"{AUG}.Normalize", mean=np.array([0.485, 0.456, 0.406]), stds=np.array([0.229, 0.224, 0.225])),
+        edict(name=f"{AUG}.ConvertToTensor"),
+    ], image_keys=[("image", 0)], calib_keys=["P2"])

@@ -167,3 +167,60 @@ def run_nusc():
 
 if __name__ == "__main__":
     run_nusc()
+
+
+def eval_predictions(n, seed=41, shape=(48, 160)):
+    """The synthetic 'network outputs' both sides evaluate: smooth positive depth maps."""
+    g = np.random.default_rng(seed)
+    return [np.exp(g.uniform(np.log(3.0), np.log(60.0), size=shape)).astype(np.float32) for _ in range(n)]
+
+
+def run_eval():
+    """The reference's LiDAR projection and evaluators on the miniature trees."""
+    import io
+    import tempfile
+    from contextlib import redirect_stdout
+    from kitti_fixture import build_tree, build_kitti360_tree, add_kitti_lidar, add_kitti360_lidar, DATE, DRIVES
+    from monodepth.networks.utils import monodepth_utils as U
+    from monodepth.evaluation.kitti_unsupervised_eval import KittiEigenEvaluator, Kitti360Evaluator
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        raw, split = build_tree(root)
+        add_kitti_lidar(raw)
+        velo = os.path.join(raw, DATE, DRIVES[0], "velodyne_points/data", "%010d.bin" % 2)
+        for cam in (2, 3):
+            for vd in (False, True):
+                out[f"depth_map/cam{cam}_vel{int(vd)}"] = U.generate_depth_map(os.path.join(raw, DATE), velo, cam, vd).astype(np.float32)
+        with redirect_stdout(io.StringIO()):
+            ev = KittiEigenEvaluator(raw, split, os.path.join(root, "gt.npz"))
+        n = len(ev.gt_depths)
+        out["kitti/n"] = np.array(n)
+        for i in (0, n - 1):
+            out[f"kitti/gt{i}"] = np.asarray(ev.gt_depths[i])
+        res = [ev.single_call(p, i) for i, p in enumerate(eval_predictions(n))]
+        out["kitti/ratio"] = np.array([r["ratio"] for r in res])
+        out["kitti/error"] = np.array([r["error"] for r in res])
+        out["kitti/abs_error"] = np.array([r["abs_error"] for r in res])
+        buf = io.StringIO()
+        with redirect_stdout(buf):
+            ev.log(None, out["kitti/error"].mean(0), out["kitti/abs_error"].mean(0), epoch_num=3)
+        out["kitti/log"] = np.array(buf.getvalue())
+        ev2 = KittiEigenEvaluator(raw, split, os.path.join(root, "gt.npz"))           # second construction: loads the saved file
+        out["kitti/reload_error"] = np.array(ev2.single_call(eval_predictions(1)[0], 0)["error"])
+    with tempfile.TemporaryDirectory() as root:
+        raw, meta, _ = build_kitti360_tree(root)
+        add_kitti360_lidar(raw)
+        with redirect_stdout(io.StringIO()):
+            ev = Kitti360Evaluator(raw, meta, os.path.join(root, "gt360.npz"))
+        n = len(ev.gt_depths)
+        out["kitti360/n"] = np.array(n)
+        out["kitti360/gt0"] = np.asarray(ev.gt_depths[0])
+        res = [ev.single_call(p, i) for i, p in enumerate(eval_predictions(n, seed=42, shape=(32, 104)))]
+        out["kitti360/error"] = np.array([r["error"] for r in res])
+        out["kitti360/abs_error"] = np.array([r["abs_error"] for r in res])
+    np.savez_compressed(os.path.join(HERE, "evaluators.npz"), **out)
+    print("evaluators", {k: v.shape for k, v in out.items()}, os.path.getsize(os.path.join(HERE, "evaluators.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    run_eval()

@@ -167,3 +167,40 @@ def build_nusc_json(root, seed=17, n=5, h0=96, w=160):
     with open(path, "w") as f:
         json.dump(dict(samples=samples), f)
     return path
+
+
+# --------------------------------------------------------------------------------------------------
+# LiDAR scans for the evaluators (separate generators: the trees above stay byte-identical)
+# --------------------------------------------------------------------------------------------------
+def _scan(g, n=6000):
+    """[n,4] float32 (forward, left, up, reflectance); the fixture's velodyne->camera rotations are near identity, so the
+    camera looks along 'up'.  Some points lie behind the sensor (forward < 0) and some behind the image plane (up < 0)."""
+    pts = np.stack([g.uniform(-5, 40, n), g.uniform(-15, 15, n), g.uniform(-2, 50, n), g.uniform(0, 1, n)], 1)
+    return pts.astype(np.float32)
+
+
+def add_kitti_lidar(raw, seed=31):
+    """Adds S_rect_02 / R_rect_00 to calib_cam_to_cam.txt and velodyne_points/data/*.bin to every drive of build_tree()."""
+    g = np.random.default_rng(seed)
+    d = os.path.join(raw, DATE)
+    R, _ = _rigid(g, 0.0)
+    with open(os.path.join(d, "calib_cam_to_cam.txt"), "a") as f:
+        f.write(f"S_rect_02: {W:.12e} {H:.12e}\n")
+        f.write("R_rect_00: " + " ".join(f"{v:.9e}" for v in R.reshape(-1)) + "\n")
+    for drive in DRIVES:
+        v = os.path.join(d, drive, "velodyne_points", "data")
+        os.makedirs(v, exist_ok=True)
+        for k in range(N):
+            _scan(g).tofile(os.path.join(v, "%010d.bin" % k))
+
+
+def add_kitti360_lidar(raw, seed=32):
+    """Adds calibration/calib_cam_to_velo.txt and data_3d_raw/<seq>/velodyne_points/data/*.bin to build_kitti360_tree()."""
+    g = np.random.default_rng(seed)
+    R, t = _rigid(g, 0.4)
+    with open(os.path.join(raw, "calibration", "calib_cam_to_velo.txt"), "w") as f:
+        f.write(" ".join(f"{v:.9e}" for v in np.concatenate([R, t[:, None]], 1).reshape(-1)) + "\n")
+    v = os.path.join(raw, "data_3d_raw", SEQ360, "velodyne_points", "data")
+    os.makedirs(v, exist_ok=True)
+    for k in range(0, 30, 3):
+        _scan(g, 4000).tofile(os.path.join(v, "%010d.bin" % k))

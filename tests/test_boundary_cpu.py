@@ -37,7 +37,12 @@ DOTTED = [
     "monodepth.data.datasets.utils.cam_relative_pose", "monodepth.networks.utils.monodepth_utils.compute_errors",
     "monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", "monodepth.data.datasets.utils.cam_relative_pose_nusc",
     "monodepth.data.datasets.kitti360_dataset.KITTI360MonoDataset",
-    "monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset"]
+    "monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset",
+    "monodepth.evaluation.kitti_unsupervised_eval.KittiEigenEvaluator", "monodepth.evaluation.kitti_unsupervised_eval.Kitti360Evaluator",
+    "monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.KittiEvaluationHook",
+    "monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.FastNuscEvaluationHook",
+    "vision_base.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.BaseEvaluationHook",
+    "monodepth.networks.utils.monodepth_utils.generate_depth_map", "monodepth.networks.utils.monodepth_utils.project_depth_map"]
 
 
 @pytest.mark.parametrize("name", DOTTED)

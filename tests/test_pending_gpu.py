@@ -1,0 +1,54 @@
+"""GPU tests written after this round's GPU minutes were spent: NOT yet run on a B200, therefore opt-in
+(FSNET_PENDING_GPU=1) so that an unvalidated test can not mask the validated suite.  First thing to run next round:
+
+    FSNET_PENDING_GPU=1 python -m pytest tests/test_pending_gpu.py -x -q -m gpu
+
+Every piece they combine is validated separately: the host side on CPU (tests/test_evaluation_cpu.py,
+tests/test_kitti_reader_cpu.py), the training step and eval-mode inference on B200 (tests/test_model_gpu.py,
+tests/test_train_script_gpu.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("FSNET_PENDING_GPU") != "1", reason="not yet validated on a B200; set FSNET_PENDING_GPU=1")]
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, args, env):
+    out = subprocess.run([sys.executable, os.path.join(REPO, "scripts", script)] + args, env=env, cwd=REPO, capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    return out.stdout
+
+
+def test_train_then_evaluate_on_kitti_files(tmp_path):
+    """KITTI recipe with the reference's evaluate_hook: LiDAR ground-truth export, training, the per-epoch Eigen evaluation,
+    then scripts/test.py on the written checkpoint."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from kitti_fixture import add_kitti_lidar, build_tree
+    raw, split = build_tree(str(tmp_path / "kitti"))
+    add_kitti_lidar(raw)
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO, FSNET_KITTI_PATH=raw, FSNET_KITTI_SPLIT=split,
+               FSNET_SHIFT_BORDER="32", FSNET_KITTI_GT=str(tmp_path / "gt.npz"), FSNET_TEST_ITER="1")
+    cfg = f"--config={os.path.join(REPO, 'configs', 'kitti_wpose_files.py')}"
+    out = _run("train.py", [cfg, "--experiment_name=pytest", "--trainer.max_steps=3", "--trainer.max_epochs=1", "--data.batch_size=2",
+                            "--data.num_workers=0"], env)
+    assert "finished 3 steps" in out and "abs_rel" in out and os.path.isfile(tmp_path / "gt.npz")
+    ckpt = [os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith("_latest.pth")][0]
+    out = _run("test.py", [cfg, f"--checkpoint_path={ckpt}"], env)
+    assert "Found evaluate function" in out and "abs_rel" in out and "finish" in out
+
+
+def test_train_script_on_nuscenes_json(tmp_path):
+    """The nuScenes recipe (ResNet-34, 64 bins, base_fx, pad-resize, overlapped_mask off) on a miniature JSON export."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from kitti_fixture import build_nusc_json
+    a = build_nusc_json(str(tmp_path / "a"), seed=3, n=6)
+    b = build_nusc_json(str(tmp_path / "b"), seed=4, n=6)
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO, FSNET_NUSC_JSON=f"{a},{b}", FSNET_NUSC_SIZE="96x160")
+    out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'nusc_wpose_files.py')}", "--experiment_name=pytest",
+                            "--trainer.max_steps=3", "--trainer.max_epochs=2", "--data.batch_size=2", "--data.num_workers=0"], env)
+    assert "finished 3 steps" in out
