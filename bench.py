@@ -132,6 +132,8 @@ def main():
     ap.add_argument("--backend", default=os.environ.get("FSNET_CONV_BACKEND", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA graph replay)")
+    ap.add_argument("--prefetch", type=int, default=int(os.environ.get("FSNET_BENCH_PREFETCH", 0)),
+                    help="e2e leg: upload batch k+1 on a side stream while step k runs (fsnet_b200.data.loading.DevicePrefetcher)")
     ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS), help="cfg2a = BASELINE.json configs[1] (default)")
     args = ap.parse_args()
     global B_PER_GPU, H, W, CONFIG
@@ -196,6 +198,14 @@ def main():
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         last = None
+        if use_host and args.prefetch:
+            # the same n host->device copies and n loss read-backs, inside the timed region; the copy of step i+1 is issued
+            # before step i is launched, so it runs on the copy engine under step i
+            from fsnet_b200.data.loading import DevicePrefetcher
+            for i, data in enumerate(DevicePrefetcher((dict(pinned) for _ in range(n)), dev)):
+                out = hook(data, model, optimizer, None, None, i, 0)
+                last = out["loss"].item()
+            n = 0
         for i in range(n):
             if head_start:
                 # eager steps are host bound (~30 ms of Python per step): a 60 ms spin kernel lets the host queue the whole step,
@@ -270,7 +280,7 @@ def main():
         "config": {"workload": wl["text"], "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
                    "parallelism": f"dp{world}" + (" (SyncBN statistics + flat gradient all-reduce over NCCL, inside the step graph)" if world > 1 else ""),
                    "conv_backend": ops.BACKEND,
-                   "cuda_graph": use_graph,
+                   "cuda_graph": use_graph, "e2e_prefetch": bool(args.prefetch),
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
         "roofline": {"kernel": "loss_bwd_kernel<0,0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

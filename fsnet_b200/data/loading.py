@@ -71,3 +71,57 @@ def build_dataloader(dataset, num_workers: int, batch_size: int, collate_fn: Cal
     sampler = build(name, size=len(dataset), rank=local_rank, world_size=world_size, **sampler_cfg)
     return DataLoader(dataset, num_workers=num_workers, batch_size=batch_size, collate_fn=collate_fn, sampler=sampler,
                       drop_last=True, **kwargs)
+
+
+class DevicePrefetcher:
+    """Iterates a loader of HOST batches one batch ahead of the consumer: while step k computes, the tensors of batch k+1
+    travel from (pinned) host memory to the device on a side stream, so the copy engine works under the training step
+    instead of in front of it.  Hand-over is stream-ordered (the consumer's stream waits for the upload's event; the
+    caching allocator is told about the consuming stream), there is no host synchronisation.
+
+    The reference uploads inside the training hook (``data[key].cuda()``, base_training_hooks.py:33-37), i.e. copy and
+    compute are serialised; a batch that already lives on the device passes through that hook unchanged, so wrapping the
+    loader is all it takes:   ``for data in DevicePrefetcher(dataloader): training_hook(data, ...)``.
+
+    ``device='cpu'`` makes it a plain look-ahead iterator (used by the CPU tests of the ordering logic)."""
+
+    def __init__(self, loader, device=None, depth: int = 1):
+        self.loader, self.depth = loader, max(int(depth), 1)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _upload(self, batch, stream):
+        if stream is None:
+            return {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}, None
+        with torch.cuda.stream(stream):
+            out = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            event = torch.cuda.Event()
+            event.record(stream)
+        return out, event
+
+    def __iter__(self):
+        from collections import deque
+        stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        source = iter(self.loader)
+        queue = deque()
+
+        def pull():
+            try:
+                queue.append(self._upload(next(source), stream))
+            except StopIteration:
+                pass
+
+        for _ in range(self.depth):
+            pull()
+        while queue:
+            batch, event = queue.popleft()
+            pull()                                         # the next upload is in flight before this batch is consumed
+            if event is not None:
+                current = torch.cuda.current_stream(self.device)
+                current.wait_event(event)
+                for v in batch.values():
+                    if isinstance(v, torch.Tensor):
+                        v.record_stream(current)
+            yield batch

@@ -67,7 +67,12 @@ def main(config="configs/config.py", experiment_name="default", world_size=1, lo
     dataset_val = build(**cfg.val_dataset) if "val_dataset" in cfg else None
     dataloader_train = build_dataloader(dataset_train, num_workers=cfg.data.num_workers, batch_size=cfg.data.batch_size,
                                         collate_fn=collate_fn, local_rank=local_rank, world_size=world_size,
-                                        sampler_cfg=getattr(cfg.data, "sampler", dict()))
+                                        sampler_cfg=getattr(cfg.data, "sampler", dict()),
+                                        pin_memory=bool(int(os.environ.get("FSNET_PREFETCH", "0"))))
+    if int(os.environ.get("FSNET_PREFETCH", "0")):
+        # upload batch k+1 on a side stream while step k runs (the reference uploads inside the hook, serialised with the step)
+        from fsnet_b200.data.loading import DevicePrefetcher
+        dataloader_train = DevicePrefetcher(dataloader_train, torch.device("cuda", gpu))
 
     meta_arch = build(**cfg.meta_arch)
     from vision_base.networks.models.meta_archs.base_meta import BaseMetaArch

@@ -204,3 +204,23 @@ def test_lazy_batch_is_a_transparent_dict():
     assert d[("image", 0)] == 1 and d.get("missing", 7) == 7 and d.get("P2") == 2 and "P2" in d and "x" not in d
     assert dict(d) == base and sorted(map(str, d.keys())) == sorted(map(str, base.keys())) and len(list(d.items())) == 3
     assert d.copy() == base
+
+
+def test_device_prefetcher_is_one_batch_ahead_and_order_preserving():
+    """Host logic of the upload look-ahead (the CUDA side is stream plumbing around the same queue)."""
+    from fsnet_b200.data.loading import DevicePrefetcher
+    pulled = []
+
+    def source():
+        for i in range(4):
+            pulled.append(i)
+            yield {"x": torch.full((2,), float(i)), "name": f"s{i}"}
+
+    seen = []
+    for batch in DevicePrefetcher(source(), device="cpu"):
+        seen.append(int(batch["x"][0]))
+        assert batch["name"] == f"s{seen[-1]}"
+        assert len(pulled) == min(seen[-1] + 2, 4)            # the next batch was requested before this one was handed over
+    assert seen == [0, 1, 2, 3]
+    assert [int(b["x"][0]) for b in DevicePrefetcher(source(), device="cpu", depth=3)] == [0, 1, 2, 3]
+    assert list(DevicePrefetcher(iter(()), device="cpu")) == []

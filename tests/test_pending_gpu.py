@@ -52,3 +52,30 @@ def test_train_script_on_nuscenes_json(tmp_path):
     out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'nusc_wpose_files.py')}", "--experiment_name=pytest",
                             "--trainer.max_steps=3", "--trainer.max_epochs=2", "--data.batch_size=2", "--data.num_workers=0"], env)
     assert "finished 3 steps" in out
+
+
+def test_prefetched_batches_train_like_host_batches():
+    """DevicePrefetcher in front of the graphed hook: same losses as handing the hook pinned host batches."""
+    import torch
+    from fsnet_b200.data.loading import DevicePrefetcher
+    from fsnet_b200.data.synthetic import make_batch
+    from fsnet_b200.networks import ops
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file, set_random_seed
+    from vision_base.networks.optimizers.optimizers import build_optimizer
+    ops.set_backend("tc")
+    cfg = cfg_from_file(os.path.join(REPO, "configs", "kitti_wpose_synthetic.py"))
+    batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in make_batch(2, 192, 640, seed=50 + i).items()} for i in range(6)]
+    losses = []
+    for prefetch in (False, True):
+        set_random_seed(7)
+        model = build(**cfg.meta_arch).cuda().train()
+        model.head.tie_break_noise = [torch.zeros(2, 2, 192, 640, device="cuda") for _ in range(4)]
+        opt = build_optimizer(model, **cfg.optimizer)
+        hook = build(**dict(cfg.trainer.training_hook, cuda_graph=True))
+        src = (dict(b) for b in batches)
+        run = []
+        for i, data in enumerate(DevicePrefetcher(src) if prefetch else src):
+            run.append(float(hook(data, model, opt, None, None, i, 0)["loss"]))
+        losses.append(run)
+    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
