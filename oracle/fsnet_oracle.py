@@ -45,6 +45,11 @@ class Topology:
     overlapped_mask: bool = True
     frame_ids: Tuple[int, ...] = (0, 1, -1)
     fisheye: bool = False                # FishEyeDecoder: MEI camera, the network output is the ray norm
+    distill: bool = False                # DistillWPoseMeta: frozen eval-mode teacher + MultiChannelDepthDecoderUncertain student
+    distill_weight: float = 0.3          # distillation_loss_weight (configs/distill_kitti_example:218)
+    uncertain_distill: bool = True       # is_uncertain_distill (configs/distill_kitti_example:219)
+    teacher_depth: int = 18
+    teacher_bins: int = 16
 
     @property
     def bottleneck(self) -> bool:
@@ -93,7 +98,7 @@ def resnet_param_specs(prefix: str, depth: int, num_input_images: int = 1):
     return specs
 
 
-def decoder_param_specs(prefix: str, topo: Topology):
+def decoder_param_specs(prefix: str, topo: Topology, uncertain: bool = False):
     """monodepth/networks/models/heads/depth_encoder.py:45-66 (creation order = ModuleList index)."""
     specs = []
     enc = topo.num_ch_enc
@@ -113,6 +118,11 @@ def decoder_param_specs(prefix: str, topo: Topology):
         specs.append((f"{prefix}decoder.{k}.weight", (topo.n_bins, NUM_CH_DEC[s], 3, 3), "conv"))
         specs.append((f"{prefix}decoder.{k}.bias", (topo.n_bins,), "bias"))
         k += 1
+    if uncertain:       # MultiChannelDepthDecoderUncertain._init_layers, depth_encoder.py:164-168: one 1-channel head per scale
+        for s in topo.scales:
+            specs.append((f"{prefix}decoder.{k}.weight", (1, NUM_CH_DEC[s], 3, 3), "conv"))
+            specs.append((f"{prefix}decoder.{k}.bias", (1,), "bias"))
+            k += 1
     return specs
 
 
@@ -137,11 +147,24 @@ def param_specs(topo: Topology):
     if topo.posenet:
         specs += resnet_param_specs("pose_backbone.", topo.pose_depth, num_input_images=2)
     specs.append(("head.depth_decoder.depth_bins", (topo.n_bins,), "bins"))
-    specs += decoder_param_specs("head.depth_decoder.", topo)
+    specs += decoder_param_specs("head.depth_decoder.", topo, uncertain=topo.distill)
     if topo.posenet:
         c_last = 512 * (4 if topo.pose_depth >= 50 else 1)
         specs += pose_decoder_param_specs("head.pose_decoder.", c_last, 1, 2)
+    if topo.distill:    # MonoDepthInference (teacher_model.py:5-13): depth_backbone + depth_decoder, appended last
+        t = teacher_topology(topo)
+        specs += resnet_param_specs("teacher_net.depth_backbone.", t.depth)
+        specs.append(("teacher_net.depth_decoder.depth_bins", (t.n_bins,), "teacher_bins"))
+        specs += decoder_param_specs("teacher_net.depth_decoder.", t)
     return specs
+
+
+def teacher_topology(topo: Topology) -> Topology:
+    """The teacher of the distillation configs: the stage-1 network (configs/distill_kitti_example:176-197), called
+    without P2 (teacher_model.py:15-18), so never fx-scaled."""
+    return Topology(depth=topo.teacher_depth, n_bins=topo.teacher_bins, scales=topo.scales, multi_channel=True,
+                    min_depth=topo.min_depth, max_depth=topo.max_depth, base_fx=None, use_skips=True,
+                    height=topo.height, width=topo.width)
 
 
 def make_state_dict(topo: Topology, seed: int = 123) -> "OrderedDict[str, Tensor]":
@@ -157,7 +180,7 @@ def make_state_dict(topo: Topology, seed: int = 123) -> "OrderedDict[str, Tensor
     for name, shape, kind in param_specs(topo):
         if kind == "conv":
             cout, cin, kh, kw = shape
-            if name.startswith(("depth_backbone", "pose_backbone")):
+            if name.startswith(("depth_backbone", "pose_backbone", "teacher_net.depth_backbone")):
                 std = math.sqrt(2.0 / (kh * kw * cout))
             else:
                 std = math.sqrt(1.0 / (3.0 * cin * kh * kw)) * math.sqrt(3.0)  # ~ kaiming_uniform(a=sqrt(5)) variance
@@ -169,13 +192,15 @@ def make_state_dict(topo: Topology, seed: int = 123) -> "OrderedDict[str, Tensor
         elif kind == "bn_b":
             sd[name] = 0.1 * torch.randn(shape, generator=g)
         elif kind == "zeros":
-            sd[name] = torch.zeros(shape)
+            sd[name] = 0.05 * torch.randn(shape, generator=g) if name.startswith("teacher_net.") else torch.zeros(shape)
         elif kind == "ones":
-            sd[name] = torch.ones(shape)
+            sd[name] = 1.0 + 0.2 * torch.rand(shape, generator=g) if name.startswith("teacher_net.") else torch.ones(shape)
         elif kind == "count":
             sd[name] = torch.zeros((), dtype=torch.long)
         elif kind == "bins":
             sd[name] = depth_bins(topo)
+        elif kind == "teacher_bins":
+            sd[name] = depth_bins(teacher_topology(topo))
         else:
             raise ValueError(kind)
     return sd
@@ -236,7 +261,7 @@ def gather_depth(logits: Tensor, bins: Tensor, topo: Topology, depth_scale) -> T
 
 
 def decoder_forward(sd, prefix: str, feats: Sequence[Tensor], topo: Topology, P2: Optional[Tensor] = None,
-                    training: bool = True) -> Dict:
+                    training: bool = True, uncertain: bool = False) -> Dict:
     """DepthDecoder / MultiChannelDepthDecoder.forward (depth_encoder.py:90-111,123-139)."""
     out: Dict = {}
     if topo.base_fx is None or P2 is None:       # _get_scale, depth_encoder.py:36-43
@@ -267,6 +292,9 @@ def decoder_forward(sd, prefix: str, feats: Sequence[Tensor], topo: Topology, P2
                 out[("disp", i)] = disp
                 depth = 1 / (1 / topo.max_depth + (1 / topo.min_depth - 1 / topo.max_depth) * disp)  # monodepth_utils.py:8-17
                 out[("depth", i, i)] = depth * depth_scale
+            if uncertain:   # MultiChannelDepthDecoderUncertain.forward, depth_encoder.py:190
+                q = f"{prefix}decoder.{disp_index[i] + len(topo.scales)}."
+                out[("uncertain_z", i)] = torch.sigmoid(_conv3x3(x, sd[q + "weight"], sd[q + "bias"], replicate=True))
     return out
 
 
@@ -563,7 +591,9 @@ def forward_train(sd, data: Dict, topo: Topology, noise: Optional[Dict[int, Tens
     """MonoDepthWPose.forward_train / MonoDepthMeta.forward_train (monodepth2_model.py:24-46,85-130)."""
     feats = resnet_forward(sd, "depth_backbone.", data[("image", 0)], topo.depth)
     P2 = None if topo.posenet else data["P2"]          # MonoDepthMeta calls forward_depth(features) without P2 (:27)
-    outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, P2)
+    outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, P2, uncertain=topo.distill)
+    if topo.distill:
+        outputs.update(teacher_depths(sd, data[("image", 0)], topo))
     cam_T: Dict[int, Tensor] = {}
     for f in topo.frame_ids[1:]:
         if topo.posenet:
@@ -574,22 +604,51 @@ def forward_train(sd, data: Dict, topo: Topology, noise: Optional[Dict[int, Tens
         else:
             cam_T[f] = data[("relative_pose", f)]
     out = loss_chain(outputs, data, cam_T, topo, noise, keep)
+    if topo.distill:        # MonoDepth2Decoder.loss, monodepth2_decoder.py:328-334: added AFTER the division by num_scales
+        total = out["loss"]
+        for s in topo.scales:
+            d = distill_loss(outputs, s, topo)
+            out["loss_dict"][f"distilation/{s}"] = d.detach()
+            total = total + d * topo.distill_weight
+        out["loss"] = total
+        out["loss_dict"]["total_loss"] = total.detach()
     out["outputs"] = outputs
     out["cam_T"] = cam_T
     return out
 
 
+def teacher_depths(sd, image: Tensor, topo: Topology) -> Dict:
+    """MonoDepthInference.compute_teacher_depth (teacher_model.py:20-32) of the frozen teacher; DistillWPoseMeta.train keeps
+    it in eval mode (monodepth2_model.py:172-174): running statistics, no gradient."""
+    t = teacher_topology(topo)
+    with torch.no_grad():
+        feats = resnet_forward(sd, "teacher_net.depth_backbone.", image, t.depth, training=False)
+        out = decoder_forward(sd, "teacher_net.depth_decoder.", feats, t, None, training=False)
+    return {("teacher_depth", k[1], k[2]): v for k, v in out.items() if k[0] == "depth"}
+
+
+def distill_loss(outputs: Dict, s: int, topo: Topology) -> Tensor:
+    """compute_distill_loss (monodepth2_decoder.py:185-203), the scaled branch every shipped config uses."""
+    error = (outputs[("teacher_depth", s, s)].detach() - outputs[("depth", s, s)]).abs()
+    if topo.uncertain_distill:
+        u = outputs[("uncertain_z", s)]
+        return (error / u + torch.log(u + 1e-5)).mean()
+    return error.mean()
+
+
 def forward_test(sd, data: Dict, topo: Topology) -> Dict:
     """forward_test (monodepth2_model.py:132-136); BN uses running statistics in eval mode."""
     feats = resnet_forward(sd, "depth_backbone.", data[("image", 0)], topo.depth, training=False)
-    outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, None if topo.posenet else data["P2"], training=False)
+    outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, None if topo.posenet else data["P2"], training=False,
+                              uncertain=topo.distill)
     if topo.fisheye:
         return fisheye_prediction(outputs[("depth", 0, 0)], data)
     return {"depth": outputs[("depth", 0, 0)]}
 
 
 def trainable(sd) -> List[str]:
-    return [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "depth_bins"))]
+    return [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "depth_bins"))
+            and not k.startswith("teacher_net.")]
 
 
 class OracleTrainer:

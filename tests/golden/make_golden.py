@@ -45,7 +45,24 @@ def ref_meta_arch(topo: O.Topology):
     backbone = edict(name="vision_base.networks.models.backbone.resnet.resnet", depth=topo.depth, pretrained=False,
                      frozen_stages=-1, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=False, dilations=(1, 1, 1, 1))
     cfg = edict(depth_backbone_cfg=backbone, head_cfg=head, train_cfg=edict(frame_ids=list(topo.frame_ids)), test_cfg=edict())
-    if topo.posenet:
+    sd = O.make_state_dict(topo)
+    if topo.distill:
+        import tempfile
+        t = O.teacher_topology(topo)
+        head.distillation_loss_weight = topo.distill_weight
+        head.is_uncertain_distill = topo.uncertain_distill
+        head.depth_decoder_cfg.name = "monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoderUncertain"
+        cfg.name = "monodepth.networks.models.meta_archs.monodepth2_model.DistillWPoseMeta"
+        cfg.teacher_net_cfg = edict(
+            name="monodepth.networks.models.meta_archs.teacher_model.MonoDepthInference", backbone_cfg=edict(backbone, depth=t.depth),
+            depth_head_cfg=edict(name="monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoder",
+                                 num_ch_enc=np.array(t.num_ch_enc), num_output_channels=t.n_bins, use_skips=True, scales=list(t.scales),
+                                 min_depth=t.min_depth, max_depth=t.max_depth))
+        # the constructor wants a teacher checkpoint on disk (monodepth2_model.py:160-163): the teacher part of the synthetic weights
+        with tempfile.NamedTemporaryFile(suffix=".pth", delete=False) as f:
+            torch.save({k[len("teacher_net."):]: v for k, v in sd.items() if k.startswith("teacher_net.")}, f.name)
+            cfg.teacher_net_path = f.name
+    elif topo.posenet:
         cfg.name = "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthMeta"
         cfg.pose_backbone_cfg = edict(backbone, depth=topo.pose_depth, num_input_images=2)
         head.pose_decoder_cfg = edict(name="monodepth.networks.models.heads.pose_decoder.PoseDecoder",
@@ -53,7 +70,8 @@ def ref_meta_arch(topo: O.Topology):
     else:
         cfg.name = "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthWPose"
     model = build(**cfg)
-    sd = O.make_state_dict(topo)
+    if topo.distill:
+        os.unlink(cfg.teacher_net_path)
     missing = model.load_state_dict(sd, strict=True)      # key layout must be identical
     model.train()
     return model, sd
@@ -92,6 +110,11 @@ def run_full(name, topo: O.Topology, B, seed=1234, noise_seed=0, store_disp=True
         for s in topo.scales:
             out[f"disp/{s}"] = outputs[("disp", s)].detach().numpy().copy()
             out[f"depth/{s}"] = outputs[("depth", s, s)].detach().numpy().copy()
+            if topo.distill:
+                out[f"uncertain_z/{s}"] = outputs[("uncertain_z", s)].detach().numpy().copy()
+    if topo.distill:
+        for k, v in model2.teacher_net.compute_teacher_depth(data[("image", 0)]).items():
+            out[f"teacher_depth/{k[1]}"] = v.detach().numpy().copy()
     if topo.posenet:
         from monodepth.networks.utils.monodepth_utils import transformation_from_parameters
         for f_i in topo.frame_ids[1:]:
@@ -187,5 +210,8 @@ if __name__ == "__main__":
         run_full("tiny_sigmoid", O.Topology(height=64, width=96, multi_channel=False, n_bins=1, min_depth=0.1, scales=(0, 1, 2, 3)), B=2)
     if want("tiny_fe"):
         run_full("tiny_fe", O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0), B=2)
+    if want("tiny_distill"):
+        run_full("tiny_distill", O.Topology(height=64, width=128, distill=True), B=2,
+                 grads_of=("head.depth_decoder.decoder.14.weight", "head.depth_decoder.decoder.17.bias", "depth_backbone.conv1.weight"))
     if want("tiny_r50"):
         run_full("tiny_r50", O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2, store_disp=True)
