@@ -476,6 +476,8 @@ def decoder_forward(tape: Tape, dec, feats: List[Act]) -> Dict[int, Fp32]:
         x = tape.conv_bn_act(cat_act, up1.sequence[0], up1.sequence[1], relu=True, grad_ring=1)
         if i in dec.scales:
             logits[i] = tape.conv_out(x, dec.convs[("dispconv", i)], ("logits", i))
+            if ("uncertain_logz", i) in dec.convs:          # MultiChannelDepthDecoderUncertain: second head on the same activation
+                logits[("uncertain", i)] = tape.conv_out(x, dec.convs[("uncertain_logz", i)], ("uncertain", i))
     return logits
 
 
@@ -521,8 +523,9 @@ class _DepthNetFn(torch.autograd.Function):
         outs = []
         for s in ctx.scales:
             t = logits[s].t.permute(0, 3, 1, 2)         # NCHW view of the NHWC buffer (channels_last strides)
-            if n != logits[s].c:
-                t = t[:, :n].contiguous(memory_format=torch.channels_last)
+            n_s = 1 if isinstance(s, tuple) else n      # ("uncertain", scale): one-channel uncertainty head
+            if n_s != logits[s].c:
+                t = t[:, :n_s].contiguous(memory_format=torch.channels_last)
             outs.append(t)
         runner.last_features = feats
         return tuple(outs)
@@ -530,7 +533,8 @@ class _DepthNetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *g_logits):
         tape = ctx.tape
-        grads = {("logits", s): _nhwc_grad(g, ctx.c_pad[s]) for s, g in zip(ctx.scales, g_logits) if g is not None}
+        grads = {(s if isinstance(s, tuple) else ("logits", s)): _nhwc_grad(g, ctx.c_pad[s])
+                 for s, g in zip(ctx.scales, g_logits) if g is not None}
         tape.run_backward(grads)
         return (None, None) + tuple(tape.param_grads.get(id(p)) for p in ctx.params)
 
@@ -590,7 +594,13 @@ class Runner:
     def depth_logits(self, img):
         self._prep()
         outs = _DepthNetFn.apply(self, img, *self.params())
-        return dict(zip([s for s in range(4, -1, -1) if s in self.decoder.scales], outs))
+        keys = []                                       # the insertion order of decoder_forward
+        for s in range(4, -1, -1):
+            if s in self.decoder.scales:
+                keys.append(s)
+                if ("uncertain_logz", s) in self.decoder.convs:
+                    keys.append(("uncertain", s))
+        return dict(zip(keys, outs))
 
     def pose_map(self, img):
         self._prep()

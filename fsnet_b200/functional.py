@@ -280,3 +280,36 @@ class _RawPtr:
 
 def depth_head(logits, bins, scale, sigmoid_head, min_depth, max_depth):
     return _DepthHead.apply(logits, bins, scale, sigmoid_head, min_depth, max_depth)
+
+
+class _DistillLoss(torch.autograd.Function):
+    """MonoDepth2Decoder.compute_distill_loss, scaled branch (monodepth2_decoder.py:185-203): one launch produces the mean
+    and the unit gradients with respect to the student's depth and the un-activated uncertainty."""
+
+    @staticmethod
+    def forward(ctx, pred, teacher, ulogit):
+        import ctypes
+        p, t = _f32c(pred), _f32c(teacher)
+        if p.shape != t.shape:
+            raise _lib.FsnetError(f"distillation: student depth {tuple(p.shape)} vs teacher depth {tuple(t.shape)}")
+        l = None if ulogit is None else _f32c(ulogit)
+        if l is not None and l.numel() != p.numel():
+            raise _lib.FsnetError(f"distillation: uncertainty map {tuple(l.shape)} vs depth map {tuple(p.shape)}")
+        out = torch.zeros(1, device=p.device, dtype=torch.float64)
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        gu = torch.empty_like(l) if (l is not None and ctx.needs_input_grad[2]) else None
+        _lib.call("fsnet_distill_loss", p, t, l, ctypes.c_longlong(p.numel()), out, gp, gu, None)
+        ctx.gp, ctx.gu = gp, gu
+        return out[0].float()
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.float()
+        gp = None if ctx.gp is None else (ctx.gp * g).view_as(ctx.gp)
+        gu = None if ctx.gu is None else (ctx.gu * g).view_as(ctx.gu)
+        return gp, None, gu
+
+
+def distill_loss(pred: torch.Tensor, teacher: torch.Tensor, uncertain_logit: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mean(|teacher - pred| / u + log(u + 1e-5)) with u = sigmoid(uncertain_logit); mean|teacher - pred| without it."""
+    return _DistillLoss.apply(pred, teacher.detach(), uncertain_logit)

@@ -89,3 +89,44 @@ class MultiChannelDepthDecoder(DepthDecoder):
             outputs[("depth", i, i)], outputs[("disp", i)] = Fn.depth_head(
                 logits, self.depth_bins, scale, False, self.min_depth, self.max_depth)
         return outputs
+
+
+class MultiChannelDepthDecoderUncertain(DepthDecoder):
+    """Second-stage (distillation) decoder: the softmax-bins depth head plus a one-channel uncertainty head per scale
+    (depth_encoder.py:142-194).  ``('uncertain_logit', s)`` is what the fused distillation loss consumes;
+    ``('uncertain_z', s)`` = sigmoid of it is the reference's output entry (detached: informational)."""
+    multi_channel = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        for s in self.scales:
+            self.convs[("uncertain_logz", s)] = nn.Conv2d(int(self.num_ch_dec[s]), 1, kernel_size=3, padding=1, padding_mode="replicate")
+        self.decoder = nn.ModuleList(list(self.convs.values()))       # same ModuleList order as the reference: heads last
+
+    def _trunk_with_uncertainty(self, input_features):
+        from .ops_tc import LazyFeatures, runner_for
+        if isinstance(input_features, LazyFeatures) and not input_features.materialized:
+            outs = runner_for(self, input_features.backbone).depth_logits(input_features.image)
+            for i in range(4, -1, -1):
+                if i in self.scales:
+                    yield i, outs[i], outs[("uncertain", i)]
+            return
+        x = input_features[-1]
+        for i in range(4, -1, -1):
+            x = self.convs[("upconv", i, 0)](x)
+            x = ops.upsample2x_concat(x, input_features[i - 1] if (self.use_skips and i > 0) else None)
+            x = self.convs[("upconv", i, 1)](x)
+            if i in self.scales:
+                yield (i, ops.conv_act(x, self.convs[("dispconv", i)], relu=False),
+                       ops.conv_act(x, self.convs[("uncertain_logz", i)], relu=False))
+
+    def forward(self, input_features, P2=None):
+        outputs = {}
+        scale = self._get_scale(P2)
+        for i, logits, ulogit in self._trunk_with_uncertainty(input_features):
+            outputs[("logits", i)] = logits
+            outputs[("depth", i, i)], outputs[("disp", i)] = Fn.depth_head(
+                logits, self.depth_bins, scale, False, self.min_depth, self.max_depth)
+            outputs[("uncertain_logit", i)] = ulogit
+            outputs[("uncertain_z", i)] = torch.sigmoid(ulogit.detach())
+        return outputs

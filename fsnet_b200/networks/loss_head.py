@@ -47,6 +47,12 @@ class MonoDepth2Decoder(nn.Module):
             loss = loss + torch.abs(input_dict[("relative_pose", f)] - output_dict[("cam_T_cam", f)]).mean()
         return loss
 
+    def compute_distill_loss(self, output_dict, input_dict, scale):
+        """monodepth2_decoder.py:185-203, scaled branch: |teacher - student| (divided by the predicted uncertainty, plus its
+        log, when ``is_uncertain_distill``) averaged over the map -- one fused launch (csrc/distill.cu)."""
+        ulogit = output_dict[("uncertain_logit", scale)] if getattr(self, "is_uncertain_distill", False) else None
+        return Fn.distill_loss(output_dict[("depth", scale, scale)], output_dict[("teacher_depth", scale, scale)], ulogit)
+
     def _mei_camera(self, input_dict, H, W):
         """None for the pinhole camera; FishEyeDecoder returns the MEI ray table + calibration."""
         return None
@@ -56,8 +62,10 @@ class MonoDepth2Decoder(nn.Module):
             if getattr(self, flag, False):
                 raise NotImplementedError(f"{flag}=True is outside the B200 hot path (no shipped config enables it; "
                                           "the reference's own branch for it is incomplete, SURVEY.md 8(a) a7/a14)")
-        if getattr(self, "distillation_loss_weight", 0) > 0 or getattr(self, "residualflow_weight", 0) > 0:
-            raise NotImplementedError("distillation / residual-flow losses are second-stage training (SURVEY.md 8(f) N4)")
+        if getattr(self, "residualflow_weight", 0) > 0:
+            raise NotImplementedError("the residual-flow loss is outside the B200 hot path (no shipped config enables it)")
+        if getattr(self, "distillation_loss_weight", 0) > 0 and getattr(self, "is_unscaled_distill", False):
+            raise NotImplementedError("is_unscaled_distill=True is not implemented (no shipped config enables it)")
 
     def compute_total_reprojection_loss(self, output_dict, input_dict):
         """Returns (losses, hm, total) like monodepth2_decoder.py:205-304."""
@@ -103,6 +111,12 @@ class MonoDepth2Decoder(nn.Module):
             pose_loss = self.compute_pose_loss(output_dict, input_dict)
             losses["pose_loss"] = pose_loss
             total = total + pose_weight * pose_loss
+        distill_weight = getattr(self, "distillation_loss_weight", 0)
+        if distill_weight > 0:                       # second training stage (monodepth2_decoder.py:328-334)
+            for scale in self.scales:
+                distill = self.compute_distill_loss(output_dict, input_dict, scale)
+                losses[f"distilation/{scale}"] = distill.detach()
+                total = total + distill * distill_weight
         losses["total_loss"] = total.detach()
         if not getattr(self, "is_log_image", True):
             hm = {}

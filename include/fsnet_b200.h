@@ -195,6 +195,17 @@ int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* sc
                          const float* grad_depth, const float* grad_disp, float* grad_logits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * distillation loss of the second training stage (monodepth2_decoder.py:185-203, scaled branch; the sigmoid of
+ * MultiChannelDepthDecoderUncertain.forward, depth_encoder.py:190, is applied here), value + unit gradients in one pass.
+ *   pred, teacher [n] fp32: the student's and the (frozen) teacher's depth map of one scale
+ *   ulogit [n] fp32: un-activated uncertainty head output, or NULL (is_uncertain_distill = False: plain L1)
+ *   out [1] fp64, accumulated: += mean_i( |t-p| / u + log(u + 1e-5) ),  u = sigmoid(ulogit)
+ *   grad_pred, grad_ulogit [n] fp32 out or NULL: d out / d pred, d out / d ulogit;  uncertain [n] fp32 out or NULL: u
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_distill_loss(const float* pred, const float* teacher, const float* ulogit, long long n, double* out,
+                       float* grad_pred, float* grad_ulogit, float* uncertain, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * loss finalisation: turns the per-scale accumulators into the reference's loss_dict entries
  * (monodepth2_decoder.py:292-303).  acc [S,4] fp64 = {num, den, smooth, unused} per scale.
  *   out [2*S+2] fp64: loss/s (S), smooth_loss/s (S), total_loss, spare

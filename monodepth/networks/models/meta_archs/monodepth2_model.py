@@ -1,2 +1,2 @@
 """Reference-compatible dotted name; the implementation lives in fsnet_b200."""
-from fsnet_b200.networks.meta_archs import MonoDepthMeta, MonoDepthWPose  # noqa: F401
+from fsnet_b200.networks.meta_archs import DistillWPoseMeta, MonoDepthMeta, MonoDepthWPose  # noqa: F401

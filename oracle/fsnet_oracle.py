@@ -143,7 +143,13 @@ def depth_bins(topo: Topology) -> Tensor:
 
 
 def param_specs(topo: Topology):
-    specs = resnet_param_specs("depth_backbone.", topo.depth)
+    specs = []
+    if topo.distill:    # MonoDepthInference (teacher_model.py:5-13): depth_backbone + depth_decoder; DistillWPoseMeta builds it first
+        t = teacher_topology(topo)
+        specs += resnet_param_specs("teacher_net.depth_backbone.", t.depth)
+        specs.append(("teacher_net.depth_decoder.depth_bins", (t.n_bins,), "teacher_bins"))
+        specs += decoder_param_specs("teacher_net.depth_decoder.", t)
+    specs += resnet_param_specs("depth_backbone.", topo.depth)
     if topo.posenet:
         specs += resnet_param_specs("pose_backbone.", topo.pose_depth, num_input_images=2)
     specs.append(("head.depth_decoder.depth_bins", (topo.n_bins,), "bins"))
@@ -151,11 +157,6 @@ def param_specs(topo: Topology):
     if topo.posenet:
         c_last = 512 * (4 if topo.pose_depth >= 50 else 1)
         specs += pose_decoder_param_specs("head.pose_decoder.", c_last, 1, 2)
-    if topo.distill:    # MonoDepthInference (teacher_model.py:5-13): depth_backbone + depth_decoder, appended last
-        t = teacher_topology(topo)
-        specs += resnet_param_specs("teacher_net.depth_backbone.", t.depth)
-        specs.append(("teacher_net.depth_decoder.depth_bins", (t.n_bins,), "teacher_bins"))
-        specs += decoder_param_specs("teacher_net.depth_decoder.", t)
     return specs
 
 

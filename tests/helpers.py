@@ -17,7 +17,25 @@ def meta_arch_cfg(topo: O.Topology, is_log_image=False):
     backbone = edict(name="vision_base.networks.models.backbone.resnet.resnet", depth=topo.depth, pretrained=False,
                      frozen_stages=-1, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=False, dilations=(1, 1, 1, 1))
     cfg = edict(depth_backbone_cfg=backbone, head_cfg=head, train_cfg=edict(frame_ids=list(topo.frame_ids)), test_cfg=edict())
-    if topo.posenet:
+    if topo.distill:
+        import tempfile
+        import torch
+        t = O.teacher_topology(topo)
+        head.distillation_loss_weight = topo.distill_weight
+        head.is_uncertain_distill = topo.uncertain_distill
+        head.depth_decoder_cfg.name = "monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoderUncertain"
+        cfg.name = "monodepth.networks.models.meta_archs.monodepth2_model.DistillWPoseMeta"
+        cfg.teacher_net_cfg = edict(
+            name="monodepth.networks.models.meta_archs.teacher_model.MonoDepthInference", backbone_cfg=edict(backbone, depth=t.depth),
+            depth_head_cfg=edict(name="monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoder",
+                                 num_ch_enc=np.array(t.num_ch_enc), num_output_channels=t.n_bins, use_skips=True, scales=list(t.scales),
+                                 min_depth=t.min_depth, max_depth=t.max_depth))
+        # the constructor reads a teacher checkpoint from disk (monodepth2_model.py:160-163)
+        sd = O.make_state_dict(topo)
+        with tempfile.NamedTemporaryFile(suffix=".pth", delete=False) as f:
+            torch.save({k[len("teacher_net."):]: v for k, v in sd.items() if k.startswith("teacher_net.")}, f.name)
+        cfg.teacher_net_path = f.name
+    elif topo.posenet:
         cfg.name = "monodepth.networks.models.meta_archs.monodepth2_model.MonoDepthMeta"
         cfg.pose_backbone_cfg = edict(backbone, depth=topo.pose_depth, num_input_images=2)
         head.pose_decoder_cfg = edict(name="monodepth.networks.models.heads.pose_decoder.PoseDecoder",
@@ -29,6 +47,10 @@ def meta_arch_cfg(topo: O.Topology, is_log_image=False):
 
 def build_model(topo: O.Topology, seed=123, **kw):
     from vision_base.utils.builder import build
-    model = build(**meta_arch_cfg(topo, **kw))
+    cfg = meta_arch_cfg(topo, **kw)
+    model = build(**cfg)
+    if topo.distill:
+        import os
+        os.unlink(cfg.teacher_net_path)
     model.load_state_dict(O.make_state_dict(topo, seed), strict=True)
     return model.train()

@@ -42,7 +42,10 @@ DOTTED = [
     "monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.KittiEvaluationHook",
     "monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.FastNuscEvaluationHook",
     "vision_base.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.BaseEvaluationHook",
-    "monodepth.networks.utils.monodepth_utils.generate_depth_map", "monodepth.networks.utils.monodepth_utils.project_depth_map"]
+    "monodepth.networks.utils.monodepth_utils.generate_depth_map", "monodepth.networks.utils.monodepth_utils.project_depth_map",
+    "monodepth.networks.models.meta_archs.monodepth2_model.DistillWPoseMeta",
+    "monodepth.networks.models.meta_archs.teacher_model.MonoDepthInference",
+    "monodepth.networks.models.heads.depth_encoder.MultiChannelDepthDecoderUncertain"]
 
 
 @pytest.mark.parametrize("name", DOTTED)
@@ -59,7 +62,7 @@ def test_find_object_error_is_module_not_found():
 
 
 @pytest.mark.parametrize("topo", [O.Topology(), O.Topology(posenet=True), O.Topology(depth=50), O.Topology(depth=34, n_bins=64),
-                                  O.Topology(multi_channel=False, n_bins=1, scales=(0, 2))])
+                                  O.Topology(multi_channel=False, n_bins=1, scales=(0, 2)), O.Topology(distill=True)])
 def test_state_dict_layout_matches_reference(topo):
     """Keys, shapes and dtypes equal the oracle's list, which loads strictly into the reference
     (tests/golden/make_golden.py ran ``load_state_dict(strict=True)`` on it)."""
@@ -224,3 +227,77 @@ def test_device_prefetcher_is_one_batch_ahead_and_order_preserving():
     assert seen == [0, 1, 2, 3]
     assert [int(b["x"][0]) for b in DevicePrefetcher(source(), device="cpu", depth=3)] == [0, 1, 2, 3]
     assert list(DevicePrefetcher(iter(()), device="cpu")) == []
+
+
+def test_distill_loss_autograd_plumbing(monkeypatch):
+    """functional.distill_loss with the kernel launch replaced by the same arithmetic in torch: checks what the Python side
+    owns (argument order of the C call, unit-gradient scaling by the upstream gradient, shapes, no gradient to the teacher)."""
+    from fsnet_b200 import _lib, functional as Fn
+    seen = {}
+
+    def fake_call(name, p, t, l, n, out, gp, gu, uz):
+        assert name == "fsnet_distill_loss" and n.value == p.numel() and out.dtype == torch.float64 and uz is None
+        seen["n"] = n.value
+        err = (t - p).abs()
+        sgn = torch.sign(t - p)
+        inv = 1.0 / p.numel()
+        if l is None:
+            out += err.double().mean()
+            gp.copy_(-sgn * inv)
+        else:
+            u = torch.sigmoid(l)
+            out += (err / u + torch.log(u + 1e-5)).double().mean()
+            gp.copy_(-sgn / u * inv)
+            gu.copy_((1 / (u + 1e-5) - err / u ** 2) * u * (1 - u) * inv)
+
+    monkeypatch.setattr(_lib, "call", fake_call)
+    g = torch.Generator().manual_seed(0)
+    for with_u in (True, False):
+        p = (torch.rand(2, 1, 6, 8, generator=g) * 30 + 1).requires_grad_(True)
+        t = (torch.rand(2, 1, 6, 8, generator=g) * 30 + 1).requires_grad_(True)
+        l = torch.randn(2, 1, 6, 8, generator=g).requires_grad_(True) if with_u else None
+        out = Fn.distill_loss(p, t, l)
+        assert out.dtype == torch.float32 and out.dim() == 0 and seen["n"] == 96
+        (out.double() * 0.3 + 1.0).backward()
+        p2, l2 = p.detach().clone().requires_grad_(True), (None if l is None else l.detach().clone().requires_grad_(True))
+        err = (t.detach() - p2).abs()
+        ref = (err / torch.sigmoid(l2) + torch.log(torch.sigmoid(l2) + 1e-5)).mean() if with_u else err.mean()
+        (ref * 0.3).backward()
+        assert t.grad is None and p.grad.shape == p.shape
+        torch.testing.assert_close(out, ref.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(p.grad, p2.grad, rtol=1e-4, atol=1e-8)
+        if with_u:
+            torch.testing.assert_close(l.grad, l2.grad, rtol=1e-4, atol=1e-8)
+
+
+def test_teacher_export_feeds_the_distillation_config(tmp_path, monkeypatch):
+    """stage-1 checkpoint -> monodepth/transform_teacher.py -> configs/kitti_distill_synthetic.py builds with that teacher:
+    teacher weights equal the stage-1 network's, frozen, eval mode; the pose head is dropped."""
+    import sys
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file
+    from vision_base.networks.utils.utils import save_models
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(repo, "monodepth"))
+    from monodepth.transform_teacher import transform_teacher_model
+    stage1 = build_model(O.Topology(posenet=True))
+    ckpt, teacher_path = str(tmp_path / "stage1_latest.pth"), str(tmp_path / "teacher.pth")
+    save_models(ckpt, stage1, None)
+    teacher = transform_teacher_model(ckpt, teacher_path)
+    assert teacher and all(k.startswith(("depth_backbone.", "depth_decoder.")) for k in teacher)
+    monkeypatch.setenv("FSNET_TEACHER", teacher_path)
+    monkeypatch.setenv("FSNET_WORKDIR", str(tmp_path / "work"))
+    cfg = cfg_from_file(os.path.join(repo, "configs", "kitti_distill_synthetic.py"))
+    model = build(**cfg.meta_arch).train()
+    sd1 = stage1.state_dict()
+    for k, v in model.teacher_net.state_dict().items():
+        src = sd1["head." + k if k.startswith("depth_decoder.") else k]
+        assert torch.equal(v, src), k
+    assert not model.teacher_net.training and model.depth_backbone.training
+    assert not any(p.requires_grad for p in model.teacher_net.parameters())
+    assert model.head.distillation_loss_weight == 0.3 and model.head.is_uncertain_distill
+    # the optimiser is built over model.parameters() as in the reference (optimizers.py:8): the frozen teacher's parameters
+    # are in the group but never receive a gradient, and FusedAdam (like torch's Adam) steps only parameters that have one
+    from fsnet_b200.optim import build_optimizer
+    opt = build_optimizer(model, **cfg.optimizer)
+    assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == sum(p.numel() for p in model.parameters())

@@ -89,15 +89,19 @@ FULL_CASES = {
     "tiny_sigmoid": dict(topo=O.Topology(height=64, width=96, multi_channel=False, n_bins=1, min_depth=0.1, scales=(0, 1, 2, 3)), B=2),
     "tiny_r50": dict(topo=O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2),
     "tiny_fe": dict(topo=O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0), B=2),
+}
+# oracle pinned here on CPU; the CUDA side of these runs from tests/test_pending_gpu.py until it has been validated on a B200
+PENDING_FULL_CASES = {
     # second training stage: frozen eval-mode teacher, uncertainty heads, distillation loss (DistillWPoseMeta)
     "tiny_distill": dict(topo=O.Topology(height=64, width=128, distill=True), B=2),
 }
+ALL_FULL_CASES = dict(FULL_CASES, **PENDING_FULL_CASES)
 
 
-@pytest.mark.parametrize("name", sorted(FULL_CASES))
+@pytest.mark.parametrize("name", sorted(ALL_FULL_CASES))
 def test_full_step_matches_reference(golden_dir, name):
     g = load(golden_dir, name)
-    topo, B = FULL_CASES[name]["topo"], FULL_CASES[name]["B"]
+    topo, B = ALL_FULL_CASES[name]["topo"], ALL_FULL_CASES[name]["B"]
     data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1234, topo.frame_ids)
     np.testing.assert_allclose(checksum(data), g["input_checksum"], rtol=1e-12)
     sd = O.make_state_dict(topo)

@@ -79,3 +79,80 @@ def test_prefetched_batches_train_like_host_batches():
             run.append(float(hook(data, model, opt, None, None, i, 0)["loss"]))
         losses.append(run)
     assert losses[0] == pytest.approx(losses[1], rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["tiny_distill"])
+def test_distillation_stage_matches_reference(golden_dir, name, monkeypatch):
+    """DistillWPoseMeta on the tcgen05 path against the reference-generated golden: losses (incl. distilation/s), gradient
+    norms, disparity / depth maps, eval-mode prediction -- the same checks as the validated full-step cases -- plus the
+    uncertainty maps and the frozen teacher's depth."""
+    import numpy as np
+    import torch
+    import test_model_gpu as T
+    from test_oracle_golden import PENDING_FULL_CASES, load, rel
+    from helpers import build_model
+    from oracle import fsnet_oracle as O
+    from fsnet_b200.networks import ops
+    ops.set_backend("tc")
+    case = PENDING_FULL_CASES[name]
+    monkeypatch.setitem(T.FULL_CASES, name, case)
+    T.test_training_forward_backward_matches_reference(golden_dir, name)
+    g = load(golden_dir, name)
+    topo, B = case["topo"], case["B"]
+    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    model = build_model(topo).cuda()
+    assert model.training and not model.teacher_net.training
+    img = data[("image", 0)].cuda()
+    outs = model.head.forward_depth(model.depth_backbone(img), data["P2"].cuda())
+    teacher = model.teacher_net.compute_teacher_depth(img)
+    for s in topo.scales:
+        assert rel(outs[("uncertain_z", s)].cpu(), g[f"uncertain_z/{s}"]) < 1e-3, s
+        assert rel(teacher[("teacher_depth", s, s)].cpu(), g[f"teacher_depth/{s}"]) < 1e-3, s
+    before = {k: v.clone() for k, v in model.teacher_net.state_dict().items()}
+    model(T.to_cuda(data), dict(is_training=True, epoch_num=0, global_step=0))["loss"].mean().backward()
+    assert all(torch.equal(before[k], v) for k, v in model.teacher_net.state_dict().items())       # frozen, eval-mode statistics
+    assert all(p.grad is None for p in model.teacher_net.parameters())
+    for s in topo.scales:           # both heads received their gradient
+        assert float(model.head.depth_decoder.convs[("uncertain_logz", s)].weight.grad.abs().sum()) > 0
+
+
+def test_distill_loss_kernel_matches_torch():
+    """fsnet_distill_loss against the same arithmetic in torch fp32 (value 1e-5, gradients 1e-4)."""
+    import torch
+    from fsnet_b200 import functional as Fn
+    g = torch.Generator().manual_seed(3)
+    for n, with_u in ((5, True), (3000, True), (70001, False), (12 * 96 * 320, True)):
+        p = (torch.rand(n, generator=g) * 40 + 1).cuda().requires_grad_(True)
+        t = (torch.rand(n, generator=g) * 40 + 1).cuda()
+        t[: n // 7] = p.detach()[: n // 7]                                   # exact ties: sign(0) = 0
+        l = (torch.randn(n, generator=g) * 2).cuda().requires_grad_(True) if with_u else None
+        out = Fn.distill_loss(p.view(1, 1, 1, n), t.view(1, 1, 1, n), None if l is None else l.view(1, 1, 1, n))
+        (out * 0.3).backward()
+        p2 = p.detach().clone().requires_grad_(True)
+        l2 = None if l is None else l.detach().clone().requires_grad_(True)
+        err = (t - p2).abs()
+        if l2 is not None:
+            u = torch.sigmoid(l2)
+            ref = (err / u + torch.log(u + 1e-5)).mean()
+        else:
+            ref = err.mean()
+        (ref * 0.3).backward()
+        assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-7
+        assert float((p.grad - p2.grad).norm() / (p2.grad.norm() + 1e-30)) < 1e-4
+        if l is not None:
+            assert float((l.grad - l2.grad).norm() / (l2.grad.norm() + 1e-30)) < 1e-4
+
+
+def test_two_stage_training_through_the_scripts(tmp_path):
+    """docs/kitti.md's recipe end to end: stage-1 training -> monodepth/transform_teacher.py -> distillation training."""
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO)
+    common = ["--experiment_name=pytest", "--trainer.max_steps=3", "--trainer.max_epochs=1", "--data.batch_size=2", "--data.num_workers=0",
+              "--train_dataset.length=16"]
+    _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'kitti_wpose_synthetic.py')}"] + common, env)
+    ckpt = [os.path.join(d, f) for d, _, fs in os.walk(tmp_path) for f in fs if f.endswith("_latest.pth")][0]
+    teacher = str(tmp_path / "teacher.pth")
+    out = subprocess.run([sys.executable, os.path.join(REPO, "monodepth", "transform_teacher.py"), ckpt, teacher], env=env, cwd=REPO,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and os.path.isfile(teacher), out.stderr[-2000:]
+    out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'kitti_distill_synthetic.py')}"] + common, dict(env, FSNET_TEACHER=teacher))
+    assert "finished 3 steps" in out
