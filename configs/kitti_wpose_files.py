@@ -3,6 +3,7 @@ through the reference's dotted names); only the path entries differ: they come f
     FSNET_KITTI_PATH   KITTI raw root (dates / drives / image_02, image_03, oxts/pose.mat, calibration files)
     FSNET_KITTI_SPLIT  training split file (default <repo>/meta_data/eigen_zhou/train_files.txt)
     FSNET_KITTI_VAL_SPLIT  evaluation split file (default = training split)
+    FSNET_DEVICE_AUG   1: augment on the GPU (uint8 frames + drawn parameters are uploaded; same list, same draws)
     FSNET_KITTI_GT     ground-truth export (npz) of the evaluation split: when set, the reference's evaluate_hook
                        (KittiEvaluationHook + KittiEigenEvaluator) is configured and runs every FSNET_TEST_ITER (5) epochs;
                        the file is written from the split's Velodyne scans on first use
@@ -79,6 +80,9 @@ train_dataset.augmentation = edict(
     ],
     **data.augmentation.key_mappings,
 )
+if int(os.environ.get("FSNET_DEVICE_AUG", "0")):
+    # same list, same random draws; the loader ships uint8 frames and the GPU does the pixel work (fsnet_b200/data/device_augment.py)
+    train_dataset.augmentation = edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=train_dataset.augmentation)
 val_dataset.augmentation = edict(
     name="vision_base.utils.builder.Sequential",
     cfg_list=[

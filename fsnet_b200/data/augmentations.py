@@ -142,9 +142,13 @@ class RandomSaturation(object):
         self.image_keys = list(image_keys)
         self.rng = _rng(random_seed)
 
+    def draw(self):
+        """The factor of this call, or None (same generator calls as the reference, so seeded runs agree)."""
+        return self.rng.uniform(self.lower, self.upper) if self.rng.random() <= self.distort_prob else None
+
     def __call__(self, data):
-        if self.rng.random() <= self.distort_prob:
-            ratio = self.rng.uniform(self.lower, self.upper)
+        ratio = self.draw()
+        if ratio is not None:
             for key in self.image_keys:
                 data[key][:, :, 1] *= ratio
         return data
@@ -159,9 +163,12 @@ class RandomContrast(object):
         self.image_keys = list(image_keys)
         self.rng = _rng(random_seed)
 
+    def draw(self):
+        return self.rng.uniform(self.lower, self.upper) if self.rng.random() <= self.distort_prob else None
+
     def __call__(self, data):
-        if self.rng.random() <= self.distort_prob:
-            alpha = self.rng.uniform(self.lower, self.upper)
+        alpha = self.draw()
+        if alpha is not None:
             for key in self.image_keys:
                 data[key] = data[key] * alpha
         return data
@@ -176,9 +183,12 @@ class RandomBrightness(object):
         self.image_keys = list(image_keys)
         self.rng = _rng(random_seed)
 
+    def draw(self):
+        return self.rng.uniform(-self.delta, self.delta) if self.rng.random() <= self.distort_prob else None
+
     def __call__(self, data):
-        if self.rng.random() <= self.distort_prob:
-            delta = self.rng.uniform(-self.delta, self.delta)
+        delta = self.draw()
+        if delta is not None:
             for key in self.image_keys:
                 data[key] = data[key] + delta
         return data
@@ -212,25 +222,32 @@ class RandomMirror(object):
         self.is_switch_lr = is_switch_left_right
         self.stereo_pairs = list(stereo_image_key_pairs) + list(stereo_calib_key_pairs)
 
+    def draw(self) -> bool:
+        return bool(np.random.rand() <= self.mirror_prob)
+
+    def mirror_entries(self, data, width):
+        """Everything a flip changes apart from the pixel arrays (calibration, objects, lidar, poses, stereo sides)."""
+        for key in self.calib_keys:
+            P = data[key]
+            P[0, 3] = -P[0, 3]
+            P[0, 2] = width - P[0, 2] - 1
+            data[key] = P
+        for key in self.object_keys:
+            data[key].flip_objects()
+        for key in self.lidar_keys:
+            data[key] = -data[key][..., 0]
+        for key, axis_num in self.pose_axis_pairs:
+            data[key] = flip_relative_pose(data[key], axis_num)
+        if self.is_switch_lr:
+            for left, right in self.stereo_pairs:
+                data[left], data[right] = data[right], data[left]
+
     def __call__(self, data):
         width = data[self.image_keys[0]].shape[1]
-        if np.random.rand() <= self.mirror_prob:
+        if self.draw():
             for key in self.image_keys + self.gt_image_keys:
                 data[key] = np.ascontiguousarray(data[key][:, ::-1])
-            for key in self.calib_keys:
-                P = data[key]
-                P[0, 3] = -P[0, 3]
-                P[0, 2] = width - P[0, 2] - 1
-                data[key] = P
-            for key in self.object_keys:
-                data[key].flip_objects()
-            for key in self.lidar_keys:
-                data[key] = -data[key][..., 0]
-            for key, axis_num in self.pose_axis_pairs:
-                data[key] = flip_relative_pose(data[key], axis_num)
-            if self.is_switch_lr:
-                for left, right in self.stereo_pairs:
-                    data[left], data[right] = data[right], data[left]
+            self.mirror_entries(data, width)
         return data
 
 
@@ -247,20 +264,15 @@ class RandomWarpAffine(object):
         self.border_mode = border_mode
         self.rng = _rng(random_seed)
 
-    def __call__(self, data):
-        height, width = data[self.image_keys[0]].shape[:2]
+    def draw(self, height, width):
+        """(s, shift_w, shift_h) of this call: output = s * input + shift."""
         scale = max(height, width) * self.rng.uniform(self.scale_lower, self.scale_upper)
         center_w = self.rng.integers(low=self.shift_border, high=width - self.shift_border)
         center_h = self.rng.integers(low=self.shift_border, high=height - self.shift_border)
         s = max(self.output_w, self.output_h) / scale
-        shift_w = self.output_w / 2 - center_w * s
-        shift_h = self.output_h / 2 - center_h * s
-        M = np.array([[s, 0, shift_w], [0, s, shift_h]], dtype=np.float32)
-        size = (self.output_w, self.output_h)
-        for key in self.image_keys:
-            data[key] = cv2.warpAffine(data[key], M, size, flags=cv2.INTER_LINEAR, borderMode=self.border_mode)
-        for key in self.gt_image_keys:
-            data[key] = cv2.warpAffine(data[key], M, size, flags=cv2.INTER_NEAREST, borderMode=self.border_mode)
+        return s, self.output_w / 2 - center_w * s, self.output_h / 2 - center_h * s
+
+    def warp_calibration(self, data, s, shift_w, shift_h):
         for key in self.calib_keys:
             P = data[key]
             P[0:2, :] *= s
@@ -269,6 +281,17 @@ class RandomWarpAffine(object):
             P[1, 2] = P[1, 2] + shift_h
             P[1, 3] = P[1, 3] + shift_h * P[2, 3]
             data[key] = P
+
+    def __call__(self, data):
+        height, width = data[self.image_keys[0]].shape[:2]
+        s, shift_w, shift_h = self.draw(height, width)
+        M = np.array([[s, 0, shift_w], [0, s, shift_h]], dtype=np.float32)
+        size = (self.output_w, self.output_h)
+        for key in self.image_keys:
+            data[key] = cv2.warpAffine(data[key], M, size, flags=cv2.INTER_LINEAR, borderMode=self.border_mode)
+        for key in self.gt_image_keys:
+            data[key] = cv2.warpAffine(data[key], M, size, flags=cv2.INTER_NEAREST, borderMode=self.border_mode)
+        self.warp_calibration(data, s, shift_w, shift_h)
         return data
 
 

@@ -83,10 +83,12 @@ class DevicePrefetcher:
     compute are serialised; a batch that already lives on the device passes through that hook unchanged, so wrapping the
     loader is all it takes:   ``for data in DevicePrefetcher(dataloader): training_hook(data, ...)``.
 
+    ``device_transform`` (optional) is applied to every uploaded batch on the upload stream (device-side augmentation).
     ``device='cpu'`` makes it a plain look-ahead iterator (used by the CPU tests of the ordering logic)."""
 
-    def __init__(self, loader, device=None, depth: int = 1):
+    def __init__(self, loader, device=None, depth: int = 1, device_transform=None):
         self.loader, self.depth = loader, max(int(depth), 1)
+        self.device_transform = device_transform       # e.g. DeviceAugmentStage: runs on the upload stream, right behind the copy
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
     def __len__(self):
@@ -94,9 +96,12 @@ class DevicePrefetcher:
 
     def _upload(self, batch, stream):
         if stream is None:
-            return {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}, None
+            out = {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            return (out if self.device_transform is None else self.device_transform(out)), None
         with torch.cuda.stream(stream):
             out = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            if self.device_transform is not None:
+                out = self.device_transform(out)
             event = torch.cuda.Event()
             event.record(stream)
         return out, event

@@ -37,9 +37,11 @@ class Sequential(_Chain):
 class Shuffle(_Chain):
     """As Sequential but in a fresh random order on every call (np.random.permutation)."""
 
+    def draw(self):
+        return np.random.permutation(len(self.children))
+
     def __call__(self, *args, **kwargs):
-        order = np.random.permutation(len(self.children))
-        return self._run([self.children[i] for i in order], *args, **kwargs)
+        return self._run([self.children[i] for i in self.draw()], *args, **kwargs)
 
 
 class Parallel(_Chain):

@@ -195,6 +195,18 @@ int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* sc
                          const float* grad_depth, const float* grad_disp, float* grad_logits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * training augmentation of uint8 frames on the device: the pixel work of the reference's CPU list RandomWarpAffine ->
+ * RandomMirror -> colour jitter -> Normalize (vision_base/data/augmentations/augmentations.py:91-109,200-226,377-498,527-592)
+ * with OpenCV's arithmetic (cv2.warpAffine fixed-point coordinates, float HSV); the random parameters are drawn on the host.
+ *   frames [B,F,H0,W0,3] uint8 (zero-padded to a common H0 x W0), mask [B,H0,W0] uint8 or NULL
+ *   plan [B,16] fp64 per sample: [0:6] inverse 2x3 affine (output -> source), [6] mirror, [7:10] colour op codes in order
+ *        (0 none, 1 brightness, 2 contrast, 3 saturation), [10:13] their values (NaN = HSV round trip only), [13] h0, [14] w0
+ *   mean_std [6] fp32;  image, original [F,B,3,H,W] fp32 out: (aug/255 - mean)/std and warped/255;  mask_out [B,H,W] fp64 or NULL
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_augment_frames(const unsigned char* frames, const unsigned char* mask, const double* plan, int B, int F, int H0, int W0,
+                         int H, int W, const float* mean_std, float* image, float* original, double* mask_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * distillation loss of the second training stage (monodepth2_decoder.py:185-203, scaled branch; the sigmoid of
  * MultiChannelDepthDecoderUncertain.forward, depth_encoder.py:190, is applied here), value + unit gradients in one pass.
  *   pred, teacher [n] fp32: the student's and the (frozen) teacher's depth map of one scale

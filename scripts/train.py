@@ -65,14 +65,19 @@ def main(config="configs/config.py", experiment_name="default", world_size=1, lo
 
     dataset_train = build(**cfg.train_dataset)
     dataset_val = build(**cfg.val_dataset) if "val_dataset" in cfg else None
+    # a dataset whose augmentation is fsnet_b200.data.device_augment.DeviceAugmentation ships uint8 frames + parameters; the pixel
+    # work runs on the GPU right behind the upload
+    from fsnet_b200.data.device_augment import device_augment_collate, find_device_stage
+    device_stage = find_device_stage(dataset_train)
+    prefetch = bool(int(os.environ.get("FSNET_PREFETCH", "0"))) or device_stage is not None
     dataloader_train = build_dataloader(dataset_train, num_workers=cfg.data.num_workers, batch_size=cfg.data.batch_size,
-                                        collate_fn=collate_fn, local_rank=local_rank, world_size=world_size,
-                                        sampler_cfg=getattr(cfg.data, "sampler", dict()),
-                                        pin_memory=bool(int(os.environ.get("FSNET_PREFETCH", "0"))))
-    if int(os.environ.get("FSNET_PREFETCH", "0")):
+                                        collate_fn=collate_fn if device_stage is None else device_augment_collate,
+                                        local_rank=local_rank, world_size=world_size,
+                                        sampler_cfg=getattr(cfg.data, "sampler", dict()), pin_memory=prefetch)
+    if prefetch:
         # upload batch k+1 on a side stream while step k runs (the reference uploads inside the hook, serialised with the step)
         from fsnet_b200.data.loading import DevicePrefetcher
-        dataloader_train = DevicePrefetcher(dataloader_train, torch.device("cuda", gpu))
+        dataloader_train = DevicePrefetcher(dataloader_train, torch.device("cuda", gpu), device_transform=device_stage)
 
     meta_arch = build(**cfg.meta_arch)
     from vision_base.networks.models.meta_archs.base_meta import BaseMetaArch

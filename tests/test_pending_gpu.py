@@ -156,3 +156,53 @@ def test_two_stage_training_through_the_scripts(tmp_path):
     assert out.returncode == 0 and os.path.isfile(teacher), out.stderr[-2000:]
     out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'kitti_distill_synthetic.py')}"] + common, dict(env, FSNET_TEACHER=teacher))
     assert "finished 3 steps" in out
+
+
+def test_device_augmentation_kernel_matches_oracle(golden_dir):
+    """fsnet_augment_frames against oracle/augment_oracle.py (itself pinned against cv2 and the reference pipeline's golden):
+    the warped originals bit-exact, the colour-jittered normalised frames to float rounding, the mask exactly."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from aug_cases import OUT_H, OUT_W, raw_sample
+    from test_device_augment_cpu import device_cfg
+    from oracle import augment_oracle as AO
+    from fsnet_b200.data.device_augment import DeviceAugmentStage, device_augment_collate
+    from vision_base.utils.builder import build
+    np.random.seed(7)
+    aug = build(**device_cfg())
+    stage = DeviceAugmentStage(aug)
+    samples = [aug(raw_sample(100 + i, h=120 - 8 * (i % 2), w=400 - 8 * (i % 3))) for i in range(6)]
+    samples[3]["aug_plan"][10:13] = np.where(samples[3]["aug_plan"][7:10] == 3, np.nan, samples[3]["aug_plan"][10:13])   # HSV round trip only
+    host = device_augment_collate(samples)
+    want = [AO.apply_plan(host["frames_u8"][b].numpy(), host["mask_u8"][b].numpy(), host["aug_plan"][b].numpy(), OUT_H, OUT_W,
+                          aug.mean, aug.std) for b in range(6)]
+    dev = stage({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in host.items()})
+    for b in range(6):
+        for k, f in enumerate(aug.frames):
+            assert torch.equal(dev[("original_image", f)][b].cpu(), torch.from_numpy(want[b][1][k])), (b, f)
+            np.testing.assert_allclose(dev[("image", f)][b].cpu().numpy(), want[b][0][k], rtol=1e-5, atol=2e-5)
+        assert torch.equal(dev["patched_mask"][b].cpu(), torch.from_numpy(want[b][2]))
+    # and against the reference pipeline's own output for the first samples (same seed as the golden run)
+    g = np.load(os.path.join(golden_dir, "aug_train.npz"))
+    np.random.seed(7)
+    aug2 = build(**device_cfg())
+    host2 = device_augment_collate([aug2(raw_sample(100 + i)) for i in range(3)])
+    dev2 = DeviceAugmentStage(aug2)({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in host2.items()})
+    for i in range(3):
+        np.testing.assert_allclose(dev2[("image", 0)][i].cpu().numpy(), g[f"{i}/full/image_0"], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(dev2[("original_image", 1)][i].cpu().numpy(), g[f"{i}/full/original_image_1"], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(dev2["P2"][i].cpu().numpy(), g[f"{i}/full/P2"], rtol=1e-6, atol=1e-6)
+
+
+def test_train_script_with_device_augmentation(tmp_path):
+    """The KITTI recipe on files with the augmentation's pixel work on the GPU: uint8 frames + drawn parameters through the
+    loader workers, upload + fsnet_augment_frames on the prefetch stream, then the usual training step."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from kitti_fixture import build_tree
+    raw, split = build_tree(str(tmp_path / "kitti"))
+    env = dict(os.environ, FSNET_WORKDIR=str(tmp_path), PYTHONPATH=REPO, FSNET_KITTI_PATH=raw, FSNET_KITTI_SPLIT=split,
+               FSNET_SHIFT_BORDER="32", FSNET_DEVICE_AUG="1")
+    out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'kitti_wpose_files.py')}", "--experiment_name=pytest",
+                            "--trainer.max_steps=3", "--trainer.max_epochs=2", "--data.batch_size=2", "--data.num_workers=2"], env)
+    assert "finished 3 steps" in out
