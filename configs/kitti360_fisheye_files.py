@@ -69,6 +69,9 @@ train_dataset.augmentation = edict(
     ],
     image_keys=image_keys, calib_keys=["P2"], gt_image_keys=["patched_mask"],
 )
+if int(os.environ.get("FSNET_DEVICE_AUG", "0")):
+    # same list, same random draws; the loader ships uint8 frames and the GPU does the pixel work (fsnet_b200/data/device_augment.py)
+    train_dataset.augmentation = edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=train_dataset.augmentation)
 val_dataset.augmentation = edict(
     name="vision_base.utils.builder.Sequential",
     cfg_list=[

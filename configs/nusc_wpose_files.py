@@ -70,6 +70,9 @@ train_dataset.augmentation = edict(
     ],
     **data.augmentation.key_mappings,
 )
+if int(os.environ.get("FSNET_DEVICE_AUG", "0")):
+    # same list, same random draws; the loader ships uint8 frames and the GPU does the pixel work (fsnet_b200/data/device_augment.py)
+    train_dataset.augmentation = edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=train_dataset.augmentation)
 val_dataset.augmentation = edict(
     name="vision_base.utils.builder.Sequential",
     cfg_list=[

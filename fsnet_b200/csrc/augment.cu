@@ -1,9 +1,10 @@
-// Training augmentation of a batch of uint8 frame triplets on the device: affine warp (bilinear) +
+// Training augmentation of a batch of uint8 frame triplets on the device: affine warp or resize + pad (bilinear) +
 // horizontal mirror + colour chain (brightness / contrast / saturation through HSV, in the drawn order) + normalisation, and
 // the nearest-neighbour warp of the validity mask -- the pixel work of the reference's CPU list
 // (vision_base/data/augmentations/augmentations.py:91-109,200-226,377-498,527-592), whose arithmetic is OpenCV's:
 //   * cv2.warpAffine: source coordinates in 10-bit fixed point, rint(coef * 1024) evaluated in double, rounded to 1/32 pixel
 //     (bilinear) or to the pixel (nearest); bilinear weights = float products of (1 - k/32, k/32); constant border 0;
+//   * cv2.resize: coordinate (d + 0.5) * scale - 0.5 in double, float fraction, horizontal then vertical pass; nearest = floor(d * scale);
 //   * cv2.cvtColor RGB<->HSV on float32: H in [0, 360), S = (V - min) / (|V| + eps), no clipping.
 // Every float operation is written with explicit round-to-nearest intrinsics so that no FMA contraction changes the result
 // relative to the numpy restatement (oracle/augment_oracle.py), which is bit-exact with cv2 for the warp.
@@ -14,7 +15,7 @@
 namespace fsnet {
 namespace {
 
-constexpr int kPlan = 16;      // [0:6] inverse affine, 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0
+constexpr int kPlan = 16;      // [0:6] geometry, 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0, 15 geometry mode
 constexpr int OP_BRIGHTNESS = 1, OP_CONTRAST = 2, OP_SATURATION = 3;
 
 __device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float& h, float& s, float& v) {
@@ -65,24 +66,56 @@ __global__ void __launch_bounds__(256) augment_frames_kernel(const uint8_t* __re
   const double* p = plan + (size_t)b * kPlan;
   const bool mirror = p[6] != 0.0;
   const int h0 = (int)p[13], w0 = (int)p[14];
-  const double xs = (double)(mirror ? W - 1 - x : x), ys = (double)y;
-  // cv2.warpAffine: adelta / bdelta per column, X0 / Y0 per row (+ the rounding offset of the interpolation mode)
-  const long long adelta = __double2ll_rn(__dmul_rn(__dmul_rn(p[0], xs), 1024.0));
-  const long long bdelta = __double2ll_rn(__dmul_rn(__dmul_rn(p[3], xs), 1024.0));
-  const long long X0 = fixed(p[1], ys, p[2]), Y0 = fixed(p[4], ys, p[5]);
-  if (mask_out != nullptr) {
-    const long long mx = (X0 + 512 + adelta) >> 10, my = (Y0 + 512 + bdelta) >> 10;
-    const bool in = mx >= 0 && mx < w0 && my >= 0 && my < h0;
-    mask_out[((size_t)b * H + y) * W + x] = in ? (double)mask[((size_t)b * H0 + my) * W0 + mx] : 0.0;
+  const bool resize = (int)p[15] == 1;
+  const int xm = mirror ? W - 1 - x : x;                     // RandomMirror acts on the finished (padded) frame
+  const double xs = (double)xm, ys = (double)y;
+  int sx, sy, sx1, sy1;                                        // tap columns / rows
+  float wa, wb, wc, wd;                                        // affine: the four tap weights; resize: (1-fx, fx, 1-fy, fy)
+  bool ok00, ok01, ok10, ok11;
+  if (!resize) {
+    // cv2.warpAffine: adelta / bdelta per column, X0 / Y0 per row (+ the rounding offset of the interpolation mode)
+    const long long adelta = __double2ll_rn(__dmul_rn(__dmul_rn(p[0], xs), 1024.0));
+    const long long bdelta = __double2ll_rn(__dmul_rn(__dmul_rn(p[3], xs), 1024.0));
+    const long long X0 = fixed(p[1], ys, p[2]), Y0 = fixed(p[4], ys, p[5]);
+    if (mask_out != nullptr) {
+      const long long mx = (X0 + 512 + adelta) >> 10, my = (Y0 + 512 + bdelta) >> 10;
+      const bool in = mx >= 0 && mx < w0 && my >= 0 && my < h0;
+      mask_out[((size_t)b * H + y) * W + x] = in ? (double)mask[((size_t)b * H0 + my) * W0 + mx] : 0.0;
+    }
+    const long long X = (X0 + 16 + adelta) >> 5, Y = (Y0 + 16 + bdelta) >> 5;
+    sx = (int)max(min(X >> 5, 32767LL), -32768LL);            // saturate_cast<short>
+    sy = (int)max(min(Y >> 5, 32767LL), -32768LL);
+    sx1 = sx + 1;
+    sy1 = sy + 1;
+    const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
+    wa = __fmul_rn(__fsub_rn(1.f, fy), __fsub_rn(1.f, fx));
+    wb = __fmul_rn(__fsub_rn(1.f, fy), fx);
+    wc = __fmul_rn(fy, __fsub_rn(1.f, fx));
+    wd = __fmul_rn(fy, fx);
+    const bool okx0 = sx >= 0 && sx < w0, okx1 = sx1 >= 0 && sx1 < w0, oky0 = sy >= 0 && sy < h0, oky1 = sy1 >= 0 && sy1 < h0;
+    ok00 = oky0 && okx0; ok01 = oky0 && okx1; ok10 = oky1 && okx0; ok11 = oky1 && okx1;
+  } else {
+    // cv2.resize to (w_eff, h_eff) at the top-left of a zero canvas: coordinate (d + 0.5) * scale - 0.5 in double, float fraction
+    const int w_eff = (int)p[2], h_eff = (int)p[3];
+    const bool in = xm < w_eff && y < h_eff;
+    if (mask_out != nullptr) {
+      const int mx = min((int)floor(__dmul_rn(xs, p[0])), w0 - 1), my = min((int)floor(__dmul_rn(ys, p[1])), h0 - 1);
+      mask_out[((size_t)b * H + y) * W + x] = in ? (double)mask[((size_t)b * H0 + my) * W0 + mx] : 0.0;
+    }
+    const double cx = __dadd_rn(__dmul_rn(__dadd_rn(xs, 0.5), p[0]), -0.5), cy = __dadd_rn(__dmul_rn(__dadd_rn(ys, 0.5), p[1]), -0.5);
+    const double flx = floor(cx), fly = floor(cy);
+    sx = (int)flx;
+    sy = (int)fly;
+    float fx = (float)__dadd_rn(cx, -flx), fy = (float)__dadd_rn(cy, -fly);
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    if (sx >= w0 - 1) { sx = w0 - 1; fx = 0.f; }
+    if (sy < 0) { sy = 0; fy = 0.f; }
+    if (sy >= h0 - 1) { sy = h0 - 1; fy = 0.f; }
+    sx1 = min(sx + 1, w0 - 1);
+    sy1 = min(sy + 1, h0 - 1);
+    wa = __fsub_rn(1.f, fx); wb = fx; wc = __fsub_rn(1.f, fy); wd = fy;
+    ok00 = ok01 = ok10 = ok11 = in;
   }
-  const long long X = (X0 + 16 + adelta) >> 5, Y = (Y0 + 16 + bdelta) >> 5;
-  const long long sxl = X >> 5, syl = Y >> 5;
-  const int sx = (int)max(min(sxl, 32767LL), -32768LL), sy = (int)max(min(syl, 32767LL), -32768LL);   // saturate_cast<short>
-  const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
-  const float w00 = __fmul_rn(__fsub_rn(1.f, fy), __fsub_rn(1.f, fx)), w01 = __fmul_rn(__fsub_rn(1.f, fy), fx);
-  const float w10 = __fmul_rn(fy, __fsub_rn(1.f, fx)), w11 = __fmul_rn(fy, fx);
-  const bool okx0 = sx >= 0 && sx < w0, okx1 = sx + 1 >= 0 && sx + 1 < w0;
-  const bool oky0 = sy >= 0 && sy < h0, oky1 = sy + 1 >= 0 && sy + 1 < h0;
   const float mean[3] = {mean_std[0], mean_std[1], mean_std[2]}, stdv[3] = {mean_std[3], mean_std[4], mean_std[5]};
   const size_t plane = (size_t)H * W, pix = (size_t)y * W + x;
   for (int f = 0; f < F; ++f) {
@@ -90,11 +123,15 @@ __global__ void __launch_bounds__(256) augment_frames_kernel(const uint8_t* __re
     float rgb[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float t00 = (oky0 && okx0) ? (float)src[((size_t)sy * W0 + sx) * 3 + c] : 0.f;
-      const float t01 = (oky0 && okx1) ? (float)src[((size_t)sy * W0 + sx + 1) * 3 + c] : 0.f;
-      const float t10 = (oky1 && okx0) ? (float)src[((size_t)(sy + 1) * W0 + sx) * 3 + c] : 0.f;
-      const float t11 = (oky1 && okx1) ? (float)src[((size_t)(sy + 1) * W0 + sx + 1) * 3 + c] : 0.f;
-      rgb[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, w00), __fmul_rn(t01, w01)), __fmul_rn(t10, w10)), __fmul_rn(t11, w11));
+      const float t00 = ok00 ? (float)src[((size_t)sy * W0 + sx) * 3 + c] : 0.f;
+      const float t01 = ok01 ? (float)src[((size_t)sy * W0 + sx1) * 3 + c] : 0.f;
+      const float t10 = ok10 ? (float)src[((size_t)sy1 * W0 + sx) * 3 + c] : 0.f;
+      const float t11 = ok11 ? (float)src[((size_t)sy1 * W0 + sx1) * 3 + c] : 0.f;
+      if (!resize)
+        rgb[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, wa), __fmul_rn(t01, wb)), __fmul_rn(t10, wc)), __fmul_rn(t11, wd));
+      else      // horizontal pass, then vertical pass
+        rgb[c] = __fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(t00, wa), __fmul_rn(t01, wb)), wc),
+                           __fmul_rn(__fadd_rn(__fmul_rn(t10, wa), __fmul_rn(t11, wb)), wd));
     }
     float* o = original + ((size_t)f * B + b) * 3 * plane + pix;
 #pragma unroll

@@ -91,9 +91,9 @@ class Resize(object):
         self.size, self.preserve_aspect_ratio, self.force_pad = size, preserve_aspect_ratio, force_pad
         self.image_keys, self.calib_keys, self.gt_image_keys = list(image_keys), list(calib_keys), list(gt_image_keys)
 
-    def __call__(self, data):
-        h0, w0 = data[self.image_keys[0]].shape[:2]
-        data[("image_resize", "original_shape")] = np.array([h0, w0]).astype(int)
+    def geometry(self, h0, w0):
+        """(h, w) of the resized frame, how it is brought to ``size`` afterwards ('none' | 'pad_0' | 'pad_1' | 'crop_1') and the
+        (y, x) factors applied to the calibration."""
         mode = "none"
         if self.preserve_aspect_ratio:
             fy, fx = self.size[0] / h0, self.size[1] / w0          # the reference calls these scale_factor_x / _y
@@ -103,11 +103,20 @@ class Resize(object):
             else:
                 f = fy
                 mode = "crop_1" if fy > fx else "pad_1"
-            h, w = int(np.round(h0 * f)), int(np.round(w0 * f))
-            scale_yx = (f, f)
-        else:
-            scale_yx = (self.size[0] / h0, self.size[1] / w0)
-            h, w = self.size[0], self.size[1]
+            return int(np.round(h0 * f)), int(np.round(w0 * f)), mode, (f, f)
+        return self.size[0], self.size[1], mode, (self.size[0] / h0, self.size[1] / w0)
+
+    def resize_calibration(self, data, scale_yx):
+        for key in self.calib_keys:
+            P = data[key]
+            P[0, :] = P[0, :] * scale_yx[1]
+            P[1, :] = P[1, :] * scale_yx[0]
+            data[key] = P
+
+    def __call__(self, data):
+        h0, w0 = data[self.image_keys[0]].shape[:2]
+        data[("image_resize", "original_shape")] = np.array([h0, w0]).astype(int)
+        h, w, mode, scale_yx = self.geometry(h0, w0)
         data[("image_resize", "effective_size")] = np.array([h, w]).astype(int)
         for key in self.image_keys:
             data[key] = cv2.resize(data[key], (w, h))
@@ -125,11 +134,7 @@ class Resize(object):
                     else:
                         pad[0] = (0, self.size[0] - img.shape[0])
                     data[key] = np.pad(img, pad, "constant")
-        for key in self.calib_keys:
-            P = data[key]
-            P[0, :] = P[0, :] * scale_yx[1]
-            P[1, :] = P[1, :] * scale_yx[0]
-            data[key] = P
+        self.resize_calibration(data, scale_yx)
         return data
 
 

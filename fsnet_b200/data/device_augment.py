@@ -1,8 +1,8 @@
 """Training augmentation with the pixel work on the GPU.
 
-The reference augments every sample on the CPU in float32 (``ConvertToFloat -> RandomWarpAffine -> RandomMirror ->
-Shuffle[RandomBrightness, RandomContrast, HSV/RandomSaturation/RGB] -> Normalize x2 -> ConvertToTensor``,
-configs/kitti_wpose_example:123-158) and ships 6 float32 frames per sample to the device.  Here the loader worker only DRAWS the
+The reference augments every sample on the CPU in float32 (``ConvertToFloat -> RandomWarpAffine (KITTI) or Resize + pad
+(nuScenes, KITTI-360 fisheye) -> RandomMirror -> Shuffle[RandomBrightness, RandomContrast, HSV/RandomSaturation/RGB] -> Normalize x2 ->
+ConvertToTensor``, configs/kitti_wpose_example:123-158, nusc_wpose_example:123-151, kitti360_fisheye_example:131-163) and ships 6 float32 frames per sample to the device.  Here the loader worker only DRAWS the
 random parameters -- with the very same augmentation objects, built from the very same config list, so a seeded run makes the
 same draws -- and updates the small entries (calibration, poses); the uint8 frames travel as they were decoded (8x fewer bytes
 than 2 x float32) and one CUDA kernel (csrc/augment.cu) does warp + mirror + colour chain + normalisation for all frames of
@@ -27,7 +27,8 @@ from . import augmentations as A
 from .loading import collate_fn
 
 OP_NONE, OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION = 0, 1, 2, 3
-PLAN_SIZE = 16           # [0:6] inverse affine (row major), 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0, 15 spare
+PLAN_SIZE = 16           # [0:6] geometry, 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0, 15 geometry mode
+GEOM_AFFINE, GEOM_RESIZE = 0, 1   # [0:6] = inverse affine (row major)  |  scale_x, scale_y, w_eff, h_eff, -, -
 
 
 def _invert_affine(M32: np.ndarray) -> np.ndarray:
@@ -59,14 +60,14 @@ class DeviceAugmentation(object):
         self.pipe = build(**pipeline)
         if not isinstance(self.pipe, Sequential):
             raise NotImplementedError("DeviceAugmentation expects the reference's Sequential augmentation list")
-        self.warp = self.mirror = self.norm = None
-        self.steps: List = []            # ("warp",), ("mirror",), ("colour", op) / ("shuffle", Shuffle, [ops]) in list order
+        self.geom = self.mirror = self.norm = None
+        self.steps: List = []            # ("geom",), ("mirror",), ("colour", op) / ("shuffle", Shuffle) in list order
         for child in self.pipe.children:
             if isinstance(child, (A.ConvertToFloat, A.ConvertToTensor)):
                 continue
-            if isinstance(child, A.RandomWarpAffine) and self.warp is None:
-                self.warp = child
-                self.steps.append(("warp",))
+            if isinstance(child, (A.RandomWarpAffine, A.Resize)) and self.geom is None and not self.steps:
+                self.geom = child
+                self.steps.append(("geom",))
             elif isinstance(child, A.RandomMirror) and self.mirror is None:
                 self.mirror = child
                 self.steps.append(("mirror",))
@@ -74,6 +75,11 @@ class DeviceAugmentation(object):
                 self.steps.append(("shuffle", child))
             elif self._colour_code(child):
                 self.steps.append(("colour", child))
+            elif isinstance(child, A.Copy) and all(isinstance(a, tuple) and isinstance(b, tuple) and a[0] == "image"
+                                                   and b[0] == "original_image" and a[1] == b[1]
+                                                   for a, b in zip(child.from_keys, child.to_keys)) and not any(
+                                                       st[0] in ("shuffle", "colour") for st in self.steps):
+                continue                                       # original_image := the geometry-only frame: what the kernel writes
             elif isinstance(child, A.Normalize):
                 if np.all(child.mean == 0) and np.all(child.stds == 1):
                     continue                                   # the 'original_image' entries: plain / 255
@@ -81,19 +87,25 @@ class DeviceAugmentation(object):
                     raise NotImplementedError("DeviceAugmentation: more than one mean/std normalisation in the list")
                 self.norm = child
             else:
-                raise NotImplementedError(f"DeviceAugmentation: {type(child).__name__} has no device implementation "
-                                          "(supported: the KITTI recipe's RandomWarpAffine / RandomMirror / colour jitter / Normalize)")
-        if self.warp is None or self.norm is None:
-            raise NotImplementedError("DeviceAugmentation needs a RandomWarpAffine and a mean/std Normalize in the list")
-        if self.warp.border_mode != 0:
+                raise NotImplementedError(f"DeviceAugmentation: {type(child).__name__} has no device implementation here (supported "
+                                          "lists: RandomWarpAffine or Resize first, then RandomMirror / colour jitter / Copy / Normalize)")
+        if self.geom is None or self.norm is None:
+            raise NotImplementedError("DeviceAugmentation needs a RandomWarpAffine or Resize first and a mean/std Normalize in the list")
+        self.is_warp = isinstance(self.geom, A.RandomWarpAffine)
+        if self.is_warp and self.geom.border_mode != 0:
             raise NotImplementedError("DeviceAugmentation: only cv2.BORDER_CONSTANT warps")
+        if not self.is_warp and len(self.geom.size) != 2:
+            raise NotImplementedError("DeviceAugmentation: Resize(size=(h, w)) expected")
         n_ops = sum(len(s[1].children) if s[0] == "shuffle" else 1 for s in self.steps if s[0] in ("shuffle", "colour"))
         if n_ops > 3:
             raise NotImplementedError("DeviceAugmentation: at most three colour operations")
         self.frames = [k[1] for k in self.norm.image_keys if isinstance(k, tuple) and k[0] == "image"]
         if not self.frames:
             raise NotImplementedError("DeviceAugmentation: Normalize(image_keys=[('image', f), ...]) expected")
-        self.output_h, self.output_w = self.warp.output_h, self.warp.output_w
+        if self.is_warp:
+            self.output_h, self.output_w = self.geom.output_h, self.geom.output_w
+        else:
+            self.output_h, self.output_w = int(self.geom.size[0]), int(self.geom.size[1])
         self.mean, self.std = self.norm.mean.astype(np.float32), self.norm.stds.astype(np.float32)
 
     @staticmethod
@@ -123,11 +135,18 @@ class DeviceAugmentation(object):
         plan = np.zeros(PLAN_SIZE, dtype=np.float64)
         codes, values = [], []
         for step in self.steps:
-            if step[0] == "warp":
-                s, shift_w, shift_h = self.warp.draw(h0, w0)
+            if step[0] == "geom" and self.is_warp:
+                s, shift_w, shift_h = self.geom.draw(h0, w0)
                 M = np.array([[s, 0, shift_w], [0, s, shift_h]], dtype=np.float32)
                 plan[0:6] = _invert_affine(M).reshape(-1)
-                self.warp.warp_calibration(data, s, shift_w, shift_h)
+                self.geom.warp_calibration(data, s, shift_w, shift_h)
+            elif step[0] == "geom":
+                h, w, _, scale_yx = self.geom.geometry(h0, w0)
+                data[("image_resize", "original_shape")] = np.array([h0, w0]).astype(int)
+                data[("image_resize", "effective_size")] = np.array([h, w]).astype(int)
+                plan[0:4] = 1.0 / (w / w0), 1.0 / (h / h0), w, h          # cv2.resize: scale = 1 / (dsize / ssize), in double
+                plan[15] = GEOM_RESIZE
+                self.geom.resize_calibration(data, scale_yx)
             elif step[0] == "mirror":
                 if self.mirror.draw():
                     plan[6] = 1.0
@@ -151,9 +170,10 @@ class DeviceAugmentation(object):
             if not np.array_equal(mask_u8, mask):
                 raise NotImplementedError("DeviceAugmentation: patched_mask must hold 0 / 1")
             data["mask_u8"] = mask_u8
+            data["mask_dtype"] = str(np.asarray(mask).dtype)      # the list keeps the mask's dtype (fp64 ones / a uint8 validity image)
         data["frames_u8"] = frames
         data["aug_plan"] = plan
-        for key in self.warp.calib_keys:                   # ConvertToTensor (augmentations.py:62-89)
+        for key in self.geom.calib_keys:                   # ConvertToTensor (augmentations.py:62-89)
             data[key] = torch.tensor(data[key], dtype=torch.float32).contiguous()
         return data
 
@@ -202,8 +222,10 @@ class DeviceAugmentStage(object):
         for i, f in enumerate(self.frames):
             batch[("image", f)] = image[i]
             batch[("original_image", f)] = original[i]
+        dtypes = batch.pop("mask_dtype", None)
         if mask_out is not None:
-            batch["patched_mask"] = mask_out
+            keep_integer = bool(dtypes) and all(d == "uint8" for d in dtypes)
+            batch["patched_mask"] = mask_out.to(torch.uint8) if keep_integer else mask_out
         return batch
 
 

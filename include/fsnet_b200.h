@@ -199,8 +199,9 @@ int fsnet_depth_head_bwd(const float* logits, const float* bins, const float* sc
  * RandomMirror -> colour jitter -> Normalize (vision_base/data/augmentations/augmentations.py:91-109,200-226,377-498,527-592)
  * with OpenCV's arithmetic (cv2.warpAffine fixed-point coordinates, float HSV); the random parameters are drawn on the host.
  *   frames [B,F,H0,W0,3] uint8 (zero-padded to a common H0 x W0), mask [B,H0,W0] uint8 or NULL
- *   plan [B,16] fp64 per sample: [0:6] inverse 2x3 affine (output -> source), [6] mirror, [7:10] colour op codes in order
- *        (0 none, 1 brightness, 2 contrast, 3 saturation), [10:13] their values (NaN = HSV round trip only), [13] h0, [14] w0
+ *   plan [B,16] fp64 per sample: [15] geometry 0 = affine: [0:6] inverse 2x3 matrix (output -> source), 1 = resize + zero pad:
+ *        [0:4] = scale_x, scale_y, w_eff, h_eff;  [6] mirror, [7:10] colour op codes in order (0 none, 1 brightness, 2 contrast,
+ *        3 saturation), [10:13] their values (NaN = HSV round trip only), [13] h0, [14] w0 (valid region of the padded source)
  *   mean_std [6] fp32;  image, original [F,B,3,H,W] fp32 out: (aug/255 - mean)/std and warped/255;  mask_out [B,H,W] fp64 or NULL
  * ------------------------------------------------------------------------------------------- */
 int fsnet_augment_frames(const unsigned char* frames, const unsigned char* mask, const double* plan, int B, int F, int H0, int W0,

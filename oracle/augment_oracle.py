@@ -10,6 +10,9 @@ pipeline (tests/golden/aug_train.npz) -- tests/test_device_augment_cpu.py.
 cv2.warpAffine (imgwarp.cpp): the 2x3 matrix is inverted in double; source coordinates are 10-bit fixed point
 (``rint(coef * 1024)``), rounded to 1/32 pixel for INTER_LINEAR (to the pixel for INTER_NEAREST); bilinear weights are float
 products of (1 - f, f) with f = k/32; taps outside the image read the constant border 0.
+cv2.resize (resize.cpp): source coordinate (d + 0.5) * scale - 0.5 with scale = 1 / (n_out / n_in) in double, split into
+floor + float fraction, clamped at the borders; horizontal pass then vertical pass in float; INTER_NEAREST: floor(d * scale).
+The Resize transform (augmentations.py:112-198) then zero-pads (or crops) to the requested size.
 cv2.cvtColor RGB<->HSV on float32 (color_hsv.simd.hpp): H in [0, 360), S = (V - min) / (|V| + eps), no clipping anywhere.
 """
 import numpy as np
@@ -17,7 +20,8 @@ import numpy as np
 F32 = np.float32
 EPS = np.finfo(np.float32).eps
 OP_NONE, OP_BRIGHTNESS, OP_CONTRAST, OP_SATURATION = 0, 1, 2, 3
-PLAN_SIZE = 16           # [0:6] inverse affine (row major), 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0, 15 spare
+PLAN_SIZE = 16           # [0:6] geometry, 6 mirror, 7:10 op codes, 10:13 op values, 13 h0, 14 w0, 15 geometry mode
+GEOM_AFFINE, GEOM_RESIZE = 0, 1   # [0:6] = inverse affine (row major)  |  scale_x, scale_y, w_eff, h_eff, -, -
 
 
 def invert_affine(M) -> np.ndarray:
@@ -75,6 +79,43 @@ def warp_nearest(img, Minv, out_h, out_w, mirror=False, h0=None, w0=None):
     return _tap(img, Y >> 10, X >> 10, h0, w0)
 
 
+def _resize_coords(n_out, n_in, scale):
+    f = (np.arange(n_out) + 0.5) * scale - 0.5
+    s = np.floor(f).astype(np.int64)
+    f = (f - s).astype(F32)
+    lo = s < 0
+    f, s = np.where(lo, F32(0), f), np.where(lo, 0, s)
+    hi = s >= n_in - 1
+    return np.where(hi, n_in - 1, s), np.where(hi, F32(0), f).astype(F32)
+
+
+def resize_pad_linear(img, scale_x, scale_y, w_eff, h_eff, out_h, out_w, mirror=False, h0=None, w0=None):
+    """cv2.resize(img, (w_eff, h_eff)) placed at the top-left of a zero [out_h, out_w] canvas (cropped if larger), then mirrored."""
+    h0, w0 = (img.shape[0] if h0 is None else h0), (img.shape[1] if w0 is None else w0)
+    img = img[:h0, :w0].astype(F32)
+    sx, fx = _resize_coords(w_eff, w0, scale_x)
+    sy, fy = _resize_coords(h_eff, h0, scale_y)
+    sx1, sy1 = np.minimum(sx + 1, w0 - 1), np.minimum(sy + 1, h0 - 1)
+    a0, a1 = (F32(1) - fx)[None, :, None], fx[None, :, None]
+    b0, b1 = (F32(1) - fy)[:, None, None], fy[:, None, None]
+    r0 = img[sy][:, sx] * a0 + img[sy][:, sx1] * a1
+    r1 = img[sy1][:, sx] * a0 + img[sy1][:, sx1] * a1
+    canvas = np.zeros((out_h, out_w, img.shape[2]), dtype=F32)
+    h, w = min(h_eff, out_h), min(w_eff, out_w)
+    canvas[:h, :w] = (r0 * b0 + r1 * b1)[:h, :w]
+    return canvas[:, ::-1] if mirror else canvas
+
+
+def resize_pad_nearest(img, scale_x, scale_y, w_eff, h_eff, out_h, out_w, mirror=False, h0=None, w0=None):
+    h0, w0 = (img.shape[0] if h0 is None else h0), (img.shape[1] if w0 is None else w0)
+    sx = np.minimum(np.floor(np.arange(w_eff) * scale_x).astype(np.int64), w0 - 1)
+    sy = np.minimum(np.floor(np.arange(h_eff) * scale_y).astype(np.int64), h0 - 1)
+    canvas = np.zeros((out_h, out_w), dtype=img.dtype)
+    h, w = min(h_eff, out_h), min(w_eff, out_w)
+    canvas[:h, :w] = img[sy][:, sx][:h, :w]
+    return canvas[:, ::-1] if mirror else canvas
+
+
 def rgb2hsv(img):
     r, g, b = img[..., 0], img[..., 1], img[..., 2]
     v = np.maximum(np.maximum(r, g), b)
@@ -122,15 +163,21 @@ def colour_chain(img, codes, values):
 def apply_plan(frames_u8, mask_u8, plan, out_h, out_w, mean, std):
     """frames_u8 [F,H,W,3], mask_u8 [H,W] or None, plan [PLAN_SIZE] float64 ->
     image [F,3,out_h,out_w] float32 (augmented, normalised), original [F,3,out_h,out_w] float32 (warped / 255), mask float64."""
-    Minv = np.asarray(plan[0:6], dtype=np.float64).reshape(2, 3)
     mirror = bool(plan[6])
     h0, w0 = int(plan[13]), int(plan[14])
+    if int(plan[15]) == GEOM_RESIZE:
+        geom = (float(plan[0]), float(plan[1]), int(plan[2]), int(plan[3]), out_h, out_w, mirror, h0, w0)
+        linear, nearest = (lambda im: resize_pad_linear(im, *geom)), (lambda im: resize_pad_nearest(im, *geom))
+    else:
+        Minv = np.asarray(plan[0:6], dtype=np.float64).reshape(2, 3)
+        linear = lambda im: warp_linear(im, Minv, out_h, out_w, mirror, h0, w0)          # noqa: E731
+        nearest = lambda im: warp_nearest(im, Minv, out_h, out_w, mirror, h0, w0)        # noqa: E731
     mean, std = np.asarray(mean, dtype=F32), np.asarray(std, dtype=F32)
     images, originals = [], []
     for frame in frames_u8:
-        warped = warp_linear(frame, Minv, out_h, out_w, mirror, h0, w0)
+        warped = linear(frame)
         originals.append((warped / F32(255)).transpose(2, 0, 1))
         img = colour_chain(warped, plan[7:10], plan[10:13])
         images.append((((img / F32(255)) - mean) / std).transpose(2, 0, 1))
-    mask = None if mask_u8 is None else warp_nearest(mask_u8, Minv, out_h, out_w, mirror, h0, w0).astype(np.float64)
+    mask = None if mask_u8 is None else nearest(mask_u8).astype(np.float64)
     return np.stack(images).astype(F32), np.stack(originals).astype(F32), mask

@@ -64,7 +64,7 @@ def test_plan_plus_oracle_reproduces_the_reference_pipeline(golden_dir):
         image, original, mask = AO.apply_plan(out["frames_u8"], out["mask_u8"], plan, OUT_H, OUT_W, aug.mean, aug.std)
         sample = {("image", f): torch.from_numpy(image[k]) for k, f in enumerate(aug.frames)}
         sample.update({("original_image", f): torch.from_numpy(original[k]) for k, f in enumerate(aug.frames)})
-        sample.update({k: v for k, v in out.items() if k not in ("frames_u8", "mask_u8", "aug_plan")})
+        sample.update({k: v for k, v in out.items() if k not in ("frames_u8", "mask_u8", "aug_plan", "mask_dtype")})
         sample["patched_mask"] = torch.from_numpy(mask)
         mine = summarize(sample)
         keys = [k[len(f"{i}/"):] for k in g.files if k.startswith(f"{i}/")]
@@ -106,11 +106,79 @@ def test_collate_pads_ragged_sources():
 def test_unsupported_lists_are_rejected():
     from easydict import EasyDict as edict
     from vision_base.utils.builder import build
-    from aug_cases import nusc_train_cfg
+    from aug_cases import val_cfg, AUG
+    bad = train_cfg()
+    bad.cfg_list.insert(3, edict(name=f"{AUG}.Resize", size=(48, 160)))                            # a second geometric step
     with pytest.raises(NotImplementedError):
-        build(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=nusc_train_cfg())     # Resize-based recipe
+        build(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=bad)
     with pytest.raises(NotImplementedError):
         build(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=edict(name="vision_base.utils.builder.Shuffle", cfg_list=[]))
+
+
+def _rebuild(sample, aug):
+    """plan + oracle -> the sample the reference's CPU list would have produced."""
+    image, original, mask = AO.apply_plan(sample["frames_u8"], sample.get("mask_u8"), sample["aug_plan"], aug.output_h, aug.output_w,
+                                          aug.mean, aug.std)
+    out = {k: v for k, v in sample.items() if k not in ("frames_u8", "mask_u8", "aug_plan", "mask_dtype")}
+    for k, f in enumerate(aug.frames):
+        out[("image", f)] = torch.from_numpy(image[k])
+        out[("original_image", f)] = torch.from_numpy(original[k])
+    if mask is not None:
+        out["patched_mask"] = torch.from_numpy(mask)
+    return out
+
+
+def _compare(got, g, i, skip=()):
+    keys = [k[len(f"{i}/"):] for k in g.files if k.startswith(f"{i}/") and k[len(f"{i}/"):] not in skip]
+    assert sorted(keys) == sorted(got.keys())
+    for k in keys:
+        if k.startswith("dtype/"):
+            assert str(g[f"{i}/{k}"]) == str(got[k]), k
+        elif k.startswith("sum/"):
+            np.testing.assert_allclose(got[k], g[f"{i}/{k}"], rtol=2e-5, err_msg=k)
+        else:
+            np.testing.assert_allclose(got[k], g[f"{i}/{k}"], rtol=1e-5, atol=2e-5, err_msg=k)
+
+
+def test_nuscenes_list_on_the_device_matches_the_reference_reader(golden_dir, tmp_path):
+    """The nuScenes recipe (Resize + pad, colour, mirror): reader + DeviceAugmentation + oracle against the golden produced by the
+    reference's reader with its CPU list (tests/golden/nusc_reader.npz) -- incl. the tall rear-camera frames (ragged sizes)."""
+    from easydict import EasyDict as edict
+    from vision_base.utils.builder import build
+    from aug_cases import nusc_train_cfg
+    from kitti_fixture import build_nusc_json
+    g = np.load(os.path.join(golden_dir, "nusc_reader.npz"))
+    path = build_nusc_json(str(tmp_path))
+    np.random.seed(15)
+    ds = build(name="monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset", json_path=path, frame_ids=[0, 1, -1],
+               augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=nusc_train_cfg()))
+    aug = ds.transform
+    assert not aug.is_warp and (aug.output_h, aug.output_w) == (64, 128)
+    for i in range(len(ds)):
+        s = ds[i]
+        assert s["aug_plan"][15] == 1 and s["frames_u8"].dtype == np.uint8
+        s = _rebuild(s, aug)
+        for k in ("camera_type", "camera_type_index", ("filename", 0)):
+            s.pop(k)
+        _compare(summarize(s), g, i, skip=("meta",))
+
+
+def test_fisheye_list_on_the_device_matches_the_reference_reader(golden_dir, tmp_path):
+    """The KITTI-360 fisheye recipe (Resize, mirror, Copy -> original_image, colour)."""
+    from easydict import EasyDict as edict
+    from vision_base.utils.builder import build
+    from aug_cases import fisheye_train_cfg
+    from kitti_fixture import build_kitti360_tree
+    g = np.load(os.path.join(golden_dir, "kitti360_fisheye_reader.npz"))
+    raw, meta, mask_path = build_kitti360_tree(str(tmp_path))
+    np.random.seed(13)
+    ds = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta,
+               frame_ids=[0, 1, -1], is_filter_static=True, use_right_image=True,
+               augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=fisheye_train_cfg()))
+    for i in range(len(ds)):
+        s = _rebuild(ds[i], ds.transform)
+        s.pop("calib_meta")
+        _compare(summarize(s), g, i, skip=("xi", "u0"))
 
 
 def test_stage_call_marshalling_and_prefetcher_hook(monkeypatch):
@@ -139,7 +207,7 @@ def test_stage_call_marshalling_and_prefetcher_hook(monkeypatch):
     batches = list(DevicePrefetcher(loader, device="cpu", device_transform=stage))
     assert len(batches) == 2
     b0 = batches[0]
-    assert "frames_u8" not in b0 and "aug_plan" not in b0
+    assert "frames_u8" not in b0 and "aug_plan" not in b0 and "mask_dtype" not in b0
     for f in (0, 1, -1):
         assert b0[("image", f)].shape == (2, 3, OUT_H, OUT_W) and b0[("original_image", f)].dtype == torch.float32
     assert b0["patched_mask"].shape == (2, OUT_H, OUT_W) and b0["patched_mask"].dtype == torch.float64
@@ -179,3 +247,18 @@ def test_kitti_reader_with_device_augmentation(tmp_path, monkeypatch):
     np.testing.assert_allclose(original[2], b[("original_image", -1)].numpy(), rtol=1e-5, atol=2e-5)
     batch = device_augment_collate([dev_ds[i] for i in range(3)])
     assert batch["frames_u8"].shape[:2] == (3, 3) and batch["aug_plan"].shape == (3, 16)
+
+
+@pytest.mark.parametrize("config", ["kitti_wpose_files.py", "nusc_wpose_files.py", "kitti360_fisheye_files.py"])
+def test_file_configs_accept_device_augmentation(config, monkeypatch, tmp_path):
+    """FSNET_DEVICE_AUG=1 wraps the train list of every file-based config, and the wrapped list is one DeviceAugmentation accepts."""
+    from fsnet_b200.data.device_augment import DeviceAugmentation
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file
+    monkeypatch.setenv("FSNET_DEVICE_AUG", "1")
+    monkeypatch.setenv("FSNET_WORKDIR", str(tmp_path))
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = cfg_from_file(os.path.join(repo, "configs", config))
+    aug = build(**cfg.train_dataset.augmentation)
+    assert isinstance(aug, DeviceAugmentation) and aug.frames == [0, 1, -1]
+    assert (aug.output_h, aug.output_w) == tuple(cfg.data.rgb_shape[:2])

@@ -206,3 +206,36 @@ def test_train_script_with_device_augmentation(tmp_path):
     out = _run("train.py", [f"--config={os.path.join(REPO, 'configs', 'kitti_wpose_files.py')}", "--experiment_name=pytest",
                             "--trainer.max_steps=3", "--trainer.max_epochs=2", "--data.batch_size=2", "--data.num_workers=2"], env)
     assert "finished 3 steps" in out
+
+
+def test_device_augmentation_kernel_resize_lists(tmp_path):
+    """The Resize-based lists (nuScenes: pad + colour + mirror; KITTI-360 fisheye: resize + mirror + Copy + colour) through the
+    readers, fsnet_augment_frames against the oracle (itself pinned against the reference readers' goldens on CPU)."""
+    import numpy as np
+    import torch
+    from easydict import EasyDict as edict
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from aug_cases import fisheye_train_cfg, nusc_train_cfg
+    from kitti_fixture import build_kitti360_tree, build_nusc_json
+    from oracle import augment_oracle as AO
+    from fsnet_b200.data.device_augment import DeviceAugmentStage, device_augment_collate
+    from vision_base.utils.builder import build
+    np.random.seed(15)
+    nusc = build(name="monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset", json_path=build_nusc_json(str(tmp_path / "n")),
+                 frame_ids=[0, 1, -1], augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=nusc_train_cfg()))
+    raw, meta, mask_path = build_kitti360_tree(str(tmp_path / "k"))
+    fish = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta, frame_ids=[0, 1, -1],
+                 is_filter_static=False, use_right_image=True, fisheye_mask=mask_path,
+                 augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=fisheye_train_cfg()))
+    for ds, n in ((nusc, 5), (fish, 4)):
+        aug = ds.transform
+        host = device_augment_collate([ds[i] for i in range(n)])                  # nuScenes: 96x160 and 720x160 frames in one batch
+        want = [AO.apply_plan(host["frames_u8"][b].numpy(), host["mask_u8"][b].numpy(), host["aug_plan"][b].numpy(), aug.output_h,
+                              aug.output_w, aug.mean, aug.std) for b in range(n)]
+        dev = DeviceAugmentStage(aug)({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in host.items()})
+        for b in range(n):
+            for k, f in enumerate(aug.frames):
+                np.testing.assert_allclose(dev[("original_image", f)][b].cpu().numpy(), want[b][1][k], rtol=0, atol=1e-6)
+                np.testing.assert_allclose(dev[("image", f)][b].cpu().numpy(), want[b][0][k], rtol=1e-5, atol=2e-5)
+            assert torch.equal(dev["patched_mask"][b].cpu().double(), torch.from_numpy(want[b][2]))
+        assert dev["patched_mask"].dtype == (torch.uint8 if ds is fish else torch.float64)
