@@ -10,6 +10,20 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// One pixel: returns its loss term and writes d term / d p, d term / d l (both already divided by n) and u = sigmoid(l).
+__device__ __forceinline__ float distill_term(float p, float t, bool has_u, float l, float inv_n, float& gp, float& gl, float& u) {
+  const float d = t - p, e = fabsf(d);
+  const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);          // d|d|/dd as autograd defines it (0 at 0)
+  gp = -sgn * inv_n;
+  gl = 0.f;
+  u = 1.f;
+  if (!has_u) return e;
+  u = 1.f / (1.f + expf(-l));
+  gp = gp / u;
+  gl = (1.f / (u + 1e-5f) - e / (u * u)) * (u * (1.f - u)) * inv_n;
+  return e / u + logf(u + 1e-5f);
+}
+
 __global__ void __launch_bounds__(kThreads) distill_loss_kernel(const float* __restrict__ pred, const float* __restrict__ teacher,
                                                                const float* __restrict__ ulogit, long long n, float inv_n,
                                                                double* __restrict__ out, float* __restrict__ grad_pred,
@@ -18,21 +32,12 @@ __global__ void __launch_bounds__(kThreads) distill_loss_kernel(const float* __r
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-    const float p = ldg(pred + i), t = ldg(teacher + i);
-    const float d = t - p, e = fabsf(d);
-    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);          // d|d|/dd as autograd defines it (0 at 0)
-    float gp = -sgn * inv_n;                                            // d loss / d p
-    if (ulogit != nullptr) {
-      const float l = ldg(ulogit + i);
-      const float u = 1.f / (1.f + expf(-l));
-      acc += (double)(e / u + logf(u + 1e-5f));
-      gp = gp / u;
-      if (grad_ulogit != nullptr) grad_ulogit[i] = (1.f / (u + 1e-5f) - e / (u * u)) * (u * (1.f - u)) * inv_n;
-      if (uncertain != nullptr) uncertain[i] = u;
-    } else {
-      acc += (double)e;
-    }
+    float gp, gl, u;
+    acc += (double)distill_term(ldg(pred + i), ldg(teacher + i), ulogit != nullptr, ulogit != nullptr ? ldg(ulogit + i) : 0.f, inv_n,
+                                gp, gl, u);
     if (grad_pred != nullptr) grad_pred[i] = gp;
+    if (grad_ulogit != nullptr) grad_ulogit[i] = gl;
+    if (uncertain != nullptr) uncertain[i] = u;
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;

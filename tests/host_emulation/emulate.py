@@ -1,0 +1,133 @@
+"""Runs the DEVICE code of a simple (shuffle-free, shared-memory-free) CUDA kernel on the CPU: the text between the anonymous
+namespace braces of the .cu file is compiled by g++ behind a small shim (CUDA qualifiers -> nothing, round-to-nearest intrinsics
+-> plain IEEE operations with FMA contraction switched off, blockIdx / threadIdx -> globals) and driven by a loop over the grid.
+
+Test infrastructure: lets the index arithmetic and branch logic of a kernel be checked against its oracle in the CPU suite, before
+(and in addition to) the -m gpu parity test of the real launch."""
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+
+SHIM = r'''
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(x)
+struct Idx { int x, y, z; };
+static Idx blockIdx, blockDim, threadIdx, gridDim;
+using std::max;
+using std::min;
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline long long __double2ll_rn(double a) { return llrint(a); }
+'''
+
+
+def device_source(cu_path):
+    text = open(cu_path).read()
+    start = text.index("namespace {") + len("namespace {")
+    end = text.index("}  // namespace", start)
+    return text[start:end]
+
+
+def build(cu_name, driver_cpp, tag):
+    """-> ctypes.CDLL of shim + device code of fsnet_b200/csrc/<cu_name> + driver (cached by content hash in the temp dir)."""
+    src = SHIM + "\nnamespace {\n" + device_source(os.path.join(REPO, "fsnet_b200", "csrc", cu_name)) + "\n}\n" + driver_cpp
+    key = hashlib.sha1(src.encode()).hexdigest()[:16]
+    out = os.path.join(tempfile.gettempdir(), f"fsnet_emul_{tag}_{key}.so")
+    if not os.path.exists(out):
+        cpp = out[:-3] + ".cpp"
+        with open(cpp, "w") as f:
+            f.write(src)
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", cpp, "-o", out])
+    return ctypes.CDLL(out)
+
+
+AUGMENT_DRIVER = r'''
+extern "C" void run_augment(const uint8_t* frames, const uint8_t* mask, const double* plan, int B, int F, int H0, int W0, int H, int W,
+                            const float* mean_std, float* image, float* original, double* mask_out) {
+  blockDim = {32, 8, 1};
+  gridDim = {(W + 31) / 32, (H + 7) / 8, B};
+  for (blockIdx.z = 0; blockIdx.z < gridDim.z; ++blockIdx.z)
+    for (blockIdx.y = 0; blockIdx.y < gridDim.y; ++blockIdx.y)
+      for (blockIdx.x = 0; blockIdx.x < gridDim.x; ++blockIdx.x)
+        for (threadIdx.y = 0; threadIdx.y < blockDim.y; ++threadIdx.y)
+          for (threadIdx.x = 0; threadIdx.x < blockDim.x; ++threadIdx.x)
+            augment_frames_kernel(frames, mask, plan, B, F, H0, W0, H, W, mean_std, image, original, mask_out);
+}
+'''
+
+
+def run_augment(frames, mask, plan, H, W, mean_std):
+    """numpy in / out twin of DeviceAugmentStage's launch: frames [B,F,H0,W0,3] uint8, mask [B,H0,W0] uint8, plan [B,16] float64."""
+    import numpy as np
+    lib = build("augment.cu", AUGMENT_DRIVER, "augment")
+    B, F, H0, W0, _ = frames.shape
+    frames, mask, plan = np.ascontiguousarray(frames), np.ascontiguousarray(mask), np.ascontiguousarray(plan, dtype=np.float64)
+    mean_std = np.ascontiguousarray(mean_std, dtype=np.float32)
+    image = np.empty((F, B, 3, H, W), dtype=np.float32)
+    original = np.empty((F, B, 3, H, W), dtype=np.float32)
+    mask_out = np.empty((B, H, W), dtype=np.float64)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)          # noqa: E731
+    lib.run_augment(ptr(frames), ptr(mask), ptr(plan), B, F, H0, W0, H, W, ptr(mean_std), ptr(image), ptr(original), ptr(mask_out))
+    return image, original, mask_out
+
+
+# The block-level reduction of distill_loss_kernel needs warp shuffles; the per-pixel arithmetic does not: the kernel is emulated as
+# "one thread, one block" (the shims below make the reduction scaffold the identity), which exercises exactly the device code that
+# is new in csrc/distill.cu -- distill_term and the grid-stride loop.
+DISTILL_SHIM = r'''
+#define __shared__ static
+static inline void __syncthreads() {}
+static inline double warp_sum(double v) { return v; }
+static inline float ldg(const float* p) { return *p; }
+static inline void atomicAdd(double* p, double v) { *p += v; }
+'''
+DISTILL_DRIVER = r'''
+extern "C" void run_distill(const float* pred, const float* teacher, const float* ulogit, long long n, double* out, float* gp, float* gl,
+                            float* u) {
+  blockIdx = {0, 0, 0}; threadIdx = {0, 0, 0}; gridDim = {1, 1, 1};
+  distill_loss_kernel(pred, teacher, ulogit, n, 1.f / (float)n, out, gp, gl, u);
+}
+'''
+
+
+def run_distill(pred, teacher, ulogit):
+    import numpy as np
+    text = device_source(os.path.join(REPO, "fsnet_b200", "csrc", "distill.cu"))
+    # one emulated thread walks the whole array: the grid-stride step becomes 1 (kThreads only appears in the launch geometry)
+    text = text.replace("constexpr int kThreads = 256;", "constexpr int kThreads = 1;").replace("kThreads / 32", "1")
+    src = SHIM + DISTILL_SHIM + "\nnamespace {\n" + text + "\n}\n" + DISTILL_DRIVER
+    key = hashlib.sha1(src.encode()).hexdigest()[:16]
+    out_so = os.path.join(tempfile.gettempdir(), f"fsnet_emul_distill_{key}.so")
+    if not os.path.exists(out_so):
+        cpp = out_so[:-3] + ".cpp"
+        with open(cpp, "w") as f:
+            f.write(src)
+        subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-w", "-shared", "-fPIC", cpp, "-o", out_so])
+    lib = ctypes.CDLL(out_so)
+    lib.run_distill.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_longlong] + [ctypes.c_void_p] * 4
+    pred, teacher = np.ascontiguousarray(pred, dtype=np.float32), np.ascontiguousarray(teacher, dtype=np.float32)
+    n = pred.size
+    out = np.zeros(1, dtype=np.float64)
+    gp, gl, u = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.float32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)          # noqa: E731
+    ul = None if ulogit is None else np.ascontiguousarray(ulogit, dtype=np.float32)
+    lib.run_distill(ptr(pred), ptr(teacher), ptr(ul), n, ptr(out), ptr(gp), ptr(gl) if ul is not None else None,
+                    ptr(u) if ul is not None else None)
+    return float(out[0]), gp, (gl if ul is not None else None), (u if ul is not None else None)

@@ -301,3 +301,24 @@ def test_teacher_export_feeds_the_distillation_config(tmp_path, monkeypatch):
     from fsnet_b200.optim import build_optimizer
     opt = build_optimizer(model, **cfg.optimizer)
     assert sum(p.numel() for g in opt.param_groups for p in g["params"]) == sum(p.numel() for p in model.parameters())
+
+
+def test_distill_kernel_device_code_emulated_on_the_host():
+    """csrc/distill.cu's per-pixel arithmetic and loop (compiled for the CPU behind tests/host_emulation's shim) against torch
+    autograd on the reference's expression (monodepth2_decoder.py:185-203)."""
+    from host_emulation.emulate import run_distill
+    g = torch.Generator().manual_seed(5)
+    for n, with_u in ((1, True), (777, True), (1000, False)):
+        p = (torch.rand(n, generator=g) * 40 + 1).requires_grad_(True)
+        t = torch.rand(n, generator=g) * 40 + 1
+        t[: n // 5] = p.detach()[: n // 5]
+        l = (torch.randn(n, generator=g) * 2).requires_grad_(True) if with_u else None
+        err = (t - p).abs()
+        ref = (err / torch.sigmoid(l) + torch.log(torch.sigmoid(l) + 1e-5)).mean() if with_u else err.mean()
+        ref.backward()
+        val, gp, gl, u = run_distill(p.detach().numpy(), t.numpy(), None if l is None else l.detach().numpy())
+        assert abs(val - float(ref.detach())) <= 1e-5 * abs(float(ref.detach())) + 1e-7
+        np.testing.assert_allclose(gp, p.grad.numpy(), rtol=1e-4, atol=1e-9)
+        if with_u:
+            np.testing.assert_allclose(gl, l.grad.numpy(), rtol=2e-4, atol=1e-8)
+            np.testing.assert_allclose(u, torch.sigmoid(l).detach().numpy(), rtol=1e-6)

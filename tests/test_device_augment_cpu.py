@@ -262,3 +262,46 @@ def test_file_configs_accept_device_augmentation(config, monkeypatch, tmp_path):
     aug = build(**cfg.train_dataset.augmentation)
     assert isinstance(aug, DeviceAugmentation) and aug.frames == [0, 1, -1]
     assert (aug.output_h, aug.output_w) == tuple(cfg.data.rgb_shape[:2])
+
+
+def test_kernel_device_code_emulated_on_the_host_matches_oracle(tmp_path):
+    """The device code of csrc/augment.cu, compiled for the CPU behind a shim (tests/host_emulation), against the oracle: all
+    three shipped lists, mirrored and not, every colour-op order that gets drawn, ragged zero-padded sources, the HSV-only case.
+    Checks the kernel's index arithmetic and branches in the CPU suite; the real launch is checked by the -m gpu test."""
+    from easydict import EasyDict as edict
+    from aug_cases import fisheye_train_cfg, nusc_train_cfg
+    from host_emulation.emulate import run_augment
+    from kitti_fixture import build_kitti360_tree, build_nusc_json
+    from fsnet_b200.data.device_augment import device_augment_collate
+    from vision_base.utils.builder import build
+
+    def check(samples, aug, exact_original):
+        host = device_augment_collate(samples)
+        frames, mask, plan = host["frames_u8"].numpy(), host["mask_u8"].numpy(), host["aug_plan"].numpy()
+        image, original, mask_out = run_augment(frames, mask, plan, aug.output_h, aug.output_w, np.concatenate([aug.mean, aug.std]))
+        for b in range(len(samples)):
+            want = AO.apply_plan(frames[b], mask[b], plan[b], aug.output_h, aug.output_w, aug.mean, aug.std)
+            if exact_original:
+                np.testing.assert_array_equal(original[:, b], want[1])
+            else:
+                np.testing.assert_allclose(original[:, b], want[1], rtol=0, atol=1e-6)
+            np.testing.assert_allclose(image[:, b], want[0], rtol=1e-5, atol=2e-5)
+            np.testing.assert_array_equal(mask_out[b], want[2])
+        return plan
+
+    np.random.seed(7)
+    aug = build(**device_cfg())
+    samples = [aug(raw_sample(100 + i, h=120 - 8 * (i % 2), w=400 - 8 * (i % 3))) for i in range(8)]
+    samples[3]["aug_plan"][10:13] = np.where(samples[3]["aug_plan"][7:10] == 3, np.nan, samples[3]["aug_plan"][10:13])
+    plan = check(samples, aug, exact_original=True)
+    assert {0.0, 1.0} == set(plan[:, 6].tolist()) and len({tuple(p[7:10]) for p in plan}) >= 3      # mirrored / not, several orders
+
+    np.random.seed(15)
+    nusc = build(name="monodepth.data.datasets.nuscene_dataset.NusceneJsonDataset", json_path=build_nusc_json(str(tmp_path / "n")),
+                 frame_ids=[0, 1, -1], augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=nusc_train_cfg()))
+    check([nusc[i] for i in range(5)], nusc.transform, exact_original=False)
+    raw, meta, mask_path = build_kitti360_tree(str(tmp_path / "k"))
+    fish = build(name="monodepth.data.datasets.fisheye_dataset.KITTI360FisheyeDataset", raw_path=raw, split_file=meta, frame_ids=[0, 1, -1],
+                 is_filter_static=False, use_right_image=True, fisheye_mask=mask_path,
+                 augmentation=edict(name="fsnet_b200.data.device_augment.DeviceAugmentation", pipeline=fisheye_train_cfg()))
+    check([fish[i] for i in range(4)], fish.transform, exact_original=False)
