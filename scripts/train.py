@@ -29,6 +29,24 @@ class _NullWriter:
         return lambda *a, **k: None
 
 
+def build_train_loader(cfg, dataset_train, local_rank, world_size, device):
+    """The reference's loader (scripts/train.py:77-81) plus two opt-in stages in front of the training hook:
+    FSNET_PREFETCH=1 uploads batch k+1 on a side stream while step k runs (the reference uploads inside the hook, serialised with
+    the step); a dataset whose augmentation is fsnet_b200.data.device_augment.DeviceAugmentation ships uint8 frames + drawn
+    parameters, and the pixel work runs on the GPU right behind that upload."""
+    from fsnet_b200.data.device_augment import device_augment_collate, find_device_stage
+    device_stage = find_device_stage(dataset_train)
+    prefetch = bool(int(os.environ.get("FSNET_PREFETCH", "0"))) or device_stage is not None
+    loader = build_dataloader(dataset_train, num_workers=cfg.data.num_workers, batch_size=cfg.data.batch_size,
+                              collate_fn=collate_fn if device_stage is None else device_augment_collate,
+                              local_rank=local_rank, world_size=world_size, sampler_cfg=getattr(cfg.data, "sampler", dict()),
+                              pin_memory=prefetch)
+    if prefetch:
+        from fsnet_b200.data.loading import DevicePrefetcher
+        loader = DevicePrefetcher(loader, device, device_transform=device_stage)
+    return loader
+
+
 def main(config="configs/config.py", experiment_name="default", world_size=1, local_rank=-1, **kwargs):
     cfg = cfg_from_file(config)
     cfg = update_cfg(cfg, **kwargs)
@@ -65,19 +83,7 @@ def main(config="configs/config.py", experiment_name="default", world_size=1, lo
 
     dataset_train = build(**cfg.train_dataset)
     dataset_val = build(**cfg.val_dataset) if "val_dataset" in cfg else None
-    # a dataset whose augmentation is fsnet_b200.data.device_augment.DeviceAugmentation ships uint8 frames + parameters; the pixel
-    # work runs on the GPU right behind the upload
-    from fsnet_b200.data.device_augment import device_augment_collate, find_device_stage
-    device_stage = find_device_stage(dataset_train)
-    prefetch = bool(int(os.environ.get("FSNET_PREFETCH", "0"))) or device_stage is not None
-    dataloader_train = build_dataloader(dataset_train, num_workers=cfg.data.num_workers, batch_size=cfg.data.batch_size,
-                                        collate_fn=collate_fn if device_stage is None else device_augment_collate,
-                                        local_rank=local_rank, world_size=world_size,
-                                        sampler_cfg=getattr(cfg.data, "sampler", dict()), pin_memory=prefetch)
-    if prefetch:
-        # upload batch k+1 on a side stream while step k runs (the reference uploads inside the hook, serialised with the step)
-        from fsnet_b200.data.loading import DevicePrefetcher
-        dataloader_train = DevicePrefetcher(dataloader_train, torch.device("cuda", gpu), device_transform=device_stage)
+    dataloader_train = build_train_loader(cfg, dataset_train, local_rank, world_size, torch.device("cuda", gpu))
 
     meta_arch = build(**cfg.meta_arch)
     from vision_base.networks.models.meta_archs.base_meta import BaseMetaArch

@@ -322,3 +322,32 @@ def test_distill_kernel_device_code_emulated_on_the_host():
         if with_u:
             np.testing.assert_allclose(gl, l.grad.numpy(), rtol=2e-4, atol=1e-8)
             np.testing.assert_allclose(u, torch.sigmoid(l).detach().numpy(), rtol=1e-6)
+
+
+def test_train_script_loader_default_is_the_plain_dataloader(monkeypatch):
+    """scripts/train.py::build_train_loader: without the opt-in switches the synthetic configs get the reference's DataLoader
+    (no prefetcher, no device stage, default collate)."""
+    import importlib.util
+    import sys
+    from torch.utils.data import DataLoader
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(repo, "scripts"))
+    spec = importlib.util.spec_from_file_location("fsnet_train_script", os.path.join(repo, "scripts", "train.py"))
+    train = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(train)
+    monkeypatch.delenv("FSNET_PREFETCH", raising=False)
+    cfg = cfg_from_file(os.path.join(repo, "configs", "kitti_wpose_synthetic.py"))
+    cfg.data.num_workers, cfg.data.batch_size = 0, 2
+    cfg.train_dataset.length, cfg.train_dataset.height, cfg.train_dataset.width = 6, 32, 64
+    ds = build(**cfg.train_dataset)
+    loader = train.build_train_loader(cfg, ds, -1, 1, torch.device("cpu"))
+    assert isinstance(loader, DataLoader) and not loader.pin_memory
+    batch = next(iter(loader))
+    assert batch[("image", 0)].shape == (2, 3, 32, 64) and len(loader) == 3
+    monkeypatch.setenv("FSNET_PREFETCH", "1")
+    from fsnet_b200.data.loading import DevicePrefetcher
+    monkeypatch.setattr(torch.utils.data.DataLoader, "__init__", (lambda orig: lambda self, *a, **k: orig(self, *a, **{**k, "pin_memory": False}))(DataLoader.__init__))
+    pf = train.build_train_loader(cfg, ds, -1, 1, torch.device("cpu"))
+    assert isinstance(pf, DevicePrefetcher) and pf.device_transform is None and len(list(pf)) == 3
