@@ -131,3 +131,72 @@ def run_distill(pred, teacher, ulogit):
     lib.run_distill(ptr(pred), ptr(teacher), ptr(ul), n, ptr(out), ptr(gp), ptr(gl) if ul is not None else None,
                     ptr(u) if ul is not None else None)
     return float(out[0]), gp, (gl if ul is not None else None), (u if ul is not None else None)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Whole-file emulation: the loss-side .cu files (host entry points included) compiled for the CPU on top of simt.h, exporting the
+# same C ABI as libfsnet_b200.so but over HOST pointers.
+# ----------------------------------------------------------------------------------------------------------------------
+SIMT_FILES = ["abi.cu", "warp_ssim.cu", "smooth_head.cu", "optim.cu", "distill.cu", "augment.cu"]
+
+
+def _split_top_level(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+def translate(cu_text, csrc_dir):
+    """CUDA C++ -> C++ over simt.h: inline the local .cuh includes, swap the CUDA headers for simt.h, rewrite kernel launches."""
+    import re
+
+    def include(m):
+        name = m.group(1)
+        if name.endswith(".cuh"):
+            return translate(open(os.path.join(csrc_dir, name)).read().replace("#pragma once", ""), csrc_dir)
+        return m.group(0)
+
+    text = re.sub(r'#include "([^"]+)"', include, cu_text)
+    text = re.sub(r"#include <cuda_runtime\.h>", '#include "simt.h"', text)
+    text = re.sub(r"\b__(exp|log|pow)f\(", r"\1f(", text)          # fast-math approximations -> the accurate libm functions
+    if re.search(r"#include <(cuda|mma|cooperative)", text):
+        raise NotImplementedError("this file needs CUDA headers the SIMT shim does not provide")
+    out, pos = "", 0
+    for m in re.finditer(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(", text, re.S):
+        cfg = _split_top_level(m.group(2))
+        rest = text[m.end():].lstrip()
+        sep = "" if rest.startswith(")") else ", "
+        out += text[pos:m.start()] + f"simt::launch({m.group(1)}, dim3({cfg[0]}), dim3({cfg[1]}){sep}"
+        pos = m.end()
+    return out + text[pos:]
+
+
+def build_simt_library(files=SIMT_FILES):
+    csrc = os.path.join(REPO, "fsnet_b200", "csrc")
+    sources = {f: translate(open(os.path.join(csrc, f)).read(), csrc) for f in files}
+    key = hashlib.sha1(("".join(sources.values()) + open(os.path.join(HERE, "simt.h")).read()).encode()).hexdigest()[:16]
+    out = os.path.join(tempfile.gettempdir(), f"fsnet_simt_{key}.so")
+    if not os.path.exists(out):
+        work = out[:-3] + "_src"
+        os.makedirs(work, exist_ok=True)
+        objs = []
+        for f, text in sources.items():
+            cpp = os.path.join(work, f[:-3] + ".cpp")
+            with open(cpp, "w") as fh:
+                fh.write(text)
+            obj = cpp[:-4] + ".o"
+            subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-fPIC", "-I", HERE, "-I", os.path.join(REPO, "include"),
+                                   "-I", csrc, "-c", cpp, "-o", obj])
+            objs.append(obj)
+        subprocess.check_call(["g++", "-shared", "-o", out] + objs)
+    return out

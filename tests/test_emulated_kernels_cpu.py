@@ -1,0 +1,137 @@
+"""The loss-side CUDA kernels themselves, in the CPU suite: fsnet_b200/csrc/{warp_ssim,smooth_head,optim,distill,augment}.cu are
+compiled for the host on top of a small SIMT runtime (tests/host_emulation/simt.h: one fiber per CUDA thread, warp shuffles /
+__syncthreads as barriers between fibers, blocks run in sequence) and driven through the SAME C ABI and the SAME Python
+autograd Functions as on the GPU -- against the golden vectors produced by the reference.
+
+What this proves: index arithmetic, warp-level data exchange, reductions, branch logic and the host-side launch planning of those
+kernels.  What it can not: anything about speed, memory-ordering bugs that need real parallelism, and the tcgen05 / TMA kernels
+(convolutions, BatchNorm planes) -- those stay with the -m gpu suite.  FSNET_EMULATE_ALL=1 adds the two larger golden cases."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fsnet_oracle as O
+from test_loss_gpu import depth_grad_ok, run_gpu_loss
+from test_oracle_golden import LOSS_CASES, build_loss_case, load, rel
+
+FAST = ["loss_b", "loss_c", "loss_fe_nomask", "loss_mm"]
+CASES = sorted(LOSS_CASES) if os.environ.get("FSNET_EMULATE_ALL") == "1" else FAST
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    from host_emulation import fixture
+    return fixture.install(monkeypatch)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fused_loss_kernels_match_golden_under_emulation(emulated, golden_dir, name):
+    """Same assertions as tests/test_loss_gpu.py::test_fused_loss_matches_golden (pinhole, motion mask, MEI fisheye incl. the
+    fp64 ray-table build; forward, fused forward+backward, pose gradients)."""
+    g = load(golden_dir, name)
+    case = LOSS_CASES[name]
+    topo = case["topo"]
+    data, outputs, noise = build_loss_case(**case)
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, dev="cpu")
+    S = len(topo.scales)
+    assert abs(float(total.detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    assert (total.dtype == torch.float64) == ("patched_mask" in data and data["patched_mask"].dtype == torch.float64)
+    for i, s in enumerate(topo.scales):
+        assert abs(float(stats[i]) - float(g[f"loss_dict/loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/loss/{s}"])), s
+        assert abs(float(stats[S + i]) - float(g[f"loss_dict/smooth_loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/smooth_loss/{s}"])), s
+        assert rel(disps[i].grad, g[f"grad_disp/{s}"]) < 1e-3, s
+        ok, e = depth_grad_ok(depths[i].grad, g[f"grad_depth/{s}"])
+        assert ok, (s, e)
+    for fi, f in enumerate(topo.frame_ids[1:]):
+        assert rel(T[fi].grad, g[f"grad_T/{f}"]) < 0.3, f
+
+
+def test_depth_head_kernels_under_emulation(emulated):
+    """fsnet_depth_head_fwd / _bwd (channels-last lane-group softmax and the NCHW kernel) against the oracle's gather_depth."""
+    from fsnet_b200 import functional as Fn
+    g = torch.Generator().manual_seed(2)
+    for n, channels_last in ((16, True), (64, True), (16, False)):
+        topo = O.Topology(n_bins=n, base_fx=40.0)
+        logits = (torch.randn(2, n, 6, 10, generator=g) * 4)
+        if channels_last:
+            logits = logits.contiguous(memory_format=torch.channels_last)
+        logits.requires_grad_(True)
+        bins = O.depth_bins(topo)
+        scale = torch.tensor([0.8, 1.3])
+        depth, disp = Fn.depth_head(logits, bins, scale, False, topo.min_depth, topo.max_depth)
+        (depth.sum() + 3 * disp.sum()).backward()
+        ref_logits = logits.detach().clone().requires_grad_(True)
+        d_ref, disp_ref = O.gather_depth(ref_logits, bins, topo, scale.reshape(-1, 1, 1, 1))
+        (d_ref.sum() + 3 * disp_ref.sum()).backward()
+        assert rel(depth, d_ref) < 1e-5 and rel(disp, disp_ref) < 1e-5
+        assert rel(logits.grad, ref_logits.grad) < 1e-4
+
+
+def test_distill_loss_kernel_under_emulation(emulated):
+    """fsnet_distill_loss, the whole kernel (grid-stride loop, warp + block reduction, atomic accumulation) through
+    functional.distill_loss, against torch autograd on the reference's expression."""
+    from fsnet_b200 import functional as Fn
+    g = torch.Generator().manual_seed(3)
+    for n, with_u in ((5, True), (3000, True), (70001, False)):
+        p = (torch.rand(n, generator=g) * 40 + 1).requires_grad_(True)
+        t = torch.rand(n, generator=g) * 40 + 1
+        t[: n // 7] = p.detach()[: n // 7]
+        l = (torch.randn(n, generator=g) * 2).requires_grad_(True) if with_u else None
+        out = Fn.distill_loss(p.view(1, 1, 1, n), t.view(1, 1, 1, n), None if l is None else l.view(1, 1, 1, n))
+        (out * 0.3).backward()
+        p2 = p.detach().clone().requires_grad_(True)
+        l2 = None if l is None else l.detach().clone().requires_grad_(True)
+        err = (t - p2).abs()
+        ref = (err / torch.sigmoid(l2) + torch.log(torch.sigmoid(l2) + 1e-5)).mean() if with_u else err.mean()
+        (ref * 0.3).backward()
+        assert abs(float(out.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach())) + 1e-7
+        assert rel(p.grad, p2.grad) < 1e-4
+        if with_u:
+            assert rel(l.grad, l2.grad) < 1e-4
+
+
+def test_device_augmentation_stage_under_emulation(emulated, golden_dir):
+    """DeviceAugmentStage -> fsnet_augment_frames through the C ABI: the reference pipeline's golden vectors."""
+    from aug_cases import raw_sample
+    from test_device_augment_cpu import device_cfg
+    from fsnet_b200.data.device_augment import DeviceAugmentStage, device_augment_collate
+    from vision_base.utils.builder import build
+    g = np.load(os.path.join(golden_dir, "aug_train.npz"))
+    np.random.seed(7)
+    aug = build(**device_cfg())
+    batch = DeviceAugmentStage(aug)(device_augment_collate([aug(raw_sample(100 + i)) for i in range(3)]))
+    for i in range(3):
+        np.testing.assert_allclose(batch[("image", 0)][i].numpy(), g[f"{i}/full/image_0"], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(batch[("original_image", 1)][i].numpy(), g[f"{i}/full/original_image_1"], rtol=1e-5, atol=2e-5)
+    assert batch["patched_mask"].dtype == torch.float64 and batch["patched_mask"].shape == (3, 48, 160)
+
+
+@pytest.mark.parametrize("clip,wd", [(35.0, 0.0), (0.05, 0.0), (None, 1e-2)])
+def test_fused_adam_kernels_under_emulation(emulated, clip, wd):
+    """fsnet_grad_sumsq + fsnet_adam_step (device tensor table, on-the-fly clip, device-resident step counter) against
+    clip_grad_norm_ + torch.optim.Adam -- the trajectory test of tests/test_optim_gpu.py."""
+    from fsnet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(8, 3, 7, 7), (64,), (5,), (16, 8, 3, 3), (1,), (4097,), (9000,)]
+    ref = [torch.randn(s, generator=g).requires_grad_(True) for s in shapes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=wd)
+    o_mine = FusedAdam(mine, lr=1e-3, weight_decay=wd)
+    sched, sched_ref = (torch.optim.lr_scheduler.StepLR(o, step_size=3, gamma=0.5) for o in (o_mine, o_ref))
+    for step in range(6):
+        for a, b in zip(ref, mine):
+            a.grad = torch.randn(a.shape, generator=g) * (0.1 + step)
+            b.grad = a.grad.clone()
+        if clip is not None:
+            norm_ref = torch.nn.utils.clip_grad_norm_(ref, clip)
+        o_ref.step()
+        o_mine.step(max_norm=clip)
+        if clip is not None:
+            assert abs(float(o_mine.total_norm()) - float(norm_ref)) <= 1e-5 * float(norm_ref)
+        sched.step()
+        sched_ref.step()
+    for a, b in zip(ref, mine):
+        assert float((a - b).abs().max()) <= 2e-6 * (1 + float(a.abs().max()))
+    assert float(o_mine.state_dict()["state"][0]["step"]) == 6

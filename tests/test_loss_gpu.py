@@ -29,9 +29,8 @@ def depth_grad_ok(got, want):
     return (float(bad.float().mean()) < 0.01 and good_rel < 2e-3), (e, float(bad.float().mean()), good_rel)
 
 
-def run_gpu_loss(topo, data, outputs, noise, need_pose=True):
+def run_gpu_loss(topo, data, outputs, noise, need_pose=True, dev="cuda"):
     from fsnet_b200 import functional as Fn
-    dev = "cuda"
     S = len(topo.scales)
     depths = [outputs[("depth", s, s)].detach().to(dev).requires_grad_(True) for s in topo.scales]
     disps = [outputs[("disp", s)].detach().to(dev).requires_grad_(True) for s in topo.scales]
