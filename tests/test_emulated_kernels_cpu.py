@@ -135,3 +135,43 @@ def test_fused_adam_kernels_under_emulation(emulated, clip, wd):
     for a, b in zip(ref, mine):
         assert float((a - b).abs().max()) <= 2e-6 * (1 + float(a.abs().max()))
     assert float(o_mine.state_dict()["state"][0]["step"]) == 6
+
+
+def test_distillation_training_step_under_emulation(emulated, golden_dir):
+    """The whole second-stage step on the CPU: DistillWPoseMeta (frozen eval-mode teacher, student with uncertainty heads) with
+    the convolutions on the stock-PyTorch comparison back-end and every loss-side kernel emulated, against the golden produced
+    by the reference's DistillWPoseMeta: loss_dict incl. distilation/s, total loss, gradient norms, frozen teacher."""
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    from test_oracle_golden import PENDING_FULL_CASES
+    case = PENDING_FULL_CASES["tiny_distill"]
+    topo, B = case["topo"], case["B"]
+    g = load(golden_dir, "tiny_distill")
+    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    backend = ops.BACKEND
+    ops.set_backend("torch")
+    try:
+        model = build_model(topo)
+        model.head.tie_break_noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+        teacher_before = {k: v.clone() for k, v in model.teacher_net.state_dict().items()}
+        ret = model(dict(data), dict(is_training=True, epoch_num=0, global_step=0))
+        ret["loss"].mean().backward()
+    finally:
+        ops.set_backend(backend)
+    assert ret["loss"].dtype == torch.float64
+    assert abs(float(ret["loss"].detach()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for k, v in ret["loss_dict"].items():
+        ref = float(g["loss_dict/" + k])
+        assert abs(float(v) - ref) <= 1e-4 * abs(ref) + 1e-12, (k, float(v), ref)
+    assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
+    gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    floor = 1e-9 + 1e-8 * max(gn.values())
+    for k, p in model.named_parameters():
+        if k.startswith("teacher_net."):
+            assert p.grad is None and k not in gn
+        elif k in gn:
+            assert abs(float(p.grad.double().norm()) - gn[k]) <= 5e-3 * gn[k] + floor, (k, float(p.grad.double().norm()), gn[k])
+    assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
+    for key in g.files:
+        if key.startswith("grad/"):
+            assert rel(dict(model.named_parameters())[key[5:]].grad, g[key]) < 5e-3, key
