@@ -137,7 +137,8 @@ def run_distill(pred, teacher, ulogit):
 # Whole-file emulation: the loss-side .cu files (host entry points included) compiled for the CPU on top of simt.h, exporting the
 # same C ABI as libfsnet_b200.so but over HOST pointers.
 # ----------------------------------------------------------------------------------------------------------------------
-SIMT_FILES = ["abi.cu", "warp_ssim.cu", "smooth_head.cu", "optim.cu", "distill.cu", "augment.cu"]
+SIMT_FILES = ["abi.cu", "warp_ssim.cu", "smooth_head.cu", "optim.cu", "distill.cu", "augment.cu", "act_tc.cu"]
+# conv_tc.cu (tcgen05 / TMA) can not be emulated: conv_ref.cpp implements its two entry points from the ABI contract
 
 
 def _split_top_level(text):
@@ -169,14 +170,17 @@ def translate(cu_text, csrc_dir):
     text = re.sub(r'#include "([^"]+)"', include, cu_text)
     text = re.sub(r"#include <cuda_runtime\.h>", '#include "simt.h"', text)
     text = re.sub(r"\b__(exp|log|pow)f\(", r"\1f(", text)          # fast-math approximations -> the accurate libm functions
-    if re.search(r"#include <(cuda|mma|cooperative)", text):
+    # dynamic shared memory: `extern __shared__ T name[];` -> a pointer into the launch's buffer
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+)\s+(\w+)\[\];", r"\1* \2 = (\1*)simt::dyn_smem();", text)
+    if re.search(r"#include <(cuda(?!_bf16)|mma|cooperative)", text):
         raise NotImplementedError("this file needs CUDA headers the SIMT shim does not provide")
     out, pos = "", 0
     for m in re.finditer(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(", text, re.S):
         cfg = _split_top_level(m.group(2))
         rest = text[m.end():].lstrip()
         sep = "" if rest.startswith(")") else ", "
-        out += text[pos:m.start()] + f"simt::launch({m.group(1)}, dim3({cfg[0]}), dim3({cfg[1]}){sep}"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        out += text[pos:m.start()] + f"simt::launch({m.group(1)}, dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}){sep}"
         pos = m.end()
     return out + text[pos:]
 
@@ -184,7 +188,8 @@ def translate(cu_text, csrc_dir):
 def build_simt_library(files=SIMT_FILES):
     csrc = os.path.join(REPO, "fsnet_b200", "csrc")
     sources = {f: translate(open(os.path.join(csrc, f)).read(), csrc) for f in files}
-    key = hashlib.sha1(("".join(sources.values()) + open(os.path.join(HERE, "simt.h")).read()).encode()).hexdigest()[:16]
+    extra = "".join(open(os.path.join(HERE, f)).read() for f in ("simt.h", "cuda_bf16.h", "conv_ref.cpp"))
+    key = hashlib.sha1(("".join(sources.values()) + extra).encode()).hexdigest()[:16]
     out = os.path.join(tempfile.gettempdir(), f"fsnet_simt_{key}.so")
     if not os.path.exists(out):
         work = out[:-3] + "_src"
@@ -198,5 +203,8 @@ def build_simt_library(files=SIMT_FILES):
             subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-w", "-fPIC", "-I", HERE, "-I", os.path.join(REPO, "include"),
                                    "-I", csrc, "-c", cpp, "-o", obj])
             objs.append(obj)
-        subprocess.check_call(["g++", "-shared", "-o", out] + objs)
+        ref = os.path.join(work, "conv_ref.o")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-I", os.path.join(REPO, "include"), "-c", os.path.join(HERE, "conv_ref.cpp"),
+                               "-o", ref])
+        subprocess.check_call(["g++", "-shared", "-o", out] + objs + [ref])
     return out

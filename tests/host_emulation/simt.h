@@ -37,6 +37,8 @@ static inline float4 make_float4(float x, float y, float z, float w) { return {x
 static inline double2 make_double2(double x, double y) { return {x, y}; }
 static inline int2 make_int2(int x, int y) { return {x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return {x, y, z, w}; }
 
 struct dim3 {
   unsigned x, y, z;
@@ -74,6 +76,8 @@ struct Block {
 inline Block* blk = nullptr;
 inline Fiber* cur = nullptr;
 inline std::vector<std::vector<char>> stacks;
+inline std::vector<char> dyn_smem_buf;                     // `extern __shared__` of the running launch (emulate.py rewrites the declaration)
+inline void* dyn_smem() { return dyn_smem_buf.data(); }
 constexpr size_t kStack = 512 * 1024;
 
 inline void yield() { swapcontext(&cur->ctx, &blk->main); }
@@ -157,7 +161,8 @@ inline void run_block(dim3 gdim, dim3 bid, dim3 bdim, Body&& body) {
 }
 
 template <class Kernel, class... Args>
-inline void launch(Kernel kernel, dim3 grid, dim3 block, Args... args) {
+inline void launch(Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+  if (dyn_smem_buf.size() < smem_bytes + 16) dyn_smem_buf.resize(smem_bytes + 16);
   for (unsigned z = 0; z < grid.z; ++z)
     for (unsigned y = 0; y < grid.y; ++y)
       for (unsigned x = 0; x < grid.x; ++x) run_block(grid, dim3(x, y, z), block, [&] { kernel(args...); });
@@ -199,6 +204,10 @@ template <class T> static inline T atomicMax(T* p, T v) { T old = *p; *p = std::
 template <class T> static inline T atomicMin(T* p, T v) { T old = *p; *p = std::min(old, v); return old; }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 static inline float __frcp_rn(float x) { return 1.f / x; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __saturatef(float x) { return fminf(fmaxf(x, 0.f), 1.f); }

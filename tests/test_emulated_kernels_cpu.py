@@ -137,41 +137,51 @@ def test_fused_adam_kernels_under_emulation(emulated, clip, wd):
     assert float(o_mine.state_dict()["state"][0]["step"]) == 6
 
 
-def test_distillation_training_step_under_emulation(emulated, golden_dir):
-    """The whole second-stage step on the CPU: DistillWPoseMeta (frozen eval-mode teacher, student with uncertainty heads) with
-    the convolutions on the stock-PyTorch comparison back-end and every loss-side kernel emulated, against the golden produced
-    by the reference's DistillWPoseMeta: loss_dict incl. distilation/s, total loss, gradient norms, frozen teacher."""
+FULL = ["tiny_distill"] + (["tiny4", "tiny_pose", "tiny_sigmoid", "tiny_fe"] if os.environ.get("FSNET_EMULATE_ALL") == "1" else [])
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_whole_training_step_through_the_executor_under_emulation(emulated, golden_dir, name):
+    """A whole training step on the CPU THROUGH THE tcgen05 EXECUTOR PATH (fsnet_b200/engine.py: planes, tape, BatchNorm /
+    activation / pooling / re-layout kernels of act_tc.cu emulated; the two tensor-core entry points replaced by the ABI-level
+    stand-ins of tests/host_emulation/conv_ref.cpp) plus the emulated loss side, against the golden produced by the reference.
+    Default case: the second-stage model (DistillWPoseMeta: frozen eval-mode teacher, student with the uncertainty heads as a
+    second convolution on the decoder activations, distillation loss) -- loss_dict incl. distilation/s, total loss, gradient
+    norms, sample gradients, untouched teacher."""
     from helpers import build_model
     from fsnet_b200.networks import ops
-    from test_oracle_golden import PENDING_FULL_CASES
-    case = PENDING_FULL_CASES["tiny_distill"]
+    from test_oracle_golden import ALL_FULL_CASES
+    case = ALL_FULL_CASES[name]
     topo, B = case["topo"], case["B"]
-    g = load(golden_dir, "tiny_distill")
-    data = O.synthetic_batch(B, topo.height, topo.width, 1234, topo.frame_ids)
+    g = load(golden_dir, name)
+    data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1234, topo.frame_ids)
+    assert ops.tc_available()
     backend = ops.BACKEND
-    ops.set_backend("torch")
+    ops.set_backend("tc")
     try:
         model = build_model(topo)
         model.head.tie_break_noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
-        teacher_before = {k: v.clone() for k, v in model.teacher_net.state_dict().items()}
+        teacher_before = {k: v.clone() for k, v in model.teacher_net.state_dict().items()} if topo.distill else {}
         ret = model(dict(data), dict(is_training=True, epoch_num=0, global_step=0))
         ret["loss"].mean().backward()
     finally:
         ops.set_backend(backend)
-    assert ret["loss"].dtype == torch.float64
-    assert abs(float(ret["loss"].detach()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert (ret["loss"].dtype == torch.float64) == bool(g["loss_is_fp64"])
+    assert abs(float(ret["loss"].detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
     for k, v in ret["loss_dict"].items():
         ref = float(g["loss_dict/" + k])
-        assert abs(float(v) - ref) <= 1e-4 * abs(ref) + 1e-12, (k, float(v), ref)
-    assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
+        assert abs(float(v) - ref) <= 1e-3 * abs(ref) + 1e-12, (k, float(v), ref)
     gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
-    floor = 1e-9 + 1e-8 * max(gn.values())
-    for k, p in model.named_parameters():
+    floor = 1e-9 + 1e-7 * max(gn.values())          # conv biases in front of a BatchNorm: exactly zero here, rounding noise there
+    params = dict(model.named_parameters())
+    for k, p in params.items():
         if k.startswith("teacher_net."):
             assert p.grad is None and k not in gn
         elif k in gn:
-            assert abs(float(p.grad.double().norm()) - gn[k]) <= 5e-3 * gn[k] + floor, (k, float(p.grad.double().norm()), gn[k])
-    assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
+            assert abs(float(p.grad.double().norm()) - gn[k]) <= 0.05 * gn[k] + floor, (k, float(p.grad.double().norm()), gn[k])
     for key in g.files:
         if key.startswith("grad/"):
-            assert rel(dict(model.named_parameters())[key[5:]].grad, g[key]) < 5e-3, key
+            assert rel(params[key[5:]].grad, g[key]) < 0.05, key      # gradients run through bf16 operands (hi planes only)
+    if topo.distill:
+        assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
+        assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
