@@ -185,3 +185,22 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
     if topo.distill:
         assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
         assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
+
+
+@pytest.mark.parametrize("H,W,B,scales,fisheye", [(40, 72, 2, (0, 1, 2), False), (24, 40, 1, (0, 3), False), (56, 104, 1, (0, 1), True)])
+def test_fused_loss_on_ragged_shapes_under_emulation(emulated, H, W, B, scales, fisheye):
+    """Image sizes that are no multiple of the warp width or of the row tiles, a single sample, scale subsets: the marching-warp
+    kernels against the oracle's loss chain (value 1e-5, disparity gradients 1e-4, depth gradients up to arg-min ties)."""
+    topo = O.Topology(height=H, width=W, scales=scales, fisheye=fisheye, max_depth=150.0 if fisheye else 100.0)
+    data, outputs, noise = build_loss_case(topo, B, 31)
+    for v in outputs.values():
+        v.requires_grad_(True)
+    cam_T = {f: data[("relative_pose", f)].clone().requires_grad_(True) for f in topo.frame_ids[1:]}
+    ref = O.loss_chain(outputs, data, cam_T, topo, noise, keep=True)
+    ref["loss"].backward()
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, dev="cpu")
+    assert abs(float(total.detach()) - float(ref["loss"].detach())) <= 1e-5 * abs(float(ref["loss"].detach()))
+    for i, s in enumerate(scales):
+        assert rel(disps[i].grad, outputs[("disp", s)].grad) < 1e-4, s
+        ok, e = depth_grad_ok(depths[i].grad, outputs[("depth", s, s)].grad.numpy())
+        assert ok, (s, e)
