@@ -204,3 +204,29 @@ def test_fused_loss_on_ragged_shapes_under_emulation(emulated, H, W, B, scales, 
         assert rel(disps[i].grad, outputs[("disp", s)].grad) < 1e-4, s
         ok, e = depth_grad_ok(depths[i].grad, outputs[("depth", s, s)].grad.numpy())
         assert ok, (s, e)
+
+
+@pytest.mark.skipif(os.environ.get("FSNET_EMULATE_ALL") != "1", reason="~2 min of emulation; FSNET_EMULATE_ALL=1")
+def test_training_hook_trains_the_distillation_model_under_emulation(emulated, monkeypatch):
+    """BaseTrainingHook (eager) + FusedAdam over model.parameters() of DistillWPoseMeta: the loss goes down, the frozen teacher is
+    never touched, optimiser state exists for the trainable parameters only."""
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    from fsnet_b200.optim import build_optimizer
+    from vision_base.utils.builder import build
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        topo = O.Topology(height=32, width=64, distill=True)
+        model = build_model(topo)
+        opt = build_optimizer(model, name="adam", lr=1e-3, weight_decay=0)
+        hook = build(name="vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0, cuda_graph=False)
+        data = O.synthetic_batch(2, 32, 64, 1234, topo.frame_ids)
+        teacher = {k: v.clone() for k, v in model.teacher_net.state_dict().items()}
+        losses = [float(hook(dict(data), model, opt, None, None, i, 0)["loss"].detach()) for i in range(3)]
+    finally:
+        ops.set_backend(backend)
+    assert losses[-1] < losses[0]
+    assert all(torch.equal(teacher[k], v) for k, v in model.teacher_net.state_dict().items())
+    assert len(opt.state_dict()["state"]) == sum(p.requires_grad for p in model.parameters())
