@@ -3,12 +3,26 @@
 // They let the executor (fsnet_b200/engine.py) and every other kernel of a training step run end to end in the CPU suite.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "fsnet_b200.h"
 
+// the host-side planning code of conv_tc.cu itself (argument checks, tiling, pipeline depth, tensor-map encodings), device code
+// stripped: emulate.py::translate_plan
+extern "C" int fsnet_conv_plan(const fsnet_view* in, int use_ring, const void* w_hi, const void* w_lo, int Cout, int KH, int KW, int stride,
+                               int pad, int nprod, const float* bias, int relu, const fsnet_view* out, int accumulate, double* stats,
+                               void* stream);
+extern "C" int fsnet_conv_wgrad_plan(const fsnet_view* x, int use_ring, const fsnet_view* dy, int KH, int KW, int stride, int pad, float* acc,
+                                     void* stream);
+extern "C" { long long fsnet_emulated_plans = 0; }          // number of planner calls that passed (read by the tests)
+
 namespace {
+inline bool plan_only() {
+  const char* e = getenv("FSNET_EMULATE_PLAN_ONLY");
+  return e && e[0] == '1';
+}
 inline float bf(uint16_t b) {
   uint32_t u = (uint32_t)b << 16;
   float f;
@@ -31,6 +45,10 @@ struct PlaneView {
 
 extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi_, const void* w_lo_, int Cout, int KH, int KW, int stride,
                           int pad, int nprod, const float* bias, int relu, const fsnet_view* out, int accumulate, double* stats, void*) {
+  const int rc = fsnet_conv_plan(in, use_ring, w_hi_, w_lo_, Cout, KH, KW, stride, pad, nprod, bias, relu, out, accumulate, stats, nullptr);
+  if (rc != FSNET_OK) return rc;
+  fsnet_emulated_plans++;
+  if (plan_only()) return FSNET_OK;
   if (!in || !in->ptr || !w_hi_ || !out || !out->ptr) return FSNET_ERR_INVALID;
   if (!(nprod == 1 || (nprod == 3 && w_lo_))) return FSNET_ERR_INVALID;
   if (in->c % 16 || Cout % 16 || (use_ring && in->ring < pad)) return FSNET_ERR_INVALID;
@@ -81,6 +99,10 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi_,
 
 extern "C" int fsnet_conv_wgrad(const fsnet_view* x_, int use_ring, const fsnet_view* dy_, int KH, int KW, int stride, int pad, float* acc,
                                 void*) {
+  const int rc = fsnet_conv_wgrad_plan(x_, use_ring, dy_, KH, KW, stride, pad, acc, nullptr);
+  if (rc != FSNET_OK) return rc;
+  fsnet_emulated_plans++;
+  if (plan_only()) return FSNET_OK;
   if (!x_ || !dy_ || !x_->ptr || !dy_->ptr || !acc) return FSNET_ERR_INVALID;
   const PlaneView x(x_), dy(dy_);
   const int Cin = x.c, Cout = dy.c, Ho = dy.h, Wo = dy.w;

@@ -172,7 +172,7 @@ def translate(cu_text, csrc_dir):
     text = re.sub(r"\b__(exp|log|pow)f\(", r"\1f(", text)          # fast-math approximations -> the accurate libm functions
     # dynamic shared memory: `extern __shared__ T name[];` -> a pointer into the launch's buffer
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+)\s+(\w+)\[\];", r"\1* \2 = (\1*)simt::dyn_smem();", text)
-    if re.search(r"#include <(cuda(?!_bf16)|mma|cooperative)", text):
+    if re.search(r"#include <(cuda(?!_bf16|\.h)|mma|cooperative)", text):
         raise NotImplementedError("this file needs CUDA headers the SIMT shim does not provide")
     out, pos = "", 0
     for m in re.finditer(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\(", text, re.S):
@@ -188,7 +188,8 @@ def translate(cu_text, csrc_dir):
 def build_simt_library(files=SIMT_FILES):
     csrc = os.path.join(REPO, "fsnet_b200", "csrc")
     sources = {f: translate(open(os.path.join(csrc, f)).read(), csrc) for f in files}
-    extra = "".join(open(os.path.join(HERE, f)).read() for f in ("simt.h", "cuda_bf16.h", "conv_ref.cpp"))
+    sources["conv_tc_plan.cu"] = translate_plan(open(os.path.join(csrc, "conv_tc.cu")).read(), csrc)
+    extra = "".join(open(os.path.join(HERE, f)).read() for f in ("simt.h", "cuda_bf16.h", "cuda.h", "conv_ref.cpp"))
     key = hashlib.sha1(("".join(sources.values()) + extra).encode()).hexdigest()[:16]
     out = os.path.join(tempfile.gettempdir(), f"fsnet_simt_{key}.so")
     if not os.path.exists(out):
@@ -208,3 +209,43 @@ def build_simt_library(files=SIMT_FILES):
                                "-o", ref])
         subprocess.check_call(["g++", "-shared", "-o", out] + objs + [ref])
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Plan check of the tensor-core entry points: the HOST code of conv_tc.cu (argument checks, tile / pipeline / K-split planning,
+# tensor-map encoding against a validating cuTensorMapEncodeTiled, tests/host_emulation/cuda.h) with every device function
+# removed and the launches dropped, exported as fsnet_conv_plan / fsnet_conv_wgrad_plan; conv_ref.cpp calls them first.
+# ----------------------------------------------------------------------------------------------------------------------
+def _strip_device_functions(text):
+    """Remove every `__device__` function; keep `__global__` kernels as empty shells (the host code takes their address)."""
+    import re
+    out, pos = "", 0
+    pat = re.compile(r"(template\s*<[^>]*>\s*)?(__device__|__global__)")
+    while True:
+        m = pat.search(text, pos)
+        if not m:
+            return out + text[pos:]
+        brace = text.index("{", m.end())
+        depth, i = 0, brace
+        while True:
+            depth += text[i] == "{"
+            depth -= text[i] == "}"
+            i += 1
+            if depth == 0:
+                break
+        out += text[pos:m.start()]
+        if m.group(2) == "__global__":
+            out += text[m.start():brace] + "{}"
+        pos = i
+
+
+def translate_plan(cu_text, csrc_dir):
+    import re
+    text = _strip_device_functions(cu_text)
+    text = re.sub(r"<<<.*?>>>", "<<<0, 0>>>", text, flags=re.S)
+    text = translate(text, csrc_dir)
+    text = text.replace("simt::launch(", "simt::no_launch(")
+    text = text.replace("#include <stdlib.h>", "#include <stdlib.h>\n#include \"cuda.h\"").replace("#include <cuda.h>", "")
+    text = re.sub(r"cudaGetDriverEntryPoint\([^;]*\)\s*!=\s*cudaSuccess", "((ptr = (void*)&cuTensorMapEncodeTiled), false)", text)
+    return text.replace('extern "C" int fsnet_conv(', 'extern "C" int fsnet_conv_plan(').replace(
+        'extern "C" int fsnet_conv_wgrad(', 'extern "C" int fsnet_conv_wgrad_plan(')

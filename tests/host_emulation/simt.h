@@ -50,6 +50,15 @@ static const cudaError_t cudaSuccess = 0;
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static const int warpSize = 32;
+// runtime calls of the host-side planning code (conv_tc.cu): a 148-SM device, attributes always accepted
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+static const unsigned long long cudaEnableDefault = 0;
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 148; return cudaSuccess; }
+#define __grid_constant__
 
 namespace simt {
 
@@ -162,11 +171,15 @@ inline void run_block(dim3 gdim, dim3 bid, dim3 bdim, Body&& body) {
 
 template <class Kernel, class... Args>
 inline void launch(Kernel kernel, dim3 grid, dim3 block, size_t smem_bytes, Args... args) {
+  const char* plan_only = getenv("FSNET_EMULATE_PLAN_ONLY");     // read per launch: tests switch it on and off within one process
+  if (plan_only && plan_only[0] == '1') return;                                   // walking a big configuration through the planners only: values are garbage
   if (dyn_smem_buf.size() < smem_bytes + 16) dyn_smem_buf.resize(smem_bytes + 16);
   for (unsigned z = 0; z < grid.z; ++z)
     for (unsigned y = 0; y < grid.y; ++y)
       for (unsigned x = 0; x < grid.x; ++x) run_block(grid, dim3(x, y, z), block, [&] { kernel(args...); });
 }
+
+template <class... A> inline void no_launch(A...) {}      // plan-only translation: the kernel is not run
 
 }  // namespace simt
 

@@ -230,3 +230,55 @@ def test_training_hook_trains_the_distillation_model_under_emulation(emulated, m
     assert losses[-1] < losses[0]
     assert all(torch.equal(teacher[k], v) for k, v in model.teacher_net.state_dict().items())
     assert len(opt.state_dict()["state"]) == sum(p.requires_grad for p in model.parameters())
+
+
+PLAN_CASES = {
+    "cfg2a kitti 192x640 R18 B12": (O.Topology(height=192, width=640), 12),
+    "cfg2b +PoseNet B12": (O.Topology(height=192, width=640, posenet=True, overlapped_mask=False), 12),
+    "cfg3 192x768 R50 B8": (O.Topology(height=192, width=768, depth=50), 8),
+    "cfg4 320x640 R18 B8": (O.Topology(height=320, width=640), 8),
+    "nusc shipped 288x512 R34 n64 B8": (O.Topology(height=288, width=512, depth=34, n_bins=64, base_fx=369.0, overlapped_mask=False), 8),
+    "cfg5 fisheye 512x512 n64 B4": (O.Topology(height=512, width=512, fisheye=True, n_bins=64, max_depth=150.0), 4),
+    "fisheye shipped 384x384 B16": (O.Topology(height=384, width=384, fisheye=True, n_bins=64, max_depth=150.0), 16),
+    "distillation 192x640 B12": (O.Topology(height=192, width=640, distill=True), 12),
+    "R101 192x640 B4": (O.Topology(height=192, width=640, depth=101), 4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PLAN_CASES))
+def test_conv_planner_accepts_every_shipped_configuration(emulated, monkeypatch, name):
+    """Every tensor-core launch of a full training step (forward, data gradient, weight gradient; all layers) of the
+    configurations BASELINE.json / the reference ship, at their real image and batch sizes, goes through conv_tc.cu's own
+    HOST code -- argument checks, tile / pipeline-depth / K-split planning, tensor-map encoding against a validating
+    cuTensorMapEncodeTiled (tests/host_emulation/cuda.h) -- with the kernels themselves skipped (values are garbage).
+    Catches 'unsupported shape' / 'does not fit shared memory' / invalid tensor-map failures without a GPU."""
+    import ctypes
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    monkeypatch.setenv("FSNET_EMULATE_PLAN_ONLY", "1")
+    topo, B = PLAN_CASES[name]
+    data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1, topo.frame_ids)
+    counter = ctypes.c_longlong.in_dll(emulated, "fsnet_emulated_plans")
+    before = counter.value
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        model = build_model(topo)
+        model(dict(data), dict(is_training=True, epoch_num=0, global_step=0))["loss"].mean().backward()
+    finally:
+        ops.set_backend(backend)
+    assert counter.value - before >= 100           # 34 convolutions x (forward, data gradient, weight gradient) for ResNet-18
+
+
+def test_conv_planner_rejects_what_the_kernels_can_not_do(emulated):
+    """The stand-in chain is not a rubber stamp: the planner's own checks fire through it."""
+    from fsnet_b200 import _lib, tc
+    x = tc.Planes(1, 8, 8, 24, ring=1, device="cpu", zero=True)            # 24 channels: not a multiple of 16
+    w = torch.zeros(2, 16, 3, 3, 24, dtype=torch.bfloat16)
+    out = tc.Fp32(1, 8, 8, 16, device="cpu")
+    with pytest.raises(_lib.FsnetError, match="multiples of 16"):
+        _lib.call("fsnet_conv", x.view(), 0, w[0], w[1], 16, 3, 3, 1, 1, 3, None, 0, out.view(), 0, None)
+    x = tc.Planes(1, 8, 8, 16, ring=0, device="cpu", zero=True)
+    with pytest.raises(_lib.FsnetError, match="ring"):                      # replicate padding without a materialised ring
+        _lib.call("fsnet_conv", x.view(), 1, w[0, :, :, :, :16].contiguous(), w[1, :, :, :, :16].contiguous(), 16, 3, 3, 1, 1, 3, None, 0,
+                  out.view(), 0, None)
