@@ -130,6 +130,8 @@ class Tape:
         self.param_grads: Dict[int, torch.Tensor] = {}      # id(parameter) -> gradient tensor
         self.weights_fresh = weights_fresh                    # operand planes already refreshed by one batched launch
         self._pools = None
+        self._sync_scaled: List[torch.Tensor] = []            # SyncBN affine gradients to divide by the world size (see _bn_bwd)
+        self._sync_world = 1
 
     def _make_pools(self):
         """One zeroed workspace per backward pass instead of one fill kernel per layer: BN-backward sums (fp64),
@@ -291,6 +293,12 @@ class Tape:
             self.param_grads[id(st.conv.bias)] = dbeta
         _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, sums, tc.c_double(inv.count),
                   dy.view(), res_mode, res_view, dgamma, dbeta, C)
+        if world > 1 and dgamma is not None:
+            # SyncBN: the kernel wrote the affine gradients from the ALL-REDUCED sums, i.e. already summed over the ranks, and the
+            # data-parallel gradient averaging that follows (hook / DDP) would count them `world` times.  torch's SyncBatchNorm
+            # keeps these two local; (global sum) / world is the same thing once the ranks are averaged.
+            self._sync_scaled += [dgamma, dbeta]
+            self._sync_world = world
         return dy
 
     def _conv_bwd(self, x: Act, st: LayerState, dy: Planes, need_dgrad=True):
@@ -413,6 +421,8 @@ class Tape:
             op()
         if self._pools is not None and self._pools["gw_used"]:
             _lib.call("fsnet_wgrad_to_param_batched", self._pools["gw_table"], len(self.states), self._pools["acc"], self._pools["gw"])
+        if self._sync_scaled:
+            torch._foreach_div_(self._sync_scaled, float(self._sync_world))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -49,3 +49,81 @@ def test_flat_gradient_allreduce_and_sampler_sharding_world2():
         assert p.exitcode == 0
     assert all(r[0] for r in results), "gradients were not averaged across ranks"
     assert all(r[1] for r in results), "sampler shards do not partition the dataset"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The N>1 DATA PATH itself: a SyncBN training step through the executor on two ranks (gloo), kernels under the SIMT emulator
+# ----------------------------------------------------------------------------------------------------------------------
+def _syncbn_worker(rank, world, port, out):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.dirname(here)]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from _pytest.monkeypatch import MonkeyPatch
+    from host_emulation import fixture
+    patch = MonkeyPatch()
+    fixture.install(patch)
+    try:
+        from oracle import fsnet_oracle as O
+        from helpers import build_model
+        from fsnet_b200.hooks.training import BaseTrainingHook
+        from fsnet_b200.networks import ops
+        ops.set_backend("tc")
+        topo = O.Topology(height=32, width=64)
+        B = 2 * world
+        data = O.synthetic_batch(B, topo.height, topo.width, 77, topo.frame_ids)
+        data.pop("patched_mask")                    # equal loss normalisers on every rank: the mean of rank losses is the global loss
+        noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+        meta = dict(is_training=True, epoch_num=0, global_step=0)
+
+        def run(model, lo, hi):
+            model.head.tie_break_noise = {s: n[lo:hi] for s, n in noise.items()}
+            shard = {k: (v[lo:hi] if torch.is_tensor(v) else v) for k, v in data.items()}
+            ret = model(shard, meta)
+            ret["loss"].mean().backward()
+            return float(ret["loss"].detach())
+
+        # data parallel: SyncBatchNorm statistics all-reduced inside the executor, flat gradient all-reduce afterwards
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo))
+        loss = run(model, 2 * rank, 2 * rank + 2)
+        BaseTrainingHook.sync_gradients(model)
+        losses = [None] * world
+        dist.all_gather_object(losses, loss)
+        result = None
+        if rank == 0:
+            single = build_model(topo)              # plain BatchNorm, whole batch, one process
+            loss_single = run(single, 0, B)
+            worst = 0.0
+            ref = dict(single.named_parameters())
+            for k, p in model.named_parameters():
+                g, r = p.grad.double(), ref[k].grad.double()
+                if float(r.norm()) > 1e-7:
+                    worst = max(worst, float((g - r).norm() / r.norm()))
+            stats = max(float((a - b).abs().max()) for (_, a), (_, b) in zip(model.named_buffers(), single.named_buffers())
+                        if a.is_floating_point())
+            result = (sum(losses) / world, loss_single, worst, stats)
+        out.put(result)
+    finally:
+        patch.undo()
+        dist.destroy_process_group()
+
+
+def test_syncbn_training_step_world2_matches_single_process():
+    """Two ranks x 2 samples with SyncBatchNorm (forward statistics and the two backward sums all-reduced inside the executor,
+    engine.py) + the hook's flat gradient all-reduce == one process x 4 samples with plain BatchNorm: loss, every parameter
+    gradient, and the running statistics.  The kernels run under the SIMT emulator (tests/host_emulation), the collectives over gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    mean_loss, loss_single, worst, stats = next(r for r in results if r is not None)
+    assert abs(mean_loss - loss_single) <= 1e-5 * abs(loss_single), (mean_loss, loss_single)
+    assert worst < 2e-2, worst                    # bf16 operands in the gradient convolutions; typical 1e-3
+    assert stats < 1e-5, stats                    # running mean / var updated from the GLOBAL batch statistics
