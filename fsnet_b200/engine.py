@@ -266,7 +266,11 @@ class Tape:
         st = inv.st
         sums = self._pool(st, "sums")                      # zeroed slice of the pass-wide workspace
         has_bn = bn is not None and bn_train
-        mi = inv.mi if has_bn else None
+        # BatchNorm in eval mode inside a training step (ResNet(norm_eval=True) / frozen stages): the same two kernels with the
+        # RUNNING statistics as (mean, invstd) and an infinite count, which removes the two batch-statistics terms of the input
+        # gradient -- what is left is the fixed per-channel scale gamma * invstd
+        eval_bn = bn is not None and not bn_train
+        mi = inv.mi if bn is not None else None
         _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, sums)
         world = _sync_world(bn) if has_bn else 1
         if world > 1:
@@ -274,9 +278,6 @@ class Tape:
         fold_dgrad = st.replicate and st.kh == 3 and st.C < 64          # see fsnet_conv: folded x-taps need ring == pad
         dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device, zero=fold_dgrad)
         gamma = st.padded(bn.weight, 1.0) if bn is not None else None
-        if bn is not None and not bn_train:
-            # BatchNorm in eval mode inside a training step (norm_eval=True): a fixed per-channel scale
-            raise NotImplementedError("norm_eval=True training is not implemented on the tcgen05 path")
         C = st.c_real
         dgamma = dbeta = None
         dev = raw.t.device
@@ -287,12 +288,15 @@ class Tape:
                 self.param_grads[id(bn.weight)] = dgamma
                 self.param_grads[id(bn.bias)] = dbeta
             if st.conv.bias is not None and st.conv.bias.requires_grad:
-                self.param_grads[id(st.conv.bias)] = self._pool(st, "zero")      # cancelled by the batch mean
+                if eval_bn:      # not cancelled by running statistics: d bias = gamma * invstd * sum(g)
+                    self.param_grads[id(st.conv.bias)] = (gamma[:C] * mi[st.C:st.C + C] * sums[:C]).float()
+                else:
+                    self.param_grads[id(st.conv.bias)] = self._pool(st, "zero")      # cancelled by the batch mean
         elif st.conv.bias is not None and st.conv.bias.requires_grad:
             dbeta = torch.empty(C, device=dev, dtype=torch.float32)
             self.param_grads[id(st.conv.bias)] = dbeta
-        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, sums, tc.c_double(inv.count),
-                  dy.view(), res_mode, res_view, dgamma, dbeta, C)
+        _lib.call("fsnet_bn_bwd_apply", g_view, up, mask_view, mask_ss, raw.view(), mi, gamma, sums,
+                  tc.c_double(float("inf") if eval_bn else inv.count), dy.view(), res_mode, res_view, dgamma, dbeta, C)
         if world > 1 and dgamma is not None:
             # SyncBN: the kernel wrote the affine gradients from the ALL-REDUCED sums, i.e. already summed over the ranks, and the
             # data-parallel gradient averaging that follows (hook / DDP) would count them `world` times.  torch's SyncBatchNorm
@@ -514,8 +518,8 @@ def _nhwc_grad(g: torch.Tensor, c_pad: int) -> torch.Tensor:
 
 
 def _check_supported(backbone):
-    if backbone.norm_eval or backbone.frozen_stages >= 0:
-        raise NotImplementedError("tcgen05 path: norm_eval=True / frozen_stages are not implemented (no shipped config uses them)")
+    if any(d != 1 for d in getattr(backbone, "dilations", (1,))):
+        raise NotImplementedError("tcgen05 path: dilated convolutions are not implemented (no shipped config uses them)")
 
 
 class _DepthNetFn(torch.autograd.Function):

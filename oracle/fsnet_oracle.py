@@ -45,6 +45,8 @@ class Topology:
     overlapped_mask: bool = True
     frame_ids: Tuple[int, ...] = (0, 1, -1)
     fisheye: bool = False                # FishEyeDecoder: MEI camera, the network output is the ray norm
+    norm_eval: bool = False              # ResNet(norm_eval=True): backbone BatchNorms stay in eval mode while training (resnet.py:169-197)
+    frozen_stages: int = -1              # ResNet(frozen_stages=k): stem + layer1..k in eval mode, no gradients (resnet.py:176-190)
     distill: bool = False                # DistillWPoseMeta: frozen eval-mode teacher + MultiChannelDepthDecoderUncertain student
     distill_weight: float = 0.3          # distillation_loss_weight (configs/distill_kitti_example:218)
     uncertain_distill: bool = True       # is_uncertain_distill (configs/distill_kitti_example:219)
@@ -178,6 +180,10 @@ def make_state_dict(topo: Topology, seed: int = 123) -> "OrderedDict[str, Tensor
     """
     g = torch.Generator().manual_seed(seed)
     sd: "OrderedDict[str, Tensor]" = OrderedDict()
+
+    def used_stats(name):       # running statistics that a TRAINING step reads get the values of a trained network, not (0, 1)
+        return name.startswith("teacher_net.") or ((topo.norm_eval or topo.frozen_stages >= 0) and name.startswith("depth_backbone."))
+
     for name, shape, kind in param_specs(topo):
         if kind == "conv":
             cout, cin, kh, kw = shape
@@ -193,9 +199,9 @@ def make_state_dict(topo: Topology, seed: int = 123) -> "OrderedDict[str, Tensor
         elif kind == "bn_b":
             sd[name] = 0.1 * torch.randn(shape, generator=g)
         elif kind == "zeros":
-            sd[name] = 0.05 * torch.randn(shape, generator=g) if name.startswith("teacher_net.") else torch.zeros(shape)
+            sd[name] = 0.05 * torch.randn(shape, generator=g) if used_stats(name) else torch.zeros(shape)
         elif kind == "ones":
-            sd[name] = 1.0 + 0.2 * torch.rand(shape, generator=g) if name.startswith("teacher_net.") else torch.ones(shape)
+            sd[name] = 1.0 + 0.2 * torch.rand(shape, generator=g) if used_stats(name) else torch.ones(shape)
         elif kind == "count":
             sd[name] = torch.zeros((), dtype=torch.long)
         elif kind == "bins":
@@ -216,15 +222,21 @@ def _bn(sd, prefix: str, x: Tensor, training: bool = True) -> Tensor:
                         sd[prefix + ".bias"], training=training, momentum=0.1, eps=1e-5)
 
 
-def resnet_forward(sd, prefix: str, x: Tensor, depth: int, training: bool = True) -> List[Tensor]:
-    """ResNet.forward, resnet.py:199-213 with out_indices=(-1,0,1,2,3); BasicBlock :34-50, Bottleneck :71-89."""
+def resnet_forward(sd, prefix: str, x: Tensor, depth: int, training: bool = True, norm_eval: bool = False,
+                   frozen_stages: int = -1) -> List[Tensor]:
+    """ResNet.forward, resnet.py:199-213 with out_indices=(-1,0,1,2,3); BasicBlock :34-50, Bottleneck :71-89.
+    ``norm_eval`` / ``frozen_stages`` (ResNet.train, resnet.py:169-197): which BatchNorms use their running statistics although
+    the model trains (all of them / those of the stem and of layer1..k)."""
     outs = []
+    stem_training = training and not norm_eval and frozen_stages < 0
     x = F.conv2d(x, sd[prefix + "conv1.weight"], None, stride=2, padding=3)
-    x = F.relu(_bn(sd, prefix + "bn1", x, training))
+    x = F.relu(_bn(sd, prefix + "bn1", x, stem_training))
     outs.append(x)
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     bottleneck = depth >= 50
+    model_training = training
     for li, nblocks in enumerate(RESNET_LAYERS[depth]):
+        training = model_training and not norm_eval and li + 1 > frozen_stages
         for bi in range(nblocks):
             p = f"{prefix}layer{li + 1}.{bi}."
             stride = 2 if (li > 0 and bi == 0) else 1
@@ -590,7 +602,8 @@ def loss_chain(outputs: Dict, data: Dict, cam_T: Dict[int, Tensor], topo: Topolo
 # --------------------------------------------------------------------------------------------
 def forward_train(sd, data: Dict, topo: Topology, noise: Optional[Dict[int, Tensor]] = None, keep: bool = False) -> Dict:
     """MonoDepthWPose.forward_train / MonoDepthMeta.forward_train (monodepth2_model.py:24-46,85-130)."""
-    feats = resnet_forward(sd, "depth_backbone.", data[("image", 0)], topo.depth)
+    feats = resnet_forward(sd, "depth_backbone.", data[("image", 0)], topo.depth, norm_eval=topo.norm_eval,
+                           frozen_stages=topo.frozen_stages)
     P2 = None if topo.posenet else data["P2"]          # MonoDepthMeta calls forward_depth(features) without P2 (:27)
     outputs = decoder_forward(sd, "head.depth_decoder.", feats, topo, P2, uncertain=topo.distill)
     if topo.distill:
@@ -647,9 +660,12 @@ def forward_test(sd, data: Dict, topo: Topology) -> Dict:
     return {"depth": outputs[("depth", 0, 0)]}
 
 
-def trainable(sd) -> List[str]:
+def trainable(sd, topo: Optional[Topology] = None) -> List[str]:
+    frozen: Tuple[str, ...] = ()
+    if topo is not None and topo.frozen_stages >= 0:       # depth encoder only (the PoseNet is built with its own arguments)
+        frozen = ("depth_backbone.conv1.", "depth_backbone.bn1.") + tuple(f"depth_backbone.layer{i}." for i in range(1, topo.frozen_stages + 1))
     return [k for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var", "depth_bins"))
-            and not k.startswith("teacher_net.")]
+            and not k.startswith("teacher_net.") and not k.startswith(frozen or ("\0",))]
 
 
 class OracleTrainer:

@@ -43,7 +43,8 @@ def ref_meta_arch(topo: O.Topology):
             num_ch_enc=np.array(topo.num_ch_enc), num_output_channels=topo.n_bins, use_skips=topo.use_skips,
             scales=list(topo.scales), min_depth=topo.min_depth, max_depth=topo.max_depth, base_fx=topo.base_fx))
     backbone = edict(name="vision_base.networks.models.backbone.resnet.resnet", depth=topo.depth, pretrained=False,
-                     frozen_stages=-1, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=False, dilations=(1, 1, 1, 1))
+                     frozen_stages=topo.frozen_stages, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=topo.norm_eval,
+                     dilations=(1, 1, 1, 1))
     cfg = edict(depth_backbone_cfg=backbone, head_cfg=head, train_cfg=edict(frame_ids=list(topo.frame_ids)), test_cfg=edict())
     sd = O.make_state_dict(topo)
     if topo.distill:
@@ -213,5 +214,14 @@ if __name__ == "__main__":
     if want("tiny_distill"):
         run_full("tiny_distill", O.Topology(height=64, width=128, distill=True), B=2,
                  grads_of=("head.depth_decoder.decoder.14.weight", "head.depth_decoder.decoder.17.bias", "depth_backbone.conv1.weight"))
+    if want("tiny_normeval"):       # ResNet constructor options: BatchNorms of the encoder in eval mode / first stages frozen
+        run_full("tiny_normeval", O.Topology(height=64, width=128, norm_eval=True), B=2,
+                 grads_of=("depth_backbone.layer1.0.bn1.weight", "depth_backbone.conv1.weight"))
+    if want("tiny_normeval_frozen"):
+        run_full("tiny_normeval_frozen", O.Topology(height=64, width=128, norm_eval=True, frozen_stages=1), B=2,
+                 grads_of=("depth_backbone.layer2.0.bn1.weight", "depth_backbone.layer2.0.conv1.weight"))
+    if want("tiny_frozen"):
+        run_full("tiny_frozen", O.Topology(height=64, width=128, frozen_stages=2), B=2,
+                 grads_of=("depth_backbone.layer3.0.bn1.weight", "depth_backbone.layer3.0.downsample.0.weight"))
     if want("tiny_r50"):
         run_full("tiny_r50", O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2, store_disp=True)

@@ -15,7 +15,8 @@ def meta_arch_cfg(topo: O.Topology, is_log_image=False):
             num_ch_enc=np.array(topo.num_ch_enc), num_output_channels=topo.n_bins, use_skips=topo.use_skips,
             scales=list(topo.scales), min_depth=topo.min_depth, max_depth=topo.max_depth, base_fx=topo.base_fx))
     backbone = edict(name="vision_base.networks.models.backbone.resnet.resnet", depth=topo.depth, pretrained=False,
-                     frozen_stages=-1, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=False, dilations=(1, 1, 1, 1))
+                     frozen_stages=topo.frozen_stages, num_stages=4, out_indices=(-1, 0, 1, 2, 3), norm_eval=topo.norm_eval,
+                     dilations=(1, 1, 1, 1))
     cfg = edict(depth_backbone_cfg=backbone, head_cfg=head, train_cfg=edict(frame_ids=list(topo.frame_ids)), test_cfg=edict())
     if topo.distill:
         import tempfile

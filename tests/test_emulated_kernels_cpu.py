@@ -137,7 +137,8 @@ def test_fused_adam_kernels_under_emulation(emulated, clip, wd):
     assert float(o_mine.state_dict()["state"][0]["step"]) == 6
 
 
-FULL = ["tiny_distill"] + (["tiny4", "tiny_pose", "tiny_sigmoid", "tiny_fe"] if os.environ.get("FSNET_EMULATE_ALL") == "1" else [])
+FULL = ["tiny_distill", "tiny_normeval_frozen"] + (
+    ["tiny4", "tiny_pose", "tiny_sigmoid", "tiny_fe", "tiny_r50", "tiny_normeval", "tiny_frozen"] if os.environ.get("FSNET_EMULATE_ALL") == "1" else [])
 
 
 @pytest.mark.parametrize("name", FULL)
@@ -174,6 +175,7 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
     gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
     floor = 1e-9 + 1e-7 * max(gn.values())          # conv biases in front of a BatchNorm: exactly zero here, rounding noise there
     params = dict(model.named_parameters())
+    assert {k for k, p in params.items() if p.grad is not None} == set(gn)      # exactly the parameters the reference trains
     for k, p in params.items():
         if k.startswith("teacher_net."):
             assert p.grad is None and k not in gn

@@ -81,6 +81,17 @@ def test_prefetched_batches_train_like_host_batches():
     assert losses[0] == pytest.approx(losses[1], rel=1e-6)
 
 
+@pytest.mark.parametrize("name", ["tiny_normeval", "tiny_frozen", "tiny_normeval_frozen"])
+def test_resnet_norm_eval_and_frozen_stages_match_reference(golden_dir, name, monkeypatch):
+    """ResNet(norm_eval=True) / ResNet(frozen_stages=k) on the tcgen05 path: eval-mode BatchNorm inside a training step."""
+    import test_model_gpu as T
+    from test_oracle_golden import PENDING_FULL_CASES
+    from fsnet_b200.networks import ops
+    ops.set_backend("tc")
+    monkeypatch.setitem(T.FULL_CASES, name, PENDING_FULL_CASES[name])
+    T.test_training_forward_backward_matches_reference(golden_dir, name)
+
+
 @pytest.mark.parametrize("name", ["tiny_distill"])
 def test_distillation_stage_matches_reference(golden_dir, name, monkeypatch):
     """DistillWPoseMeta on the tcgen05 path against the reference-generated golden: losses (incl. distilation/s), gradient
