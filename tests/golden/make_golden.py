@@ -223,5 +223,12 @@ if __name__ == "__main__":
     if want("tiny_frozen"):
         run_full("tiny_frozen", O.Topology(height=64, width=128, frozen_stages=2), B=2,
                  grads_of=("depth_backbone.layer3.0.bn1.weight", "depth_backbone.layer3.0.downsample.0.weight"))
+    # 32x64 twins of two cases above: what the CPU suite runs through the emulated executor by default (3x cheaper)
+    if want("micro_distill"):
+        run_full("micro_distill", O.Topology(height=32, width=64, distill=True), B=2, store_disp=False,
+                 grads_of=("head.depth_decoder.decoder.14.weight", "head.depth_decoder.decoder.17.bias", "depth_backbone.conv1.weight"))
+    if want("micro_normeval_frozen"):
+        run_full("micro_normeval_frozen", O.Topology(height=32, width=64, norm_eval=True, frozen_stages=1), B=2, store_disp=False,
+                 grads_of=("depth_backbone.layer2.0.bn1.weight", "depth_backbone.layer2.0.conv1.weight"))
     if want("tiny_r50"):
         run_full("tiny_r50", O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2, store_disp=True)

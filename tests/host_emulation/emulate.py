@@ -189,7 +189,7 @@ def build_simt_library(files=SIMT_FILES):
     csrc = os.path.join(REPO, "fsnet_b200", "csrc")
     sources = {f: translate(open(os.path.join(csrc, f)).read(), csrc) for f in files}
     sources["conv_tc_plan.cu"] = translate_plan(open(os.path.join(csrc, "conv_tc.cu")).read(), csrc)
-    extra = "".join(open(os.path.join(HERE, f)).read() for f in ("simt.h", "cuda_bf16.h", "cuda.h", "conv_ref.cpp"))
+    extra = "".join(open(os.path.join(HERE, f)).read() for f in ("simt.h", "cuda_bf16.h", "cuda.h", "conv_ref.cpp", "simt_switch.cpp"))
     key = hashlib.sha1(("".join(sources.values()) + extra).encode()).hexdigest()[:16]
     out = os.path.join(tempfile.gettempdir(), f"fsnet_simt_{key}.so")
     if not os.path.exists(out):
@@ -207,7 +207,9 @@ def build_simt_library(files=SIMT_FILES):
         ref = os.path.join(work, "conv_ref.o")
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-I", os.path.join(REPO, "include"), "-c", os.path.join(HERE, "conv_ref.cpp"),
                                "-o", ref])
-        subprocess.check_call(["g++", "-shared", "-o", out] + objs + [ref])
+        switch = os.path.join(work, "simt_switch.o")
+        subprocess.check_call(["g++", "-fPIC", "-c", os.path.join(HERE, "simt_switch.cpp"), "-o", switch])
+        subprocess.check_call(["g++", "-shared", "-o", out] + objs + [ref, switch])
     return out
 
 

@@ -62,8 +62,18 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { 
 
 namespace simt {
 
+// Context switch between fibers.  glibc's swapcontext saves the signal mask with a system call on every switch (~1 us); on x86-64
+// a few callee-saved registers and the stack pointer are all that is needed (tests/host_emulation/simt_switch.cpp, ~10 ns).
+#if defined(__x86_64__)
+#define SIMT_FAST_SWITCH 1
+extern "C" void simt_switch(void** save_sp, void* new_sp);
+#else
+#define SIMT_FAST_SWITCH 0
+#endif
+
 struct Fiber {
   ucontext_t ctx;
+  void* sp = nullptr;
   dim3 tid;
   int lane = 0, warp = 0;
   bool done = false;
@@ -81,6 +91,7 @@ struct Block {
   unsigned phase = 0;
   std::function<void()> body;
   ucontext_t main;
+  void* main_sp = nullptr;
 };
 inline Block* blk = nullptr;
 inline Fiber* cur = nullptr;
@@ -89,14 +100,30 @@ inline std::vector<char> dyn_smem_buf;                     // `extern __shared__
 inline void* dyn_smem() { return dyn_smem_buf.data(); }
 constexpr size_t kStack = 512 * 1024;
 
-inline void yield() { swapcontext(&cur->ctx, &blk->main); }
+inline void to_main() {
+#if SIMT_FAST_SWITCH
+  simt_switch(&cur->sp, blk->main_sp);
+#else
+  swapcontext(&cur->ctx, &blk->main);
+#endif
+}
+inline void to_fiber(Fiber* f) {
+  cur = f;
+#if SIMT_FAST_SWITCH
+  simt_switch(&blk->main_sp, f->sp);
+#else
+  swapcontext(&blk->main, &f->ctx);
+#endif
+}
+inline void yield() { to_main(); }
 
 inline void trampoline() {
   blk->body();
   cur->done = true;
   blk->live--;
   blk->warps[cur->warp].live--;
-  swapcontext(&cur->ctx, &blk->main);
+  to_main();
+  abort();                                                 // a finished fiber is never resumed
 }
 
 // Barrier over the live threads of a warp / of the block.  Whoever sees the count complete (the last arriver, or a waiter after
@@ -153,18 +180,26 @@ inline void run_block(dim3 gdim, dim3 bid, dim3 bdim, Body&& body) {
     f.warp = i / 32;
     b.warps[f.warp].live++;
     if (stacks[i].empty()) stacks[i].resize(kStack);
+#if SIMT_FAST_SWITCH
+    // initial frame: six callee-saved registers (popped by simt_switch), then the entry address it returns into, then one
+    // alignment slot so that the entry sees the stack as after a call (rsp = 16n + 8)
+    uintptr_t top = ((uintptr_t)stacks[i].data() + kStack) & ~(uintptr_t)15;
+    void** frame = (void**)(top - 64);
+    for (int k = 0; k < 6; ++k) frame[k] = nullptr;
+    frame[6] = (void*)trampoline;
+    frame[7] = nullptr;
+    f.sp = frame;
+#else
     getcontext(&f.ctx);
     f.ctx.uc_stack.ss_sp = stacks[i].data();
     f.ctx.uc_stack.ss_size = kStack;
     f.ctx.uc_link = &b.main;
     makecontext(&f.ctx, (void (*)())trampoline, 0);
+#endif
   }
   while (b.live > 0)
     for (int i = 0; i < n; ++i)
-      if (!b.fibers[i].done) {
-        cur = &b.fibers[i];
-        swapcontext(&b.main, &cur->ctx);
-      }
+      if (!b.fibers[i].done) to_fiber(&b.fibers[i]);
   blk = outer_blk;
   cur = outer_cur;
 }

@@ -5,7 +5,7 @@ autograd Functions as on the GPU -- against the golden vectors produced by the r
 
 What this proves: index arithmetic, warp-level data exchange, reductions, branch logic and the host-side launch planning of those
 kernels.  What it can not: anything about speed, memory-ordering bugs that need real parallelism, and the tcgen05 / TMA kernels
-(convolutions, BatchNorm planes) -- those stay with the -m gpu suite.  FSNET_EMULATE_ALL=1 adds the two larger golden cases."""
+(convolutions, BatchNorm planes) -- those stay with the -m gpu suite.  FSNET_EMULATE_ALL=1 adds the remaining model families (~2 more minutes)."""
 import os
 
 import numpy as np
@@ -16,8 +16,7 @@ from oracle import fsnet_oracle as O
 from test_loss_gpu import depth_grad_ok, run_gpu_loss
 from test_oracle_golden import LOSS_CASES, build_loss_case, load, rel
 
-FAST = ["loss_b", "loss_c", "loss_fe_nomask", "loss_mm"]
-CASES = sorted(LOSS_CASES) if os.environ.get("FSNET_EMULATE_ALL") == "1" else FAST
+CASES = sorted(LOSS_CASES)
 
 
 @pytest.fixture
@@ -137,8 +136,9 @@ def test_fused_adam_kernels_under_emulation(emulated, clip, wd):
     assert float(o_mine.state_dict()["state"][0]["step"]) == 6
 
 
-FULL = ["tiny_distill", "tiny_normeval_frozen"] + (
-    ["tiny4", "tiny_pose", "tiny_sigmoid", "tiny_fe", "tiny_r50", "tiny_normeval", "tiny_frozen"] if os.environ.get("FSNET_EMULATE_ALL") == "1" else [])
+FULL = ["micro_distill", "micro_normeval_frozen", "tiny4", "tiny_pose", "tiny_fe"] + (
+    ["tiny_sigmoid", "tiny_r50", "tiny_distill", "tiny_normeval", "tiny_frozen", "tiny_normeval_frozen"]
+    if os.environ.get("FSNET_EMULATE_ALL") == "1" else [])
 
 
 @pytest.mark.parametrize("name", FULL)
@@ -146,9 +146,10 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
     """A whole training step on the CPU THROUGH THE tcgen05 EXECUTOR PATH (fsnet_b200/engine.py: planes, tape, BatchNorm /
     activation / pooling / re-layout kernels of act_tc.cu emulated; the two tensor-core entry points replaced by the ABI-level
     stand-ins of tests/host_emulation/conv_ref.cpp) plus the emulated loss side, against the golden produced by the reference.
-    Default case: the second-stage model (DistillWPoseMeta: frozen eval-mode teacher, student with the uncertainty heads as a
-    second convolution on the decoder activations, distillation loss) -- loss_dict incl. distilation/s, total loss, gradient
-    norms, sample gradients, untouched teacher."""
+    Default cases: the second-stage model (DistillWPoseMeta: frozen eval-mode teacher, student with the uncertainty heads as a
+    second convolution on the decoder activations, distillation loss), ResNet(norm_eval, frozen_stages), the cfg2a topology, the
+    PoseNet variant and the fisheye head -- loss_dict, total loss, gradient norms, sample gradients, exactly the reference's set
+    of trained parameters, untouched teacher."""
     from helpers import build_model
     from fsnet_b200.networks import ops
     from test_oracle_golden import ALL_FULL_CASES
@@ -183,7 +184,9 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
             assert abs(float(p.grad.double().norm()) - gn[k]) <= 0.05 * gn[k] + floor, (k, float(p.grad.double().norm()), gn[k])
     for key in g.files:
         if key.startswith("grad/"):
-            assert rel(params[key[5:]].grad, g[key]) < 0.05, key      # gradients run through bf16 operands (hi planes only)
+            # gradients run through bf16 operands (hi planes only); at 32x64 the deepest maps are 1x2 pixels and the BatchNorm
+            # batches 4 values, which amplifies that rounding
+            assert rel(params[key[5:]].grad, g[key]) < (0.15 if name.startswith("micro") else 0.05), key
     if topo.distill:
         assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
         assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
@@ -208,7 +211,6 @@ def test_fused_loss_on_ragged_shapes_under_emulation(emulated, H, W, B, scales, 
         assert ok, (s, e)
 
 
-@pytest.mark.skipif(os.environ.get("FSNET_EMULATE_ALL") != "1", reason="~2 min of emulation; FSNET_EMULATE_ALL=1")
 def test_training_hook_trains_the_distillation_model_under_emulation(emulated, monkeypatch):
     """BaseTrainingHook (eager) + FusedAdam over model.parameters() of DistillWPoseMeta: the loss goes down, the frozen teacher is
     never touched, optimiser state exists for the trainable parameters only."""
