@@ -112,14 +112,23 @@ def _syncbn_worker(rank, world, port, out):
 def test_syncbn_training_step_world2_matches_single_process():
     """Two ranks x 2 samples with SyncBatchNorm (forward statistics and the two backward sums all-reduced inside the executor,
     engine.py) + the hook's flat gradient all-reduce == one process x 4 samples with plain BatchNorm: loss, every parameter
-    gradient, and the running statistics.  The kernels run under the SIMT emulator (tests/host_emulation), the collectives over gloo."""
+    gradient, and the running statistics.  The kernels run under the SIMT emulator (tests/host_emulation), the collectives over gloo.
+    (scripts/train.py's DistributedDataParallel wrapping can not be exercised here: torch refuses SyncBatchNorm in CPU modules.)"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=900) for _ in procs]
+    import queue
+    import time
+    results, deadline = [], time.time() + 600
+    while len(results) < len(procs):
+        try:
+            results.append(q.get(timeout=2))
+        except queue.Empty:
+            assert all(p.is_alive() or p.exitcode == 0 for p in procs), "a rank died: " + str([p.exitcode for p in procs])
+            assert time.time() < deadline, "timed out"
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
