@@ -286,3 +286,38 @@ def test_conv_planner_rejects_what_the_kernels_can_not_do(emulated):
     with pytest.raises(_lib.FsnetError, match="ring"):                      # replicate padding without a materialised ring
         _lib.call("fsnet_conv", x.view(), 1, w[0, :, :, :, :16].contiguous(), w[1, :, :, :, :16].contiguous(), 16, 3, 3, 1, 1, 3, None, 0,
                   out.view(), 0, None)
+
+
+def test_training_trajectory_matches_the_reference_step_for_step(emulated, monkeypatch):
+    """Three consecutive steps of BaseTrainingHook (zero_grad, forward, backward, clip 35, FusedAdam) through the executor against
+    the oracle's restatement of the reference's training step (torch Adam on the CPU): per-step losses to north_star's 1e-3,
+    parameters and BatchNorm running statistics after the last step.  Exercises what a single step can not: the batched
+    operand-plane refresh from updated weights, running-statistics updates feeding nothing but later eval, the optimiser state."""
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    from fsnet_b200.optim import build_optimizer
+    from vision_base.utils.builder import build
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    topo, B = O.Topology(height=32, width=64), 2
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        model = build_model(topo)
+        opt = build_optimizer(model, name="adam", lr=1e-4, weight_decay=0)
+        hook = build(name="vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0, cuda_graph=False)
+        trainer = O.OracleTrainer(topo, lr=1e-4, clip=35.0)
+        for i in range(3):
+            data = O.synthetic_batch(B, topo.height, topo.width, 100 + i, topo.frame_ids)
+            noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, i)
+            model.head.tie_break_noise = noise
+            mine = float(hook(dict(data), model, opt, None, None, i, 0)["loss"].detach())
+            ref = float(trainer.step(data, noise)["loss"].detach())
+            assert abs(mine - ref) <= 1e-3 * abs(ref), (i, mine, ref)
+    finally:
+        ops.set_backend(backend)
+    sd = model.state_dict()
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith("depth_bins"):
+            assert rel(v, trainer.sd[k]) < 2e-2, k
+        elif k.endswith("num_batches_tracked"):
+            assert int(v) == 3, k          # nn.BatchNorm2d's counter (the functional oracle does not keep one)
