@@ -321,3 +321,49 @@ def test_training_trajectory_matches_the_reference_step_for_step(emulated, monke
             assert rel(v, trainer.sd[k]) < 5e-2, k        # 1x2-pixel maps at this size: statistics over 4 values amplify the bf16x3 rounding
         elif k.endswith("num_batches_tracked"):
             assert int(v) == 3, k          # nn.BatchNorm2d's counter (the functional oracle does not keep one)
+
+
+def test_files_to_training_step_with_device_augmentation_under_emulation(emulated, monkeypatch, tmp_path):
+    """The whole input side in one chain: miniature KITTI tree -> reader with DeviceAugmentation (uint8 frames + drawn parameters)
+    -> padded collate -> DevicePrefetcher with the device stage (fsnet_augment_frames) -> BaseTrainingHook step through the
+    executor.  The batch the model sees has the reference pipeline's schema; two steps run and produce finite, different losses."""
+    from kitti_fixture import build_tree
+    from fsnet_b200.data.device_augment import device_augment_collate, find_device_stage
+    from fsnet_b200.data.loading import DevicePrefetcher, build_dataloader
+    from fsnet_b200.networks import ops
+    from fsnet_b200.optim import build_optimizer
+    from vision_base.utils.builder import build
+    from vision_base.utils.utils import cfg_from_file
+    raw, split = build_tree(str(tmp_path))
+    for k, v in dict(FSNET_KITTI_PATH=raw, FSNET_KITTI_SPLIT=split, FSNET_SHIFT_BORDER="32", FSNET_WORKDIR=str(tmp_path / "w"),
+                     FSNET_DEVICE_AUG="1").items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = cfg_from_file(os.path.join(repo, "configs", "kitti_wpose_files.py"))
+    cfg.data.rgb_shape = (32, 64, 3)
+    for aug in cfg.train_dataset.augmentation.pipeline.cfg_list:
+        if aug.name.endswith("RandomWarpAffine"):
+            aug.output_h, aug.output_w = 32, 64
+    cfg.meta_arch.head_cfg.height, cfg.meta_arch.head_cfg.width = 32, 64
+    np.random.seed(3)
+    dataset = build(**cfg.train_dataset)
+    stage = find_device_stage(dataset)
+    loader = build_dataloader(dataset, num_workers=0, batch_size=2, collate_fn=device_augment_collate)
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        model = build(**cfg.meta_arch).train()
+        opt = build_optimizer(model, **cfg.optimizer)
+        hook = build(**dict(cfg.trainer.training_hook, cuda_graph=False))
+        losses = []
+        for i, batch in enumerate(DevicePrefetcher(loader, device="cpu", device_transform=stage)):
+            assert batch[("image", 0)].shape == (2, 3, 32, 64) and batch[("original_image", -1)].dtype == torch.float32
+            assert batch["patched_mask"].dtype == torch.float64 and batch["P2"].shape == (2, 3, 4) and "frames_u8" not in batch
+            assert 0.0 <= float(batch[("original_image", 1)].min()) and float(batch[("original_image", 1)].max()) <= 1.0
+            losses.append(float(hook(batch, model, opt, None, None, i, 0)["loss"].detach()))
+            if i == 1:
+                break
+    finally:
+        ops.set_backend(backend)
+    assert all(np.isfinite(losses)) and losses[0] != losses[1] and 0.0 < losses[0] < 1.0
