@@ -367,3 +367,34 @@ def test_files_to_training_step_with_device_augmentation_under_emulation(emulate
     finally:
         ops.set_backend(backend)
     assert all(np.isfinite(losses)) and losses[0] != losses[1] and 0.0 < losses[0] < 1.0
+
+
+def test_evaluation_hook_with_the_real_network_under_emulation(emulated, monkeypatch, tmp_path, capsys):
+    """The evaluation side end to end: Eigen test reader -> BaseValidationHook -> eval-mode forward_test through the executor
+    (running statistics) -> inverse-depth resize -> KittiEigenEvaluator on LiDAR ground truth exported from the miniature tree."""
+    from aug_cases import eval_cfg
+    from kitti_fixture import add_kitti_lidar, build_tree
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    from vision_base.utils.builder import build
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    raw, split = build_tree(str(tmp_path))
+    add_kitti_lidar(raw)
+    hook = build(name="monodepth.pipeline_hooks.evaluation_hooks.base_evaluation_hooks.KittiEvaluationHook",
+                 test_run_hook_cfg=dict(name="vision_base.pipeline_hooks.train_val_hooks.base_validation_hooks.BaseValidationHook"),
+                 dataset_eval_cfg=dict(name="monodepth.evaluation.kitti_unsupervised_eval.KittiEigenEvaluator", data_path=raw,
+                                       split_file=split, gt_saved_file=str(tmp_path / "gt.npz")),
+                 num_workers=0, batch_size=4)
+    ds = build(name="monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset", raw_path=raw, split_file=split,
+               augmentation=eval_cfg(size=(32, 64)))
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        model = build_model(O.Topology(height=32, width=64)).train()
+        res = hook(model, ds, None, 0, 1)
+    finally:
+        ops.set_backend(backend)
+    assert not model.training
+    assert res["error"].shape == (7,) and np.all(np.isfinite(res["error"])) and np.all(np.isfinite(res["abs_error"]))
+    assert 0.0 <= res["error"][4] <= res["error"][5] <= res["error"][6] <= 1.0          # a1 <= a2 <= a3
+    assert "abs_rel" in capsys.readouterr().out
