@@ -52,8 +52,9 @@ def test_training_forward_backward_matches_reference(golden_dir, name):
     ret["loss"].mean().backward()
     gn = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
     bad = []
+    floor = 1e-9 + 1e-7 * max(gn.values())       # conv biases in front of a BatchNorm: exactly zero here, rounding noise in the reference
     for k, p in model2.named_parameters():
-        if k in gn and gn[k] > 1e-9:
+        if k in gn and gn[k] > floor:
             e = abs(float(p.grad.double().norm()) - gn[k]) / gn[k]
             if e > (0.2 if topo.depth >= 50 else 0.1):      # gradients run through bf16 tensor-core operands
                 bad.append((k, e))
