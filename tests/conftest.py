@@ -33,4 +33,14 @@ def _emulated_gpu(request, monkeypatch):
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.Tensor, "cpu", lambda self, *a, **k: self)
+    plain_to = torch.Tensor.to
+
+    def to(self, *args, **kwargs):
+        def host(d):
+            return "cpu" if (isinstance(d, str) and d.startswith("cuda")) or (isinstance(d, torch.device) and d.type == "cuda") else d
+        if "device" in kwargs:
+            kwargs["device"] = host(kwargs["device"])
+        return plain_to(self, *[host(a) for a in args], **kwargs)
+
+    monkeypatch.setattr(torch.Tensor, "to", to)
     yield
