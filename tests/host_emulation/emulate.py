@@ -193,8 +193,8 @@ def build_simt_library(files=SIMT_FILES):
     key = hashlib.sha1(("".join(sources.values()) + extra).encode()).hexdigest()[:16]
     out = os.path.join(tempfile.gettempdir(), f"fsnet_simt_{key}.so")
     if not os.path.exists(out):
-        work = out[:-3] + "_src"
-        os.makedirs(work, exist_ok=True)
+        # private work directory + atomic rename: several processes (the world-2 tests) may ask for the library at the same time
+        work = tempfile.mkdtemp(prefix=f"fsnet_simt_{key}_")
         objs = []
         for f, text in sources.items():
             cpp = os.path.join(work, f[:-3] + ".cpp")
@@ -205,11 +205,13 @@ def build_simt_library(files=SIMT_FILES):
                                    "-I", csrc, "-c", cpp, "-o", obj])
             objs.append(obj)
         ref = os.path.join(work, "conv_ref.o")
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-I", os.path.join(REPO, "include"), "-c", os.path.join(HERE, "conv_ref.cpp"),
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-w", "-fPIC", "-I", os.path.join(REPO, "include"), "-c", os.path.join(HERE, "conv_ref.cpp"),
                                "-o", ref])
         switch = os.path.join(work, "simt_switch.o")
         subprocess.check_call(["g++", "-fPIC", "-c", os.path.join(HERE, "simt_switch.cpp"), "-o", switch])
-        subprocess.check_call(["g++", "-shared", "-o", out] + objs + [ref, switch])
+        staged = os.path.join(work, "lib.so")
+        subprocess.check_call(["g++", "-shared", "-o", staged] + objs + [ref, switch])
+        os.replace(staged, out)
     return out
 
 

@@ -114,6 +114,10 @@ def test_syncbn_training_step_world2_matches_single_process():
     engine.py) + the hook's flat gradient all-reduce == one process x 4 samples with plain BatchNorm: loss, every parameter
     gradient, and the running statistics.  The kernels run under the SIMT emulator (tests/host_emulation), the collectives over gloo.
     (scripts/train.py's DistributedDataParallel wrapping can not be exercised here: torch refuses SyncBatchNorm in CPU modules.)"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from host_emulation import emulate
+    emulate.build_simt_library()                  # compiled once here, found in the cache by both ranks
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
