@@ -398,3 +398,36 @@ def test_evaluation_hook_with_the_real_network_under_emulation(emulated, monkeyp
     assert res["error"].shape == (7,) and np.all(np.isfinite(res["error"])) and np.all(np.isfinite(res["abs_error"]))
     assert 0.0 <= res["error"][4] <= res["error"][5] <= res["error"][6] <= 1.0          # a1 <= a2 <= a3
     assert "abs_rel" in capsys.readouterr().out
+
+
+def test_changing_batch_and_image_sizes_and_train_eval_transitions_under_emulation(emulated):
+    """One model object through train(B=3, 32x64) -> eval(B=1) -> eval(B=4) -> train(B=2, 64x96) -> eval(64x96) -> eval(32x64):
+    the executor's cached per-layer state must not depend on shapes, and the running statistics left by the training calls must
+    be the ones the oracle accumulates (eval predictions to 1e-5)."""
+    from helpers import build_model
+    from fsnet_b200.networks import ops
+    backend = ops.BACKEND
+    ops.set_backend("tc")
+    try:
+        base = O.Topology(height=32, width=64)
+        model = build_model(base)
+        sd = O.make_state_dict(base)
+        for mode, B, H, W in [("train", 3, 32, 64), ("eval", 1, 32, 64), ("eval", 4, 32, 64), ("train", 2, 64, 96), ("eval", 2, 64, 96),
+                              ("eval", 3, 32, 64)]:
+            topo = O.Topology(height=H, width=W)
+            data = O.synthetic_batch(B, H, W, 5 + B + H, topo.frame_ids)
+            if mode == "train":
+                noise = O.tie_break_noise(B, H, W, topo.scales, 0)
+                model.train()
+                model.head.tie_break_noise = noise
+                mine = float(model(dict(data), dict(is_training=True, epoch_num=0, global_step=0))["loss"].detach())
+                ref = float(O.forward_train(sd, data, topo, noise)["loss"].detach())          # updates sd's running statistics
+                assert abs(mine - ref) <= 1e-4 * abs(ref), (mode, B, H, W)
+            else:
+                model.eval()
+                with torch.no_grad():
+                    pred = model(dict(data), dict(is_training=False))["depth"]
+                    want = O.forward_test(sd, data, topo)["depth"]
+                assert rel(pred, want) < 1e-5, (mode, B, H, W)
+    finally:
+        ops.set_backend(backend)
