@@ -246,9 +246,29 @@ def _strip_device_functions(text):
 def translate_plan(cu_text, csrc_dir):
     import re
     text = _strip_device_functions(cu_text)
-    text = re.sub(r"<<<.*?>>>", "<<<0, 0>>>", text, flags=re.S)
     text = translate(text, csrc_dir)
-    text = text.replace("simt::launch(", "simt::no_launch(")
+    text = text.replace("simt::launch(", "plan_record(")
+    recorder = r"""
+// plan check: what would have been launched (FSNET_PLAN_PRINT=1 prints one line per planned launch)
+template <class K> static void plan_record(K, dim3 grid, dim3 block, size_t smem, CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap,
+                                           const fsnet::ConvParams& p) {
+  const char* e = getenv("FSNET_PLAN_PRINT");
+  if (!e || e[0] != '1') return;
+  printf("PLAN conv  N=%d %dx%d Cin=%d Cout=%d k=%d s=%d | tile %dx%d BN=%d fold=%d KC=%d kiters=%d stages=%d | tiles=%d grid=%u smem=%zu\n",
+         p.N, p.H, p.W, p.Cin, p.Cout, p.KH, p.stride, p.TH, p.TW, p.BN, p.fold, p.KC, p.kiters, p.stages, p.total_tiles, grid.x, smem);
+}
+"""
+    text = text.replace('extern "C" int fsnet_conv(', recorder + 'extern "C" int fsnet_conv(', 1)
+    recorder_w = r"""
+template <class K> static void plan_record(K, dim3 grid, dim3 block, size_t smem, CUtensorMap, CUtensorMap, const fsnet::WgradParams& p) {
+  const char* e = getenv("FSNET_PLAN_PRINT");
+  if (!e || e[0] != '1') return;
+  printf("PLAN wgrad N=%d %dx%d Cin=%d Cout=%d k=%d s=%d | BM=%d BN=%d fold=%d pix=%d ksplit=%d stages=%d | items=%d grid=%u smem=%zu\n",
+         p.N, p.Ho, p.Wo, p.Cin, p.Cout, p.KH, p.stride, p.BM_real, p.BN, p.fold, p.pix, p.ksplit, p.stages,
+         p.taps * p.co_tiles * p.ci_tiles, grid.x, smem);
+}
+"""
+    text = text.replace('extern "C" int fsnet_conv_wgrad(', recorder_w + 'extern "C" int fsnet_conv_wgrad(', 1)
     text = text.replace("#include <stdlib.h>", "#include <stdlib.h>\n#include \"cuda.h\"").replace("#include <cuda.h>", "")
     text = re.sub(r"cudaGetDriverEntryPoint\([^;]*\)\s*!=\s*cudaSuccess", "((ptr = (void*)&cuTensorMapEncodeTiled), false)", text)
     return text.replace('extern "C" int fsnet_conv(', 'extern "C" int fsnet_conv_plan(').replace(
