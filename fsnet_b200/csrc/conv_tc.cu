@@ -499,6 +499,19 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     p.BN /= 2; p.n_tiles = Cout / p.BN;
     p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles;
   }
+  // wave quantisation (opt-in, FSNET_CONV_WAVE=1|2, off by default until measured): 180 tiles on 148 SMs run as two waves with the
+  // second one 22 % full; half-width channel tiles (twice the tiles, half the MMA time each) fill the last wave better.
+  // 2 also allows quarter-width tiles for a single under-filled wave (the 96-tile layers at 128 channels per tile).
+  static int wave_env = -1;
+  if (wave_env < 0) { const char* e = getenv("FSNET_CONV_WAVE"); wave_env = e ? atoi(e) : 0; }
+  if (wave_env && p.total_tiles > 74) {
+    auto fill = [](int tiles) { return (double)tiles / (148.0 * ((tiles + 147) / 148)); };
+    int best = 1;
+    if (p.BN >= 64 && Cout % (p.BN / 2) == 0 && fill(p.total_tiles * 2) > fill(p.total_tiles) + 0.1) best = 2;
+    else if (wave_env >= 2 && p.total_tiles <= 148 && p.BN >= 128 && Cout % (p.BN / 4) == 0 &&
+             fill(p.total_tiles * 4) > fill(p.total_tiles) + 0.15) best = 4;
+    if (best > 1) { p.BN /= best; p.n_tiles = Cout / p.BN; p.total_tiles = N * p.tiles_x * p.tiles_y * p.n_tiles; }
+  }
   p.KC = pick_kc(Cin); p.cchunks = Cin / p.KC; p.kiters = KH * KW * p.cchunks;
   // x-tap folding for thin replicate-padded layers: the KW taps x Cin channels of a kernel row are one contiguous
   // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
