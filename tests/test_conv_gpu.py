@@ -31,30 +31,35 @@ CASES = [
 
 @pytest.mark.parametrize("N,Cin,Cout,H,W,k,stride,pad,mode", CASES)
 def test_conv_forward_and_gradients(N, Cin, Cout, H, W, k, stride, pad, mode):
+    run_conv_case("cuda", N, Cin, Cout, H, W, k, stride, pad, mode)
+
+
+def run_conv_case(dev, N, Cin, Cout, H, W, k, stride, pad, mode):
+    """``dev`` = "cuda" here; tests/test_emulated_kernels_cpu.py runs the same checks on "cpu" against the ABI-level stand-ins."""
     from fsnet_b200 import _lib, tc
-    g = torch.Generator(device="cuda").manual_seed(1)
-    x = torch.randn(N, Cin, H, W, device="cuda", generator=g).requires_grad_(True)
-    w = (torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5).requires_grad_(True)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(N, Cin, H, W, device=dev, generator=g).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, device=dev, generator=g) / (Cin * k * k) ** 0.5).requires_grad_(True)
     rep = mode == "rep"
     xin = F.pad(x, (pad,) * 4, mode="replicate") if rep else x
     y = F.conv2d(xin, w, stride=stride, padding=0 if rep else pad)
-    gy = torch.randn(y.shape, device="cuda", generator=g)
+    gy = torch.randn(y.shape, device=dev, generator=g)
     gx_ref, gw_ref = torch.autograd.grad(y, (x, w), gy)
     ring = pad if mode == "zring" else 1
-    xp = tc.Planes(N, H, W, tc.pad16(Cin), ring, zero=True)
+    xp = tc.Planes(N, H, W, tc.pad16(Cin), ring, zero=True, device=dev)
     _lib.call("fsnet_image_to_planes_ring", x.detach().contiguous(), Cin, xp.view(), int(mode == "zring"))
     use_ring = mode in ("rep", "zring")
     cw = tc.ConvWeights(w)
     cw.refresh(w)
     Ho, Wo = y.shape[-2:]
-    out = tc.Fp32(N, Ho, Wo, cw.co_pad)
-    stats = torch.zeros(2 * cw.co_pad, device="cuda", dtype=torch.float64)
+    out = tc.Fp32(N, Ho, Wo, cw.co_pad, device=dev)
+    stats = torch.zeros(2 * cw.co_pad, device=dev, dtype=torch.float64)
     tc.conv(xp, cw, out, stride, pad, use_ring=use_ring, stats=stats)
     assert rel(out.nchw()[:, :Cout], y.detach()) < 2e-5                      # bf16x3 split operands: fp32-class accuracy
     assert rel(stats[:Cout], y.detach().double().sum((0, 2, 3))) < 1e-4       # fused BatchNorm statistics
     assert rel(stats[cw.co_pad:cw.co_pad + Cout], (y.detach().double() ** 2).sum((0, 2, 3))) < 1e-4
     # weight gradient (single bf16 product)
-    dy = tc.Planes(N, Ho, Wo, cw.co_pad, ring=0, zero=True)
+    dy = tc.Planes(N, Ho, Wo, cw.co_pad, ring=0, zero=True, device=dev)
     dy.t[0, :, :, :, :Cout] = gy.permute(0, 2, 3, 1).bfloat16()
     acc = tc.conv_wgrad(xp.view(), use_ring, dy.view(), cw, stride, pad)
     gw = torch.zeros_like(w)
@@ -65,19 +70,19 @@ def test_conv_forward_and_gradients(N, Cin, Cout, H, W, k, stride, pad, mode):
     # data gradient of the stride-1 layers
     if stride == 1:
         if rep:
-            gx = tc.Fp32(N, H, W, cw.ci_pad, ring=1)
+            gx = tc.Fp32(N, H, W, cw.ci_pad, ring=1, device=dev)
             full = tc.View(gx.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
             tc.conv_dgrad(dy, cw, full, pad=k - 1)
             _lib.call("fsnet_fold_ring", gx.view())
             # the executor's variant: dy with a materialised zero ring of k-1 pixels read as data (folded-tap / TMEM-operand paths)
-            dyr = tc.Planes(N, Ho, Wo, cw.co_pad, ring=k - 1, zero=True)
+            dyr = tc.Planes(N, Ho, Wo, cw.co_pad, ring=k - 1, zero=True, device=dev)
             dyr.t[0, :, k - 1:k - 1 + Ho, k - 1:k - 1 + Wo, :Cout] = gy.permute(0, 2, 3, 1).bfloat16()
-            gx2 = tc.Fp32(N, H, W, cw.ci_pad, ring=1)
+            gx2 = tc.Fp32(N, H, W, cw.ci_pad, ring=1, device=dev)
             full2 = tc.View(gx2.t.data_ptr(), N, H + 2, W + 2, cw.ci_pad, 0, cw.ci_pad, 0)
             tc.conv_dgrad(dyr, cw, full2, pad=k - 1, use_ring=True)
             _lib.call("fsnet_fold_ring", gx2.view())
             assert rel(gx2.nchw()[:, :Cin], gx_ref) < 1e-2
         else:
-            gx = tc.Fp32(N, H, W, cw.ci_pad)
+            gx = tc.Fp32(N, H, W, cw.ci_pad, device=dev)
             tc.conv_dgrad(dy, cw, gx.view(), pad=k - 1 - pad)
         assert rel(gx.nchw()[:, :Cin], gx_ref) < 1e-2

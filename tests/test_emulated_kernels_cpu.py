@@ -431,3 +431,17 @@ def test_changing_batch_and_image_sizes_and_train_eval_transitions_under_emulati
                 assert rel(pred, want) < 1e-5, (mode, B, H, W)
     finally:
         ops.set_backend(backend)
+
+
+def _conv_cases():
+    from test_conv_gpu import CASES
+    return CASES
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,k,stride,pad,mode", _conv_cases())
+def test_abi_level_conv_stand_ins_follow_the_contract(emulated, N, Cin, Cout, H, W, k, stride, pad, mode):
+    """The two stand-ins of tests/host_emulation/conv_ref.cpp (what the executor emulation rests on) pass the very checks the
+    tcgen05 kernels pass on the B200 (tests/test_conv_gpu.py: forward, fused statistics, weight gradient per tap, data gradient
+    incl. the ringed variants) -- with the real planner in front and the emulated operand-plane / re-layout kernels around them."""
+    from test_conv_gpu import run_conv_case
+    run_conv_case("cpu", N, Cin, Cout, H, W, k, stride, pad, mode)
