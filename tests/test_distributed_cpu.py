@@ -70,7 +70,8 @@ def _syncbn_worker(rank, world, port, out):
         from fsnet_b200.hooks.training import BaseTrainingHook
         from fsnet_b200.networks import ops
         ops.set_backend("tc")
-        topo = O.Topology(height=32, width=64)
+        posenet = os.environ.get("FSNET_DIST_POSENET") == "1"        # opt-in variant: depth net + PoseNet (two executor tapes per step)
+        topo = O.Topology(height=32, width=64, posenet=posenet, overlapped_mask=not posenet)
         B = 2 * world
         data = O.synthetic_batch(B, topo.height, topo.width, 77, topo.frame_ids)
         data.pop("patched_mask")                    # equal loss normalisers on every rank: the mean of rank losses is the global loss
