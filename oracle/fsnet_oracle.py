@@ -675,7 +675,7 @@ class OracleTrainer:
     def __init__(self, topo: Topology, seed: int = 123, lr: float = 1e-4, clip: Optional[float] = 35.0):
         self.topo = topo
         self.sd = make_state_dict(topo, seed)
-        self.params = [self.sd[k].requires_grad_(True) for k in trainable(self.sd)]
+        self.params = [self.sd[k].requires_grad_(True) for k in trainable(self.sd, topo)]
         self.opt = torch.optim.Adam(self.params, lr=lr, weight_decay=0)
         self.clip = clip
 
