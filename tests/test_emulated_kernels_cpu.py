@@ -288,7 +288,8 @@ def test_conv_planner_rejects_what_the_kernels_can_not_do(emulated):
                   out.view(), 0, None)
 
 
-def test_training_trajectory_matches_the_reference_step_for_step(emulated, monkeypatch):
+@pytest.mark.parametrize("variant", ["plain"] + (["norm_eval_frozen"] if os.environ.get("FSNET_EMULATE_ALL") == "1" else []))
+def test_training_trajectory_matches_the_reference_step_for_step(emulated, monkeypatch, variant):
     """Three consecutive steps of BaseTrainingHook (zero_grad, forward, backward, clip 35, FusedAdam) through the executor against
     the oracle's restatement of the reference's training step (torch Adam on the CPU): per-step losses to north_star's 1e-3,
     parameters and BatchNorm running statistics after the last step.  Exercises what a single step can not: the batched
@@ -298,11 +299,13 @@ def test_training_trajectory_matches_the_reference_step_for_step(emulated, monke
     from fsnet_b200.optim import build_optimizer
     from vision_base.utils.builder import build
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    topo, B = O.Topology(height=32, width=64), 2
+    frozen = variant == "norm_eval_frozen"
+    topo, B = O.Topology(height=32, width=64, norm_eval=frozen, frozen_stages=1 if frozen else -1), 2
     backend = ops.BACKEND
     ops.set_backend("tc")
     try:
         model = build_model(topo)
+        before = {k: v.clone() for k, v in model.state_dict().items()}
         opt = build_optimizer(model, name="adam", lr=1e-4, weight_decay=0)
         hook = build(name="vision_base.pipeline_hooks.train_val_hooks.base_training_hooks.BaseTrainingHook", clip_gradients=35.0, cuda_graph=False)
         trainer = O.OracleTrainer(topo, lr=1e-4, clip=35.0)
@@ -316,7 +319,14 @@ def test_training_trajectory_matches_the_reference_step_for_step(emulated, monke
     finally:
         ops.set_backend(backend)
     sd = model.state_dict()
+    if frozen:      # frozen stem + layer1 and every encoder running statistic are exactly what they were
+        assert all(torch.equal(before[k], v) for k, v in sd.items()
+                   if k.startswith(("depth_backbone.conv1", "depth_backbone.bn1", "depth_backbone.layer1")) or
+                   (k.startswith("depth_backbone") and "running" in k))
     for k, v in sd.items():
+        if frozen and k.endswith("num_batches_tracked") and k.startswith("depth_backbone"):
+            assert int(v) == 0, k
+            continue
         if v.is_floating_point() and not k.endswith("depth_bins"):
             assert rel(v, trainer.sd[k]) < 5e-2, k        # 1x2-pixel maps at this size: statistics over 4 values amplify the bf16x3 rounding
         elif k.endswith("num_batches_tracked"):
