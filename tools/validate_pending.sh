@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call that validates everything written after round 1's GPU minutes were spent, then re-measures.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/validate_pending.sh'
+#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/validate_pending.sh'   (~35 GPU-minutes)
 # Outputs land in gpurun_out/ (merged back): pending_tests.txt, bench_default.txt, bench_prefetch.txt, gpu_tests.txt
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.txt
