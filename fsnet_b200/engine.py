@@ -235,7 +235,10 @@ class Tape:
             dist.all_reduce(st.stats)
             count = count * world
         inv.count = count
-        momentum = MOMENTUM_DEFAULT if bn.momentum is None else bn.momentum
+        if bn.momentum is None:
+            raise NotImplementedError("BatchNorm(momentum=None) (cumulative moving average) is not implemented on the tcgen05 path; "
+                                      "no reference configuration uses it")
+        momentum = bn.momentum
         _lib.call("fsnet_bn_finalize", st.stats, tc.c_double(count), st.padded(bn.weight, 1.0), st.padded(bn.bias),
                   st.padded(conv.bias), self._buf(bn.running_mean, st), self._buf(bn.running_var, st),
                   bn.num_batches_tracked if bn_train else None, float(momentum), float(bn.eps), int(bn_train), st.C,
@@ -518,6 +521,10 @@ def _nhwc_grad(g: torch.Tensor, c_pad: int) -> torch.Tensor:
 
 
 def _check_supported(backbone):
+    want = tuple([-1] + list(range(getattr(backbone, "num_stages", 4))))
+    if tuple(getattr(backbone, "out_indices", want)) != want:
+        raise NotImplementedError(f"tcgen05 path: out_indices must be {want} (stem + every stage, as in every reference config), "
+                                  f"got {tuple(backbone.out_indices)}")
     if any(d != 1 for d in getattr(backbone, "dilations", (1,))):
         raise NotImplementedError("tcgen05 path: dilated convolutions are not implemented (no shipped config uses them)")
 

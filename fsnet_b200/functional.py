@@ -90,7 +90,15 @@ class _ReprojectionLoss(torch.autograd.Function):
         ctx.fused = fused_s
         unit_gd, unit_gP = [None] * S, None
         if fused:
-            _lib.call("fsnet_mask_sum", mask_c, mdt, _lib.ctypes.c_longlong(B * H * W), acc, S, 4)
+            # the normaliser sum(patched_mask) goes ONLY into the rows of fused scales: the forward-only kernel of a non-fused
+            # scale (scale 0 of a log-image head) accumulates its own into acc[i, 1]
+            i0 = fused_s.index(True)
+            if all(fused_s[i0:]):
+                _lib.call("fsnet_mask_sum", mask_c, mdt, _lib.ctypes.c_longlong(B * H * W), acc[i0:], S - i0, 4)
+            else:
+                for i in range(S):
+                    if fused_s[i]:
+                        _lib.call("fsnet_mask_sum", mask_c, mdt, _lib.ctypes.c_longlong(B * H * W), acc[i], 1, 4)
             unit = torch.full((1,), 1.0 / S, device=dev, dtype=torch.float32)
             unit_gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
         for i, s in enumerate(cfg["scales"]):
@@ -202,6 +210,13 @@ class MeiRayTable:
         self.key = None
         self.state = None
         self._calib_cache = {}
+
+    @staticmethod
+    def calib_host_tensor(calib_meta) -> torch.Tensor:
+        """[B,3] fp64 (xi, k1, k2) on the host (pinned when CUDA is there): the graph-replayed hook copies it every step."""
+        t = torch.tensor([(float(c["mirror_parameters"]["xi"]), float(c["distortion_parameters"]["k1"]),
+                           float(c["distortion_parameters"]["k2"])) for c in calib_meta], dtype=torch.float64)
+        return t.pin_memory() if torch.cuda.is_available() else t
 
     def calib_tensor(self, calib_meta, device):
         """[B,3] fp64 (xi, k1, k2) of the dataset's ``calib_meta`` dicts (fisheye_dataset.py:45-58,254)."""

@@ -130,7 +130,19 @@ class BaseTrainingHook(object):
         return output
 
     # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _tensorise(data):
+        """Graph replay only refreshes TENSOR entries of the static batch.  The fisheye datasets deliver their per-sample MEI
+        calibration as a list of dicts (`calib_meta`, fisheye_dataset.py:45-58,254; KITTI360FisheyeDataset picks image_02 or
+        image_03 per sample): pack it into the `calib_mei` [B,3] fp64 tensor FishEyeDecoder reads, so that it is copied every step
+        (replays used the capture batch's calibration for every later batch)."""
+        if "calib_meta" in data and "calib_mei" not in data:
+            from ..functional import MeiRayTable
+            data["calib_mei"] = MeiRayTable.calib_host_tensor(data["calib_meta"])
+        return data
+
     def _graphed(self, data, meta_arch, optimizer, meta):
+        data = self._tensorise(data)
         if self._calls == 0:
             for group in optimizer.param_groups:          # Adam must keep its step counters on the device
                 if "capturable" in group and not optimizer.state:
@@ -149,7 +161,7 @@ class BaseTrainingHook(object):
             dev = next(meta_arch.parameters()).device
             self._static_in = {}
             for k, v in data.items():
-                if isinstance(v, torch.Tensor) and (self.tensor_keys is None or k in self.tensor_keys):
+                if isinstance(v, torch.Tensor) and (self.tensor_keys is None or k in self.tensor_keys or k == "calib_mei"):
                     self._static_in[k] = torch.empty(v.shape, dtype=v.dtype, device=dev)
                 else:
                     self._static_in[k] = v

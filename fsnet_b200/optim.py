@@ -41,8 +41,26 @@ class FusedAdam(optim.Adam):
             if st is None:
                 continue
             h = st["host"]
+            self._wait_staging(st, "host_ev")              # the previous copy out of this pinned buffer has executed
             h[0], h[1], h[2], h[3], h[4] = group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["weight_decay"]
             st["hyper"][:5].copy_(h[:5], non_blocking=True)
+            self._mark_staging(st, "host_ev")
+
+    @staticmethod
+    def _wait_staging(st, key):
+        ev = st.get(key)
+        if ev is not None:
+            ev.synchronize()
+
+    @staticmethod
+    def _mark_staging(st, key):
+        """A pinned staging buffer is rewritten by the host on a later step; the asynchronous copy out of it must have run by
+        then (the CPU may run more than one step ahead of the GPU)."""
+        if torch.cuda.is_available() and not torch.cuda.is_current_stream_capturing():
+            ev = st.get(key)
+            if ev is None:
+                ev = st[key] = torch.cuda.Event()
+            ev.record()
 
     @torch.no_grad()
     def step(self, closure=None, max_norm=None):
@@ -78,6 +96,7 @@ class FusedAdam(optim.Adam):
                     # allocated on the first (eager) step; a later capture only rewrites the pinned rows and re-issues the copy
                     st["table_host"] = torch.zeros(len(ps), 6, dtype=torch.int64).pin_memory()
                     st["table"] = torch.empty(len(ps), 6, dtype=torch.int64, device=dev)
+                self._wait_staging(st, "table_ev")
                 rows, chunk = st["table_host"], 0
                 for i, p in enumerate(ps):
                     s = self.state[p]
@@ -85,6 +104,7 @@ class FusedAdam(optim.Adam):
                     rows[i, 4], rows[i, 5] = p.numel(), chunk
                     chunk += (p.numel() + self.CHUNK - 1) // self.CHUNK
                 st["table"].copy_(rows, non_blocking=True)
+                self._mark_staging(st, "table_ev")
                 st["key"], st["n_chunks"] = key, chunk
                 if st["step"] is None:                      # resume: the device counter starts from the checkpointed step
                     st["hyper"][6:7].fill_(float(self.state[ps[0]]["step"]))

@@ -47,6 +47,12 @@ def test_fused_loss_kernels_match_golden_under_emulation(emulated, golden_dir, n
         assert rel(T[fi].grad, g[f"grad_T/{f}"]) < 0.3, f
 
 
+def test_log_image_head_keeps_the_loss_and_gradients_under_emulation(emulated, golden_dir):
+    """the patched-mask normaliser of a non-fused scale 0 (log-image head) must not be counted twice."""
+    from test_loss_gpu import check_log_image_case
+    check_log_image_case(golden_dir, "loss_a", "cpu")
+
+
 def test_depth_head_kernels_under_emulation(emulated):
     """fsnet_depth_head_fwd / _bwd (channels-last lane-group softmax and the NCHW kernel) against the oracle's gather_depth."""
     from fsnet_b200 import functional as Fn

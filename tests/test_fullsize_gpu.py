@@ -1,0 +1,98 @@
+"""Whole-step parity at the REAL sizes of the BASELINE configurations, through the public `meta_arch(data, meta)` entry, against
+the oracle run on the host in the same test (the oracle itself is pinned by the reference-generated goldens at small sizes,
+tests/test_oracle_golden.py).  The small goldens never reach the plans the convolution planner picks at these shapes (K-split
+weight gradients with > 100 splits, folded halo tiles with > 10 000 tiles, 2-CTA tiles, wave-fitted channel tiles).
+
+Checks per case: loss and every loss_dict entry (1e-3, north_star), disparity and depth maps of every scale (1e-3 relative L2),
+EVERY parameter gradient element-wise (relative L2 per tensor; the worst tensor and the median are reported), BatchNorm running
+statistics after the step.
+
+Shapes: cfg2a configs/kitti_wpose_example:174-215 (R18, 192x640, 16 bins); cfg3 configs/multi_dataset_example:250 topology at
+192x768 (R50); shipped nuScenes configs/nusc_wpose_example:183-209 (R34, 288x512, 64 bins, base_fx=369, overlapped_mask off);
+cfg4 BASELINE size 320x640 (R18)."""
+import time
+
+import pytest
+import torch
+
+from oracle import fsnet_oracle as O
+from helpers import build_model
+from test_oracle_golden import rel
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "cfg2a_r18_192x640": dict(topo=O.Topology(depth=18, height=192, width=640), B=4, fx=0.58),
+    "cfg3_r50_192x768": dict(topo=O.Topology(depth=50, height=192, width=768), B=2, fx=0.58),
+    "nusc_r34_288x512": dict(topo=O.Topology(depth=34, height=288, width=512, n_bins=64, base_fx=369.0, overlapped_mask=False), B=2, fx=0.79),
+    "cfg4_r18_320x640": dict(topo=O.Topology(depth=18, height=320, width=640), B=2, fx=0.79),
+}
+# relative L2 per parameter tensor: dgrad / wgrad run ONE bf16 product (8 mantissa bits per operand, fp32 accumulate) through up to
+# 50 layers; the forward runs three products (~16 bits).  Measured on B200 (profiles/r2_parity.md): median ~3e-3, worst tensor < 2e-2.
+GRAD_TOL = 2e-2
+
+
+def to_cuda(data):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in data.items()}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_whole_step_at_full_size_matches_oracle(name):
+    case = CASES[name]
+    topo, B = case["topo"], case["B"]
+    data = O.synthetic_batch(B, topo.height, topo.width, 4321, topo.frame_ids, fx_scale=case["fx"], fy_scale=case["fx"] * topo.width / topo.height)
+    noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+    # ---- oracle on the host ----------------------------------------------------------------------
+    t0 = time.time()
+    sd = O.make_state_dict(topo)
+    names = O.trainable(sd, topo)
+    for k in names:
+        sd[k].requires_grad_(True)
+    ref = O.forward_train(sd, data, topo, noise)
+    ref["loss"].mean().backward()
+    t_oracle = time.time() - t0
+    # ---- this repo on the GPU ---------------------------------------------------------------------
+    model = build_model(topo).cuda()
+    model.head.tie_break_noise = noise
+    ret = model(to_cuda(data), dict(is_training=True, epoch_num=0, global_step=0))
+    ret["loss"].mean().backward()
+    torch.cuda.synchronize()
+    want = float(ref["loss"].detach())
+    assert abs(float(ret["loss"].detach()) - want) <= 1e-3 * abs(want), (float(ret["loss"].detach()), want)
+    for k, v in ret["loss_dict"].items():
+        r = float(ref["loss_dict"][k])
+        assert abs(float(v) - r) <= 1e-3 * abs(r) + 1e-12, (k, float(v), r)
+    # maps: a second forward of the depth network alone (the public entry does not return them); training mode, same statistics
+    with torch.no_grad():
+        outs = model.head.forward_depth(model.depth_backbone(data[("image", 0)].cuda()), data["P2"].cuda())
+    for s in topo.scales:
+        assert rel(outs[("disp", s)].cpu(), ref["outputs"][("disp", s)]) < 1e-3, s
+        assert rel(outs[("depth", s, s)].cpu(), ref["outputs"][("depth", s, s)]) < 1e-3, s
+    # every parameter gradient, element-wise
+    errs = {}
+    gmax = max(float(sd[k].grad.norm()) for k in names if sd[k].grad is not None)
+    for k, p in model.named_parameters():
+        if k not in names or sd[k].grad is None:
+            continue
+        r = sd[k].grad.double()
+        if float(r.norm()) <= 1e-7 * gmax:          # conv biases in front of a train-mode BatchNorm: zero up to rounding
+            assert p.grad is None or float(p.grad.double().norm()) <= 1e-5 * gmax, k
+            continue
+        assert p.grad is not None, k
+        errs[k] = float((p.grad.double().cpu() - r).norm() / r.norm())
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    med = sorted(errs.values())[len(errs) // 2]
+    print(f"[{name}] oracle {t_oracle:.1f}s; {len(errs)} gradient tensors: median rel L2 {med:.2e}, worst {worst[0][1]:.2e} ({worst[0][0]})")
+    assert worst[0][1] < GRAD_TOL, worst
+    # running statistics (two training forwards here; the oracle did one: compare after rewinding is not possible, so compare
+    # the statistic a single momentum step from the initial value would give -- done on a fresh model)
+    model1 = build_model(topo).cuda()
+    model1.head.tie_break_noise = noise
+    model1(to_cuda(data), dict(is_training=True, epoch_num=0, global_step=0))
+    bad = []
+    for k, v in model1.state_dict().items():
+        if k.endswith(("running_mean", "running_var")) and k in sd:
+            e = float((v.cpu().double() - sd[k].double()).norm() / (sd[k].double().norm() + 1e-12))
+            if e > 1e-3:
+                bad.append((k, e))
+    assert not bad, bad[:5]

@@ -29,7 +29,7 @@ def depth_grad_ok(got, want):
     return (float(bad.float().mean()) < 0.01 and good_rel < 2e-3), (e, float(bad.float().mean()), good_rel)
 
 
-def run_gpu_loss(topo, data, outputs, noise, need_pose=True, dev="cuda"):
+def run_gpu_loss(topo, data, outputs, noise, need_pose=True, dev="cuda", log_image=False):
     from fsnet_b200 import functional as Fn
     S = len(topo.scales)
     depths = [outputs[("depth", s, s)].detach().to(dev).requires_grad_(True) for s in topo.scales]
@@ -45,7 +45,7 @@ def run_gpu_loss(topo, data, outputs, noise, need_pose=True, dev="cuda"):
     total, stats, _, _ = Fn.reprojection_loss(
         depths, disps, T[0], T[1], data["P2"].to(dev), data[("original_image", 0)].to(dev),
         data[("original_image", topo.frame_ids[1])].to(dev), data[("original_image", topo.frame_ids[2])].to(dev),
-        mask, motion, nz, scales=topo.scales, overlapped_mask=topo.overlapped_mask, mei=mei)
+        mask, motion, nz, scales=topo.scales, overlapped_mask=topo.overlapped_mask, mei=mei, log_image=log_image)
     total.backward()
     return total, stats, depths, disps, T
 
@@ -72,6 +72,27 @@ def test_fused_loss_matches_golden(golden_dir, name):
     for fi, f in enumerate(topo.frame_ids[1:]):
         e = rel(T[fi].grad.cpu(), g[f"grad_T/{f}"])
         assert e < 0.3, (f, e)    # heavily cancelling sum: one flipped arg-min shows at the 10% level
+
+
+@pytest.mark.parametrize("name", ["loss_a", "loss_fe"])
+def test_log_image_head_keeps_the_loss_and_gradients(golden_dir, name):
+    """is_log_image=True (the fisheye config's default): scale 0 runs the forward-only + backward kernels, scales 1.. the fused
+    launch.  Loss, per-scale losses and d loss / d depth must not depend on it (round-1 bug: sum(patched_mask) was added twice
+    into scale 0's normaliser, halving loss/0 and its gradients)."""
+    check_log_image_case(golden_dir, name, "cuda")
+
+
+def check_log_image_case(golden_dir, name, dev):
+    g = load(golden_dir, name)
+    case = LOSS_CASES[name]
+    topo = case["topo"]
+    data, outputs, noise = build_loss_case(**case)
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, dev=dev, log_image=True)
+    assert abs(float(total.detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    for i, s in enumerate(topo.scales):
+        assert abs(float(stats[i]) - float(g[f"loss_dict/loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/loss/{s}"])), s
+        ok, e = depth_grad_ok(depths[i].grad.cpu(), g[f"grad_depth/{s}"])
+        assert ok, (s, e)
 
 
 def test_fused_loss_vs_oracle_cfg2_shape():

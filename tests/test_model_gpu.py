@@ -137,7 +137,9 @@ def test_fisheye_graphed_hook_matches_eager_hook():
         opt = torch.optim.Adam(model.parameters(), lr=1e-4)
         seq = []
         for step in range(7):
-            out = hook(O.synthetic_fisheye_batch(2, 64, 64, 1234 + step), model, opt, None, None, step, 0)
+            # the calibration changes from batch to batch (KITTI360FisheyeDataset draws image_02 / image_03 per sample): replays must
+            # see it (the list-of-dicts `calib_meta` was frozen at its capture value)
+            out = hook(O.synthetic_fisheye_batch(2, 64, 64, 1234 + step, two_calibrations=(step % 2 == 1)), model, opt, None, None, step, 0)
             seq.append(float(out["loss"].detach()))
         assert out["hm"]["predicted_image_1"].shape == (1, 3, 64, 64) and out["hm"]["loss_mask_0"]["data"].dtype == torch.bool
         losses[mode] = seq

@@ -1,0 +1,170 @@
+"""The N>1 data path ON GPUS (reference scripts/train.py:100-102): two ranks x 2 samples with SyncBatchNorm
+(statistics exchanged inside the executor) + the hook's gradient exchange == one process x 4 samples with plain BatchNorm:
+loss, EVERY parameter gradient element-wise, and the running statistics.  NCCL over NVLink, one process per GPU.
+Needs two visible GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_multigpu_gpu.py -m gpu`); skipped on a 1-GPU box."""
+import os
+import queue
+import socket
+import sys
+import time
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, posenet, graphed, out):
+    sys.path[:0] = [HERE, os.path.dirname(HERE)]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import fsnet_oracle as O
+        from helpers import build_model
+        from fsnet_b200.hooks.training import BaseTrainingHook
+        from fsnet_b200.networks import ops
+        ops.set_backend("tc")
+        topo = O.Topology(height=64, width=128, posenet=posenet, overlapped_mask=not posenet)
+        B = 2 * world
+        data = O.synthetic_batch(B, topo.height, topo.width, 77, topo.frame_ids)
+        data.pop("patched_mask")                    # equal loss normalisers on every rank: the mean of rank losses is the global loss
+        noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+        meta = dict(is_training=True, epoch_num=0, global_step=0)
+
+        def run(model, lo, hi):
+            model.head.tie_break_noise = {s: n[lo:hi].cuda() for s, n in noise.items()}
+            shard = {k: (v[lo:hi].cuda() if torch.is_tensor(v) else v) for k, v in data.items()}
+            ret = model(shard, meta)
+            ret["loss"].mean().backward()
+            return float(ret["loss"].detach())
+
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo)).cuda()
+        loss = run(model, 2 * rank, 2 * rank + 2)
+        BaseTrainingHook.sync_gradients(model)
+        torch.cuda.synchronize()
+        losses = [None] * world
+        dist.all_gather_object(losses, loss)
+        result = None
+        if rank == 0:
+            single = build_model(topo).cuda()       # plain BatchNorm, whole batch, one process
+            loss_single = run(single, 0, B)
+            errs = {}
+            ref = dict(single.named_parameters())
+            gmax = max(float(p.grad.norm()) for p in ref.values() if p.grad is not None)
+            for k, p in model.named_parameters():
+                if ref[k].grad is None:
+                    continue
+                g, r = p.grad.double(), ref[k].grad.double()
+                if float(r.norm()) > 1e-7 * gmax:
+                    errs[k] = float((g - r).norm() / r.norm())
+            stats = max(float((a - b).abs().max()) for (_, a), (_, b) in zip(model.named_buffers(), single.named_buffers())
+                        if a.is_floating_point())
+            worst = max(errs.items(), key=lambda kv: kv[1])
+            result = (sum(losses) / world, loss_single, worst, stats, len(errs))
+        out.put(result)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _run(posenet, graphed=False):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, posenet, graphed, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results, deadline = [], time.time() + 600
+    while len(results) < len(procs):
+        try:
+            results.append(q.get(timeout=2))
+        except queue.Empty:
+            assert all(p.is_alive() or p.exitcode == 0 for p in procs), "a rank died: " + str([p.exitcode for p in procs])
+            assert time.time() < deadline, "timed out"
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return next(r for r in results if r is not None)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("posenet", [False, True])
+def test_syncbn_step_on_two_gpus_matches_one_gpu(posenet):
+    mean_loss, loss_single, worst, stats, n = _run(posenet)
+    print(f"2-GPU SyncBN step (posenet={posenet}): loss {mean_loss:.8f} vs {loss_single:.8f}; {n} gradient tensors, worst rel L2 "
+          f"{worst[1]:.2e} ({worst[0]}); running statistics max abs diff {stats:.2e}")
+    assert abs(mean_loss - loss_single) <= 1e-5 * abs(loss_single), (mean_loss, loss_single)
+    assert worst[1] < 2e-2, worst                 # bf16 operands in the gradient convolutions, different summation order
+    assert stats < 1e-5, stats                    # running mean / var updated from the GLOBAL batch statistics
+
+
+def _ddp_worker(rank, world, port, out):
+    """scripts/train.py's wrapping (SyncBatchNorm + DistributedDataParallel, reference scripts/train.py:100-102) for two steps."""
+    sys.path[:0] = [HERE, os.path.dirname(HERE)]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from oracle import fsnet_oracle as O
+        from helpers import build_model
+        from fsnet_b200.hooks.training import BaseTrainingHook
+        topo = O.Topology(height=64, width=128)
+        B = 2 * world
+        data = O.synthetic_batch(B, topo.height, topo.width, 78, topo.frame_ids)
+        data.pop("patched_mask")
+        noise = O.tie_break_noise(B, topo.height, topo.width, topo.scales, 0)
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo)).cuda()
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank], output_device=rank)
+        model.head.tie_break_noise = {s: n[2 * rank:2 * rank + 2].cuda() for s, n in noise.items()}
+        hook = BaseTrainingHook(clip_gradients=35.0)
+        opt = torch.optim.Adam(ddp.parameters(), lr=1e-4)
+        shard = {k: (v[2 * rank:2 * rank + 2] if torch.is_tensor(v) else v) for k, v in data.items()}
+
+        out_ = hook(dict(shard), ddp, opt, None, None, 0, 0)
+        g_ddp = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        # same step without DDP: the hook's own gradient exchange
+        model2 = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo)).cuda()
+        model2.head.tie_break_noise = model.head.tie_break_noise
+        opt2 = torch.optim.Adam(model2.parameters(), lr=1e-4)
+        hook(dict(shard), model2, opt2, None, None, 0, 0)
+        worst = 0.0
+        for k, p in model2.named_parameters():
+            if p.grad is not None and k in g_ddp and float(p.grad.norm()) > 0:
+                worst = max(worst, float((g_ddp[k] - p.grad).norm() / p.grad.norm()))
+        out.put((float(out_["loss"].detach()), worst) if rank == 0 else None)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_ddp_wrapped_step_matches_hook_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results, deadline = [], time.time() + 600
+    while len(results) < len(procs):
+        try:
+            results.append(q.get(timeout=2))
+        except queue.Empty:
+            assert all(p.is_alive() or p.exitcode == 0 for p in procs), "a rank died: " + str([p.exitcode for p in procs])
+            assert time.time() < deadline, "timed out"
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    loss, worst = next(r for r in results if r is not None)
+    print(f"DDP-wrapped step: loss {loss:.6f}; worst gradient difference vs the hook's own exchange {worst:.2e}")
+    assert worst < 1e-4, worst                    # fp32 atomics of the K-split weight gradients: summation order differs run to run
