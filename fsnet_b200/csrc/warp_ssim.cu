@@ -819,6 +819,312 @@ __global__ void __launch_bounds__(kWarps * 32, LOSS_BWD_OCC) loss_bwd_kernel(Los
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused forward+backward, "frame pair" decomposition (round 2; replaces loss_bwd_kernel<0, CAM> in training steps).
+//
+// A CTA is TWO warps working on the same 30-column strip / row chunk: warp k owns source frame k -- its projection, gather,
+// the 15 SSIM moments of (target, warped frame k), the SSIM partials and the 9-channel adjoint box filter.  Per row the two
+// warps exchange one number per pixel (their photometric loss) through shared memory to agree on the arg-min of
+// [identity(+1), identity(-1), reprojection(+1), reprojection(-1)] (monodepth2_decoder.py:261-263).  Halving the per-thread
+// state (rolling 3x3 sums of 15 + 9 instead of 24 + 18 quantities) takes the kernel from 168 to < 100 registers, i.e. from 12 to
+// 20 resident warps per SM: the old kernel was issue / latency bound at 44 % issue utilisation (profiles/r1_summary.md C.3).
+//
+// Halo of ONE pixel instead of two: SSIM partials w(p) are evaluated only at the pixels the CTA owns; the adjoint box filter
+// G(q) = sum_{p in N(q), p owned} w(p) is evaluated on the owned region grown by one pixel, multiplied by the LOCAL derivative
+// d pred(q) / d D and ADDED (red.global.add.f32) into the gradient at the pixel the lane actually read: reflect(q).  Partial
+// sums of neighbouring CTAs meet in memory; ReflectionPad2d's fold-back (monodepth_utils.py:189) needs no special case, the halo
+// lane at x = -1 holds pixel 1 and adds there.  The projection is folded per sample, p = D * (P[:, :3] K^-1 (x, y, 1)) + P[:, 3]:
+// 6 FMAs per pixel and frame instead of 21 (the reference multiplies inv_K first, monodepth_utils.py:139-141,155-159; the
+// coordinates differ by rounding, ~1e-7 relative).
+// ------------------------------------------------------------------------------------------------
+#ifndef LOSS_PAIR_OCC
+#define LOSS_PAIR_OCC 10
+#endif
+constexpr int kPairCols = 30;
+
+// horizontal 3-tap sums of the 15 moments of (target, one warped frame): St, Stt, Sx, Sxx, Sxt per channel
+__device__ __forceinline__ void hsum15(const float (&t)[3], const float (&x)[3], float (&h)[15]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float tl = __shfl_up_sync(0xffffffffu, t[c], 1), tr = __shfl_down_sync(0xffffffffu, t[c], 1);
+    const float xl = __shfl_up_sync(0xffffffffu, x[c], 1), xr = __shfl_down_sync(0xffffffffu, x[c], 1);
+    h[c] = tl + t[c] + tr;
+    h[3 + c] = fmaf(tl, tl, fmaf(t[c], t[c], tr * tr));
+    h[6 + c] = xl + x[c] + xr;
+    h[9 + c] = fmaf(xl, xl, fmaf(x[c], x[c], xr * xr));
+    h[12 + c] = fmaf(xl, tl, fmaf(x[c], t[c], xr * tr));
+  }
+}
+
+template <int CAM>
+__global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams p) {
+  __shared__ float s_cam[2][20];                // per frame: M = P[:, :3] K^-1 (9), t = P[:, 3] (3), MEI intrinsics (7)
+  __shared__ float s_ring[2][3][9][32];         // per frame: the last three rows of (target 3, warped 3, d warped / d D 3)
+  __shared__ float s_ex[2][2][2][32];           // [row parity][frame][photometric | identity][lane]
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, W = p.W, HW = H * W;
+  int item = blockIdx.x;
+  const int strip = item % p.n_strips; item /= p.n_strips;
+  const int chunk = item % p.n_chunks;
+  const int b = item / p.n_chunks;
+  const int y_begin = chunk * p.rows_per_item, y_end = min(y_begin + p.rows_per_item, H);
+  const int x = strip * kPairCols + lane - 1;
+  const int xr = reflect_idx(x, W);
+  const bool own_col = lane >= 1 && lane <= kPairCols && x < W;
+  const bool live_col = x <= W;                 // further right than the reflected halo column: nothing to add
+  const bool overlap = (p.flags & FSNET_FLAG_OVERLAP_MASK) != 0;
+  const bool use_ident = (p.flags & FSNET_FLAG_MOTION_MASK) == 0;
+  const bool full_res = (p.hs == H && p.ws == W);
+
+  {
+    const float* cb = p.cam + ((size_t)b * 2 + k) * 21;
+    if (lane < 9) {
+      const int i = lane / 3, j = lane - 3 * i;
+      float m;
+      if (CAM == 0) m = fmaf(__ldg(cb + 9 + 4 * i), __ldg(cb + j), fmaf(__ldg(cb + 10 + 4 * i), __ldg(cb + 3 + j), __ldg(cb + 11 + 4 * i) * __ldg(cb + 6 + j)));
+      else m = __ldg(cb + 9 + 4 * i + j);
+      s_cam[k][lane] = m;
+    } else if (lane < 12) {
+      s_cam[k][lane] = __ldg(cb + 9 + 4 * (lane - 9) + 3);
+    } else if (lane < 19) {
+      s_cam[k][lane] = __ldg(cb + lane - 12);
+    }
+  }
+  __syncwarp();
+  const float* cm = s_cam[k];
+  const float* in = s_cam[k] + 12;
+  // pinhole: q = M (x, y, 1) = qc + y * M[:, 1]
+  float qc0 = 0.f, qc1 = 0.f, qc2 = 0.f;
+  if (CAM == 0) {
+    qc0 = fmaf(cm[0], (float)xr, cm[2]); qc1 = fmaf(cm[3], (float)xr, cm[5]); qc2 = fmaf(cm[6], (float)xr, cm[8]);
+  }
+  const float t0 = cm[9], t1 = cm[10], t2 = cm[11];
+  const float xm = (float)(W - 1), ym = (float)(H - 1);
+
+  const float4* tg4 = p.packed + (size_t)b * HW;
+  const float4* sk4 = p.packed + ((size_t)(1 + k) * p.B + b) * HW;
+  const float* depth = p.depth + (size_t)b * p.hs * p.ws;
+  const void* mask_b = p.mask ? mask_dtype_ptr_add(p.mask, p.mask_dtype, (size_t)b * HW) : nullptr;
+  const float* ident_k = use_ident ? p.ident + ((size_t)b * 2 + k) * HW : nullptr;
+  const float* noise_k = (use_ident && p.noise) ? p.noise + ((size_t)b * 2 + k) * HW : nullptr;
+  const float* motion_b = use_ident ? nullptr : p.motion + (size_t)b * HW;
+  const float4* lut_b = CAM == 1 ? p.lut + (size_t)(p.lut_idx ? __ldg(p.lut_idx + b) : 0) * HW : nullptr;
+  const UpW wx = up_weights(xr, p.sx, p.ws);
+  float* gd = p.grad_depth + (size_t)b * p.hs * p.ws;
+  const float gbase = (float)((double)__ldg(p.gout) / (__ldg(p.accum_in + 1) + 1e-6));
+
+  float h1[15], h2[15], g1[9], g2[9];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) { h1[i] = 0.f; h2[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { g1[i] = 0.f; g2[i] = 0.f; }
+  float l1_prev = 0.f, gf_prev = 0.f, acc_num = 0.f;
+  bool valid_prev = true;
+
+  // next row's depth (and MEI ray): requested one iteration ahead
+  const int y_first = y_begin - 1, y_stop = y_end + 2;
+  float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f, dly = 0.f;
+  float4 ray = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto request_depth = [&](int yr) {
+    if (full_res) {
+      d00 = __ldg(depth + yr * W + xr);
+    } else {
+      const UpW wy = up_weights(yr, p.sy, p.hs);
+      const float* r0 = depth + wy.i0 * p.ws;
+      const float* r1 = depth + wy.i1 * p.ws;
+      d00 = __ldg(r0 + wx.i0); d01 = __ldg(r0 + wx.i1); d10 = __ldg(r1 + wx.i0); d11 = __ldg(r1 + wx.i1); dly = wy.l;
+    }
+    if (CAM == 1) ray = __ldg(lut_b + yr * W + xr);
+  };
+  request_depth(reflect_idx(y_first, H));
+
+  int itn = 0;
+#pragma unroll 1
+  for (int yy = y_first; yy <= y_stop; ++yy, ++itn) {
+    const bool rowA = yy <= y_end;                       // gather / moments of raw row yy
+    const bool rowB = yy >= y_begin + 1 && yy <= y_end;  // SSIM + arg-min at centre row yc = yy - 1
+    const bool rowC = yy >= y_begin + 1;                 // adjoint + chain at row yq = yy - 2
+    const bool centre = rowB && own_col;
+    // ---- centre-pixel inputs (row yy-1): independent of everything computed below, issue first ----------------
+    float c_id = 0.f, c_m = 1.f, c_gate = 1.f;
+    if (centre) {
+      const int pix = (yy - 1) * W + x;
+      if (use_ident) {
+        c_id = __ldg(ident_k + pix);
+        if (noise_k) c_id = fmaf(__ldg(noise_k + pix), 1e-5f, c_id);
+      } else {
+        c_gate = 1.f - __ldg(motion_b + pix);
+      }
+      if (mask_b) c_m = load_mask(mask_b, p.mask_dtype, pix);
+    }
+    float h[15];
+    float l1 = 0.f;
+    bool valid = true;
+    float ph = 0.f, da[3], db[3], dc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { da[c] = 0.f; db[c] = 0.f; dc[c] = 0.f; }
+    if (rowA) {
+      // ---- A: warp frame k at (xr, yr) ----------------------------------------------------------------------
+      const int yr = reflect_idx(yy, H);
+      float D;
+      if (full_res) D = d00;
+      else {
+        const float top = (1.f - wx.l) * d00 + wx.l * d01, bot = (1.f - wx.l) * d10 + wx.l * d11;
+        D = (1.f - dly) * top + dly * bot;
+      }
+      const float4 tq = __ldg(tg4 + yr * W + xr);
+      float q0, q1, q2;
+      if (CAM == 0) {
+        const float fy_ = (float)yr;
+        q0 = fmaf(cm[1], fy_, qc0); q1 = fmaf(cm[4], fy_, qc1); q2 = fmaf(cm[7], fy_, qc2);
+      } else {
+        q0 = fmaf(cm[0], ray.x, fmaf(cm[1], ray.y, cm[2] * ray.z));
+        q1 = fmaf(cm[3], ray.x, fmaf(cm[4], ray.y, cm[5] * ray.z));
+        q2 = fmaf(cm[6], ray.x, fmaf(cm[7], ray.y, cm[8] * ray.z));
+      }
+      const float px = fmaf(D, q0, t0), py = fmaf(D, q1, t1), pz = fmaf(D, q2, t2);
+      float ix, iy, du, dv;
+      if (CAM == 0) {
+        const float rz = __fdividef(1.f, pz + 1e-7f);
+        ix = px * rz; iy = py * rz;
+        du = (q0 - ix * q2) * rz; dv = (q1 - iy * q2) * rz;
+      } else {
+        const Mei mei = mei_project(in, px, py, pz, ix, iy);
+        mei_jvp(in, mei, px, py, pz, q0, q1, q2, du, dv);
+      }
+      request_depth(reflect_idx(min(yy + 1, y_end), H));       // next row's depth: in flight during this row's arithmetic
+      if (overlap) {                                           // nearest, zeros padding, "== 1" (monodepth2_decoder.py:110-116)
+        const float xn = rintf(ix), yn = rintf(iy);
+        valid = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
+        if (valid) {
+          const int pn = (int)yn * W + (int)xn;
+          float mv = 1.f;
+          if (mask_b) mv = load_mask(mask_b, p.mask_dtype, pn);
+          if (CAM == 1) mv *= __ldg(reinterpret_cast<const float*>(lut_b + pn) + 3);
+          valid = mv == 1.f;
+        }
+      }
+      const float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);   // padding_mode='border'
+      const float x0f = floorf(ixc), y0f = floorf(iyc);
+      const float fx = ixc - x0f, fy = iyc - y0f;
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const int dx = x0 < W - 1 ? 1 : 0, dy = y0 < H - 1 ? W : 0;
+      const float4* p00 = sk4 + y0 * W + x0;
+      const float4 nw = __ldg(p00), ne = __ldg(p00 + dx), sw = __ldg(p00 + dy), se = __ldg(p00 + dy + dx);
+      // clip_coordinates_set_grad: no coordinate gradient on or outside the border
+      du = (ix > 0.f && ix < xm) ? du : 0.f;
+      dv = (iy > 0.f && iy < ym) ? dv : 0.f;
+      const float tt[3] = {tq.x, tq.y, tq.z};
+      const float a_nw[3] = {nw.x, nw.y, nw.z}, a_ne[3] = {ne.x, ne.y, ne.z}, a_sw[3] = {sw.x, sw.y, sw.z}, a_se[3] = {se.x, se.y, se.z};
+      float pred[3];
+      float(*slot)[32] = s_ring[k][(yy + 3) % 3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float dxt = a_ne[c] - a_nw[c], dxb = a_se[c] - a_sw[c];
+        const float top = fmaf(fx, dxt, a_nw[c]), bot = fmaf(fx, dxb, a_sw[c]);
+        const float dyv = bot - top;
+        pred[c] = fmaf(fy, dyv, top);
+        const float dix = fmaf(fy, dxb - dxt, dxt);
+        slot[c][lane] = tt[c];
+        slot[3 + c][lane] = pred[c];
+        slot[6 + c][lane] = fmaf(dix, du, dyv * dv);            // d pred_c / d D
+        l1 += fabsf(tt[c] - pred[c]);
+      }
+      hsum15(tt, pred, h);
+      // ---- B (first half): SSIM value and partials at the centre row from the three rows of horizontal sums ---
+      if (rowB) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          s += ssim_sums_grad(h2[6 + c] + h1[6 + c] + h[6 + c], h2[9 + c] + h1[9 + c] + h[9 + c], h2[12 + c] + h1[12 + c] + h[12 + c],
+                              h2[c] + h1[c] + h[c], h2[3 + c] + h1[3 + c] + h[3 + c], da[c], db[c], dc[c]);
+        ph = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_prev);
+        if (overlap && !valid_prev) ph = 100.f;
+      }
+    }
+    s_ex[itn & 1][k][0][lane] = ph;
+    s_ex[itn & 1][k][1][lane] = c_id;
+    __syncthreads();
+    // ---- B (second half): arg-min over [identity(+1), identity(-1), reprojection(+1), reprojection(-1)] ----------
+    float w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[i] = 0.f;
+    float gf = 0.f;
+    if (rowB) {
+      const float ph_o = s_ex[itn & 1][1 - k][0][lane], id_o = s_ex[itn & 1][1 - k][1][lane];
+      const float p0 = k == 0 ? ph : ph_o, p1 = k == 0 ? ph_o : ph;
+      float best;
+      int arg;
+      if (use_ident) {
+        const float i0 = k == 0 ? c_id : id_o, i1 = k == 0 ? id_o : c_id;
+        best = i0; arg = 0;
+        if (i1 < best) { best = i1; arg = 1; }
+        if (p0 < best) { best = p0; arg = 2; }
+        if (p1 < best) { best = p1; arg = 3; }
+        arg -= 2;
+      } else {
+        arg = p1 < p0 ? 1 : 0;
+        best = fminf(p0, p1);
+      }
+      if (centre) {
+        if (k == 0 && p.accum != nullptr) acc_num = fmaf(best, c_m, acc_num);
+        if (arg == k && (!overlap || valid_prev)) {
+          gf = gbase * c_m * c_gate;
+          const float ws_ = (0.85f / 3.f) * gf;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { w[c] = ws_ * da[c]; w[3 + c] = ws_ * db[c]; w[6 + c] = ws_ * dc[c]; }
+        }
+      }
+    }
+    // ---- C: adjoint of the 3x3 box filter over the OWNED centres, chain to the depth at row yq = yy - 2 ----------
+    float hw[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float wl = __shfl_up_sync(0xffffffffu, w[i], 1), wr = __shfl_down_sync(0xffffffffu, w[i], 1);
+      hw[i] = (lane == 0 ? 0.f : wl) + w[i] + (lane == 31 ? 0.f : wr);
+    }
+    if (rowC) {
+      const int yq = yy - 2;
+      float(*slot)[32] = s_ring[k][(yq + 3) % 3];
+      float gD = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float t = slot[c][lane], pr = slot[3 + c][lane];
+        const float d = t - pr;
+        const float sgn = (d > 0.f ? 1.f : 0.f) - (d < 0.f ? 1.f : 0.f);
+        float gp = fmaf(2.f * pr, g2[3 + c] + g1[3 + c] + hw[3 + c], fmaf(t, g2[6 + c] + g1[6 + c] + hw[6 + c], g2[c] + g1[c] + hw[c]));
+        gp = fmaf(-(0.15f / 3.f) * gf_prev, sgn, gp);
+        gD = fmaf(gp, slot[6 + c][lane], gD);
+      }
+      if (live_col && gD != 0.f) {
+        const int yw = reflect_idx(yq, H);
+        if (full_res) {
+          atomicAdd(gd + yw * W + xr, gD);
+        } else {                                 // transposed align_corners=True bilinear up-sample
+          const UpW wy = up_weights(yw, p.sy, p.hs);
+          const float a = gD * (1.f - wy.l), c2 = gD * wy.l;
+          atomicAdd(gd + wy.i0 * p.ws + wx.i0, a * (1.f - wx.l));
+          atomicAdd(gd + wy.i0 * p.ws + wx.i1, a * wx.l);
+          atomicAdd(gd + wy.i1 * p.ws + wx.i0, c2 * (1.f - wx.l));
+          atomicAdd(gd + wy.i1 * p.ws + wx.i1, c2 * wx.l);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { g2[i] = g1[i]; g1[i] = hw[i]; }
+    if (rowA) {
+#pragma unroll
+      for (int i = 0; i < 15; ++i) { h2[i] = h1[i]; h1[i] = h[i]; }
+      l1_prev = l1; valid_prev = valid;
+    }
+    gf_prev = gf;
+  }
+  if (k == 0 && p.accum != nullptr) {
+    const double n = warp_sum((double)acc_num);
+    if (lane == 0) atomicAdd(p.accum, n);
+  }
+}
+
 __global__ void camera_setup_kernel(const float* __restrict__ P2, const float* __restrict__ T0,
                                     const float* __restrict__ T1, int B, float* __restrict__ cam) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -997,6 +1303,26 @@ int plan(LossParams& p, int cols_per_warp, int halo_rows, int warps_per_sm) {
   return ceil_div(p.B * p.n_strips * p.n_chunks, kWarps);
 }
 
+// frame-pair kernel: one CTA per (sample, 30-column strip, row chunk); rows per chunk chosen so that the CTAs make whole waves of
+// 148 SMs x LOSS_PAIR_OCC resident CTAs (each chunk walks rows + 3: two halo rows of gathers, one more of the adjoint)
+int plan_pair(LossParams& p) {
+  p.n_strips = ceil_div(p.W, kPairCols);
+  const long cap = 148L * LOSS_PAIR_OCC;
+  int best_rows = 8;
+  double best_cost = 1e30;
+  for (int rows = 8; rows <= 96; ++rows) {
+    const long items = (long)p.B * p.n_strips * ceil_div(p.H, rows);
+    const long waves = (items + cap - 1) / cap;
+    const double cost = (double)waves * (rows + 3) * (1.0 + 0.002 * rows);
+    if (cost < best_cost) { best_cost = cost; best_rows = rows; }
+  }
+  p.rows_per_item = best_rows;
+  p.n_chunks = ceil_div(p.H, best_rows);
+  p.sy = p.H > 1 ? (float)(p.hs - 1) / (float)(p.H - 1) : 0.f;
+  p.sx = p.W > 1 ? (float)(p.ws - 1) / (float)(p.W - 1) : 0.f;
+  return p.B * p.n_strips * p.n_chunks;
+}
+
 }  // namespace
 }  // namespace fsnet
 
@@ -1072,8 +1398,18 @@ static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
   p.flags = flags; p.B = B; p.H = H; p.W = W; p.accum_in = accum; p.gout = gout;
   p.grad_depth = grad_depth; p.grad_P = grad_P; p.accum = accum_out;
   p.lut = reinterpret_cast<const float4*>(lut); p.lut_idx = lut_idx;
-  int blocks = plan(p, 28, 4, 4 * LOSS_BWD_OCC);
   cudaStream_t st = (cudaStream_t)stream;
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("FSNET_LOSS_PAIR"); pair_env = e ? atoi(e) : 1; }
+  if (pair_env && grad_P == nullptr && accum_out != nullptr) {
+    // fused forward+backward of a training step: the frame-pair kernel (every gradient write is an add: the caller zeroes grad_depth)
+    const int items = plan_pair(p);
+    if (cam_model == 0) loss_pair_kernel<0><<<items, 64, 0, st>>>(p);
+    else loss_pair_kernel<1><<<items, 64, 0, st>>>(p);
+    FSNET_LAUNCH_OK();
+    return FSNET_OK;
+  }
+  int blocks = plan(p, 28, 4, 4 * LOSS_BWD_OCC);
   if (cam_model == 0) {
     if (grad_P) loss_bwd_kernel<1, 0><<<blocks, kWarps * 32, 0, st>>>(p);
     else loss_bwd_kernel<0, 0><<<blocks, kWarps * 32, 0, st>>>(p);

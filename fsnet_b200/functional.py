@@ -105,7 +105,7 @@ class _ReprojectionLoss(torch.autograd.Function):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
             if fused_s[i]:
-                gd = (torch.empty if (hs == H and ws == W) else torch.zeros)(depths[i].shape, device=dev, dtype=torch.float32)
+                gd = torch.zeros(depths[i].shape, device=dev, dtype=torch.float32)     # the fused kernel ADDS its partial gradients
                 _lib.call("fsnet_warp_ssim_fwdbwd", *(lut_args if lut_args else (None, None)), depths[i], hs, ws, packed, mask_c, mdt, cam,
                           ident, noise_c[i], motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], unit, gd, unit_gP)
                 unit_gd[i] = gd

@@ -49,7 +49,7 @@ class FusedAdam(optim.Adam):
     @staticmethod
     def _wait_staging(st, key):
         ev = st.get(key)
-        if ev is not None:
+        if ev is not None and not torch.cuda.is_current_stream_capturing():      # (a capture is preceded by a device synchronise)
             ev.synchronize()
 
     @staticmethod

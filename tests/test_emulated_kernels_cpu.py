@@ -47,6 +47,41 @@ def test_fused_loss_kernels_match_golden_under_emulation(emulated, golden_dir, n
         assert rel(T[fi].grad, g[f"grad_T/{f}"]) < 0.3, f
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_frame_pair_loss_kernel_matches_golden_under_emulation(emulated, golden_dir, name):
+    """The fused forward+backward launch of a training step WITHOUT pose gradients (dataset poses: every shipped config) runs
+    loss_pair_kernel (two warps per strip, one per source frame; halo of one pixel, partial gradients added in memory)."""
+    g = load(golden_dir, name)
+    case = LOSS_CASES[name]
+    topo = case["topo"]
+    data, outputs, noise = build_loss_case(**case)
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, need_pose=False, dev="cpu")
+    S = len(topo.scales)
+    assert abs(float(total.detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    for i, s in enumerate(topo.scales):
+        assert abs(float(stats[i]) - float(g[f"loss_dict/loss/{s}"])) <= 1e-4 * abs(float(g[f"loss_dict/loss/{s}"])), s
+        ok, e = depth_grad_ok(depths[i].grad, g[f"grad_depth/{s}"])
+        assert ok, (s, e)
+
+
+@pytest.mark.parametrize("H,W,B,scales,fisheye", [(40, 72, 2, (0, 1, 2), False), (24, 61, 1, (0,), False), (24, 88, 1, (0, 3), False), (56, 104, 1, (0, 1), True),
+                                                  (9, 31, 1, (0,), False), (16, 30, 2, (0, 1), False)])
+def test_frame_pair_loss_kernel_on_ragged_shapes_under_emulation(emulated, H, W, B, scales, fisheye):
+    """Widths around the 30-column strip (30, 31, 61), heights that leave short last chunks, single samples."""
+    topo = O.Topology(height=H, width=W, scales=scales, fisheye=fisheye, max_depth=150.0 if fisheye else 100.0)
+    data, outputs, noise = build_loss_case(topo, B, 31)
+    for v in outputs.values():
+        v.requires_grad_(True)
+    cam_T = {f: data[("relative_pose", f)] for f in topo.frame_ids[1:]}
+    ref = O.loss_chain(outputs, data, cam_T, topo, noise, keep=True)
+    ref["loss"].backward()
+    total, stats, depths, disps, T = run_gpu_loss(topo, data, outputs, noise, need_pose=False, dev="cpu")
+    assert abs(float(total.detach()) - float(ref["loss"].detach())) <= 1e-5 * abs(float(ref["loss"].detach()))
+    for i, s in enumerate(scales):
+        ok, e = depth_grad_ok(depths[i].grad, outputs[("depth", s, s)].grad)
+        assert ok, (s, e)
+
+
 def test_log_image_head_keeps_the_loss_and_gradients_under_emulation(emulated, golden_dir):
     """the patched-mask normaliser of a non-fused scale 0 (log-image head) must not be counted twice."""
     from test_loss_gpu import check_log_image_case

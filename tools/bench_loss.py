@@ -51,7 +51,20 @@ def main(B=12, H=192, W=640, iters=20):
                               _lib.ctypes.c_uint(1), B, H, W, acc, None, None)
         bwd = lambda: _lib.call("fsnet_warp_ssim_bwd", d, hs, ws, packed, mask, 1, cam, ident, noise, None,
                                 _lib.ctypes.c_uint(1), B, H, W, acc, gout, gd, None)
+        acc2 = torch.zeros(4, dtype=torch.float64, device=dev)
+        acc2[1] = float(mask.sum())
+        unit = torch.full((1,), 0.25, device=dev)
+
+        def fused():
+            gd.zero_()
+            _lib.call("fsnet_warp_ssim_fwdbwd", None, None, d, hs, ws, packed, mask, 1, cam, ident, noise, None,
+                      _lib.ctypes.c_uint(1), B, H, W, acc2, unit, gd, None)
+        fused_only = lambda: _lib.call("fsnet_warp_ssim_fwdbwd", None, None, d, hs, ws, packed, mask, 1, cam, ident, noise, None,
+                                       _lib.ctypes.c_uint(1), B, H, W, acc2, unit, gd, None)
         tf, tb = timeit(f), timeit(bwd)
+        tfu = timeit(fused_only)
+        res[f"fused_s{s}_us"] = tfu
+        res[f"fused_s{s}_GBs"] = B * H * W * (40 + 16 / 4 ** s) / tfu / 1e3
         bytes_f = B * H * W * (40 + 8 / 4 ** s)
         bytes_b = B * H * W * (40 + 16 / 4 ** s)
         res[f"fwd_s{s}_us"] = tf
