@@ -468,9 +468,10 @@ __global__ void __launch_bounds__(kWarps * 32, 4) loss_fwd_kernel(LossParams p) 
       }
       if (p.packed_out != nullptr && out_lane && yy >= it.y_begin && yy < it.y_end) {
         const size_t pix = (size_t)yy * W + x;
-        p.packed_out[((size_t)0 * p.B + b) * HW + pix] = make_float4(raw[0], raw[1], raw[2], 0.f);
-        p.packed_out[((size_t)1 * p.B + b) * HW + pix] = make_float4(raw[3], raw[4], raw[5], 0.f);
-        p.packed_out[((size_t)2 * p.B + b) * HW + pix] = make_float4(raw[6], raw[7], raw[8], 0.f);
+        const float mw = (p.flags & FSNET_FLAG_PACKED_MASK) ? (mask_b ? load_mask(mask_b, p.mask_dtype, pix) : 1.f) : 0.f;
+        p.packed_out[((size_t)0 * p.B + b) * HW + pix] = make_float4(raw[0], raw[1], raw[2], mw);
+        p.packed_out[((size_t)1 * p.B + b) * HW + pix] = make_float4(raw[3], raw[4], raw[5], mw);
+        p.packed_out[((size_t)2 * p.B + b) * HW + pix] = make_float4(raw[6], raw[7], raw[8], mw);
       }
     } else {
       // this row's depth (and ray) was requested one iteration ago: the gathers can go out immediately
@@ -838,7 +839,10 @@ __global__ void __launch_bounds__(kWarps * 32, LOSS_BWD_OCC) loss_bwd_kernel(Los
 // coordinates differ by rounding, ~1e-7 relative).
 // ------------------------------------------------------------------------------------------------
 #ifndef LOSS_PAIR_OCC
-#define LOSS_PAIR_OCC 10
+#define LOSS_PAIR_OCC 8
+#endif
+#ifndef LOSS_PAIR_PIPELINE
+#define LOSS_PAIR_PIPELINE 0
 #endif
 constexpr int kPairCols = 30;
 
@@ -855,6 +859,17 @@ __device__ __forceinline__ void hsum15(const float (&t)[3], const float (&x)[3],
     h[12 + c] = fmaf(xl, tl, fmaf(x[c], t[c], xr * tr));
   }
 }
+
+// One row of inputs of the pair kernel, requested one loop iteration before it is consumed (software pipeline: every global
+// load of an iteration is issued in ONE phase and has a whole iteration of arithmetic to land; the first version issued and
+// consumed four dependent load groups per row and sat at 5.4 long-scoreboard stalls per issue, profiles/r2_loss_pair.md).
+struct PairRow {
+  float4 nw, ne, sw, se, tq;      // bilinear corners of the source frame (RGBX), target pixel
+  float fx, fy, du, dv;           // bilinear fractions, d(u, v) / d D (zeroed where grid_sample's border clamp blocks the gradient)
+  float mv;                       // MEI camera: validity of the ray table at the nearest source pixel (1 otherwise)
+  int sel;                        // which corner is the nearest source pixel (bit 0 east, bit 1 south), 4 = out of bounds
+  float id, nz;                   // centre-pixel inputs of the NEXT iteration: identity term, tie-break noise (or the motion mask)
+};
 
 template <int CAM>
 __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams p) {
@@ -898,7 +913,6 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
   if (CAM == 0) {
     qc0 = fmaf(cm[0], (float)xr, cm[2]); qc1 = fmaf(cm[3], (float)xr, cm[5]); qc2 = fmaf(cm[6], (float)xr, cm[8]);
   }
-  const float t0 = cm[9], t1 = cm[10], t2 = cm[11];
   const float xm = (float)(W - 1), ym = (float)(H - 1);
 
   const float4* tg4 = p.packed + (size_t)b * HW;
@@ -913,121 +927,160 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
   float* gd = p.grad_depth + (size_t)b * p.hs * p.ws;
   const float gbase = (float)((double)__ldg(p.gout) / (__ldg(p.accum_in + 1) + 1e-6));
 
+  // depth (and MEI ray) of a row: raw loads now, blended when consumed
+  struct DepthRaw { float d00, d01, d10, d11, ly; float4 ray; };
+  auto request_depth = [&](int yr) {
+    DepthRaw r;
+    r.d01 = r.d10 = r.d11 = r.ly = 0.f;
+    r.ray = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (full_res) {
+      r.d00 = __ldg(depth + yr * W + xr);
+    } else {
+      const UpW wy = up_weights(yr, p.sy, p.hs);
+      const float* r0 = depth + wy.i0 * p.ws;
+      const float* r1 = depth + wy.i1 * p.ws;
+      r.d00 = __ldg(r0 + wx.i0); r.d01 = __ldg(r0 + wx.i1); r.d10 = __ldg(r1 + wx.i0); r.d11 = __ldg(r1 + wx.i1); r.ly = wy.l;
+    }
+    if (CAM == 1) r.ray = __ldg(lut_b + yr * W + xr);
+    return r;
+  };
+  auto blend_depth = [&](const DepthRaw& r) {
+    if (full_res) return r.d00;
+    const float top = (1.f - wx.l) * r.d00 + wx.l * r.d01, bot = (1.f - wx.l) * r.d10 + wx.l * r.d11;
+    return (1.f - r.ly) * top + r.ly * bot;
+  };
+  // project the pixel of raw row yy with depth D and issue every load that row needs; centre inputs of row yy - 1 ride along
+  auto request_row = [&](int yy, float D, const float4& ray, bool want_centre) {
+    PairRow r;
+    const int yr = reflect_idx(yy, H);
+    r.tq = __ldg(tg4 + yr * W + xr);
+    float q0, q1, q2;
+    if (CAM == 0) {
+      const float fy_ = (float)yr;
+      q0 = fmaf(cm[1], fy_, qc0); q1 = fmaf(cm[4], fy_, qc1); q2 = fmaf(cm[7], fy_, qc2);
+    } else {
+      q0 = fmaf(cm[0], ray.x, fmaf(cm[1], ray.y, cm[2] * ray.z));
+      q1 = fmaf(cm[3], ray.x, fmaf(cm[4], ray.y, cm[5] * ray.z));
+      q2 = fmaf(cm[6], ray.x, fmaf(cm[7], ray.y, cm[8] * ray.z));
+    }
+    const float px = fmaf(D, q0, cm[9]), py = fmaf(D, q1, cm[10]), pz = fmaf(D, q2, cm[11]);
+    float ix, iy, du, dv;
+    if (CAM == 0) {
+      const float rz = __fdividef(1.f, pz + 1e-7f);
+      ix = px * rz; iy = py * rz;
+      du = (q0 - ix * q2) * rz; dv = (q1 - iy * q2) * rz;
+    } else {
+      const Mei mei = mei_project(in, px, py, pz, ix, iy);
+      mei_jvp(in, mei, px, py, pz, q0, q1, q2, du, dv);
+    }
+    const float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);   // padding_mode='border'
+    const float x0f = floorf(ixc), y0f = floorf(iyc);
+    r.fx = ixc - x0f; r.fy = iyc - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int dx = x0 < W - 1 ? 1 : 0, dy = y0 < H - 1 ? W : 0;
+    const float4* p00 = sk4 + y0 * W + x0;
+    r.nw = __ldg(p00); r.ne = __ldg(p00 + dx); r.sw = __ldg(p00 + dy); r.se = __ldg(p00 + dy + dx);
+    // overlap mask: nearest sample of patched_mask, zeros padding, "== 1" (monodepth2_decoder.py:110-116).  The nearest pixel
+    // (round half to even, like grid_sample) is one of the four corners just requested; their 4th component holds the mask.
+    // sel: bit 0 = east column, bit 1 = south row, 4 = out of bounds (mask reads as 0)
+    r.sel = 4;
+    r.mv = 1.f;
+    if (overlap) {
+      const float xn = rintf(ix), yn = rintf(iy);
+      const bool inb = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
+      r.sel = inb ? ((xn != x0f ? 1 : 0) | (yn != y0f ? 2 : 0)) : 4;
+      if (CAM == 1 && inb) r.mv = __ldg(reinterpret_cast<const float*>(lut_b + (int)yn * W + (int)xn) + 3);
+    }
+    // clip_coordinates_set_grad: no coordinate gradient on or outside the border
+    r.du = (ix > 0.f && ix < xm) ? du : 0.f;
+    r.dv = (iy > 0.f && iy < ym) ? dv : 0.f;
+    r.id = 0.f; r.nz = 0.f;
+    if (want_centre) {                                       // centre pixel of the iteration that consumes this row: (x, yy - 1)
+      const int pix = (yy - 1) * W + x;
+      if (use_ident) {
+        r.id = __ldg(ident_k + pix);
+        if (noise_k) r.nz = __ldg(noise_k + pix);
+      } else {
+        r.nz = __ldg(motion_b + pix);                        // motion mask rides in nz
+      }
+    }
+    return r;
+  };
+
   float h1[15], h2[15], g1[9], g2[9];
 #pragma unroll
   for (int i = 0; i < 15; ++i) { h1[i] = 0.f; h2[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < 9; ++i) { g1[i] = 0.f; g2[i] = 0.f; }
-  float l1_prev = 0.f, gf_prev = 0.f, acc_num = 0.f;
+  float l1_prev = 0.f, gf_prev = 0.f, acc_num = 0.f, c_m_prev = 1.f;
   bool valid_prev = true;
 
-  // next row's depth (and MEI ray): requested one iteration ahead
   const int y_first = y_begin - 1, y_stop = y_end + 2;
-  float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f, dly = 0.f;
-  float4 ray = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto request_depth = [&](int yr) {
-    if (full_res) {
-      d00 = __ldg(depth + yr * W + xr);
-    } else {
-      const UpW wy = up_weights(yr, p.sy, p.hs);
-      const float* r0 = depth + wy.i0 * p.ws;
-      const float* r1 = depth + wy.i1 * p.ws;
-      d00 = __ldg(r0 + wx.i0); d01 = __ldg(r0 + wx.i1); d10 = __ldg(r1 + wx.i0); d11 = __ldg(r1 + wx.i1); dly = wy.l;
-    }
-    if (CAM == 1) ray = __ldg(lut_b + yr * W + xr);
-  };
-  request_depth(reflect_idx(y_first, H));
+  // prologue: row y_first is requested here (one exposed round trip per CTA), the depth of row y_first + 1 is in flight
+  PairRow cur;
+#if LOSS_PAIR_PIPELINE
+  {
+    const DepthRaw d0 = request_depth(reflect_idx(y_first, H));
+    cur = request_row(y_first, blend_depth(d0), d0.ray, false);
+  }
+  DepthRaw dnext = request_depth(reflect_idx(min(y_first + 1, y_end), H));
+#else
+  DepthRaw dnext = request_depth(reflect_idx(y_first, H));
+#endif
 
   int itn = 0;
 #pragma unroll 1
   for (int yy = y_first; yy <= y_stop; ++yy, ++itn) {
-    const bool rowA = yy <= y_end;                       // gather / moments of raw row yy
+    const bool rowA = yy <= y_end;                       // moments of raw row yy
     const bool rowB = yy >= y_begin + 1 && yy <= y_end;  // SSIM + arg-min at centre row yc = yy - 1
     const bool rowC = yy >= y_begin + 1;                 // adjoint + chain at row yq = yy - 2
     const bool centre = rowB && own_col;
-    // ---- centre-pixel inputs (row yy-1): independent of everything computed below, issue first ----------------
-    float c_id = 0.f, c_m = 1.f, c_gate = 1.f;
-    if (centre) {
-      const int pix = (yy - 1) * W + x;
-      if (use_ident) {
-        c_id = __ldg(ident_k + pix);
-        if (noise_k) c_id = fmaf(__ldg(noise_k + pix), 1e-5f, c_id);
-      } else {
-        c_gate = 1.f - __ldg(motion_b + pix);
-      }
-      if (mask_b) c_m = load_mask(mask_b, p.mask_dtype, pix);
-    }
+    float c_id = 0.f, c_gate = 1.f, c_m_next = 1.f;
+    const float c_m = c_m_prev;                          // target row yy - 1 was consumed one iteration ago
     float h[15];
     float l1 = 0.f;
     bool valid = true;
     float ph = 0.f, da[3], db[3], dc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { da[c] = 0.f; db[c] = 0.f; dc[c] = 0.f; }
+#if LOSS_PAIR_PIPELINE
+    PairRow nxt = cur;
+#endif
     if (rowA) {
-      // ---- A: warp frame k at (xr, yr) ----------------------------------------------------------------------
-      const int yr = reflect_idx(yy, H);
-      float D;
-      if (full_res) D = d00;
-      else {
-        const float top = (1.f - wx.l) * d00 + wx.l * d01, bot = (1.f - wx.l) * d10 + wx.l * d11;
-        D = (1.f - dly) * top + dly * bot;
+#if LOSS_PAIR_PIPELINE
+      // ---- load phase: everything row yy + 1 needs (its depth arrived during the previous iteration) ---------------
+      if (yy + 1 <= y_end) {
+        nxt = request_row(yy + 1, blend_depth(dnext), dnext.ray, yy + 1 >= y_begin + 1 && own_col);
+        dnext = request_depth(reflect_idx(min(yy + 2, y_end), H));
       }
-      const float4 tq = __ldg(tg4 + yr * W + xr);
-      float q0, q1, q2;
-      if (CAM == 0) {
-        const float fy_ = (float)yr;
-        q0 = fmaf(cm[1], fy_, qc0); q1 = fmaf(cm[4], fy_, qc1); q2 = fmaf(cm[7], fy_, qc2);
-      } else {
-        q0 = fmaf(cm[0], ray.x, fmaf(cm[1], ray.y, cm[2] * ray.z));
-        q1 = fmaf(cm[3], ray.x, fmaf(cm[4], ray.y, cm[5] * ray.z));
-        q2 = fmaf(cm[6], ray.x, fmaf(cm[7], ray.y, cm[8] * ray.z));
+#else
+      // ---- load phase: this row's gathers (its depth was requested one iteration ago), then the next row's depth ---
+      cur = request_row(yy, blend_depth(dnext), dnext.ray, centre);
+      dnext = request_depth(reflect_idx(min(yy + 1, y_end), H));
+#endif
+      // ---- A: bilinear blend of the corners requested one iteration ago ------------------------------------------
+      // (every component of the 128-bit pixels is used: a dead 4th component lets the register allocator reuse that register
+      // while the load is in flight, and the write-after-write hazard exposes the full memory latency behind every gather --
+      // 1250 + 1210 of 11 470 stall samples sat on two such instructions in the first versions, profiles/r2_loss_pair.md)
+      if (use_ident) c_id = fmaf(cur.nz, 1e-5f, cur.id); else c_gate = 1.f - cur.nz;
+      c_m_next = cur.tq.w;                                   // patched mask of the pixel that is the centre one iteration later
+      {
+        const float mw = (cur.sel & 2) ? ((cur.sel & 1) ? cur.se.w : cur.sw.w) : ((cur.sel & 1) ? cur.ne.w : cur.nw.w);
+        valid = !overlap || ((cur.sel < 4) && mw * cur.mv == 1.f);
       }
-      const float px = fmaf(D, q0, t0), py = fmaf(D, q1, t1), pz = fmaf(D, q2, t2);
-      float ix, iy, du, dv;
-      if (CAM == 0) {
-        const float rz = __fdividef(1.f, pz + 1e-7f);
-        ix = px * rz; iy = py * rz;
-        du = (q0 - ix * q2) * rz; dv = (q1 - iy * q2) * rz;
-      } else {
-        const Mei mei = mei_project(in, px, py, pz, ix, iy);
-        mei_jvp(in, mei, px, py, pz, q0, q1, q2, du, dv);
-      }
-      request_depth(reflect_idx(min(yy + 1, y_end), H));       // next row's depth: in flight during this row's arithmetic
-      if (overlap) {                                           // nearest, zeros padding, "== 1" (monodepth2_decoder.py:110-116)
-        const float xn = rintf(ix), yn = rintf(iy);
-        valid = (xn >= 0.f) && (xn <= xm) && (yn >= 0.f) && (yn <= ym);
-        if (valid) {
-          const int pn = (int)yn * W + (int)xn;
-          float mv = 1.f;
-          if (mask_b) mv = load_mask(mask_b, p.mask_dtype, pn);
-          if (CAM == 1) mv *= __ldg(reinterpret_cast<const float*>(lut_b + pn) + 3);
-          valid = mv == 1.f;
-        }
-      }
-      const float ixc = fminf(fmaxf(ix, 0.f), xm), iyc = fminf(fmaxf(iy, 0.f), ym);   // padding_mode='border'
-      const float x0f = floorf(ixc), y0f = floorf(iyc);
-      const float fx = ixc - x0f, fy = iyc - y0f;
-      const int x0 = (int)x0f, y0 = (int)y0f;
-      const int dx = x0 < W - 1 ? 1 : 0, dy = y0 < H - 1 ? W : 0;
-      const float4* p00 = sk4 + y0 * W + x0;
-      const float4 nw = __ldg(p00), ne = __ldg(p00 + dx), sw = __ldg(p00 + dy), se = __ldg(p00 + dy + dx);
-      // clip_coordinates_set_grad: no coordinate gradient on or outside the border
-      du = (ix > 0.f && ix < xm) ? du : 0.f;
-      dv = (iy > 0.f && iy < ym) ? dv : 0.f;
-      const float tt[3] = {tq.x, tq.y, tq.z};
-      const float a_nw[3] = {nw.x, nw.y, nw.z}, a_ne[3] = {ne.x, ne.y, ne.z}, a_sw[3] = {sw.x, sw.y, sw.z}, a_se[3] = {se.x, se.y, se.z};
+      const float tt[3] = {cur.tq.x, cur.tq.y, cur.tq.z};
+      const float a_nw[3] = {cur.nw.x, cur.nw.y, cur.nw.z}, a_ne[3] = {cur.ne.x, cur.ne.y, cur.ne.z};
+      const float a_sw[3] = {cur.sw.x, cur.sw.y, cur.sw.z}, a_se[3] = {cur.se.x, cur.se.y, cur.se.z};
       float pred[3];
       float(*slot)[32] = s_ring[k][(yy + 3) % 3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float dxt = a_ne[c] - a_nw[c], dxb = a_se[c] - a_sw[c];
-        const float top = fmaf(fx, dxt, a_nw[c]), bot = fmaf(fx, dxb, a_sw[c]);
+        const float top = fmaf(cur.fx, dxt, a_nw[c]), bot = fmaf(cur.fx, dxb, a_sw[c]);
         const float dyv = bot - top;
-        pred[c] = fmaf(fy, dyv, top);
-        const float dix = fmaf(fy, dxb - dxt, dxt);
+        pred[c] = fmaf(cur.fy, dyv, top);
+        const float dix = fmaf(cur.fy, dxb - dxt, dxt);
         slot[c][lane] = tt[c];
         slot[3 + c][lane] = pred[c];
-        slot[6 + c][lane] = fmaf(dix, du, dyv * dv);            // d pred_c / d D
+        slot[6 + c][lane] = fmaf(dix, cur.du, dyv * cur.dv);    // d pred_c / d D
         l1 += fabsf(tt[c] - pred[c]);
       }
       hsum15(tt, pred, h);
@@ -1046,10 +1099,7 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
     s_ex[itn & 1][k][1][lane] = c_id;
     __syncthreads();
     // ---- B (second half): arg-min over [identity(+1), identity(-1), reprojection(+1), reprojection(-1)] ----------
-    float w[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) w[i] = 0.f;
-    float gf = 0.f;
+    float ws_ = 0.f, gf = 0.f;
     if (rowB) {
       const float ph_o = s_ex[itn & 1][1 - k][0][lane], id_o = s_ex[itn & 1][1 - k][1][lane];
       const float p0 = k == 0 ? ph : ph_o, p1 = k == 0 ? ph_o : ph;
@@ -1070,18 +1120,26 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
         if (k == 0 && p.accum != nullptr) acc_num = fmaf(best, c_m, acc_num);
         if (arg == k && (!overlap || valid_prev)) {
           gf = gbase * c_m * c_gate;
-          const float ws_ = (0.85f / 3.f) * gf;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) { w[c] = ws_ * da[c]; w[3 + c] = ws_ * db[c]; w[6 + c] = ws_ * dc[c]; }
+          ws_ = (0.85f / 3.f) * gf;
         }
       }
     }
     // ---- C: adjoint of the 3x3 box filter over the OWNED centres, chain to the depth at row yq = yy - 2 ----------
+    // (rows in which no lane of the warp won for three centre rows carry no gradient: the whole phase is skipped)
+    const bool any_w = __any_sync(0xffffffffu, ws_ != 0.f);
     float hw[9];
+    if (any_w) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const float wl = __shfl_up_sync(0xffffffffu, w[i], 1), wr = __shfl_down_sync(0xffffffffu, w[i], 1);
-      hw[i] = (lane == 0 ? 0.f : wl) + w[i] + (lane == 31 ? 0.f : wr);
+      for (int c = 0; c < 3; ++c) {
+        // (halo lanes 0 and 31 hold w = 0 and a shuffle from outside the warp returns the lane's own value: no edge case)
+        const float w0 = ws_ * da[c], w1 = ws_ * db[c], w2 = ws_ * dc[c];
+        hw[c] = __shfl_up_sync(0xffffffffu, w0, 1) + w0 + __shfl_down_sync(0xffffffffu, w0, 1);
+        hw[3 + c] = __shfl_up_sync(0xffffffffu, w1, 1) + w1 + __shfl_down_sync(0xffffffffu, w1, 1);
+        hw[6 + c] = __shfl_up_sync(0xffffffffu, w2, 1) + w2 + __shfl_down_sync(0xffffffffu, w2, 1);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) hw[i] = 0.f;
     }
     if (rowC) {
       const int yq = yy - 2;
@@ -1115,9 +1173,12 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
     if (rowA) {
 #pragma unroll
       for (int i = 0; i < 15; ++i) { h2[i] = h1[i]; h1[i] = h[i]; }
-      l1_prev = l1; valid_prev = valid;
+      l1_prev = l1; valid_prev = valid; c_m_prev = c_m_next;
     }
     gf_prev = gf;
+#if LOSS_PAIR_PIPELINE
+    cur = nxt;
+#endif
   }
   if (k == 0 && p.accum != nullptr) {
     const double n = warp_sum((double)acc_num);
@@ -1335,6 +1396,23 @@ extern "C" int fsnet_camera_setup(const float* P2, const float* T0, const float*
   return FSNET_OK;
 }
 
+extern "C" int fsnet_identity_photometric_masked(const float* tgt, const float* src0, const float* src1, const void* mask, int mask_dtype,
+                                                 int B, int H, int W, float* ident, float* packed, void* stream) {
+  FSNET_REQUIRE(tgt && src0 && src1 && ident && packed, "fsnet_identity_photometric_masked: null pointer");
+  FSNET_REQUIRE(((uintptr_t)packed & 15) == 0, "fsnet_identity_photometric_masked: packed buffer must be 16-byte aligned");
+  FSNET_REQUIRE(B > 0 && H >= 3 && W >= 3, "fsnet_identity_photometric_masked: need B>0, H>=3, W>=3 (got %d,%d,%d)", B, H, W);
+  FSNET_REQUIRE((mask == nullptr) == (mask_dtype == FSNET_MASK_NONE) && mask_dtype >= 0 && mask_dtype <= 2,
+                "fsnet_identity_photometric_masked: mask pointer / dtype mismatch");
+  LossParams p = {};
+  p.tgt = tgt; p.src0 = src0; p.src1 = src1; p.B = B; p.H = H; p.W = W; p.hs = H; p.ws = W;
+  p.mask = mask; p.mask_dtype = mask_dtype; p.flags = FSNET_FLAG_PACKED_MASK;
+  p.ident_out = ident; p.packed_out = reinterpret_cast<float4*>(packed);
+  int blocks = plan(p, 30, 2, 16);
+  loss_fwd_kernel<0, 0><<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
 extern "C" int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
                                           int B, int H, int W, float* ident, float* packed, void* stream) {
   FSNET_REQUIRE(tgt && src0 && src1 && ident, "fsnet_identity_photometric: null pointer");
@@ -1401,7 +1479,7 @@ static int launch_bwd(int cam_model, const float* lut, const int* lut_idx,
   cudaStream_t st = (cudaStream_t)stream;
   static int pair_env = -1;
   if (pair_env < 0) { const char* e = getenv("FSNET_LOSS_PAIR"); pair_env = e ? atoi(e) : 1; }
-  if (pair_env && grad_P == nullptr && accum_out != nullptr) {
+  if (pair_env && grad_P == nullptr && accum_out != nullptr && (flags & FSNET_FLAG_PACKED_MASK)) {
     // fused forward+backward of a training step: the frame-pair kernel (every gradient write is an add: the caller zeroes grad_depth)
     const int items = plan_pair(p);
     if (cam_model == 0) loss_pair_kernel<0><<<items, 64, 0, st>>>(p);

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 
 MASK_NONE, MASK_F32, MASK_F64 = 0, 1, 2
-FLAG_OVERLAP, FLAG_MOTION = 1, 2
+FLAG_OVERLAP, FLAG_MOTION, FLAG_PACKED_MASK = 1, 2, 4
 
 
 def _mask_dtype(mask: Optional[torch.Tensor]) -> int:
@@ -71,7 +71,9 @@ class _ReprojectionLoss(torch.autograd.Function):
         # identity terms (needed unless the motion-mask branch is on) + the RGBX-packed images for the gathers
         ident = torch.empty(B, 2, H, W, device=dev, dtype=torch.float32)
         packed = torch.empty(3, B, H, W, 4, device=dev, dtype=torch.float32)
-        _lib.call("fsnet_identity_photometric", tgt, src0, src1, B, H, W, ident, packed)
+        # (the packed pixels' 4th component carries patched_mask: the frame-pair kernel reads loss weight and overlap mask from it)
+        _lib.call("fsnet_identity_photometric_masked", tgt, src0, src1, mask_c, mdt, B, H, W, ident, packed)
+        flags |= FLAG_PACKED_MASK
         if motion is not None:
             ident = None
         acc = torch.zeros(S, 4, device=dev, dtype=torch.float64)

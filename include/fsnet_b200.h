@@ -42,6 +42,8 @@ typedef enum {
 /* flags of the fused reprojection kernels */
 #define FSNET_FLAG_OVERLAP_MASK 1u   /* overlapped_mask=True: nearest-sample patched_mask, invalid := 100 */
 #define FSNET_FLAG_MOTION_MASK 2u    /* 'motion_mask' branch: min over the two reprojections only   */
+#define FSNET_FLAG_PACKED_MASK 4u    /* the 4th component of every packed pixel holds patched_mask at that pixel (1 without a mask):
+                                        written by fsnet_identity_photometric_masked, read by fsnet_warp_ssim_fwdbwd */
 
 int fsnet_abi_version(void);
 const char* fsnet_last_error(void);
@@ -66,6 +68,12 @@ int fsnet_camera_setup(const float* P2, const float* T0, const float* T1, int B,
  * ------------------------------------------------------------------------------------------- */
 int fsnet_identity_photometric(const float* tgt, const float* src0, const float* src1,
                                int B, int H, int W, float* ident, float* packed, void* stream);
+/* Same pass; the fourth component of each packed pixel additionally carries patched_mask[b, y, x] as fp32 (1 when mask == NULL).
+ * The frame-pair training kernel then gets the loss weight of a pixel with its target colour and the overlap mask of a warped
+ * pixel (nearest sample of patched_mask, monodepth2_decoder.py:110-116) with the bilinear corners it loads anyway: the nearest
+ * pixel IS one of the four corners.  Pass FSNET_FLAG_PACKED_MASK to fsnet_warp_ssim_fwdbwd. */
+int fsnet_identity_photometric_masked(const float* tgt, const float* src0, const float* src1, const void* mask, int mask_dtype,
+                                      int B, int H, int W, float* ident, float* packed, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * fused per-scale reprojection loss, forward.  One launch replaces, for one scale,

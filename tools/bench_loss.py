@@ -41,7 +41,7 @@ def main(B=12, H=192, W=640, iters=20):
         ts.sort()
         return ts[len(ts) // 2]
 
-    res["identity_us"] = timeit(lambda: _lib.call("fsnet_identity_photometric", tgt, s0, s1, B, H, W, ident, packed))
+    res["identity_us"] = timeit(lambda: _lib.call("fsnet_identity_photometric_masked", tgt, s0, s1, mask, 1, B, H, W, ident, packed))
     for s in range(4):
         d = outs[("depth", s, s)].to(dev)
         hs, ws = d.shape[-2:]
@@ -58,9 +58,9 @@ def main(B=12, H=192, W=640, iters=20):
         def fused():
             gd.zero_()
             _lib.call("fsnet_warp_ssim_fwdbwd", None, None, d, hs, ws, packed, mask, 1, cam, ident, noise, None,
-                      _lib.ctypes.c_uint(1), B, H, W, acc2, unit, gd, None)
+                      _lib.ctypes.c_uint(5), B, H, W, acc2, unit, gd, None)
         fused_only = lambda: _lib.call("fsnet_warp_ssim_fwdbwd", None, None, d, hs, ws, packed, mask, 1, cam, ident, noise, None,
-                                       _lib.ctypes.c_uint(1), B, H, W, acc2, unit, gd, None)
+                                       _lib.ctypes.c_uint(5), B, H, W, acc2, unit, gd, None)
         tf, tb = timeit(f), timeit(bwd)
         tfu = timeit(fused_only)
         res[f"fused_s{s}_us"] = tfu

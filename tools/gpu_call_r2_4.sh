@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out/r2c6
+timeout 600 python -m pytest tests/test_loss_gpu.py -q -m gpu -x --timeout 600 -p no:cacheprovider > ${O}_tests.txt 2>&1
+echo "rc=$?" >> ${O}_tests.txt
+timeout 200 python tools/bench_loss.py > ${O}_loss_o6p1.json 2>&1
+for v in o10p0 o8p0 o5p1; do
+FSNET_B200_LIB=$PWD/fsnet_b200/lib/libfsnet_b200_$v.so timeout 200 python tools/bench_loss.py > ${O}_loss_$v.json 2>&1
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:loss_pair -s 8 -c 1 -o ${O}_pair python tools/bench_loss.py > ${O}_ncu.log 2>&1
+tail -3 ${O}_tests.txt
+grep -E "fused_s._us" ${O}_loss_*.json
