@@ -26,6 +26,12 @@ class WgradDesc(ctypes.Structure):
                 ("kh", ctypes.c_int), ("kw", ctypes.c_int), ("cout_pad", ctypes.c_int), ("cin_pad", ctypes.c_int)]
 
 
+class Peer(ctypes.Structure):
+    """fsnet_peer of include/fsnet_b200.h."""
+    _fields_ = [("bufs", ctypes.c_void_p), ("flags", ctypes.c_void_p), ("rank", ctypes.c_int), ("world", ctypes.c_int),
+                ("slot_off", ctypes.c_longlong), ("flag_off", ctypes.c_int), ("seq", ctypes.c_void_p)]
+
+
 _lock = threading.Lock()
 _lib = None
 launch_count = 0          # entry-point calls issued through this binding
@@ -128,7 +134,7 @@ def call(name, *args):
             if not a.t.is_cuda:
                 raise FsnetError("fsnet_b200 kernels take CUDA tensors only (there is no CPU path)")
             cargs.append(ctypes.c_void_p(a.t.data_ptr()))
-        elif isinstance(a, View):
+        elif isinstance(a, (View, Peer)):
             cargs.append(ctypes.byref(a))
         elif isinstance(a, bool):
             cargs.append(ctypes.c_int(int(a)))

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import _lib, tc
+from . import _lib, peer, tc
 from .tc import Fp32, Planes, View, pad16
 
 MOMENTUM_DEFAULT = 0.1
@@ -231,14 +231,23 @@ class Tape:
             inv.ss[st.C:] = 0.0 if conv.bias is None else st.padded(conv.bias)
             return
         world = _sync_world(bn) if bn_train else 1
+        px = None
         if world > 1:
-            dist.all_reduce(st.stats)
             count = count * world
+            px = peer.get()
+            if px is None:
+                dist.all_reduce(st.stats)
         inv.count = count
         if bn.momentum is None:
             raise NotImplementedError("BatchNorm(momentum=None) (cumulative moving average) is not implemented on the tcgen05 path; "
                                       "no reference configuration uses it")
         momentum = bn.momentum
+        if px is not None:
+            # SyncBatchNorm: the cross-rank sum of the statistics happens INSIDE the finalize kernel, over NVLink peer memory
+            _lib.call("fsnet_bn_finalize_sync", st.stats, tc.c_double(count), st.padded(bn.weight, 1.0), st.padded(bn.bias),
+                      st.padded(conv.bias), self._buf(bn.running_mean, st), self._buf(bn.running_var, st), bn.num_batches_tracked,
+                      float(momentum), float(bn.eps), st.C, inv.ss, inv.mi, px.slot((id(st), "fwd"), 2 * st.C))
+            return
         _lib.call("fsnet_bn_finalize", st.stats, tc.c_double(count), st.padded(bn.weight, 1.0), st.padded(bn.bias),
                   st.padded(conv.bias), self._buf(bn.running_mean, st), self._buf(bn.running_var, st),
                   bn.num_batches_tracked if bn_train else None, float(momentum), float(bn.eps), int(bn_train), st.C,
@@ -277,7 +286,11 @@ class Tape:
         _lib.call("fsnet_bn_bwd_reduce", g_view, up, mask_view, mask_ss, raw.view(), mi, sums)
         world = _sync_world(bn) if has_bn else 1
         if world > 1:
-            dist.all_reduce(sums)
+            px = peer.get()
+            if px is not None:
+                _lib.call("fsnet_peer_allreduce_f64", sums, 2 * st.C, px.slot((id(st), "bwd"), 2 * st.C))
+            else:
+                dist.all_reduce(sums)
         fold_dgrad = st.replicate and st.kh == 3 and st.C < 64          # see fsnet_conv: folded x-taps need ring == pad
         dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device, zero=fold_dgrad)
         gamma = st.padded(bn.weight, 1.0) if bn is not None else None

@@ -323,6 +323,31 @@ int fsnet_wgrad_to_param_batched(const fsnet_wgrad_desc* table_device, int n_lay
 int fsnet_bn_finalize(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,
                       float* running_mean, float* running_var, long long* num_batches, float momentum, float eps,
                       int training, int C, float* scale_shift, float* mean_invstd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SyncBatchNorm statistics over NVLink / NVSwitch peer memory (fsnet_b200/csrc/peer.cu).  Replaces the all_gather of
+ * torch.nn.SyncBatchNorm (the reference converts every BatchNorm, scripts/train.py:100-102) on the data-parallel path.
+ *   fsnet_peer          one exchange slot: `bufs` / `flags` are DEVICE arrays [world] of pointers to every rank's data (fp64) and
+ *                       flag (u32) buffers, all mapped into this process (symmetric memory); the slot occupies
+ *                       [slot_off, slot_off + world*n) doubles and [flag_off, flag_off + world) flags in each of them;
+ *                       `seq` is this slot's use counter in LOCAL device memory (zero-initialised, same history on every rank)
+ *   fsnet_peer_allreduce_f64   data[0..n) := sum over ranks, bit-identical on every rank (one CTA, one-shot: every rank stores
+ *                       into every peer's slot, release/acquire flags at system scope)
+ *   fsnet_bn_finalize_sync     the same exchange on stats[2C] fused in front of fsnet_bn_finalize's arithmetic (training mode);
+ *                       `count` = elements per channel over ALL ranks
+ * Every rank must issue the same sequence of calls (like any collective); the calls are CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* bufs; const void* flags;
+  int rank, world;
+  long long slot_off;
+  int flag_off;
+  void* seq;
+} fsnet_peer;
+int fsnet_peer_allreduce_f64(double* data, int n, const fsnet_peer* peer, void* stream);
+int fsnet_bn_finalize_sync(double* stats, double count, const float* gamma, const float* beta, const float* conv_bias,
+                           float* running_mean, float* running_var, long long* num_batches, float momentum, float eps,
+                           int C, float* scale_shift, float* mean_invstd, const fsnet_peer* peer, void* stream);
 int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift, int res_mode, const fsnet_view* res,
                      const float* res_scale_shift, int relu, int up, const fsnet_view* dst, void* stream);
 int fsnet_copy_planes(const fsnet_view* src, const fsnet_view* dst, void* stream);

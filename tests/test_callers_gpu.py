@@ -1,19 +1,13 @@
-"""GPU tests written after this round's GPU minutes were spent: NOT yet run on a B200, therefore opt-in
-(FSNET_PENDING_GPU=1) so that an unvalidated test can not mask the validated suite.  First thing to run next round:
-
-    FSNET_PENDING_GPU=1 python -m pytest tests/test_pending_gpu.py -x -q -m gpu
-
-Every piece they combine is validated separately: the host side on CPU (tests/test_evaluation_cpu.py,
-tests/test_kitti_reader_cpu.py), the training step and eval-mode inference on B200 (tests/test_model_gpu.py,
-tests/test_train_script_gpu.py)."""
+"""GPU tests of the callers on either side of the training step and of the next-stage components: training +
+per-epoch evaluation + scripts/test.py on KITTI files, the nuScenes recipe, the upload prefetcher, ResNet(norm_eval / frozen_stages),
+the distillation stage (N4), the device augmentation kernel (N3).  First run on a B200 in round 2 (gpurun_out/r2c1, r2c7): all green."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FSNET_PENDING_GPU") != "1", reason="not yet validated on a B200; set FSNET_PENDING_GPU=1")]
+pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -78,7 +72,9 @@ def test_prefetched_batches_train_like_host_batches():
         for i, data in enumerate(DevicePrefetcher(src) if prefetch else src):
             run.append(float(hook(data, model, opt, None, None, i, 0)["loss"]))
         losses.append(run)
-    assert losses[0] == pytest.approx(losses[1], rel=1e-6)
+    # not bit-identical: the K-split weight gradients and the loss kernel's partial depth gradients are summed with fp32 atomics,
+    # whose order changes from run to run; three Adam steps amplify the last-bit differences to ~2e-5 (measured, r2c7)
+    assert losses[0] == pytest.approx(losses[1], rel=2e-4)
 
 
 @pytest.mark.parametrize("name", ["tiny_normeval", "tiny_frozen", "tiny_normeval_frozen"])

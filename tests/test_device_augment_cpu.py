@@ -183,7 +183,7 @@ def test_fisheye_list_on_the_device_matches_the_reference_reader(golden_dir, tmp
 
 def test_stage_call_marshalling_and_prefetcher_hook(monkeypatch):
     """DeviceAugmentStage with the kernel launch replaced by the oracle: argument order / shapes of the C call, output keys
-    and layouts, and its place inside DevicePrefetcher.  (The kernel itself: tests/test_pending_gpu.py.)"""
+    and layouts, and its place inside DevicePrefetcher.  (The kernel itself: tests/test_callers_gpu.py.)"""
     from fsnet_b200 import _lib
     from fsnet_b200.data.device_augment import DeviceAugmentStage, device_augment_collate
     from fsnet_b200.data.loading import DevicePrefetcher

@@ -23,9 +23,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, posenet, graphed, out):
+def _worker(rank, world, port, posenet, peer_mem, out):
     sys.path[:0] = [HERE, os.path.dirname(HERE)]
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      FSNET_PEER_SYNCBN="1" if peer_mem else "0")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
@@ -70,18 +71,19 @@ def _worker(rank, world, port, posenet, graphed, out):
             stats = max(float((a - b).abs().max()) for (_, a), (_, b) in zip(model.named_buffers(), single.named_buffers())
                         if a.is_floating_point())
             worst = max(errs.items(), key=lambda kv: kv[1])
-            result = (sum(losses) / world, loss_single, worst, stats, len(errs))
+            from fsnet_b200 import peer
+            result = (sum(losses) / world, loss_single, worst, stats, len(errs), peer._state["inst"] is not None, peer._state["why"])
         out.put(result)
     finally:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def _run(posenet, graphed=False):
+def _run(posenet, peer_mem):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, posenet, graphed, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, posenet, peer_mem, q)) for r in range(2)]
     for p in procs:
         p.start()
     results, deadline = [], time.time() + 600
@@ -98,10 +100,13 @@ def _run(posenet, graphed=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("posenet", [False, True])
-def test_syncbn_step_on_two_gpus_matches_one_gpu(posenet):
-    mean_loss, loss_single, worst, stats, n = _run(posenet)
-    print(f"2-GPU SyncBN step (posenet={posenet}): loss {mean_loss:.8f} vs {loss_single:.8f}; {n} gradient tensors, worst rel L2 "
+@pytest.mark.parametrize("posenet,peer_mem", [(False, True), (True, True), (False, False)])
+def test_syncbn_step_on_two_gpus_matches_one_gpu(posenet, peer_mem):
+    """peer_mem: SyncBN statistics through the one-shot NVLink peer-memory exchange fused into bn_finalize (csrc/peer.cu);
+    otherwise through NCCL all_reduce."""
+    mean_loss, loss_single, worst, stats, n, peer_active, why = _run(posenet, peer_mem)
+    assert peer_active == peer_mem, why
+    print(f"2-GPU SyncBN step (posenet={posenet}, peer memory={peer_active}): loss {mean_loss:.8f} vs {loss_single:.8f}; {n} gradient tensors, worst rel L2 "
           f"{worst[1]:.2e} ({worst[0]}); running statistics max abs diff {stats:.2e}")
     assert abs(mean_loss - loss_single) <= 1e-5 * abs(loss_single), (mean_loss, loss_single)
     assert worst[1] < 2e-2, worst                 # bf16 operands in the gradient convolutions, different summation order

@@ -90,7 +90,7 @@ FULL_CASES = {
     "tiny_r50": dict(topo=O.Topology(height=64, width=96, depth=50, base_fx=40.0), B=2),
     "tiny_fe": dict(topo=O.Topology(height=64, width=64, fisheye=True, n_bins=64, max_depth=150.0), B=2),
 }
-# oracle pinned here on CPU; the CUDA side of these runs from tests/test_pending_gpu.py until it has been validated on a B200
+# oracle pinned here on CPU; the CUDA side of these runs from tests/test_callers_gpu.py
 PENDING_FULL_CASES = {
     # second training stage: frozen eval-mode teacher, uncertainty heads, distillation loss (DistillWPoseMeta)
     "tiny_distill": dict(topo=O.Topology(height=64, width=128, distill=True), B=2),
