@@ -120,9 +120,19 @@ def _sync_world(bn) -> int:
     return 1
 
 
+REDUCED_STORAGES = set()      # storages whose gradients were already averaged over the ranks during backward (see Tape._reduce_bucket)
+
+
 class Tape:
     """Forward executor + backward tape for one network invocation."""
     _wgrad_tables: Dict = {}
+    # Data-parallel gradient exchange overlapped with the backward pass (switched on by BaseTrainingHook for models that are not
+    # wrapped in DistributedDataParallel): the pooled weight-gradient accumulators are averaged over the ranks in a few buckets,
+    # each launched (NCCL, asynchronous) as soon as the backward walk has finished the bucket's layers -- the reference gets the
+    # same overlap from DDP's reducer (scripts/train.py:102).  The batched re-layout into parameter gradients then reads reduced
+    # accumulators, so the bulk of the gradient bytes never goes through the hook's post-backward exchange.
+    bucketed_allreduce = False
+    N_BUCKETS = 4
 
     def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool, weights_fresh=False):
         self.states, self.training, self.need_grad = states, training, need_grad
@@ -161,6 +171,18 @@ class Tape:
             Tape._wgrad_tables[id(self.states)] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
             Tape._wgrad_tables["sig:%d" % id(self.states)] = sig
         self._pools["gw_table"] = Tape._wgrad_tables[id(self.states)]
+        # gradient buckets: contiguous layer ranges of the accumulator pool, keyed by their FIRST layer (the last one the backward
+        # walk reaches); boundaries only depend on the layer list, so every rank cuts the same buckets
+        self._buckets, self._works = {}, []
+        if Tape.bucketed_allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            keys = list(self.states.keys())
+            sizes = [self.states[k].w.acc_numel for k in keys]
+            target, start, run, lo = max(n_acc // Tape.N_BUCKETS, 1), 0, 0, 0
+            for i, k in enumerate(keys):
+                run += sizes[i]
+                if run >= target or i == len(keys) - 1:
+                    self._buckets[keys[start]] = (lo, lo + run)
+                    lo, run, start = lo + run, 0, i + 1
 
     def _pool(self, st: LayerState, which: str):
         if self._pools is None:
@@ -332,6 +354,7 @@ class Tape:
             o_w = self._pools["gw_off"][id(st.conv)]
             self.param_grads[id(conv.weight)] = self._pools["gw"][o_w:o_w + conv.weight.numel()].view_as(conv.weight)
             self._pools["gw_used"] = True
+        self._reduce_bucket(id(conv))
         if not need_dgrad or x.grad is None:
             return
         k = st.kh
@@ -351,6 +374,15 @@ class Tape:
             _lib.call("fsnet_zero_insert", dy.view(), src.view())
         tc.conv_dgrad(src, st.w, x.gview(), pad=k - 1 - st.pad, accumulate=x.grad_written)
         x.grad_written = True
+
+    def _reduce_bucket(self, key):
+        """The backward walk has finished layer `key`: if it is the first layer of a gradient bucket, every accumulator of the
+        bucket is final -- average it over the ranks now, concurrently with the rest of the backward pass."""
+        rng = self._buckets.pop(key, None) if self._pools is not None else None
+        if rng is not None:
+            op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+            t = self._pools["acc"][rng[0]:rng[1]]
+            self._works.append((dist.all_reduce(t, op=op, async_op=True), t, op))
 
     def _fold_if_needed(self, a: Act):
         if getattr(a, "ring_dirty", False):
@@ -440,6 +472,14 @@ class Tape:
         for op in reversed(self.backward_ops):
             op()
         if self._pools is not None and self._pools["gw_used"]:
+            if self._buckets or self._works:
+                for key in list(self._buckets):              # buckets whose first layer has no weight gradient (frozen stages)
+                    self._reduce_bucket(key)
+                for work, t, op in self._works:
+                    work.wait()
+                    if op == dist.ReduceOp.SUM:
+                        t.div_(dist.get_world_size())
+                REDUCED_STORAGES.add(self._pools["gw"].untyped_storage().data_ptr())
             _lib.call("fsnet_wgrad_to_param_batched", self._pools["gw_table"], len(self.states), self._pools["acc"], self._pools["gw"])
         if self._sync_scaled:
             torch._foreach_div_(self._sync_scaled, float(self._sync_world))

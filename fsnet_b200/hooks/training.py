@@ -89,22 +89,49 @@ class BaseTrainingHook(object):
 
     @staticmethod
     def sync_gradients(meta_arch):
-        """Data-parallel gradient averaging for models that are NOT wrapped in DistributedDataParallel: one
-        flat NCCL all-reduce after backward (57-107 MB over NVLink, ~0.3 ms -- no need to overlap it) that, unlike
-        DDP's reducer hooks, can be captured into the step's CUDA graph.  A DDP-wrapped model is left alone."""
+        """Data-parallel gradient averaging for models that are NOT wrapped in DistributedDataParallel (a DDP-wrapped model is left
+        alone: its reducer does it).  Capturable into the step's CUDA graph, unlike DDP's reducer hooks.  The bulk of the bytes --
+        the convolution weights -- was already averaged DURING backward, bucket by bucket, by the executor (engine.Tape); what is
+        left here are the small BatchNorm / bias gradients (one concatenated all-reduce) and, as a fall-back, any flat gradient
+        buffer the executor did not reduce (all-reduced in place: parameter gradients are views of it, no copies)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
         if isinstance(meta_arch, nn.parallel.DistributedDataParallel):
             return
-        grads = [p.grad for p in meta_arch.parameters() if p.grad is not None]
-        if not grads:
-            return
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat)
-        flat.div_(dist.get_world_size())
-        torch._foreach_copy_(grads, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in grads]), grads)])
+        from .. import engine
+        world = dist.get_world_size()
+        avg = dist.get_backend() == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        by_storage = {}
+        for p in meta_arch.parameters():
+            if p.grad is not None:
+                by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p.grad)
+        small = []
+        for ptr, grads in by_storage.items():
+            if ptr in engine.REDUCED_STORAGES:
+                continue
+            st = grads[0].untyped_storage()
+            n = sum(g.numel() for g in grads)
+            if len(grads) > 1 and n * 4 == st.nbytes() and all(g.dtype == torch.float32 and g.is_contiguous() for g in grads):
+                flat = torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, 0, (n,))     # the whole pool, in place
+                dist.all_reduce(flat, op=op)
+                if not avg:
+                    flat.div_(world)
+            else:
+                small += grads
+        engine.REDUCED_STORAGES.clear()
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            dist.all_reduce(flat, op=op)
+            if not avg:
+                flat.div_(world)
+            torch._foreach_copy_(small, [t.view_as(g) for t, g in zip(flat.split([g.numel() for g in small]), small)])
 
     def _step(self, data, meta_arch, optimizer, meta):
+        from .. import engine
+        engine.Tape.bucketed_allreduce = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                                          and not isinstance(meta_arch, nn.parallel.DistributedDataParallel)
+                                          and os.environ.get("FSNET_BUCKETED_ALLREDUCE", "1") != "0")
         optimizer.zero_grad()
         output: dict = meta_arch(data, meta)
         output["loss"].mean().backward()

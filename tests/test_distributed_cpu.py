@@ -70,6 +70,8 @@ def _syncbn_worker(rank, world, port, out):
         from fsnet_b200.hooks.training import BaseTrainingHook
         from fsnet_b200.networks import ops
         ops.set_backend("tc")
+        from fsnet_b200 import engine
+        engine.Tape.bucketed_allreduce = True      # the hook's setting for models that are not DDP-wrapped: buckets reduced during backward
         posenet = os.environ.get("FSNET_DIST_POSENET") == "1"        # opt-in variant: depth net + PoseNet (two executor tapes per step)
         topo = O.Topology(height=32, width=64, posenet=posenet, overlapped_mask=not posenet)
         B = 2 * world
@@ -92,6 +94,7 @@ def _syncbn_worker(rank, world, port, out):
         losses = [None] * world
         dist.all_gather_object(losses, loss)
         result = None
+        engine.Tape.bucketed_allreduce = False     # the reference run below is one process on the whole batch
         if rank == 0:
             single = build_model(topo)              # plain BatchNorm, whole batch, one process
             loss_single = run(single, 0, B)
