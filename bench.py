@@ -123,6 +123,40 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+class LossReader:
+    """Device -> host read of every step's loss inside the timed region.  sync=1: ``loss.item()`` per step (the host blocks on
+    the GPU and its launch work for the next step is exposed).  sync=0: every step's loss is copied to a pinned host slot on the
+    step's stream and read once the NEXT step has been queued -- what a logging loop does; every value still reaches the host
+    inside the timed region (``last()`` drains the final one)."""
+
+    def __init__(self, sync):
+        self.sync = bool(sync)
+        self.slots = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self.value = None
+
+    def push(self, loss):
+        if self.sync:
+            self.value = loss.item()
+            return
+        if self.i > 0:
+            j = (self.i - 1) % 2
+            self.events[j].synchronize()
+            self.value = float(self.slots[j][0])
+        j = self.i % 2
+        self.slots[j].copy_(loss.detach().reshape(1).double(), non_blocking=True)
+        self.events[j].record()
+        self.i += 1
+
+    def last(self):
+        if not self.sync and self.i > 0:
+            j = (self.i - 1) % 2
+            self.events[j].synchronize()
+            self.value = float(self.slots[j][0])
+        return self.value
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,8 +166,12 @@ def main():
     ap.add_argument("--backend", default=os.environ.get("FSNET_CONV_BACKEND", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run every step eagerly (no CUDA graph replay)")
-    ap.add_argument("--prefetch", type=int, default=int(os.environ.get("FSNET_BENCH_PREFETCH", 0)),
-                    help="e2e leg: upload batch k+1 on a side stream while step k runs (fsnet_b200.data.loading.DevicePrefetcher)")
+    ap.add_argument("--prefetch", type=int, default=int(os.environ.get("FSNET_BENCH_PREFETCH", 1)),
+                    help="e2e leg: upload batch k+1 on a side stream while step k runs (fsnet_b200.data.loading.DevicePrefetcher, "
+                         "the default loader stage of scripts/train.py); 0 = the reference's serial upload inside the hook")
+    ap.add_argument("--e2e-sync", type=int, default=0,
+                    help="e2e leg: 1 = block on every step's loss (loss.item()); 0 (default) = copy every step's loss to pinned host "
+                         "memory asynchronously and read it one step later, as a logging loop would")
     ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS), help="cfg2a = BASELINE.json configs[1] (default)")
     args = ap.parse_args()
     global B_PER_GPU, H, W, CONFIG
@@ -202,10 +240,13 @@ def main():
             # the same n host->device copies and n loss read-backs, inside the timed region; the copy of step i+1 is issued
             # before step i is launched, so it runs on the copy engine under step i
             from fsnet_b200.data.loading import DevicePrefetcher
+            reader = LossReader(args.e2e_sync)
             for i, data in enumerate(DevicePrefetcher((dict(pinned) for _ in range(n)), dev)):
                 out = hook(data, model, optimizer, None, None, i, 0)
-                last = out["loss"].item()
+                reader.push(out["loss"])
+            last = reader.last()
             n = 0
+        reader = LossReader(args.e2e_sync) if use_host else None
         for i in range(n):
             if head_start:
                 # eager steps are host bound (~30 ms of Python per step): a 60 ms spin kernel lets the host queue the whole step,
@@ -214,7 +255,9 @@ def main():
             data = dict(pinned) if use_host else dict(resident)
             out = hook(data, model, optimizer, None, None, i, 0)
             if use_host:
-                last = out["loss"].item()            # device -> host read of the step's result
+                reader.push(out["loss"])             # device -> host read of the step's result
+        if reader is not None and n:
+            last = reader.last()
         t1.record()
         barrier()
         ms = t0.elapsed_time(t1)
@@ -281,6 +324,7 @@ def main():
                    "parallelism": f"dp{world}" + (" (SyncBN statistics + flat gradient all-reduce over NCCL, inside the step graph)" if world > 1 else ""),
                    "conv_backend": ops.BACKEND,
                    "cuda_graph": use_graph, "e2e_prefetch": bool(args.prefetch),
+                   "e2e_loss_read": "blocking .item() per step" if args.e2e_sync else "async copy to pinned memory per step, read one step later",
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
         "roofline": {"kernel": "loss_bwd_kernel<0,0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

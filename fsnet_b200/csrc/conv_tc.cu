@@ -184,7 +184,7 @@ __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
 // (+bias, ReLU) -> fp32 NHWC store (optionally accumulating) + per-channel sum / sum-of-squares of the tile.
 // `first_tid` = threadIdx.x of the first epilogue thread (for the final statistics flush).
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, int lane, uint32_t tmem_base,
-                                               uint64_t* tmem_full, uint64_t* tmem_empty, float* s_stats, int first_tid) {
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, double* s_stats, int first_tid) {
   const int q = warp & 3;                         // TMEM lane quadrant of this warp
   const int m = q * 32 + lane;                    // row of the tile = pixel
   int it = 0;
@@ -231,8 +231,11 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
         float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
         if ((lane & 1) == 0) {
           int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          atomicAdd(&s_stats[nt * p.BN + c0 + col], s1);
-          atomicAdd(&s_stats[p.Cout + nt * p.BN + c0 + col], s2);
+          // fp64 from here on: the per-tile column sums (128 pixels, shuffle tree, deterministic) are accumulated over the CTA's
+          // tiles in double.  With fp32 shared-memory atomics the order-dependent rounding of sum(x^2) was amplified by the
+          // cancellation in E[x^2] - mean^2: forward maps differed by ~1e-5 from run to run (tools/diag_determinism2.py)
+          atomicAdd(&s_stats[nt * p.BN + c0 + col], (double)s1);
+          atomicAdd(&s_stats[p.Cout + nt * p.BN + c0 + col], (double)s2);
         }
       }
     }
@@ -243,8 +246,8 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
   if (p.stats) {
     asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
     for (int i = threadIdx.x - first_tid; i < 2 * p.Cout; i += 128) {
-      float s = s_stats[i];
-      if (s != 0.f) atomicAdd(p.stats + i, (double)s);
+      const double s = s_stats[i];
+      if (s != 0.0) atomicAdd(p.stats + i, s);
     }
   }
 }
@@ -258,9 +261,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  // dynamic smem: [stages * stage_bytes | 2*Cout floats of statistics]
+  // dynamic smem: [stages * stage_bytes | 2*Cout doubles of statistics]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* s_stats = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);
+  double* s_stats = reinterpret_cast<double*>(smem + (size_t)p.stages * p.stage_bytes);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -274,7 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += kThreads) s_stats[i] = 0.f;
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += kThreads) s_stats[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -548,7 +551,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     p.tx_bytes = (nprod == 3 ? 2u : 1u) * (rows * 128u + (uint32_t)KH * p.BN * 128u);
   }
   p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
-  const uint32_t stats_bytes = stats ? 2u * Cout * 4u : 0u;
+  const uint32_t stats_bytes = stats ? 2u * Cout * 8u : 0u;
   int stages = (int)((200u * 1024u - stats_bytes) / p.stage_bytes);
   p.stages = stages > kMaxStages ? kMaxStages : stages;
   FSNET_REQUIRE(p.stages >= 2, "fsnet_conv: tile does not fit shared memory");

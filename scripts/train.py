@@ -31,12 +31,12 @@ class _NullWriter:
 
 def build_train_loader(cfg, dataset_train, local_rank, world_size, device):
     """The reference's loader (scripts/train.py:77-81) plus two opt-in stages in front of the training hook:
-    FSNET_PREFETCH=1 uploads batch k+1 on a side stream while step k runs (the reference uploads inside the hook, serialised with
+    the upload of batch k+1 runs on a side stream while step k computes (default; FSNET_PREFETCH=0 = the reference: upload inside the hook, serialised with
     the step); a dataset whose augmentation is fsnet_b200.data.device_augment.DeviceAugmentation ships uint8 frames + drawn
     parameters, and the pixel work runs on the GPU right behind that upload."""
     from fsnet_b200.data.device_augment import device_augment_collate, find_device_stage
     device_stage = find_device_stage(dataset_train)
-    prefetch = bool(int(os.environ.get("FSNET_PREFETCH", "0"))) or device_stage is not None
+    prefetch = bool(int(os.environ.get("FSNET_PREFETCH", "1"))) or device_stage is not None
     loader = build_dataloader(dataset_train, num_workers=cfg.data.num_workers, batch_size=cfg.data.batch_size,
                               collate_fn=collate_fn if device_stage is None else device_augment_collate,
                               local_rank=local_rank, world_size=world_size, sampler_cfg=getattr(cfg.data, "sampler", dict()),

@@ -142,19 +142,27 @@ def _ddp_worker(rank, world, port, out):
 
         out_ = hook(dict(shard), ddp, opt, None, None, 0, 0)
         g_ddp = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
-        # same step without DDP: the hook's own gradient exchange
-        model2 = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo)).cuda()
-        model2.head.tie_break_noise = model.head.tie_break_noise
-        opt2 = torch.optim.Adam(model2.parameters(), lr=1e-4)
-        hook(dict(shard), model2, opt2, None, None, 0, 0)
-        worst, worst_k = 0.0, None
-        gmax = max(float(p.grad.norm()) for p in model2.parameters() if p.grad is not None)
-        for k, p in model2.named_parameters():
-            if p.grad is not None and k in g_ddp and float(p.grad.norm()) > 1e-7 * gmax:
-                e = float((g_ddp[k] - p.grad).norm() / p.grad.norm())
-                if e > worst:
-                    worst, worst_k = e, k
-        out.put((float(out_["loss"].detach()), worst, worst_k) if rank == 0 else None)
+        # same step without DDP: the hook's own gradient exchange (twice: the run-to-run spread of the atomically summed gradients)
+        def plain_step():
+            m = torch.nn.SyncBatchNorm.convert_sync_batchnorm(build_model(topo)).cuda()
+            m.head.tie_break_noise = model.head.tie_break_noise
+            hook(dict(shard), m, torch.optim.Adam(m.parameters(), lr=1e-4), None, None, 0, 0)
+            return m
+
+        def spread(ga, mb):
+            worst, worst_k = 0.0, None
+            gmax = max(float(p.grad.norm()) for p in mb.parameters() if p.grad is not None)
+            for k, p in mb.named_parameters():
+                if p.grad is not None and k in ga and float(p.grad.norm()) > 1e-7 * gmax:
+                    e = float((ga[k] - p.grad).norm() / p.grad.norm())
+                    if e > worst:
+                        worst, worst_k = e, k
+            return worst, worst_k
+        model2, model3 = plain_step(), plain_step()
+        worst, worst_k = spread(g_ddp, model2)
+        rerun, rerun_k = spread({k: p.grad for k, p in model3.named_parameters() if p.grad is not None}, model2)
+        print(f"[rank {rank}] DDP vs hook exchange {worst:.2e} ({worst_k}); hook exchange run twice {rerun:.2e} ({rerun_k})", flush=True)
+        out.put((float(out_["loss"].detach()), worst, worst_k, rerun) if rank == 0 else None)
     finally:
         dist.barrier()
         dist.destroy_process_group()
@@ -178,6 +186,12 @@ def test_ddp_wrapped_step_matches_hook_exchange():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    loss, worst, worst_k = next(r for r in results if r is not None)
-    print(f"DDP-wrapped step: loss {loss:.6f}; worst gradient difference vs the hook's own exchange {worst:.2e} ({worst_k})")
-    assert worst < 1e-3, (worst, worst_k)                    # fp32 atomics of the K-split weight gradients: summation order differs run to run
+    loss, worst, worst_k, rerun = next(r for r in results if r is not None)
+    print(f"DDP-wrapped step: loss {loss:.6f}; worst gradient difference vs the hook's own exchange {worst:.2e} ({worst_k}); "
+          f"the hook's exchange run twice: {rerun:.2e}")
+    # The backward pass is not bit-reproducible: fp32 atomics (K-split weight gradients, BatchNorm-backward sums, the loss kernel's
+    # partial depth gradients) change the last bit from run to run, and every bf16 rounding of a dy plane turns such a difference
+    # into a 2^-9 one for the elements whose rounding flips -- the spread saturates at the bf16 noise floor of the chain
+    # (tools/diag_determinism2.py: 5e-8 at the last decoder layer, 2e-3 at the first, 7e-3 at the stem; the forward pass is
+    # bit-identical).  DDP's exchange must agree with the hook's own within that spread.
+    assert worst < max(3.0 * rerun, 3e-2), (worst, worst_k, rerun)
