@@ -324,46 +324,46 @@ __device__ __forceinline__ F8 masked_g8(const BnBwdParams& p, const Px& q, const
   }
   return g;
 }
-// Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory
-// float atomics, then one fp64 atomic per channel and block.
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
-  extern __shared__ float s_acc[];           // [2*C]
+// Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory atomics (fp64: the
+// order of the atomics changes from run to run, in double that does not reach the fp32 results), then one fp64 atomic per
+// channel and block.  sums[C + c] = inv * sum g * (raw - mean): the mean is subtracted per element (no cancellation), the
+// 1/std factor once per block.  Round 2: one pixel per iteration and no per-element 1/std -> 64 instead of 126 registers, three
+// resident blocks per SM instead of two (ncu r2c8: 14 warps/SM, 31 % issue utilisation, 5-7 long-scoreboard stalls per issue,
+// 31-35 % of the DRAM bandwidth), grid = one wave of 3-4 blocks per SM.
+__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
+  extern __shared__ double s_acc[];          // [2*C]
   const V& r = p.raw;
   const int C = r.c, groups = C >> 3;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   if ((int)threadIdx.x < threads_used) {
     const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
     const int c = cg << 3;
     const unsigned npix = (unsigned)r.n * r.h * r.w;
-    F8 mean, inv;
+    F8 mean;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { mean.v[k] = 0.f; inv.v[k] = 0.f; }
-    if (p.mean_invstd) { mean = ld_f8(p.mean_invstd + c); inv = ld_f8(p.mean_invstd + C + c); }
+    for (int k = 0; k < 8; ++k) mean.v[k] = 0.f;
+    if (p.mean_invstd) mean = ld_f8(p.mean_invstd + c);
     float s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    // two pixels per iteration: their loads are independent, which doubles the bytes in flight per thread
     const unsigned step = gridDim.x * pix_per_iter;
-    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += 2 * step) {
-      const unsigned pix2 = pix + step;
-      const bool has2 = pix2 < npix;
+#pragma unroll 1
+    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += step) {
       Px q; unsigned t = pix / (unsigned)r.w; q.x = (int)(pix - t * r.w);
       unsigned n = t / (unsigned)r.h; q.y = (int)(t - n * r.h); q.n = (int)n; q.c = c;
-      Px q2 = q;
-      if (has2) { unsigned t2 = pix2 / (unsigned)r.w; q2.x = (int)(pix2 - t2 * r.w);
-                  unsigned n2 = t2 / (unsigned)r.h; q2.y = (int)(t2 - n2 * r.h); q2.n = (int)n2; }
       const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, c));
-      const F8 rv2 = ld_f8((const float*)r.ptr + vidx(r, q2.n, q2.y, q2.x, c));
       const F8 g = masked_g8(p, q, rv);
-      const F8 g2 = masked_g8(p, q2, rv2);
-      const float w2 = has2 ? 1.f : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], (rv.v[k] - mean.v[k]) * inv.v[k], s2[k]);
-        const float gg = g2.v[k] * w2;
-        s1[k] += gg; s2[k] = fmaf(gg, (rv2.v[k] - mean.v[k]) * inv.v[k], s2[k]);
-      }
+      for (int k = 0; k < 8; ++k) { s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], rv.v[k] - mean.v[k], s2[k]); }
+    }
+    if (p.mean_invstd) {
+      const F8 inv = ld_f8(p.mean_invstd + C + c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s2[k] *= inv.v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s2[k] = 0.f;
     }
     // lanes of a warp that own the same channel group (lane % groups, when groups divides 32) combine by shuffles first:
     // for the 16..64-channel full-resolution layers the shared-memory atomics were 128-way contended
@@ -377,58 +377,67 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int p
       }
       if ((int)(threadIdx.x & 31) < groups) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], (double)s1[k]); atomicAdd(&s_acc[C + c + k], (double)s2[k]); }
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
+      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], (double)s1[k]); atomicAdd(&s_acc[C + c + k], (double)s2[k]); }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float v = s_acc[i];
-    if (v != 0.f) atomicAdd(p.sums + i, (double)v);
+    const double v = s_acc[i];
+    if (v != 0.0) atomicAdd(p.sums + i, v);
   }
 }
+
+// dy = A * g + B * raw + K per channel: the BatchNorm input gradient gamma*inv*(g - mean(g) - xhat*mean(g*xhat)) with
+// xhat = (raw - mean)*inv, rearranged so that an element costs two FMAs.  The three coefficients per channel are built once
+// per block from the fp64 sums into shared memory (round 1 read 16 doubles and converted them per 8 elements: the kernel sat
+// on the LSU queue, lg_throttle up to 3.9 per issue in ncu r2c8); persistent blocks walk the tensor.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
+  extern __shared__ float s_coef[];          // A[C], B[C], K[C]
   const V& r = p.raw;
   const int C = r.c;
   const unsigned total = (unsigned)r.n * r.h * r.w * (C >> 3);
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < p.c_real; c += blockDim.x) {
       if (p.dbeta) p.dbeta[c] = (float)p.sums[c];
       if (p.dgamma) p.dgamma[c] = (float)p.sums[C + c];
     }
   }
-  if (i >= total) return;
-  const Px q = decode8(i, r.h, r.w, C);
-  const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, q.c));
-  const F8 g = masked_g8(p, q, rv);
-  if (p.res_mode) {
-    float* o = (float*)p.res.ptr + vidx(p.res, q.n, q.y, q.x, q.c);
-    F8 w = g;
-    if (p.res_mode == 2) { F8 old = ld_f8(o);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) w.v[k] += old.v[k]; }
-    st_f8(o, w);
-  }
-  F8 d = g;
-  if (p.mean_invstd) {
-    const F8 mean = ld_f8(p.mean_invstd + q.c), inv = ld_f8(p.mean_invstd + C + q.c);
-    F8 gam;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) gam.v[k] = 1.f;
-    if (p.gamma) gam = ld_f8(p.gamma + q.c);
-    const float rc = (float)(1.0 / p.count);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float xh = (rv.v[k] - mean.v[k]) * inv.v[k];
-      const float sg = (float)p.sums[q.c + k] * rc, sgx = (float)p.sums[C + q.c + k] * rc;
-      d.v[k] = gam.v[k] * inv.v[k] * (g.v[k] - sg - xh * sgx);
+  const float rc = (float)(1.0 / p.count);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float A = 1.f, B = 0.f, K = 0.f;
+    if (p.mean_invstd) {
+      const float mean = p.mean_invstd[c], inv = p.mean_invstd[C + c];
+      const float gam = p.gamma ? p.gamma[c] : 1.f;
+      const float sg = (float)p.sums[c] * rc, sgx = (float)p.sums[C + c] * rc;
+      A = gam * inv;
+      B = -A * inv * sgx;
+      K = -A * sg - B * mean;
     }
+    s_coef[c] = A; s_coef[C + c] = B; s_coef[2 * C + c] = K;
   }
-  st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, q.n, q.y, q.x, q.c), d);
+  __syncthreads();
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const Px q = decode8(i, r.h, r.w, C);
+    const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, q.c));
+    const F8 g = masked_g8(p, q, rv);
+    if (p.res_mode) {
+      float* o = (float*)p.res.ptr + vidx(p.res, q.n, q.y, q.x, q.c);
+      F8 w = g;
+      if (p.res_mode == 2) { F8 old = ld_f8(o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w.v[k] += old.v[k]; }
+      st_f8(o, w);
+    }
+    const F8 A = ld_f8(s_coef + q.c), B = ld_f8(s_coef + C + q.c), K = ld_f8(s_coef + 2 * C + q.c);
+    F8 d;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d.v[k] = fmaf(A.v[k], g.v[k], fmaf(B.v[k], rv.v[k], K.v[k]));
+    st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, q.n, q.y, q.x, q.c), d);
+  }
 }
 
 // ---- ring folding: adjoint of replicate padding on a ringed fp32 gradient ----------------------------------------------
@@ -690,17 +699,14 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   const int pix_per_iter = 256 / groups > 0 ? 256 / groups : 1;
   const int threads_used = groups * pix_per_iter;
   size_t npix = (size_t)raw->n * raw->h * raw->w;
-  // at most 16 pixels per thread, but never fewer than ~2 blocks per SM: the small deep layers were latency bound
-  // with a few dozen blocks walking their pixels serially
-  size_t per_thread = npix / ((size_t)pix_per_iter * 296);
-  per_thread = per_thread < 4 ? 4 : (per_thread > 16 ? 16 : per_thread);
-  unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * per_thread - 1) / ((size_t)pix_per_iter * per_thread));
-  if (grid > 148 * 4) grid = 148 * 4;
-  // every block ends with 2C fp64 atomics on the same 2C addresses: wide layers get fewer blocks
-  const unsigned cap = (unsigned)(49152 / raw->c) > 24u ? (unsigned)(49152 / raw->c) : 24u;
+  // one wave of four blocks per SM, at least two pixels per thread; every block ends with 2C fp64 atomics on the same 2C
+  // addresses, so wide layers get fewer blocks
+  size_t want = (npix + (size_t)pix_per_iter * 2 - 1) / ((size_t)pix_per_iter * 2);
+  unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+  const unsigned cap = (unsigned)(98304 / raw->c) > 48u ? (unsigned)(98304 / raw->c) : 48u;
   if (grid > cap) grid = cap;
   if (grid == 0) grid = 1;
-  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
+  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(double), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -716,7 +722,10 @@ extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view*
   p.dy = *dy; p.res_mode = res_mode; if (res) p.res = *res;
   p.dgamma = dgamma; p.dbeta = dbeta; p.c_real = c_real;
   size_t total = (size_t)raw->n * raw->h * raw->w * (raw->c / 8);
-  bn_bwd_apply_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p);
+  FSNET_REQUIRE(raw->c <= 2048 && total < (1ull << 32), "fsnet_bn_bwd_apply: channels <= 2048, 32-bit indexing");
+  unsigned grid = blocks_for(total);
+  if (grid > 148u * 8u) grid = 148u * 8u;          // persistent blocks: the per-channel coefficients are built once per block
+  bn_bwd_apply_kernel<<<grid, 256, 3 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

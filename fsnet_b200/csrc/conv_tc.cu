@@ -474,7 +474,8 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   FSNET_REQUIRE(in && in->ptr && w_hi && out && out->ptr, "fsnet_conv: null pointer");
   FSNET_REQUIRE(nprod == 1 || (nprod == 3 && w_lo), "fsnet_conv: nprod must be 1 or 3 (3 needs the lo planes)");
   const int N = in->n, H = in->h, W = in->w, Cin = in->c;
-  FSNET_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 16 == 0 && Cout % 16 == 0, "fsnet_conv: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
+  // (Cin = 8: only the 7x7 / stride-2 network stem -- 3 or 6 image channels padded to 8 -- on its folded-tap path, see below)
+  FSNET_REQUIRE(N > 0 && H > 0 && W > 0 && (Cin % 16 == 0 || Cin == 8) && Cout % 16 == 0, "fsnet_conv: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
   FSNET_REQUIRE(stride == 1 || stride == 2, "fsnet_conv: stride %d unsupported", stride);
   FSNET_REQUIRE(!use_ring || (in->ring >= pad), "fsnet_conv: replicate padding needs a materialised ring >= pad");
   EncodeTiledFn enc = encode_fn();
@@ -522,11 +523,13 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 2; }
   p.fold = fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
            in->c == in->c_total && (Cin < 64 || Cin == 96);
-  // the 7x7 / stride-2 stem on 16-channel (3 real) image planes with a materialised zero ring: 7 taps x 16 channels = 112 -> two
-  // 64-element slices per kernel row instead of 49 separate 4 KB tap loads
+  // the 7x7 / stride-2 stem on 8-channel (3 or 6 real) image planes with a materialised zero ring: the 7 taps x 8 channels of a
+  // kernel row are 56 contiguous elements = ONE 64-element slice (K = 7 x 64 for a real K of 147; 16-channel planes needed two
+  // slices per row, i.e. twice the TMA bytes and 1.75x the MMAs -- the stem was the longest forward launch, 165 us at cfg2a)
   const bool stem_fold = fold_env && stride == 2 && use_ring && in->ring == pad && pad == 3 && KH == 7 && KW == 7 && in->c_off == 0 &&
-                         in->c == in->c_total && Cin == 16;
+                         in->c == in->c_total && (Cin == 16 || Cin == 8);
   if (stem_fold) p.fold = 1;
+  FSNET_REQUIRE(Cin % 16 == 0 || stem_fold, "fsnet_conv: 8 input channels are only supported by the folded 7x7/2 stem (zero ring of 3)");
 
   if (p.fold) {
     p.KC = 64; p.cchunks = ceil_div(KW * Cin, 64); p.kiters = KH * p.cchunks;
@@ -763,13 +766,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         if (p.ksplit == 1) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
-                                                                   __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+            if (c0 + j < n_cols)                // (a folded row of 7 taps x 8 channels = 56 columns ends inside a group of 16)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]),
+                                                                     __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
         } else {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)       // one 128-bit reduction per four accumulators (the L2 atomic units are the limit)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(raw[j])),
-                         "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3])) : "memory");
+            if (c0 + j < n_cols)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(raw[j])),
+                           "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3])) : "memory");
         }
       }
     }
@@ -788,27 +793,28 @@ uint32_t layout_for_atom(int a) { return a == 64 ? 2u : (a == 32 ? 4u : 6u); }
 extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, int KH, int KW, int stride, int pad,
                                 float* acc, void* stream) {
   FSNET_REQUIRE(x && dy && x->ptr && dy->ptr && acc, "fsnet_conv_wgrad: null pointer");
-  FSNET_REQUIRE(x->c % 16 == 0 && dy->c % 16 == 0, "fsnet_conv_wgrad: channels must be multiples of 16");
+  FSNET_REQUIRE((x->c % 16 == 0 || x->c == 8) && dy->c % 16 == 0, "fsnet_conv_wgrad: channels must be multiples of 16");
   FSNET_REQUIRE(stride == 1 || stride == 2, "fsnet_conv_wgrad: stride %d unsupported", stride);
   WgradParams p = {};
   p.N = dy->n; p.Ho = dy->h; p.Wo = dy->w; p.KH = KH; p.KW = KW; p.stride = stride; p.pad = pad;
   p.org = use_ring ? x->ring : 0;
   p.Cout = dy->c; p.Cin = x->c; p.taps = KH * KW;
   FSNET_REQUIRE((x->h + 2 * pad - KH) / stride + 1 == p.Ho && (x->w + 2 * pad - KW) / stride + 1 == p.Wo, "fsnet_conv_wgrad: shape mismatch");
-  p.atomA = atom_channels(p.Cout); p.atomB = atom_channels(p.Cin);
+  p.atomA = atom_channels(p.Cout); p.atomB = atom_channels(p.Cin % 16 == 0 ? p.Cin : 16);
   const int BMr = p.Cout < 128 ? p.Cout : 128;
   FSNET_REQUIRE(p.Cout % BMr == 0, "fsnet_conv_wgrad: cannot tile Cout=%d", p.Cout);
   p.BM_real = BMr; p.co_tiles = p.Cout / BMr;
   p.nA = BMr / p.atomA;
   FSNET_REQUIRE(p.nA == 1 || p.nA * p.atomA == 128, "fsnet_conv_wgrad: Cout=%d needs partial atom aliasing (unsupported)", p.Cout);
-  p.BN = p.Cin <= 128 ? p.Cin : (p.Cin % 128 == 0 ? 128 : (p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16)));
-  FSNET_REQUIRE(p.Cin % p.BN == 0, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
+  p.BN = p.Cin <= 128 ? (p.Cin % 16 == 0 ? p.Cin : 16) : (p.Cin % 128 == 0 ? 128 : (p.Cin % 64 == 0 ? 64 : (p.Cin % 32 == 0 ? 32 : 16)));
+  FSNET_REQUIRE(p.Cin % p.BN == 0 || p.Cin == 8, "fsnet_conv_wgrad: cannot tile Cin=%d", p.Cin);
   p.ci_tiles = p.Cin / p.BN; p.nB = p.BN / p.atomB;
   p.row_elems = p.Cin;
   static int wfold_env = -1;
   if (wfold_env < 0) { const char* e = getenv("FSNET_WGRAD_FOLD"); wfold_env = e ? atoi(e) : 1; }
   p.fold = wfold_env && use_ring && x->ring == pad && x->c_off == 0 && x->c == x->c_total &&
-           ((stride == 1 && KH == 3 && KW == 3 && pad == 1 && p.Cin < 64) || (stride == 2 && KH == 7 && KW == 7 && pad == 3 && p.Cin == 16));
+           ((stride == 1 && KH == 3 && KW == 3 && pad == 1 && p.Cin < 64) || (stride == 2 && KH == 7 && KW == 7 && pad == 3 && (p.Cin == 16 || p.Cin == 8)));
+  FSNET_REQUIRE(p.Cin % 16 == 0 || p.fold, "fsnet_conv_wgrad: 8 input channels are only supported by the folded 7x7/2 stem");
   if (p.fold) {
     p.row_elems = KW * p.Cin;
     p.taps = KH;

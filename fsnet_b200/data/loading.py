@@ -94,12 +94,24 @@ class DevicePrefetcher:
     def __len__(self):
         return len(self.loader)
 
-    def _upload(self, batch, stream):
+    def _upload(self, batch, stream, slot=0):
         if stream is None:
             out = {k: (v.to(self.device) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
             return (out if self.device_transform is None else self.device_transform(out)), None
+        bufs = self._slots[slot]
         with torch.cuda.stream(stream):
-            out = {k: (v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+            if self._released[slot] is not None:
+                stream.wait_event(self._released[slot])         # the consumer of this slot's previous batch has queued all its reads
+            out = {}
+            for k, v in batch.items():
+                if isinstance(v, torch.Tensor):
+                    dst = bufs.get(k)
+                    if dst is None or dst.shape != v.shape or dst.dtype != v.dtype:
+                        dst = bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                    dst.copy_(v, non_blocking=True)
+                    out[k] = dst
+                else:
+                    out[k] = v
             if self.device_transform is not None:
                 out = self.device_transform(out)
             event = torch.cuda.Event()
@@ -107,21 +119,33 @@ class DevicePrefetcher:
         return out, event
 
     def __iter__(self):
+        """Uploads land in ``depth + 1`` persistent sets of device buffers used round-robin (no allocator traffic per batch, which
+        matters once the host runs ahead of the GPU: freshly allocated tensors tied to two streams made the caching allocator
+        synchronise).  A yielded batch therefore stays valid until ``depth`` more batches have been requested -- consume it inside
+        the loop body, as the training loop does; the hand-back is stream-ordered (an event recorded on the consumer's stream when
+        it asks for the next batch)."""
         from collections import deque
         stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         source = iter(self.loader)
         queue = deque()
+        n_slots = self.depth + 1
+        self._slots = [dict() for _ in range(n_slots)]
+        self._released = [None] * n_slots
+        state = {"next": 0}
 
         def pull():
             try:
-                queue.append(self._upload(next(source), stream))
+                slot = state["next"] % n_slots
+                batch, event = self._upload(next(source), stream, slot)
+                queue.append((batch, event, slot))
+                state["next"] += 1
             except StopIteration:
                 pass
 
         for _ in range(self.depth):
             pull()
         while queue:
-            batch, event = queue.popleft()
+            batch, event, slot = queue.popleft()
             pull()                                         # the next upload is in flight before this batch is consumed
             if event is not None:
                 current = torch.cuda.current_stream(self.device)
@@ -130,3 +154,7 @@ class DevicePrefetcher:
                     if isinstance(v, torch.Tensor):
                         v.record_stream(current)
             yield batch
+            if stream is not None:                         # the consumer is back for more: everything it does with `batch` is queued
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._released[slot] = ev

@@ -16,7 +16,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib, peer, tc
-from .tc import Fp32, Planes, View, pad16
+from .tc import Fp32, Planes, View, pad16, pad_in
 
 MOMENTUM_DEFAULT = 0.1
 
@@ -81,7 +81,9 @@ class LayerState:
     def __init__(self, conv: nn.Conv2d, bn: Optional[nn.Module], need_dgrad=True):
         self.conv, self.bn = conv, bn
         w = conv.weight
-        self.w = tc.ConvWeights(w, need_dgrad)
+        # the 7x7 / stride-2 stem reads image planes padded to 8 channels (tc.pad_in), every other layer multiples of 16
+        stem = tuple(conv.kernel_size) == (7, 7) and tuple(conv.stride) == (2, 2) and tuple(conv.padding) == (3, 3) and w.shape[1] <= 8
+        self.w = tc.ConvWeights(w, need_dgrad, ci_pad=pad_in(w.shape[1]) if stem else None)
         C = self.w.co_pad
         dev = w.device
         self.C, self.c_real = C, w.shape[0]
@@ -491,7 +493,7 @@ class Tape:
 def _image_act(img: torch.Tensor) -> Act:
     n, c, h, w = img.shape
     # ring 3 = the stem's zero padding, materialised (the 7x7/2 stem then runs on the folded-tap convolution path)
-    p = Planes(n, h, w, pad16(c), ring=3, device=img.device)
+    p = Planes(n, h, w, pad_in(c), ring=3, device=img.device)
     _lib.call("fsnet_image_to_planes_ring", img.detach().float().contiguous(), c, p.view(), 1)
     a = Act(p, relu=False)
     a.zero_ring = True

@@ -16,6 +16,12 @@ def pad16(c: int) -> int:
     return (c + 15) // 16 * 16
 
 
+def pad_in(c: int) -> int:
+    """Input-channel padding of a convolution: multiples of 16, except the network stems (3 / 6 image channels -> 8: the seven
+    x-taps of a 7x7 kernel row are then 56 contiguous elements = one 64-element K slice of the folded-tap path, csrc/conv_tc.cu)."""
+    return 8 if c <= 8 else pad16(c)
+
+
 class _Buf:
     def __init__(self, t, n, h, w, c, ring):
         self.t, self.n, self.h, self.w, self.c, self.ring = t, n, h, w, c, ring
@@ -68,10 +74,10 @@ class Fp32(_Buf):
 class ConvWeights:
     """bf16 operand planes of one convolution, refreshed from the fp32 parameter every step."""
 
-    def __init__(self, weight: torch.Tensor, need_dgrad=True):
+    def __init__(self, weight: torch.Tensor, need_dgrad=True, ci_pad=None):
         co, ci, kh, kw = weight.shape
         self.co, self.ci, self.kh, self.kw = co, ci, kh, kw
-        self.co_pad, self.ci_pad = pad16(co), pad16(ci)
+        self.co_pad, self.ci_pad = pad16(co), (pad16(ci) if ci_pad is None else ci_pad)      # ci_pad = 8: the network stem (pad_in)
         dev = weight.device
         self.fwd = torch.empty(2, self.co_pad, kh, kw, self.ci_pad, device=dev, dtype=torch.bfloat16)
         self.dgrad = torch.empty(self.ci_pad, kh, kw, self.co_pad, device=dev, dtype=torch.bfloat16) if need_dgrad else None

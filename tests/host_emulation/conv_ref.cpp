@@ -51,7 +51,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi_,
   if (plan_only()) return FSNET_OK;
   if (!in || !in->ptr || !w_hi_ || !out || !out->ptr) return FSNET_ERR_INVALID;
   if (!(nprod == 1 || (nprod == 3 && w_lo_))) return FSNET_ERR_INVALID;
-  if (in->c % 16 || Cout % 16 || (use_ring && in->ring < pad)) return FSNET_ERR_INVALID;
+  if ((in->c % 16 && in->c != 8) || Cout % 16 || (use_ring && in->ring < pad)) return FSNET_ERR_INVALID;   // 8: the network stem
   const PlaneView x(in);
   const int Cin = x.c, Ho = (x.h + 2 * pad - KH) / stride + 1, Wo = (x.w + 2 * pad - KW) / stride + 1;
   if (out->n != x.n || out->h != Ho || out->w != Wo || out->c != Cout) return FSNET_ERR_INVALID;

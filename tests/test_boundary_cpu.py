@@ -324,9 +324,9 @@ def test_distill_kernel_device_code_emulated_on_the_host():
             np.testing.assert_allclose(u, torch.sigmoid(l).detach().numpy(), rtol=1e-6)
 
 
-def test_train_script_loader_default_is_the_plain_dataloader(monkeypatch):
-    """scripts/train.py::build_train_loader: without the opt-in switches the synthetic configs get the reference's DataLoader
-    (no prefetcher, no device stage, default collate)."""
+def test_train_script_loader_stages(monkeypatch):
+    """scripts/train.py::build_train_loader: FSNET_PREFETCH=0 gives the reference's plain DataLoader (upload inside the hook);
+    the default puts the upload prefetcher in front of the hook (no device stage, default collate, for the synthetic configs)."""
     import importlib.util
     import sys
     from torch.utils.data import DataLoader
@@ -337,7 +337,7 @@ def test_train_script_loader_default_is_the_plain_dataloader(monkeypatch):
     spec = importlib.util.spec_from_file_location("fsnet_train_script", os.path.join(repo, "scripts", "train.py"))
     train = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(train)
-    monkeypatch.delenv("FSNET_PREFETCH", raising=False)
+    monkeypatch.setenv("FSNET_PREFETCH", "0")
     cfg = cfg_from_file(os.path.join(repo, "configs", "kitti_wpose_synthetic.py"))
     cfg.data.num_workers, cfg.data.batch_size = 0, 2
     cfg.train_dataset.length, cfg.train_dataset.height, cfg.train_dataset.width = 6, 32, 64
@@ -346,7 +346,7 @@ def test_train_script_loader_default_is_the_plain_dataloader(monkeypatch):
     assert isinstance(loader, DataLoader) and not loader.pin_memory
     batch = next(iter(loader))
     assert batch[("image", 0)].shape == (2, 3, 32, 64) and len(loader) == 3
-    monkeypatch.setenv("FSNET_PREFETCH", "1")
+    monkeypatch.delenv("FSNET_PREFETCH", raising=False)
     from fsnet_b200.data.loading import DevicePrefetcher
     monkeypatch.setattr(torch.utils.data.DataLoader, "__init__", (lambda orig: lambda self, *a, **k: orig(self, *a, **{**k, "pin_memory": False}))(DataLoader.__init__))
     pf = train.build_train_loader(cfg, ds, -1, 1, torch.device("cpu"))

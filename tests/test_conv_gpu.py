@@ -22,6 +22,9 @@ CASES = [
     (2, 96, 32, 24, 48, 3, 1, 1, "rep"),
     (2, 3, 64, 48, 80, 7, 2, 3, "zring"),
     (3, 6, 64, 64, 96, 7, 2, 3, "zring"),
+    (2, 3, 64, 48, 80, 7, 2, 3, "zring8"),      # the networks' stem as the executor runs it: image planes padded to 8 channels
+    (3, 6, 64, 64, 96, 7, 2, 3, "zring8"),      # (7 taps x 8 channels = one 64-element K slice per kernel row)
+    (2, 3, 64, 192, 640, 7, 2, 3, "zring8"),    # full cfg2 image: 2-row x 64-pixel tiles, K-split weight gradient
     (2, 3, 64, 48, 80, 7, 2, 3, "zero"),
     (2, 64, 128, 24, 40, 3, 2, 1, "zero"),
     (2, 256, 512, 6, 10, 3, 1, 1, "zero"),
@@ -45,11 +48,12 @@ def run_conv_case(dev, N, Cin, Cout, H, W, k, stride, pad, mode):
     y = F.conv2d(xin, w, stride=stride, padding=0 if rep else pad)
     gy = torch.randn(y.shape, device=dev, generator=g)
     gx_ref, gw_ref = torch.autograd.grad(y, (x, w), gy)
-    ring = pad if mode == "zring" else 1
-    xp = tc.Planes(N, H, W, tc.pad16(Cin), ring, zero=True, device=dev)
-    _lib.call("fsnet_image_to_planes_ring", x.detach().contiguous(), Cin, xp.view(), int(mode == "zring"))
-    use_ring = mode in ("rep", "zring")
-    cw = tc.ConvWeights(w)
+    ring = pad if mode.startswith("zring") else 1
+    ci_pad = tc.pad_in(Cin) if mode == "zring8" else tc.pad16(Cin)
+    xp = tc.Planes(N, H, W, ci_pad, ring, zero=True, device=dev)
+    _lib.call("fsnet_image_to_planes_ring", x.detach().contiguous(), Cin, xp.view(), int(mode.startswith("zring")))
+    use_ring = mode in ("rep", "zring", "zring8")
+    cw = tc.ConvWeights(w, ci_pad=ci_pad)
     cw.refresh(w)
     Ho, Wo = y.shape[-2:]
     out = tc.Fp32(N, Ho, Wo, cw.co_pad, device=dev)
