@@ -198,6 +198,69 @@ int smooth_check(const float* disp, const float* img, int B, int h, int w, int H
   return FSNET_OK;
 }
 
+
+// ---- axis-angle + translation -> 4x4 (PoseNet output to cam_T_cam) --------------------------------------------------------------
+// rot_from_axisangle / get_translation_matrix / transformation_from_parameters (monodepth_utils.py:298-337, 31-44, 46-63): Rodrigues with
+// the reference's axis = v / (|v| + 1e-7); M = T * R, or R^T * T(-t) when inverted.  One thread per sample; the backward contracts the
+// incoming d loss / d M with forward-mode derivatives of the same formula (six dual-number evaluations) -- ~40 eager PyTorch launches per
+// direction in the reference, one tiny launch here.
+struct Dual { float v, d; };
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) { const float q = a.v / b.v; return {q, (a.d - q * b.d) / b.v}; }
+__device__ __forceinline__ Dual operator-(Dual a) { return {-a.v, -a.d}; }
+__device__ __forceinline__ Dual dsqrt(Dual a) { const float r = sqrtf(a.v); return {r, r > 0.f ? 0.5f * a.d / r : 0.f}; }
+__device__ __forceinline__ Dual dsin(Dual a) { return {sinf(a.v), cosf(a.v) * a.d}; }
+__device__ __forceinline__ Dual dcos(Dual a) { return {cosf(a.v), -sinf(a.v) * a.d}; }
+__device__ __forceinline__ Dual cst(float c) { return {c, 0.f}; }
+
+// M[3][4] (the last row is 0 0 0 1) from the six parameters; `seed` = index of the parameter whose derivative rides along (-1: none)
+__device__ __forceinline__ void pose_matrix_dual(const float* aa, const float* tr, int invert, int seed, Dual (&M)[12]) {
+  Dual v[3], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { v[i] = {aa[i], seed == i ? 1.f : 0.f}; t[i] = {tr[i], seed == 3 + i ? 1.f : 0.f}; }
+  const Dual angle = dsqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const Dual den = angle + cst(1e-7f);
+  const Dual x = v[0] / den, y = v[1] / den, z = v[2] / den;
+  const Dual ca = dcos(angle), sa = dsin(angle), C = cst(1.f) - ca;
+  Dual R[9] = {x * x * C + ca, x * y * C - z * sa, z * x * C + y * sa,
+               x * y * C + z * sa, y * y * C + ca, y * z * C - x * sa,
+               z * x * C - y * sa, y * z * C + x * sa, z * z * C + ca};
+  if (!invert) {                              // T * R = [R | t]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { M[4 * i] = R[3 * i]; M[4 * i + 1] = R[3 * i + 1]; M[4 * i + 2] = R[3 * i + 2]; M[4 * i + 3] = t[i]; }
+  } else {                                    // R^T * T(-t) = [R^T | -R^T t]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      M[4 * i] = R[i]; M[4 * i + 1] = R[3 + i]; M[4 * i + 2] = R[6 + i];
+      M[4 * i + 3] = -(R[i] * t[0] + R[3 + i] * t[1] + R[6 + i] * t[2]);
+    }
+  }
+}
+__global__ void pose_matrix_kernel(const float* __restrict__ aa, const float* __restrict__ tr, int B, int invert, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Dual M[12];
+  pose_matrix_dual(aa + 3 * b, tr + 3 * b, invert, -1, M);
+  float* o = out + 16 * b;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) o[i] = M[i].v;
+  o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+__global__ void pose_matrix_bwd_kernel(const float* __restrict__ aa, const float* __restrict__ tr, const float* __restrict__ gM, int B,
+                                       int invert, float* __restrict__ g_aa, float* __restrict__ g_tr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 6) return;
+  const int b = i / 6, k = i - 6 * b;
+  Dual M[12];
+  pose_matrix_dual(aa + 3 * b, tr + 3 * b, invert, k, M);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) s = fmaf(gM[16 * b + j], M[j].d, s);
+  if (k < 3) g_aa[3 * b + k] = s; else g_tr[3 * b + k - 3] = s;
+}
+
 }  // namespace
 }  // namespace fsnet
 
@@ -320,6 +383,21 @@ extern "C" int fsnet_depth_head_bwd(const float* logits, const float* bins, cons
 extern "C" int fsnet_loss_finalize(const double* acc, int S, double* out, void* stream) {
   FSNET_REQUIRE(acc && out && S > 0 && S <= 8, "fsnet_loss_finalize: bad arguments");
   loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, S, out);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_pose_matrix(const float* axisangle, const float* translation, int B, int invert, float* T, void* stream) {
+  FSNET_REQUIRE(axisangle && translation && T && B > 0, "fsnet_pose_matrix: bad arguments");
+  pose_matrix_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(axisangle, translation, B, invert, T);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_T, int B, int invert,
+                                     float* grad_axisangle, float* grad_translation, void* stream) {
+  FSNET_REQUIRE(axisangle && translation && grad_T && grad_axisangle && grad_translation && B > 0, "fsnet_pose_matrix_bwd: bad arguments");
+  pose_matrix_bwd_kernel<<<ceil_div(B * 6, 64), 64, 0, (cudaStream_t)stream>>>(axisangle, translation, grad_T, B, invert, grad_axisangle, grad_translation);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

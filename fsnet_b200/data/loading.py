@@ -73,6 +73,23 @@ def build_dataloader(dataset, num_workers: int, batch_size: int, collate_fn: Cal
                       drop_last=True, **kwargs)
 
 
+_UPLOAD_STREAMS = {}
+
+
+def _upload_stream(device):
+    """ONE upload stream per device for the life of the process.  A fresh torch.cuda.Stream per epoch / iterator walks through
+    torch's stream pool, and once more streams exist than the GPU has hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default)
+    the upload stream shares a queue with the compute stream: copies and training steps serialise, and erratically so (measured
+    on B200, tools/diag_e2e.py: 7.2 ms/step for the first iterators, 8-18 ms/step after a dozen)."""
+    if device.type != "cuda":
+        return None
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _UPLOAD_STREAMS.get(key)
+    if st is None:
+        st = _UPLOAD_STREAMS[key] = torch.cuda.Stream(device)
+    return st
+
+
 class DevicePrefetcher:
     """Iterates a loader of HOST batches one batch ahead of the consumer: while step k computes, the tensors of batch k+1
     travel from (pinned) host memory to the device on a side stream, so the copy engine works under the training step
@@ -125,11 +142,12 @@ class DevicePrefetcher:
         the loop body, as the training loop does; the hand-back is stream-ordered (an event recorded on the consumer's stream when
         it asks for the next batch)."""
         from collections import deque
-        stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        stream = _upload_stream(self.device)
         source = iter(self.loader)
         queue = deque()
         n_slots = self.depth + 1
-        self._slots = [dict() for _ in range(n_slots)]
+        if len(getattr(self, "_slots", ())) != n_slots:
+            self._slots = [dict() for _ in range(n_slots)]     # kept across epochs: the buffers are allocated once
         self._released = [None] * n_slots
         state = {"next": 0}
 

@@ -200,6 +200,33 @@ def reprojection_loss(depths: Sequence[torch.Tensor], disps: Sequence[torch.Tens
     return _ReprojectionLoss.apply(S, cfg, *depths, *disps, T0, T1, P2, tgt, src0, src1, mask, motion, *extra)
 
 
+class _PoseMatrix(torch.autograd.Function):
+    """transformation_from_parameters (monodepth_utils.py:46-63) as one launch per direction (csrc/smooth_head.cu)."""
+
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert: bool):
+        B = axisangle.shape[0]
+        aa, tr = _f32c(axisangle).reshape(B, 3), _f32c(translation).reshape(B, 3)
+        T = torch.empty(B, 4, 4, device=aa.device, dtype=torch.float32)
+        _lib.call("fsnet_pose_matrix", aa, tr, B, int(bool(invert)), T)
+        ctx.save_for_backward(aa, tr)
+        ctx.invert, ctx.shapes = bool(invert), (axisangle.shape, translation.shape)
+        return T
+
+    @staticmethod
+    def backward(ctx, gT):
+        aa, tr = ctx.saved_tensors
+        B = aa.shape[0]
+        g_aa, g_tr = torch.empty_like(aa), torch.empty_like(tr)
+        _lib.call("fsnet_pose_matrix_bwd", aa, tr, _f32c(gT), B, int(ctx.invert), g_aa, g_tr)
+        return g_aa.view(ctx.shapes[0]), g_tr.view(ctx.shapes[1]), None
+
+
+def pose_matrix(axisangle: torch.Tensor, translation: torch.Tensor, invert: bool = False) -> torch.Tensor:
+    """[B,1,3] axis-angle and translation -> [B,4,4] cam_T_cam."""
+    return _PoseMatrix.apply(axisangle, translation, invert)
+
+
 class MeiRayTable:
     """Device-resident cache of MeiCameraProjection.image2cam's look-up tables (mei_fisheye_utils.py:139-170).
 

@@ -65,6 +65,9 @@ def get_translation_matrix(t):
 
 
 def transformation_from_parameters(axisangle, translation, invert=False):
+    if axisangle.is_cuda:        # one fused launch per direction (fsnet_pose_matrix); the composition below documents the arithmetic
+        from .. import functional as Fn
+        return Fn.pose_matrix(axisangle, translation, invert)
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:

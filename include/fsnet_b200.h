@@ -58,6 +58,16 @@ const char* fsnet_last_error(void);
 int fsnet_camera_setup(const float* P2, const float* T0, const float* T1, int B, float* cam, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * PoseNet output -> cam_T_cam: rot_from_axisangle (Rodrigues, axis = v / (|v| + 1e-7)), get_translation_matrix and
+ * transformation_from_parameters (monodepth_utils.py:298-337, 31-44, 46-63) in one launch; M = T*R, or R^T * T(-t) with invert.
+ *   axisangle, translation [B,3] fp32      T [B,4,4] fp32 out
+ * backward: grad_T [B,4,4] -> grad_axisangle, grad_translation [B,3]
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_pose_matrix(const float* axisangle, const float* translation, int B, int invert, float* T, void* stream);
+int fsnet_pose_matrix_bwd(const float* axisangle, const float* translation, const float* grad_T, int B, int invert,
+                          float* grad_axisangle, float* grad_translation, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * identity photometric terms: 0.85*mean_c SSIM(src_f, tgt) + 0.15*mean_c |tgt - src_f| for both
  * source frames.  monodepth2_decoder.py:248-254 (+ :118-128, monodepth_utils.py:184-215).  They do
  * not depend on the scale, so they are computed once per step.  The same pass also emits the

@@ -88,6 +88,26 @@ def test_log_image_head_keeps_the_loss_and_gradients_under_emulation(emulated, g
     check_log_image_case(golden_dir, "loss_a", "cpu")
 
 
+def test_pose_matrix_kernels_under_emulation(emulated):
+    """fsnet_pose_matrix / _bwd (axis-angle + translation -> 4x4, forward-mode duals contracted with the incoming gradient) against
+    autograd through the oracle's transformation_from_parameters, both orientations, incl. a near-zero rotation."""
+    from fsnet_b200 import functional as Fn
+    g = torch.Generator().manual_seed(4)
+    for invert in (False, True):
+        aa = (torch.randn(5, 1, 3, generator=g) * 0.05)
+        aa[0] = 1e-6 * torch.randn(1, 3, generator=g)
+        tr = torch.randn(5, 1, 3, generator=g)
+        gT = torch.randn(5, 4, 4, generator=g)
+        a1, t1 = aa.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+        ref = O.transformation_from_parameters(a1, t1, invert)
+        (ref * gT).sum().backward()
+        a2, t2 = aa.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+        got = Fn.pose_matrix(a2, t2, invert)
+        (got * gT).sum().backward()
+        assert float((got - ref).abs().max()) < 1e-6
+        assert rel(a2.grad, a1.grad) < 1e-5 and rel(t2.grad, t1.grad) < 1e-6
+
+
 def test_depth_head_kernels_under_emulation(emulated):
     """fsnet_depth_head_fwd / _bwd (channels-last lane-group softmax and the NCHW kernel) against the oracle's gather_depth."""
     from fsnet_b200 import functional as Fn
