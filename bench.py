@@ -200,8 +200,10 @@ def main():
         if not ops.tc_available():
             raise SystemExit("libfsnet_b200.so lacks the tcgen05 convolution kernels: rebuild with `python -m fsnet_b200.build`")
         ops.set_backend("tc")
-    else:
-        ops.set_backend(args.backend)                 # "torch": cuDNN comparison path
+    else:                                             # "torch": the same module tree through stock PyTorch / cuDNN (comparator)
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import torch_reference_backend
+        torch_reference_backend.enable()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = cfg_from_file(CONFIG)
@@ -216,7 +218,7 @@ def main():
     model.train()
     from vision_base.networks.optimizers.optimizers import build_optimizer
     optimizer = build_optimizer(model, **cfg.optimizer)
-    use_graph = ops.BACKEND == "tc" and not args.no_graph
+    use_graph = ops.COMPARATOR is None and not args.no_graph
     hook = build(**dict(cfg.trainer.training_hook, cuda_graph=use_graph))
     probe_hook = build(**dict(cfg.trainer.training_hook, cuda_graph=False))     # eager steps for per-kernel event timing
 
@@ -322,7 +324,7 @@ def main():
         "vs_baseline": None, "dtype": "f32 (convs: " + ops.precision_note() + ")", "data": "synthetic",
         "config": {"workload": wl["text"], "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
                    "parallelism": f"dp{world}" + (" (SyncBN statistics + flat gradient all-reduce over NCCL, inside the step graph)" if world > 1 else ""),
-                   "conv_backend": ops.BACKEND,
+                   "conv_backend": "tc" if ops.COMPARATOR is None else "torch (comparator)",
                    "cuda_graph": use_graph, "e2e_prefetch": bool(args.prefetch),
                    "e2e_loss_read": "blocking .item() per step" if args.e2e_sync else "async copy to pinned memory per step, read one step later",
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},

@@ -324,46 +324,46 @@ __device__ __forceinline__ F8 masked_g8(const BnBwdParams& p, const Px& q, const
   }
   return g;
 }
-// Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory atomics (fp64: the
-// order of the atomics changes from run to run, in double that does not reach the fp32 results), then one fp64 atomic per
-// channel and block.  sums[C + c] = inv * sum g * (raw - mean): the mean is subtracted per element (no cancellation), the
-// 1/std factor once per block.  Round 2: one pixel per iteration and no per-element 1/std -> 64 instead of 126 registers, three
-// resident blocks per SM instead of two (ncu r2c8: 14 warps/SM, 31 % issue utilisation, 5-7 long-scoreboard stalls per issue,
-// 31-35 % of the DRAM bandwidth), grid = one wave of 3-4 blocks per SM.
-__global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
-  extern __shared__ double s_acc[];          // [2*C]
+// Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory
+// float atomics, then one fp64 atomic per channel and block.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
+  extern __shared__ float s_acc[];           // [2*C]
   const V& r = p.raw;
   const int C = r.c, groups = C >> 3;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.0;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   if ((int)threadIdx.x < threads_used) {
     const int cg = threadIdx.x % groups, pl = threadIdx.x / groups;
     const int c = cg << 3;
     const unsigned npix = (unsigned)r.n * r.h * r.w;
-    F8 mean;
+    F8 mean, inv;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mean.v[k] = 0.f;
-    if (p.mean_invstd) mean = ld_f8(p.mean_invstd + c);
+    for (int k = 0; k < 8; ++k) { mean.v[k] = 0.f; inv.v[k] = 0.f; }
+    if (p.mean_invstd) { mean = ld_f8(p.mean_invstd + c); inv = ld_f8(p.mean_invstd + C + c); }
     float s1[8], s2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    // two pixels per iteration: their loads are independent, which doubles the bytes in flight per thread
     const unsigned step = gridDim.x * pix_per_iter;
-#pragma unroll 1
-    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += step) {
+    for (unsigned pix = blockIdx.x * pix_per_iter + pl; pix < npix; pix += 2 * step) {
+      const unsigned pix2 = pix + step;
+      const bool has2 = pix2 < npix;
       Px q; unsigned t = pix / (unsigned)r.w; q.x = (int)(pix - t * r.w);
       unsigned n = t / (unsigned)r.h; q.y = (int)(t - n * r.h); q.n = (int)n; q.c = c;
+      Px q2 = q;
+      if (has2) { unsigned t2 = pix2 / (unsigned)r.w; q2.x = (int)(pix2 - t2 * r.w);
+                  unsigned n2 = t2 / (unsigned)r.h; q2.y = (int)(t2 - n2 * r.h); q2.n = (int)n2; }
       const F8 rv = ld_f8((const float*)r.ptr + vidx(r, q.n, q.y, q.x, c));
+      const F8 rv2 = ld_f8((const float*)r.ptr + vidx(r, q2.n, q2.y, q2.x, c));
       const F8 g = masked_g8(p, q, rv);
+      const F8 g2 = masked_g8(p, q2, rv2);
+      const float w2 = has2 ? 1.f : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], rv.v[k] - mean.v[k], s2[k]); }
-    }
-    if (p.mean_invstd) {
-      const F8 inv = ld_f8(p.mean_invstd + C + c);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s2[k] *= inv.v[k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s2[k] = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        s1[k] += g.v[k]; s2[k] = fmaf(g.v[k], (rv.v[k] - mean.v[k]) * inv.v[k], s2[k]);
+        const float gg = g2.v[k] * w2;
+        s1[k] += gg; s2[k] = fmaf(gg, (rv2.v[k] - mean.v[k]) * inv.v[k], s2[k]);
+      }
     }
     // lanes of a warp that own the same channel group (lane % groups, when groups divides 32) combine by shuffles first:
     // for the 16..64-channel full-resolution layers the shared-memory atomics were 128-way contended
@@ -377,20 +377,19 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_reduce_kernel(BnBwdParams p, in
       }
       if ((int)(threadIdx.x & 31) < groups) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], (double)s1[k]); atomicAdd(&s_acc[C + c + k], (double)s2[k]); }
+        for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], (double)s1[k]); atomicAdd(&s_acc[C + c + k], (double)s2[k]); }
+      for (int k = 0; k < 8; ++k) { atomicAdd(&s_acc[c + k], s1[k]); atomicAdd(&s_acc[C + c + k], s2[k]); }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    const double v = s_acc[i];
-    if (v != 0.0) atomicAdd(p.sums + i, v);
+    float v = s_acc[i];
+    if (v != 0.f) atomicAdd(p.sums + i, (double)v);
   }
 }
-
 // dy = A * g + B * raw + K per channel: the BatchNorm input gradient gamma*inv*(g - mean(g) - xhat*mean(g*xhat)) with
 // xhat = (raw - mean)*inv, rearranged so that an element costs two FMAs.  The three coefficients per channel are built once
 // per block from the fp64 sums into shared memory (round 1 read 16 doubles and converted them per 8 elements: the kernel sat
@@ -699,14 +698,17 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   const int pix_per_iter = 256 / groups > 0 ? 256 / groups : 1;
   const int threads_used = groups * pix_per_iter;
   size_t npix = (size_t)raw->n * raw->h * raw->w;
-  // one wave of four blocks per SM, at least two pixels per thread; every block ends with 2C fp64 atomics on the same 2C
-  // addresses, so wide layers get fewer blocks
-  size_t want = (npix + (size_t)pix_per_iter * 2 - 1) / ((size_t)pix_per_iter * 2);
-  unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
-  const unsigned cap = (unsigned)(98304 / raw->c) > 48u ? (unsigned)(98304 / raw->c) : 48u;
+  // at most 16 pixels per thread, but never fewer than ~2 blocks per SM: the small deep layers were latency bound
+  // with a few dozen blocks walking their pixels serially
+  size_t per_thread = npix / ((size_t)pix_per_iter * 296);
+  per_thread = per_thread < 4 ? 4 : (per_thread > 16 ? 16 : per_thread);
+  unsigned grid = (unsigned)((npix + (size_t)pix_per_iter * per_thread - 1) / ((size_t)pix_per_iter * per_thread));
+  if (grid > 148 * 4) grid = 148 * 4;
+  // every block ends with 2C fp64 atomics on the same 2C addresses: wide layers get fewer blocks
+  const unsigned cap = (unsigned)(49152 / raw->c) > 24u ? (unsigned)(49152 / raw->c) : 24u;
   if (grid > cap) grid = cap;
   if (grid == 0) grid = 1;
-  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(double), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
+  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

@@ -51,21 +51,19 @@ class DepthDecoder(nn.Module):
         return (P2[:, 0, 0] / self.base_fx).float()
 
     def _trunk(self, input_features):
+        """Encoder + decoder as one autograd node of the tcgen05 executor.  ``input_features`` is the deferred handle ResNet.forward
+        returned; if some other code has already indexed it (the list then holds exported copies of the five feature maps), the
+        network is still executed from the image, so gradients and BatchNorm statistics are those of the real path."""
         from .ops_tc import LazyFeatures, runner_for
-        if isinstance(input_features, LazyFeatures) and not input_features.materialized:
-            # tcgen05 path: encoder + decoder as one autograd node
+        if isinstance(input_features, LazyFeatures):
             logits = runner_for(self, input_features.backbone).depth_logits(input_features.image)
             for i in range(4, -1, -1):
                 if i in self.scales:
                     yield i, logits[i]
             return
-        x = input_features[-1]
-        for i in range(4, -1, -1):
-            x = self.convs[("upconv", i, 0)](x)
-            x = ops.upsample2x_concat(x, input_features[i - 1] if (self.use_skips and i > 0) else None)
-            x = self.convs[("upconv", i, 1)](x)
-            if i in self.scales:
-                yield i, ops.conv_act(x, self.convs[("dispconv", i)], relu=False)
+        if ops.COMPARATOR is None:
+            raise TypeError("DepthDecoder expects the deferred features returned by fsnet_b200's ResNet.forward. " + ops.NO_CPU)
+        yield from ops.COMPARATOR.decoder_trunk(self, input_features)
 
     def forward(self, input_features, P2=None):
         outputs = {}
@@ -105,20 +103,15 @@ class MultiChannelDepthDecoderUncertain(DepthDecoder):
 
     def _trunk_with_uncertainty(self, input_features):
         from .ops_tc import LazyFeatures, runner_for
-        if isinstance(input_features, LazyFeatures) and not input_features.materialized:
+        if isinstance(input_features, LazyFeatures):
             outs = runner_for(self, input_features.backbone).depth_logits(input_features.image)
             for i in range(4, -1, -1):
                 if i in self.scales:
                     yield i, outs[i], outs[("uncertain", i)]
             return
-        x = input_features[-1]
-        for i in range(4, -1, -1):
-            x = self.convs[("upconv", i, 0)](x)
-            x = ops.upsample2x_concat(x, input_features[i - 1] if (self.use_skips and i > 0) else None)
-            x = self.convs[("upconv", i, 1)](x)
-            if i in self.scales:
-                yield (i, ops.conv_act(x, self.convs[("dispconv", i)], relu=False),
-                       ops.conv_act(x, self.convs[("uncertain_logz", i)], relu=False))
+        if ops.COMPARATOR is None:
+            raise TypeError("DepthDecoder expects the deferred features returned by fsnet_b200's ResNet.forward. " + ops.NO_CPU)
+        yield from ops.COMPARATOR.decoder_trunk(self, input_features, with_uncertainty=True)
 
     def forward(self, input_features, P2=None):
         outputs = {}

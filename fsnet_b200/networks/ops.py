@@ -1,28 +1,17 @@
-"""Composite layer operations used by the network modules.
+"""Where the network modules' arithmetic lives.
 
-Two back-ends:
-  "tc"     (default) the whole network runs as hand-written tcgen05 kernels through fsnet_b200/engine.py:
-           ``ResNet.forward`` only returns a deferred handle and the consuming head executes encoder + decoder
-           as one autograd node.  The functions below are then not on the path at all.
-  "torch"  stock PyTorch ops (cuDNN): a comparison / debugging path and the route for the few constructor
-           options the tcgen05 executor rejects (norm_eval=True, frozen_stages, dilation), never a silent
-           fallback: the executor raises NotImplementedError and the user selects this back-end explicitly
-           (``ops.set_backend("torch")`` or FSNET_CONV_BACKEND=torch).
-The network modules only hold parameters (reference names / state-dict layout).
+The modules of this package (ResNet, DepthDecoder, PoseDecoder, ConvBnReLU ...) only hold parameters in the reference's names /
+state-dict layout.  Their arithmetic is the tcgen05 executor: ``ResNet.forward`` returns a deferred handle and the consuming head
+runs encoder + decoder as ONE autograd node of hand-written kernels (fsnet_b200/engine.py).  There is no second back-end in the
+product and no CPU path: CPU tensors raise.
+
+``COMPARATOR`` is a test / tooling hook: ``tools/torch_reference_backend.enable()`` plugs stock-PyTorch forwards into the same
+module tree (``bench.py --backend torch``, feature-map comparisons in the tests).  It is None unless a tool sets it.
 """
-import os
+COMPARATOR = None          # set by tools/torch_reference_backend.enable(); never by product code
 
-import torch
-import torch.nn as nn
-import torch.nn.functional as F
-
-BACKEND = os.environ.get("FSNET_CONV_BACKEND", "tc")      # "tc" needs CUDA tensors; CPU tensors always take the torch ops
-
-
-def set_backend(name: str) -> None:
-    global BACKEND
-    assert name in ("torch", "tc")
-    BACKEND = name
+NO_CPU = ("fsnet_b200 has no CPU / eager-PyTorch path: the network runs as tcgen05 kernels on CUDA tensors (fsnet_b200/engine.py). "
+          "For a stock-PyTorch comparison call tools/torch_reference_backend.enable() first.")
 
 
 def tc_available() -> bool:
@@ -35,30 +24,14 @@ def tc_available() -> bool:
 
 
 def precision_note() -> str:
-    if BACKEND == "tc":
+    if COMPARATOR is None:
         return "tcgen05 bf16x3 split operands, fp32 accumulate"
-    return "cuDNN fp32 (comparison path)"
+    return "cuDNN fp32 (comparison path, tools/torch_reference_backend.py)"
 
 
-def conv_bn_act(x, conv: nn.Conv2d, bn, relu: bool = True, residual=None):
-    """conv -> (train-mode) batch-norm -> (+ residual) -> ReLU."""
-    y = conv(x)
-    if bn is not None:
-        y = bn(y)
-    if residual is not None:
-        y = y + residual
-    return F.relu(y) if relu else y
-
-
-def conv_act(x, conv: nn.Conv2d, relu: bool = False):
-    y = conv(x)
-    return F.relu(y) if relu else y
-
-
-def maxpool3x3s2(x):
-    return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-
-
-def upsample2x_concat(x, skip=None):
-    x = F.interpolate(x, scale_factor=2, mode="nearest")
-    return x if skip is None else torch.cat([x, skip], 1)
+def set_backend(name: str) -> None:
+    """Kept for callers of round 1: "tc" is the only product back-end (clears a comparator a tool may have plugged in)."""
+    global COMPARATOR
+    if name != "tc":
+        raise ValueError("the product has one back-end (tcgen05); the cuDNN comparator is tools/torch_reference_backend.enable()")
+    COMPARATOR = None

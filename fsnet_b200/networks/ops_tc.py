@@ -1,9 +1,10 @@
 """Glue between the reference-shaped modules and the tcgen05 executor (fsnet_b200/engine.py).
 
-On the "tc" back-end ``ResNet.forward`` does not run anything: it returns ``LazyFeatures``.  The head
-that consumes them (DepthDecoder / PoseDecoder) runs encoder + decoder as ONE autograd node.  Code that
-really wants the five feature tensors (``feats[i]``, ``len(feats)``, iteration) gets them: the list
-materialises itself from the executor's planes on first access.
+``ResNet.forward`` does not run anything: it returns ``LazyFeatures``.  The head that consumes them
+(DepthDecoder / PoseDecoder) runs encoder + decoder as ONE autograd node.  Code that really wants the five
+feature tensors (``feats[i]``, ``len(feats)``, iteration) gets them: the list materialises itself from the
+executor's planes on first access -- as detached EXPORT copies (no autograd, BatchNorm statistics untouched);
+the heads ignore those copies and always execute the network from the image.
 """
 import torch
 

@@ -26,20 +26,15 @@ class PoseDecoder(nn.Module):
 
     def forward(self, input_features):
         from .ops_tc import LazyFeatures, runner_for
-        if len(input_features) == 1 and isinstance(input_features[0], LazyFeatures) and not input_features[0].materialized:
+        if len(input_features) == 1 and isinstance(input_features[0], LazyFeatures):
             lazy = input_features[0]
-            out = runner_for(self, lazy.backbone).pose_map(lazy.image)      # tcgen05 path: PoseNet as one autograd node
+            out = runner_for(self, lazy.backbone).pose_map(lazy.image)      # PoseNet as one autograd node of the tcgen05 executor
             out = out.float().mean(3).mean(2)
             out = 0.01 * out.view(-1, self.num_frames_to_predict_for, 1, 6)
             return out[..., :3], out[..., 3:]
-        last = [f[-1] for f in input_features]
-        cat = torch.cat([ops.conv_act(f, self.convs["squeeze"], relu=True) for f in last], 1)
-        out = ops.conv_act(cat, self.convs[("pose", 0)], relu=True)
-        out = ops.conv_act(out, self.convs[("pose", 1)], relu=True)
-        out = ops.conv_act(out, self.convs[("pose", 2)], relu=False)
-        out = out.float().mean(3).mean(2)
-        out = 0.01 * out.view(-1, self.num_frames_to_predict_for, 1, 6)
-        return out[..., :3], out[..., 3:]
+        if ops.COMPARATOR is None:
+            raise TypeError("PoseDecoder expects [deferred features of fsnet_b200's ResNet.forward] (num_input_features = 1). " + ops.NO_CPU)
+        return ops.COMPARATOR.pose_decoder_forward(self, input_features)
 
 
 def rot_from_axisangle(vec):

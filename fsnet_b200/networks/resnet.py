@@ -2,7 +2,8 @@
 
 Mirror of vision_base/networks/models/backbone/resnet.py (constructor arguments :96-105, forward
 :199-213, stage/BN freezing :169-197, 6-channel stem for the PoseNet :119,155-160) with the same
-attribute names, hence the same state-dict keys.  The arithmetic goes through networks/ops.py."""
+attribute names, hence the same state-dict keys.  The modules only hold parameters: the arithmetic is the tcgen05 executor
+(fsnet_b200/engine.py), see networks/ops.py."""
 import math
 from typing import Tuple
 
@@ -28,9 +29,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        res = x if self.downsample is None else ops.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
-        return ops.conv_bn_act(out, self.conv2, self.bn2, relu=True, residual=res)
+        if ops.COMPARATOR is None:
+            raise RuntimeError("BasicBlock is a parameter container on the tcgen05 path. " + ops.NO_CPU)
+        return ops.COMPARATOR.block_forward(self, x)
 
 
 class Bottleneck(nn.Module):
@@ -49,10 +50,9 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        out = ops.conv_bn_act(x, self.conv1, self.bn1, relu=True)
-        out = ops.conv_bn_act(out, self.conv2, self.bn2, relu=True)
-        res = x if self.downsample is None else ops.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
-        return ops.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=res)
+        if ops.COMPARATOR is None:
+            raise RuntimeError("Bottleneck is a parameter container on the tcgen05 path. " + ops.NO_CPU)
+        return ops.COMPARATOR.block_forward(self, x)
 
 
 class ResNet(nn.Module):
@@ -120,19 +120,12 @@ class ResNet(nn.Module):
                 p.requires_grad = False
 
     def forward(self, img_batch):
-        if ops.BACKEND == "tc" and img_batch.is_cuda:
-            from .ops_tc import LazyFeatures
-            return LazyFeatures(self, img_batch)      # executed by the consuming head (fsnet_b200/engine.py)
-        outs = []
-        x = ops.conv_bn_act(img_batch, self.conv1, self.bn1, relu=True)
-        if -1 in self.out_indices:
-            outs.append(x)
-        x = ops.maxpool3x3s2(x)
-        for i in range(self.num_stages):
-            x = getattr(self, f"layer{i + 1}")(x)
-            if i in self.out_indices:
-                outs.append(x)
-        return outs
+        if ops.COMPARATOR is not None:
+            return ops.COMPARATOR.resnet_forward(self, img_batch)
+        if not img_batch.is_cuda:
+            raise RuntimeError(ops.NO_CPU)
+        from .ops_tc import LazyFeatures
+        return LazyFeatures(self, img_batch)      # executed by the consuming head (fsnet_b200/engine.py)
 
 
 def resnet(depth, pretrained=True, **kwargs):

@@ -142,6 +142,25 @@ def test_no_cpu_fallback():
         Fn.depth_head(torch.zeros(1, 4, 8, 8), torch.ones(4), None, False, 0.5, 100.0)
     src = open(os.path.join(os.path.dirname(_lib.__file__), "functional.py")).read()
     assert "oracle" not in src
+    # the network modules are parameter containers: CPU tensors raise, nothing falls back to eager PyTorch
+    from helpers import build_model
+    from oracle import fsnet_oracle as O
+    from fsnet_b200.networks import ops
+    assert ops.COMPARATOR is None
+    model = build_model(O.Topology(height=32, width=64))
+    data = O.synthetic_batch(2, 32, 64, 1)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(data, dict(is_training=True, epoch_num=0, global_step=0))
+    with pytest.raises(RuntimeError, match="parameter container"):
+        model.depth_backbone.layer1[0](torch.zeros(1, 64, 8, 8))
+    with pytest.raises(TypeError):
+        model.head.depth_decoder([torch.zeros(1, c, 4, 4) for c in (64, 64, 128, 256, 512)])
+    pkg = os.path.dirname(_lib.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
 
 
 def test_sampler_and_collate():

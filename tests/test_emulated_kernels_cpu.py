@@ -219,7 +219,7 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
     g = load(golden_dir, name)
     data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1234, topo.frame_ids)
     assert ops.tc_available()
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         model = build_model(topo)
@@ -280,7 +280,7 @@ def test_training_hook_trains_the_distillation_model_under_emulation(emulated, m
     from fsnet_b200.optim import build_optimizer
     from vision_base.utils.builder import build
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         topo = O.Topology(height=32, width=64, distill=True)
@@ -325,7 +325,7 @@ def test_conv_planner_accepts_every_shipped_configuration(emulated, monkeypatch,
     data = (O.synthetic_fisheye_batch if topo.fisheye else O.synthetic_batch)(B, topo.height, topo.width, 1, topo.frame_ids)
     counter = ctypes.c_longlong.in_dll(emulated, "fsnet_emulated_plans")
     before = counter.value
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         model = build_model(topo)
@@ -362,7 +362,7 @@ def test_training_trajectory_matches_the_reference_step_for_step(emulated, monke
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     frozen = variant == "norm_eval_frozen"
     topo, B = O.Topology(height=32, width=64, norm_eval=frozen, frozen_stages=1 if frozen else -1), 2
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         model = build_model(topo)
@@ -421,7 +421,7 @@ def test_files_to_training_step_with_device_augmentation_under_emulation(emulate
     dataset = build(**cfg.train_dataset)
     stage = find_device_stage(dataset)
     loader = build_dataloader(dataset, num_workers=0, batch_size=2, collate_fn=device_augment_collate)
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         model = build(**cfg.meta_arch).train()
@@ -458,7 +458,7 @@ def test_evaluation_hook_with_the_real_network_under_emulation(emulated, monkeyp
                  num_workers=0, batch_size=4)
     ds = build(name="monodepth.data.datasets.mono_dataset.KittiDepthMonoEigenTestDataset", raw_path=raw, split_file=split,
                augmentation=eval_cfg(size=(32, 64)))
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         model = build_model(O.Topology(height=32, width=64)).train()
@@ -477,7 +477,7 @@ def test_changing_batch_and_image_sizes_and_train_eval_transitions_under_emulati
     be the ones the oracle accumulates (eval predictions to 1e-5)."""
     from helpers import build_model
     from fsnet_b200.networks import ops
-    backend = ops.BACKEND
+    backend = "tc"
     ops.set_backend("tc")
     try:
         base = O.Topology(height=32, width=64)

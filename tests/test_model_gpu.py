@@ -86,18 +86,32 @@ def test_training_hook_steps_and_loss_decreases():
 
 
 def test_lazy_features_materialise_and_match_torch_backend():
-    """`backbone(img)` is a drop-in list of five [B,C,h,w] tensors even on the tcgen05 path."""
-    from fsnet_b200.networks import ops
+    """`backbone(img)` is a drop-in list of five [B,C,h,w] tensors even on the tcgen05 path; the decoder still runs the real
+    (differentiable) network when handed features somebody has already looked at (it used to fall back to eager ops
+    on detached copies)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import torch_reference_backend
     topo = O.Topology(height=64, width=128)
-    img = O.synthetic_batch(2, 64, 128, 1234)[("image", 0)].cuda()
+    data = O.synthetic_batch(2, 64, 128, 1234)
+    img = data[("image", 0)].cuda()
     model = build_model(topo).cuda()
     feats = model.depth_backbone(img)
     assert len(feats) == 5
     got = [f for f in feats]
-    ops.set_backend("torch")
-    ref = build_model(topo).cuda().depth_backbone(img)
+    outs = model.head.forward_depth(feats, data["P2"].cuda())            # AFTER the features were materialised
+    outs[("disp", 0)].sum().backward()
+    assert model.depth_backbone.conv1.weight.grad is not None and float(model.depth_backbone.conv1.weight.grad.abs().sum()) > 0
+    torch_reference_backend.enable()
+    try:
+        ref = build_model(topo).cuda().depth_backbone(img)
+    finally:
+        torch_reference_backend.disable()
     for a, b in zip(got, ref):
         assert a.shape == b.shape and rel(a.cpu(), b.detach().cpu()) < 1e-4
+    with pytest.raises(RuntimeError):
+        build_model(topo).depth_backbone(data[("image", 0)])              # CPU tensors: no eager fallback
 
 
 def test_graphed_hook_matches_eager_hook():
