@@ -30,7 +30,7 @@ SCALES = (0, 1, 2, 3)
 CONFIG = os.path.join(REPO, "configs", "kitti_wpose_synthetic.py")
 # --workload: the default is BASELINE.json's configs[1] (what the driver runs); the others are extra, informational lines
 WORKLOADS = {
-    "cfg2a": dict(config="kitti_wpose_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02,
+    "cfg2a": dict(config="kitti_wpose_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02, enc_convs=20, enc_gflop_per_image=8.883,
                   text="cfg2a kitti_wpose_synthetic: ResNet-18 depth net, 192x640, 4 scales, 16 bins, dataset poses, fwd+bwd+clip(35)+Adam"),
     "cfg2b": dict(config="kitti_posenet_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02 + 2 * 9.776,
                   text="cfg2b kitti_posenet_synthetic: MonoDepthMeta, ResNet-18 depth net + ResNet-18 PoseNet (2 pairs), 192x640, 4 scales, "
@@ -87,20 +87,37 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_step_rate(batch, steps, warmup):
-    """The oracle's full training step on the host cores -> triplets/s."""
+def oracle_step_rate(batch, steps, warmup, split=None):
+    """The oracle's full training step on the host cores -> triplets/s.  ``split`` (a dict) receives the mean seconds per phase:
+    encoder forward, decoder forward, loss chain forward, backward, clip + Adam."""
     from oracle import fsnet_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     topo = O.Topology(height=H, width=W, scales=SCALES)
     trainer = O.OracleTrainer(topo, seed=123, lr=1e-4, clip=35.0)
-    times = []
+    times, phases = [], {"encoder_fwd": 0.0, "decoder_fwd": 0.0, "loss_fwd": 0.0, "backward": 0.0, "clip_adam": 0.0}
     for i in range(warmup + steps):
         data = O.synthetic_batch(batch, H, W, seed=1234 + i)
         noise = O.tie_break_noise(batch, H, W, SCALES, seed=i)
-        t0 = time.perf_counter()
-        trainer.step(data, noise)
+        t = [time.perf_counter()]
+        # OracleTrainer.step, phase by phase (same calls, same order)
+        trainer.opt.zero_grad()
+        feats = O.resnet_forward(trainer.sd, "depth_backbone.", data[("image", 0)], topo.depth)
+        t.append(time.perf_counter())
+        outputs = O.decoder_forward(trainer.sd, "head.depth_decoder.", feats, topo, data["P2"])
+        t.append(time.perf_counter())
+        out = O.loss_chain(outputs, data, {f: data[("relative_pose", f)] for f in topo.frame_ids[1:]}, topo, noise, False)
+        t.append(time.perf_counter())
+        out["loss"].mean().backward()
+        t.append(time.perf_counter())
+        torch.nn.utils.clip_grad_norm_(trainer.params, trainer.clip)
+        trainer.opt.step()
+        t.append(time.perf_counter())
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(t[-1] - t[0])
+            for k, a, b in zip(phases, t[:-1], t[1:]):
+                phases[k] += b - a
+    if split is not None:
+        split.update({k: v / len(times) for k, v in phases.items()})
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
@@ -108,15 +125,19 @@ def run_reference(args, rank):
     if rank != 0:
         return
     batch = 4 if (args.steps + args.warmup) <= 12 else 2
-    rate, sec = oracle_step_rate(batch, args.steps, args.warmup)
+    split = {}
+    rate, sec = oracle_step_rate(batch, args.steps, args.warmup, split)
     cores = os.cpu_count() or 1
-    sample = f"B={batch} of {B_PER_GPU} triplets per step (192x640, ResNet-18, 4 scales), full step fwd+bwd+clip+Adam"
+    sample = (f"B={batch} of {B_PER_GPU} triplets per step (192x640, ResNet-18, 4 scales), full step fwd+bwd+clip+Adam; "
+              "deviation from BASELINE.md: the CPU restatement of the reference (oracle/, pinned to the reference by 28 golden "
+              "fixtures), not the reference package itself (/root/reference does not exist on the GPU box), at a bounded batch")
     line = {
         "impl": "reference", "metric": "images/sec (640x192 triplets), full training step", "value": rate, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2a kitti_wpose 192x640 R18 4-scale n=16 (CPU restatement of the reference, oracle/)", "batch": batch},
-        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "seconds_per_step_split": split},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -305,7 +326,7 @@ def main():
     avg_us = sum(kern_us) / max(len(kern_us), 1) if kern_us else float("nan")
     achieved = bytes_per_launch / (avg_us * 1e-6) / 1e9 if kern_us else None
     traffic = None
-    prof = os.path.join(REPO, "profiles", "r1_loss_fwdbwd_ncu.json")
+    prof = os.path.join(REPO, "profiles", "r2_loss_pair_ncu.json")
     if os.path.exists(prof):
         with open(prof) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
@@ -318,6 +339,13 @@ def main():
         with open(pk) as f:
             tf_peak = float(json.load(f).get("bf16_tflops_sustained", tf_peak))
     conv_tf = conv_flops / (fwd_us * 1e-6) / 1e12 if fwd_us > 0 else None
+    # encoder only (what north_star's 50 % tensor-pipe target is quoted on): the first `enc_convs` forward launches of every step
+    fwd_rows = [t for t, tag in conv_rows if tag == 3]
+    per_step = len(fwd_rows) // max(probe_steps, 1)
+    enc_n = wl.get("enc_convs", 0)
+    enc_us = (sum(sum(fwd_rows[i * per_step:i * per_step + enc_n]) for i in range(probe_steps)) / max(probe_steps, 1)) if (enc_n and per_step) else 0.0
+    enc_flops = wl.get("enc_gflop_per_image", 0.0) * 1e9 * B_PER_GPU
+    enc_tf = enc_flops / (enc_us * 1e-6) / 1e12 if enc_us > 0 else None
     line = {
         "metric": "images/sec (640x192 triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -328,7 +356,7 @@ def main():
                    "cuda_graph": use_graph, "e2e_prefetch": bool(args.prefetch),
                    "e2e_loss_read": "blocking .item() per step" if args.e2e_sync else "async copy to pinned memory per step, read one step later",
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
-        "roofline": {"kernel": "loss_bwd_kernel<0,0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
+        "roofline": {"kernel": "loss_pair_kernel<0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
@@ -338,14 +366,23 @@ def main():
                           "algorithmic_flops_per_step": conv_flops,
                           "note": "useful fp32-equivalent FLOPs; the tensor pipe executes 3x as many (bf16x3 split)",
                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+        "roofline_conv_encoder": {"kernel": f"conv_tc_kernel<3>, the {enc_n} convolutions of the ResNet encoder (forward)", "bound": "tensor",
+                                  "achieved": enc_tf, "achieved_on_pipe": (3 * enc_tf) if enc_tf else None, "peak": tf_peak, "unit": "TFLOP/s",
+                                  "frac": (enc_tf / tf_peak) if enc_tf else None, "frac_on_pipe": (3 * enc_tf / tf_peak) if enc_tf else None,
+                                  "us_per_step": enc_us, "algorithmic_flops_per_step": enc_flops,
+                                  "note": "achieved = useful fp32-equivalent FLOPs; on_pipe = x3 (three bf16 products per K-step)"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
         "gpu_launches": launches, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2a":
-        rate, sec = oracle_step_rate(4, 2, 1)
+        split = {}
+        rate, sec = oracle_step_rate(4, 2, 1, split)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/, torch CPU fp32)"}
+                                "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/ = CPU restatement of the "
+                                          "reference in torch fp32, pinned by reference-generated goldens; not the reference package, "
+                                          "which does not travel to the GPU box)",
+                                "seconds_per_step_split": split}
     print(json.dumps(line), flush=True)
     _finish(world)
 

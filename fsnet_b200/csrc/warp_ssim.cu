@@ -1364,18 +1364,21 @@ int plan(LossParams& p, int cols_per_warp, int halo_rows, int warps_per_sm) {
   return ceil_div(p.B * p.n_strips * p.n_chunks, kWarps);
 }
 
-// frame-pair kernel: one CTA per (sample, 30-column strip, row chunk); rows per chunk chosen so that the CTAs make whole waves of
-// 148 SMs x LOSS_PAIR_OCC resident CTAs (each chunk walks rows + 3: two halo rows of gathers, one more of the adjoint)
+// frame-pair kernel: one CTA per (sample, 30-column strip, row chunk).  The kernel is issue bound (71 % issue utilisation, ncu
+// r2c7), so the cost of a plan is its instruction count: every chunk walks rows + 3 rows (two halo rows of gathers, one more of the
+// adjoint) -> long chunks, as long as the CTAs still fill ~80 % of the 148 SMs x LOSS_PAIR_OCC resident slots.
 int plan_pair(LossParams& p) {
   p.n_strips = ceil_div(p.W, kPairCols);
-  const long cap = 148L * LOSS_PAIR_OCC;
+  const double cap = 148.0 * LOSS_PAIR_OCC;
   int best_rows = 8;
   double best_cost = 1e30;
   for (int rows = 8; rows <= 96; ++rows) {
-    const long items = (long)p.B * p.n_strips * ceil_div(p.H, rows);
-    const long waves = (items + cap - 1) / cap;
-    const double cost = (double)waves * (rows + 3) * (1.0 + 0.002 * rows);
-    if (cost < best_cost) { best_cost = cost; best_rows = rows; }
+    const int chunks = ceil_div(p.H, rows);
+    const double items = (double)p.B * p.n_strips * chunks;
+    const double walked = (double)chunks * (rows + 3) / p.H;                 // rows walked per image row
+    const double fill = items >= 0.8 * cap ? 1.0 : 0.8 * cap / items;          // too few CTAs: latency is no longer hidden
+    const double cost = walked * fill;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_rows = rows; }
   }
   p.rows_per_item = best_rows;
   p.n_chunks = ceil_div(p.H, best_rows);
