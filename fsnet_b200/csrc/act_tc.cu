@@ -707,6 +707,9 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   // every block ends with 2C fp64 atomics on the same 2C addresses: wide layers get fewer blocks
   const unsigned cap = (unsigned)(49152 / raw->c) > 24u ? (unsigned)(49152 / raw->c) : 24u;
   if (grid > cap) grid = cap;
+  // whole waves: the kernel keeps two blocks per SM resident (126 registers), so 320 or 360 blocks ran as one full wave plus a
+  // second, nearly empty one of the same length (ncu r2c8: 5 loop iterations per warp, the launch twice as long as a block)
+  if (grid > 296u) grid = grid >= 592u ? 592u : 296u;
   if (grid == 0) grid = 1;
   bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();

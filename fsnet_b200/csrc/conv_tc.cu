@@ -555,12 +555,29 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   }
   p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
   const uint32_t stats_bytes = stats ? 2u * Cout * 8u : 0u;
-  int stages = (int)((200u * 1024u - stats_bytes) / p.stage_bytes);
-  p.stages = stages > kMaxStages ? kMaxStages : stages;
-  FSNET_REQUIRE(p.stages >= 2, "fsnet_conv: tile does not fit shared memory");
   uint32_t cols = 32;
   while (cols < 2u * p.BN) cols <<= 1;
   p.tmem_cols = cols;
+  // CTAs per SM.  A tile of a thin layer is a handful of small MMAs between fixed latencies (TMA round trip, commit, accumulator
+  // hand-over, the accumulating epilogue's read of the old gradient): with one CTA per SM the 16..32-channel full-resolution layers
+  // spent ~2600 cycles per 128-pixel tile (ncu r2c10: tensor pipe 4 %, 0.6 warp instructions per cycle and SM, DRAM 10 %).
+  // Several CTAs per SM -- each with a shallower pipeline out of the same shared memory, each with its own TMEM columns -- overlap
+  // those latencies.  FSNET_CONV_OCC: 0 = one CTA per SM (round 1), 1 = thin layers only (default), 2 = every layer that fits.
+  static int occ_env = -1;
+  if (occ_env < 0) { const char* e = getenv("FSNET_CONV_OCC"); occ_env = e ? atoi(e) : 1; }
+  int occ = 1;
+  if (occ_env > 0 && (occ_env >= 2 || p.stage_bytes <= 56u * 1024u)) {
+    for (int o = 4; o >= 2; --o) {
+      const uint32_t per_cta = 216u * 1024u / (uint32_t)o;
+      if (per_cta < stats_bytes + 2048u) continue;
+      const int st = (int)((per_cta - stats_bytes - 2048u) / p.stage_bytes);
+      if (st >= 2 && (uint32_t)o * cols <= 512u && p.total_tiles >= 148 * o * 2) { occ = o; break; }
+    }
+  }
+  const uint32_t smem_budget = occ == 1 ? 200u * 1024u : 216u * 1024u / (uint32_t)occ - 2048u;
+  int stages = (int)((smem_budget - stats_bytes) / p.stage_bytes);
+  p.stages = stages > kMaxStages ? kMaxStages : stages;
+  FSNET_REQUIRE(p.stages >= 2, "fsnet_conv: tile does not fit shared memory");
   p.sbo = 8u * p.KC * 2;
   p.layout_type = p.KC == 64 ? 2u : (p.KC == 32 ? 4u : 6u);
   p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
@@ -616,7 +633,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
 
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int grid = p.total_tiles < sms * occ ? p.total_tiles : sms * occ;
   const size_t smem = (size_t)p.stages * p.stage_bytes + stats_bytes + 1024;
   auto kern = nprod == 3 ? conv_tc_kernel<3> : conv_tc_kernel<1>;
   static bool attr_set[2] = {false, false};
