@@ -49,6 +49,7 @@ struct ConvParams {
   const float* bias;           // [Cout] or null
   double* stats;               // [2*Cout] (sum, sumsq) or null
   int relu;
+  int dbg;                     // diagnostics (FSNET_CONV_DBG, tools/bench_conv.py): 1 skip the accumulate read, 2 skip the stores, 4 skip the statistics
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -215,16 +216,16 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       }
-      if (valid) {
+      if (valid && !(p.dbg & 2)) {
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
           float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.accumulate) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          if (p.accumulate && !(p.dbg & 1)) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
           *dst = o;
         }
       }
-      if (p.stats) {
+      if (p.stats && !(p.dbg & 4)) {
         float sq[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
@@ -583,6 +584,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
   p.out_ct = out->c_total; p.out_coff = out->c_off; p.accumulate = accumulate;
   p.bias = bias; p.stats = stats; p.relu = relu;
+  { static int dbg_env = -1; if (dbg_env < 0) { const char* e = getenv("FSNET_CONV_DBG"); dbg_env = e ? atoi(e) : 0; } p.dbg = dbg_env; }
 
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   if (p.fold) {

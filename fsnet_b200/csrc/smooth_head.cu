@@ -199,6 +199,21 @@ int smooth_check(const float* disp, const float* img, int B, int h, int w, int H
 }
 
 
+// k x k box average of an NCHW image (== F.adaptive_avg_pool2d for H = h*k, monodepth2_decoder.py:219): the colour image of the
+// smoothness term at scale s, computed ONCE per step and scale instead of inside both smoothness kernels.
+__global__ void __launch_bounds__(256) box_pool_kernel(const float* __restrict__ img, int planes, int H, int W, int k, float* __restrict__ out) {
+  const int h = H / k, w = W / k;
+  const unsigned total = (unsigned)planes * h * w;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned x = i % w, t = i / w, y = t % h, pl = t / h;
+  const float* base = img + ((size_t)pl * H + (size_t)y * k) * W + (size_t)x * k;
+  float s = 0.f;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) s += __ldg(base + (size_t)dy * W + dx);
+  out[i] = s * (1.f / (float)(k * k));
+}
+
 // ---- axis-angle + translation -> 4x4 (PoseNet output to cam_T_cam) --------------------------------------------------------------
 // rot_from_axisangle / get_translation_matrix / transformation_from_parameters (monodepth_utils.py:298-337, 31-44, 46-63): Rodrigues with
 // the reference's axis = v / (|v| + 1e-7); M = T * R, or R^T * T(-t) when inverted.  One thread per sample; the backward contracts the
@@ -398,6 +413,15 @@ extern "C" int fsnet_pose_matrix_bwd(const float* axisangle, const float* transl
                                      float* grad_axisangle, float* grad_translation, void* stream) {
   FSNET_REQUIRE(axisangle && translation && grad_T && grad_axisangle && grad_translation && B > 0, "fsnet_pose_matrix_bwd: bad arguments");
   pose_matrix_bwd_kernel<<<ceil_div(B * 6, 64), 64, 0, (cudaStream_t)stream>>>(axisangle, translation, grad_T, B, invert, grad_axisangle, grad_translation);
+  FSNET_LAUNCH_OK();
+  return FSNET_OK;
+}
+
+extern "C" int fsnet_box_pool(const float* img, int planes, int H, int W, int k, float* out, void* stream) {
+  FSNET_REQUIRE(img && out && planes > 0 && k >= 1 && H % k == 0 && W % k == 0 && H >= k && W >= k, "fsnet_box_pool: bad arguments");
+  const size_t total = (size_t)planes * (H / k) * (W / k);
+  FSNET_REQUIRE(total < (1ull << 32), "fsnet_box_pool: tensor too large for 32-bit indexing");
+  box_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, planes, H, W, k, out);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

@@ -103,6 +103,7 @@ class _ReprojectionLoss(torch.autograd.Function):
                         _lib.call("fsnet_mask_sum", mask_c, mdt, _lib.ctypes.c_longlong(B * H * W), acc[i], 1, 4)
             unit = torch.full((1,), 1.0 / S, device=dev, dtype=torch.float32)
             unit_gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
+        colour = []
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
@@ -116,12 +117,19 @@ class _ReprojectionLoss(torch.autograd.Function):
                           motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
                           pred0 if want_log else None)
             h, w = disps[i].shape[-2:]
-            _lib.call("fsnet_smooth_fwd", disps[i], tgt, B, h, w, H, W, float(cfg["smooth_weight"] / (2 ** s)), sums[i], acc[i, 2:])
+            if h == H and w == W:
+                colour.append(tgt)
+            else:                      # colour image of the smoothness term at this scale (adaptive_avg_pool2d), shared with backward
+                pooled = torch.empty(B, 3, h, w, device=dev, dtype=torch.float32)
+                _lib.call("fsnet_box_pool", tgt, B * 3, H, W, H // h, pooled)
+                colour.append(pooled)
+            _lib.call("fsnet_smooth_fwd", disps[i], colour[i], B, h, w, h, w, float(cfg["smooth_weight"] / (2 ** s)), sums[i], acc[i, 2:])
         stats = torch.empty(2 * S + 2, device=dev, dtype=torch.float64)
         _lib.call("fsnet_loss_finalize", acc, S, stats)
         ctx.S, ctx.cfg, ctx.flags, ctx.mdt = S, cfg, flags, mdt
         ctx.shapes = (B, H, W)
         ctx.unit_grads = (unit_gd, unit_gP)
+        ctx.colour = colour
         ctx.save_for_backward(*depths, *disps, tgt, packed, cam, P2c, acc, sums,
                               *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
                               *( [motion_c] if motion_c is not None else []), *[n for n in noise_c if n is not None])
@@ -169,7 +177,7 @@ class _ReprojectionLoss(torch.autograd.Function):
                 g_depths.append(gd)
             h, w = disps[i].shape[-2:]
             gs = torch.empty(disps[i].shape, device=dev, dtype=torch.float32)
-            _lib.call("fsnet_smooth_bwd", disps[i], tgt, B, h, w, H, W, float(cfg["smooth_weight"] / (2 ** s)), sums[i], gout, gs)
+            _lib.call("fsnet_smooth_bwd", disps[i], ctx.colour[i], B, h, w, h, w, float(cfg["smooth_weight"] / (2 ** s)), sums[i], gout, gs)
             g_disps.append(gs)
         gT = [None, None]
         if gP is not None and mei is not None:

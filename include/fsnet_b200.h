@@ -186,6 +186,12 @@ int fsnet_mei_depth(const float* norm, const float* lut, const int* lut_idx, int
                     float* depth, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * k x k box average of `planes` = B*C image planes [H,W] -> [H/k, W/k]: F.adaptive_avg_pool2d(original_image_0, (h, w)) of
+ * monodepth2_decoder.py:219, once per step and scale; fsnet_smooth_* then take the pooled image with H = h, W = w.
+ * ------------------------------------------------------------------------------------------- */
+int fsnet_box_pool(const float* img, int planes, int H, int W, int k, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * edge-aware smoothness on mean-normalised disparity (monodepth2_decoder.py:214-219,294-296,
  * monodepth_utils.py:168-181), forward and backward.  `img` is original_image_0 at full resolution;
  * the 2^s x 2^s box average (adaptive_avg_pool2d) is taken inside the kernel.
