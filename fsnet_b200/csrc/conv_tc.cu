@@ -16,8 +16,8 @@
 // * epilogue: tcgen05.ld -> (+bias) -> fp32 NHWC store, plus per-channel sum / sum-of-squares of the
 //   tile (train-mode BatchNorm statistics) reduced with a shuffle transpose and accumulated in fp64.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 =
-// epilogue (TMEM lane quadrant = warp_id % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 =
+// epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant on alternate 16-column groups).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -26,7 +26,7 @@
 namespace fsnet {
 namespace {
 
-constexpr int kThreads = 192;          // warp 0 TMA producer, 1 MMA issuer, 2-5 epilogue
+constexpr int kThreads = 320;          // warp 0 TMA producer, 1 MMA issuer, 2-9 epilogue
 constexpr int kMaxStages = 8;
 
 struct ConvParams {
@@ -49,6 +49,14 @@ struct ConvParams {
   const float* bias;           // [Cout] or null
   double* stats;               // [2*Cout] (sum, sumsq) or null
   int relu;
+  // thread-block cluster of cm x cn CTAs working on cm pixel tiles x cn channel tiles at once: the A tile (pixels) is multicast to the
+  // cn CTAs of a cluster row, the B tile (weights) to the cm CTAs of a cluster column (L2 -> SM delivery bounds these kernels)
+  int cm, cn, super_n, total_super, m_tiles;
+  // halo path (conv_halo_kernel): 3x3 / stride 1, 64-channel K chunks.  The (TH+2) x (TW+2) halo of a 128-pixel tile is loaded ONCE per
+  // chunk and plane; tap (r, s) is the same shared-memory tile read from a start address shifted by whole pixels.
+  // halo = 1: 16 rows x 8 pixels (box [64, 10, 18]);  halo = 2: 8 rows x 16 pixels, y fastest in shared memory (box [64 ch, 10 rows, 18 cols])
+  int halo, a_stages, b_stages;
+  uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes, a_tx, b_tx;
   int dbg;                     // diagnostics (FSNET_CONV_DBG, tools/bench_conv.py): 1 skip the accumulate read, 2 skip the stores, 4 skip the statistics
 };
 
@@ -98,6 +106,29 @@ __device__ __forceinline__ void tma_load_2d_elect(void* dst, const CUtensorMap* 
       "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n}\n"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variants: the box lands at the same shared-memory offset of every CTA in `mask` and completes on each one's own barrier
+__device__ __forceinline__ void tma_load_4d_mc_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc_elect(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "{\n.reg .pred pe;\nelect.sync _|pe, 0xffffffff;\n"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n}\n"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -123,6 +154,55 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc
       "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One 64-element K chunk of a stage in ONE statement: a single election, then the 4 (NPROD = 1) or 12 (NPROD = 3: hi*hi, lo*hi,
+// hi*lo) K-steps back to back, descriptor advances (32 B = 2 units per K-step) done in PTX.  The tensor pipe's queue is shallow:
+// whatever the issuing warp executes between two tcgen05.mma (an election per MMA, 64-bit descriptor assembly per tap: ~400 cycles
+// per stage in the first version) showed up as idle pipe time on top of the MMAs (profiles/r2_conv_halo.md, DBG ablation).
+template <int NPROD>
+__device__ __forceinline__ void umma_chunk_elect(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                 uint32_t idesc, uint32_t accumulate_first) {
+  if (NPROD == 3) {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pz, pt;\n"
+        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pz, %6, 0;\n"
+        "setp.eq.b32 pt, %6, %6;\n"
+        "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
+        "add.u64 al1, %2, 2;\n add.u64 al2, %2, 4;\n add.u64 al3, %2, 6;\n"
+        "add.u64 bh1, %3, 2;\n add.u64 bh2, %3, 4;\n add.u64 bh3, %3, 6;\n"
+        "add.u64 bl1, %4, 2;\n add.u64 bl2, %4, 4;\n add.u64 bl3, %4, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, pz;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bh3, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al1, bh1, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al2, bh2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al3, bh3, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bl1, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bl2, %5, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bl3, %5, pt;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred pe, pz, pt;\n"
+        ".reg .b64 ah1, ah2, ah3, bh1, bh2, bh3;\n"
+        "elect.sync _|pe, 0xffffffff;\n"
+        "setp.ne.b32 pz, %4, 0;\n"
+        "setp.eq.b32 pt, %4, %4;\n"
+        "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
+        "add.u64 bh1, %2, 2;\n add.u64 bh2, %2, 4;\n add.u64 bh3, %2, 6;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pz;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %3, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %3, pt;\n"
+        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bh3, %3, pt;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(b_hi), "r"(idesc), "r"(accumulate_first) : "memory");
+  }
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n"
@@ -130,6 +210,15 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
       "elect.sync _|pe, 0xffffffff;\n"
       "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
       "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrival on the barrier at this offset in every CTA of `mask` (frees a multicast stage in all its producers)
+__device__ __forceinline__ void umma_commit_mc_elect(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+      "}\n" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -181,27 +270,78 @@ __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
   return v[0];      // column index = ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
 }
 
-// Epilogue of both convolution kernels, run by four warps (TMEM lane quadrant = warp % 4): accumulator ->
-// (+bias, ReLU) -> fp32 NHWC store (optionally accumulating) + per-channel sum / sum-of-squares of the tile.
-// `first_tid` = threadIdx.x of the first epilogue thread (for the final statistics flush).
+// Epilogue of the convolution kernels, run by EIGHT warps (2..9): accumulator -> (+bias, ReLU) -> fp32 NHWC store (optionally
+// accumulating) + per-channel sum / sum-of-squares of the tile.  A warp reads the TMEM lane quadrant warp % 4 (its 32 pixels);
+// the two warps of a quadrant take alternate 16-column groups.  With four warps and shared-memory fp64 atomics for the statistics
+// the epilogue (~12 K cycles per 128 x 64 tile, 38 % of it in the atomics' compare-and-swap loops) was slower than the tile's
+// MMAs (~5.4 K cycles) and bounded the halo kernel (ncu: profiles/r2_conv_halo.md).
+// Statistics: every (quadrant, column) has ONE owning lane that adds its per-tile column sum (shuffle tree over 32 pixels, fp32,
+// deterministic) into a private fp64 slot -- no atomics, no order dependence inside the CTA -- and the slots are reduced over
+// the quadrants and flushed to global memory (fp64 atomics) when the CTA moves to another channel tile and at the end.
+constexpr int kEpiWarps = 8;
+__device__ __forceinline__ void epilogue_flush_stats(const ConvParams& p, double* s_slots, int nt, int tid_e) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps: all slots of this channel tile are written
+  if (tid_e < 2 * p.BN) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s += s_slots[q * 2 * p.BN + tid_e]; s_slots[q * 2 * p.BN + tid_e] = 0.0; }
+    const int ch = tid_e < p.BN ? nt * p.BN + tid_e : p.Cout + nt * p.BN + (tid_e - p.BN);
+    if (s != 0.0) atomicAdd(p.stats + ch, s);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
 __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, int lane, uint32_t tmem_base,
-                                               uint64_t* tmem_full, uint64_t* tmem_empty, double* s_stats, int first_tid) {
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, double* s_slots) {
   const int q = warp & 3;                         // TMEM lane quadrant of this warp
+  const int half = (warp - 2) >> 2;               // which of the quadrant's two warps: 16-column groups half, half + 2, ...
+  const int tid_e = (warp - 2) * 32 + lane;
   const int m = q * 32 + lane;                    // row of the tile = pixel
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+  int cur_nt = -1;
+  // per-lane running column sums of the CTA's tiles (this warp's 16-column groups: at most 4 for BN = 128): even lanes own one
+  // column per group.  fp32 over a handful of per-tile partials, in a fixed order; converted to fp64 only when flushed.
+  float run_s[4] = {0.f, 0.f, 0.f, 0.f}, run_q[4] = {0.f, 0.f, 0.f, 0.f};
+  const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  auto spill_running = [&]() {                    // running sums -> this quadrant's fp64 slots (no other writer of these slots)
+    if ((lane & 1) == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c0 = half * 16 + g * 32;
+        if (c0 < p.BN) {
+          double* slot = s_slots + q * 2 * p.BN + c0 + col;
+          slot[0] = (double)run_s[g];
+          slot[p.BN] = (double)run_q[g];
+        }
+        run_s[g] = 0.f; run_q[g] = 0.f;
+      }
+    }
+  };
+  const int csz = p.cm * p.cn;
+  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
+  const int rank_m = crank / p.cn, rank_n = crank - rank_m * p.cn;
+  for (int sup = blockIdx.x / csz; sup < p.total_super; sup += gridDim.x / csz, ++it) {
     const int acc = it & 1;
-    int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+    const int snt = sup % p.super_n;
+    const int nt = snt * p.cn + rank_n, mt = (sup / p.super_n) * p.cm + rank_m;      // mt >= m_tiles: ghost tile of a partial cluster
+    if (p.stats && nt != cur_nt) {
+      if (cur_nt >= 0) { spill_running(); epilogue_flush_stats(p, s_slots, cur_nt, tid_e); }
+      cur_nt = nt;
+    }
     int tx = mt % p.tiles_x; int rest = mt / p.tiles_x;
     int ty = rest % p.tiles_y; int img = rest / p.tiles_y;
-    const int py = m / p.TW, px = m - py * p.TW;
+    int py = m / p.TW, px = m - py * p.TW;
+    if (p.halo == 2) { px = m / p.TH; py = m - px * p.TH; }     // groups of 8 accumulator rows run down a column
     const int oy = ty * p.TH + py, ox = tx * p.TW + px;
-    const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo;
+    const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo && mt < p.m_tiles;
     float* orow = p.out + (((size_t)img * p.out_ph + oy + p.out_ring) * p.out_pw + ox + p.out_ring) * p.out_ct + p.out_coff + nt * p.BN;
     mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = half * 16 + g * 32;
+      if (c0 >= p.BN) break;
       uint32_t raw[16];
       tmem_ld16(taddr + c0, raw);
       tmem_ld_wait();
@@ -229,40 +369,27 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
         float sq[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { v[j] = valid ? v[j] : 0.f; sq[j] = v[j] * v[j]; }
-        float s1 = colsum16(v, lane), s2 = colsum16(sq, lane);
-        if ((lane & 1) == 0) {
-          int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          // fp64 from here on: the per-tile column sums (128 pixels, shuffle tree, deterministic) are accumulated over the CTA's
-          // tiles in double.  With fp32 shared-memory atomics the order-dependent rounding of sum(x^2) was amplified by the
-          // cancellation in E[x^2] - mean^2: forward maps differed by ~1e-5 from run to run (tools/diag_determinism2.py)
-          atomicAdd(&s_stats[nt * p.BN + c0 + col], (double)s1);
-          atomicAdd(&s_stats[p.Cout + nt * p.BN + c0 + col], (double)s2);
-        }
+        // (order-dependent fp32 atomics made the forward maps differ by ~1e-5 from run to run through the cancellation in
+        // E[x^2] - mean^2, tools/diag_determinism2.py: everything here runs in a fixed order; fp64 from the flush on)
+        run_s[g] += colsum16(v, lane);
+        run_q[g] += colsum16(sq, lane);
       }
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
   }
-  if (p.stats) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-    for (int i = threadIdx.x - first_tid; i < 2 * p.Cout; i += 128) {
-      const double s = s_stats[i];
-      if (s != 0.0) atomicAdd(p.stats + i, s);
-    }
-  }
+  if (p.stats && cur_nt >= 0) { spill_running(); epilogue_flush_stats(p, s_slots, cur_nt, tid_e); }
 }
 
 template <int NPROD>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const ConvParams p) {
+__device__ __forceinline__ void conv_tc_body(const CUtensorMap& map_a_hi, const CUtensorMap& map_a_lo,
+                                             const CUtensorMap& map_b_hi, const CUtensorMap& map_b_lo, const ConvParams& p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  // dynamic smem: [stages * stage_bytes | 2*Cout doubles of statistics]
+  // dynamic smem: [stages * stage_bytes | 4 x 2*BN fp64 statistics slots]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   double* s_stats = reinterpret_cast<double*>(smem + (size_t)p.stages * p.stage_bytes);
 
@@ -273,23 +400,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
     if (NPROD == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
-    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    // a stage is free once EVERY CTA of the cluster has retired its MMAs on it (the receivers of this CTA's multicasts are its
+    // cluster row and column; waiting for the whole cluster also keeps a fast neighbour from arriving twice in one phase)
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], p.cm * p.cn); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
-  if (p.stats) for (int i = threadIdx.x; i < 2 * p.Cout; i += kThreads) s_stats[i] = 0.0;
+  if (p.stats) for (int i = threadIdx.x; i < 8 * p.BN; i += kThreads) s_stats[i] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const int csz = p.cm * p.cn;
+  const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
+  const int rank_m = crank / p.cn, rank_n = crank - rank_m * p.cn;
+  // cluster row = the cn CTAs on the same pixel tile (share A), cluster column = the cm CTAs on the same channel tile (share B)
+  const uint16_t mask_row = (uint16_t)(((1u << p.cn) - 1u) << (rank_m * p.cn));
+  uint16_t mask_col = 0;
+  for (int i = 0; i < p.cm; ++i) mask_col |= (uint16_t)(1u << (i * p.cn + rank_n));
+  if (csz > 1) cluster_sync_all();               // every CTA's barriers are initialised before anything arrives on them remotely
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
     {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const bool mc_a = p.cn > 1, mc_b = p.cm > 1;
+      // loads of the shared operands take turns: K-iteration kit's A tile is fetched (and multicast) by the CTA of the cluster row
+      // with rank_n == kit % cn, its B tile by the CTA of the cluster column with rank_m == kit % cm
+      auto load_a = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int kit, int c0, int c1, int c2, int c3) {
+        if (!mc_a) tma_load_4d_elect(dst, map, bar, c0, c1, c2, c3);
+        else if (kit % p.cn == rank_n) tma_load_4d_mc_elect(dst, map, bar, c0, c1, c2, c3, mask_row);
+      };
+      auto load_b3 = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int kit, int c0, int c1, int c2) {
+        if (!mc_b) tma_load_3d_elect(dst, map, bar, c0, c1, c2);
+        else if (kit % p.cm == rank_m) tma_load_3d_mc_elect(dst, map, bar, c0, c1, c2, mask_col);
+      };
+      auto load_b2 = [&](void* dst, const CUtensorMap* map, uint64_t* bar, int kit, int c0, int c1) {
+        if (!mc_b) tma_load_2d_elect(dst, map, bar, c0, c1);
+        else if (kit % p.cm == rank_m) tma_load_2d_mc_elect(dst, map, bar, c0, c1, mask_col);
+      };
+      for (int sup = blockIdx.x / csz; sup < p.total_super; sup += gridDim.x / csz) {
+        const int snt = sup % p.super_n;
+        const int nt = snt * p.cn + rank_n, mt = (sup / p.super_n) * p.cm + rank_m;   // ghost tiles (mt >= m_tiles) load image N: zero fill
         int tx = mt % p.tiles_x; int rest = mt / p.tiles_x;
         int ty = rest % p.tiles_y; int img = rest / p.tiles_y;
         const int x_base = tx * p.TW * p.stride - p.pad + p.org;
@@ -298,35 +451,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int kit = 0; kit < p.kiters; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * p.stage_bytes;
-          mbar_expect_tx_elect(&full_bar[stage], p.tx_bytes);
+          uint64_t* fb = &full_bar[stage];
+          mbar_expect_tx_elect(fb, p.tx_bytes);
           if (p.fold == 2) {
             // A: the whole (TH+KH-1) x TW halo tile of 64-element fat-pixel slice cc, loaded ONCE for all kernel rows
             const int xo = tx * p.TW, yo = ty * p.TH;
-            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], kit * 64, xo, yo, img);
+            load_a(st, &map_a_hi, fb, kit, kit * 64, xo, yo, img);
             for (int rr = 0; rr < p.KH; ++rr)
-              tma_load_3d_elect(st + p.a_bytes + rr * p.b_each, &map_b_hi, &full_bar[stage], kit * 64, rr, nt * p.BN);
+              load_b3(st + p.a_bytes + rr * p.b_each, &map_b_hi, fb, kit, kit * 64, rr, nt * p.BN);
             if (NPROD == 3) {
               uint8_t* lo = st + p.a_bytes + p.b_bytes;
-              tma_load_4d_elect(lo, &map_a_lo, &full_bar[stage], kit * 64, xo, yo, img);
+              load_a(lo, &map_a_lo, fb, kit, kit * 64, xo, yo, img);
               for (int rr = 0; rr < p.KH; ++rr)
-                tma_load_3d_elect(lo + p.a_bytes + rr * p.b_each, &map_b_lo, &full_bar[stage], kit * 64, rr, nt * p.BN);
+                load_b3(lo + p.a_bytes + rr * p.b_each, &map_b_lo, fb, kit, kit * 64, rr, nt * p.BN);
             }
           } else if (p.fold) {
             // A: 64-element slice cc of the "fat pixel" row (KW taps x Cin channels, contiguous in NHWC) of kernel row r
             const int xo = tx * p.TW, yo = ty * p.TH * p.stride + r;
-            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], cc * 64, xo, yo, img);
-            tma_load_3d_elect(st + p.a_bytes, &map_b_hi, &full_bar[stage], cc * 64, r, nt * p.BN);
+            load_a(st, &map_a_hi, fb, kit, cc * 64, xo, yo, img);
+            load_b3(st + p.a_bytes, &map_b_hi, fb, kit, cc * 64, r, nt * p.BN);
             if (NPROD == 3) {
-              tma_load_4d_elect(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * 64, xo, yo, img);
-              tma_load_3d_elect(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], cc * 64, r, nt * p.BN);
+              load_a(st + p.a_bytes + p.b_bytes, &map_a_lo, fb, kit, cc * 64, xo, yo, img);
+              load_b3(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, fb, kit, cc * 64, r, nt * p.BN);
             }
             if (++cc == p.cchunks) { cc = 0; ++r; }
           } else {
-            tma_load_4d_elect(st, &map_a_hi, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
-            tma_load_2d_elect(st + p.a_bytes, &map_b_hi, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+            load_a(st, &map_a_hi, fb, kit, cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+            load_b2(st + p.a_bytes, &map_b_hi, fb, kit, tap * p.Cin + cc * p.KC, nt * p.BN);
             if (NPROD == 3) {
-              tma_load_4d_elect(st + p.a_bytes + p.b_bytes, &map_a_lo, &full_bar[stage], cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
-              tma_load_2d_elect(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, &full_bar[stage], tap * p.Cin + cc * p.KC, nt * p.BN);
+              load_a(st + p.a_bytes + p.b_bytes, &map_a_lo, fb, kit, cc * p.KC, x_base + sx * p.dil, y_base + r * p.dil, img);
+              load_b2(st + 2 * p.a_bytes + p.b_bytes, &map_b_lo, fb, kit, tap * p.Cin + cc * p.KC, nt * p.BN);
             }
             if (++cc == p.cchunks) { cc = 0; ++tap; if (++sx == p.KW) { sx = 0; ++r; } }
           }
@@ -351,7 +505,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (ks > 3) umma_bf16_elect(d, a + 6, b + 6, idesc, 1);
       };
       int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint16_t mask_free = (uint16_t)((1u << csz) - 1u);
+      const uint64_t desc0 = make_desc(smem_u32(smem), p.sbo, p.layout_type);
+      const uint32_t stage16 = p.stage_bytes >> 4, ab16 = p.a_bytes >> 4, lo16 = (p.a_bytes + p.b_bytes) >> 4;
+      for (int sup = blockIdx.x / csz; sup < p.total_super; sup += gridDim.x / csz, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -360,7 +517,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          if (p.fold == 2) {
+          if (!p.fold && ksteps == 4) {
+            // one election for the 4 / 12 MMAs of the stage, descriptors by 64-bit adds on a base descriptor
+            const uint64_t a_hi = desc0 + (uint64_t)((uint32_t)stage * stage16);
+            const uint64_t a_lo = a_hi + lo16;
+            umma_chunk_elect<NPROD>(d_tmem, a_hi, a_lo, a_hi + ab16, a_lo + ab16, idesc, kit != 0);
+          } else if (p.fold == 2) {
             // the last 64-element slice of a fat pixel is partly padding (zero weights): skip its dead K-steps
             const int ks2 = min(ksteps, (p.KW * p.Cin - kit * 64 + 15) >> 4);
             const uint32_t lo = st + p.a_bytes + p.b_bytes;
@@ -389,7 +551,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               group(d_tmem, a_hi, b_lo, ks1, false);
             }
           }
-          umma_commit_elect(&empty_bar[stage]);     // frees the smem stage when these MMAs retire
+          // frees the smem stage when these MMAs retire (in every CTA that multicasts into it)
+          if (csz > 1) umma_commit_mc_elect(&empty_bar[stage], mask_free); else umma_commit_elect(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit_elect(&tmem_full[acc]);         // accumulator complete
@@ -397,7 +560,155 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else {
     // ===================== epilogue =====================
-    epilogue_warps(p, warp, lane, tmem_base, tmem_full, tmem_empty, s_stats, 64);
+    epilogue_warps(p, warp, lane, tmem_base, tmem_full, tmem_empty, s_stats);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (csz > 1) cluster_sync_all();               // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+}
+
+#define FSNET_CONV_KERNEL(name, cluster_attr)                                                                              \
+  template <int NPROD>                                                                                                     \
+  __global__ void cluster_attr __launch_bounds__(kThreads, 3)                                                              \
+  name(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,                         \
+       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {   \
+    conv_tc_body<NPROD>(map_a_hi, map_a_lo, map_b_hi, map_b_lo, p);                                                        \
+  }
+FSNET_CONV_KERNEL(conv_tc_kernel, )
+FSNET_CONV_KERNEL(conv_tc_kernel_c2, __cluster_dims__(2, 1, 1))
+FSNET_CONV_KERNEL(conv_tc_kernel_c4, __cluster_dims__(4, 1, 1))
+FSNET_CONV_KERNEL(conv_tc_kernel_c8, __cluster_dims__(8, 1, 1))
+#undef FSNET_CONV_KERNEL
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Halo variant for 3x3 / stride-1 layers with >= 64 input channels.
+//
+// Why: the delivery of TMA bytes into an SM is capped near 32 B/clk (tools/ubench/mc_bw.cu: 9-10 TB/s over 148 SMs, the same for
+// unicast and for cluster multicast), and the per-tap kernel above needs 85-128 B/clk to keep the tensor pipe busy (it re-reads the
+// A tile for each of the nine taps).  Here the 18 x 10 pixel halo of a 16 x 8 pixel tile is loaded once per 64-channel chunk and
+// plane; tap (r, s) is that same tile seen through an operand descriptor whose start address is shifted by (r * 10 + s) pixels and
+// whose 8-row group stride is the halo pitch (1280 B).  The 128-byte swizzle is a function of the shared-memory ADDRESS bits, so
+// shifted descriptors read what TMA wrote (checked on the B200 by tools/ubench/umma_shift.cu for all nine shifts).
+// A and the per-tap weight tiles ride in two separate rings with their own producer warps (0: weights, 10: halo tiles).
+// ---------------------------------------------------------------------------------------------------------------------------------
+constexpr int kHaloThreads = 352;      // warp 0 weight producer, 1 MMA issuer, 2-9 epilogue, 10 halo producer
+constexpr int kHaloMaxA = 4, kHaloMaxB = 8;
+
+template <int NPROD>
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kHaloMaxA], a_empty[kHaloMaxA], b_full[kHaloMaxB], b_empty[kHaloMaxB], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  // dynamic smem: [a_stages * a_stage_bytes | b_stages * b_stage_bytes | 4 x 2*BN fp64 statistics slots]
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  double* s_stats = reinterpret_cast<double*>(smem_b + (size_t)p.b_stages * p.b_stage_bytes);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (NPROD == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, p.tmem_cols);
+  if (p.stats) for (int i = threadIdx.x; i < 8 * p.BN; i += kHaloThreads) s_stats[i] = 0.0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (p.dbg & 32) {
+    // diagnostics: prologue and teardown only
+  } else if (warp == 10) {
+    // ===================== halo producer: one box per (tile, 64-channel chunk, plane) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
+      const int ty = rest % p.tiles_y; const int img = rest / p.tiles_y;
+      const int x0 = tx * p.TW - 1 + p.org, y0 = ty * p.TH - 1 + p.org;
+      const int c1 = p.halo == 2 ? y0 : x0, c2 = p.halo == 2 ? x0 : y0;          // halo 2: the tensor map's dimension 1 is the image row
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * p.a_stage_bytes;
+        if (p.dbg & 8) { if (lane == 0) mbar_arrive(&a_full[stage]); __syncwarp(); }      // diagnostics: no loads
+        else {
+        mbar_expect_tx_elect(&a_full[stage], p.a_tx);
+        tma_load_4d_elect(st, &map_a_hi, &a_full[stage], cc * 64, c1, c2, img);
+        if (NPROD == 3) tma_load_4d_elect(st + p.a_plane_bytes, &map_a_lo, &a_full[stage], cc * 64, c1, c2, img);
+        }
+        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
+    // ===================== weight producer: one [BN x 64] box per (chunk, tap, plane) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          uint8_t* st = smem_b + (size_t)stage * p.b_stage_bytes;
+          if (p.dbg & 8) { if (lane == 0) mbar_arrive(&b_full[stage]); __syncwarp(); }
+          else {
+          mbar_expect_tx_elect(&b_full[stage], p.b_tx);
+          tma_load_2d_elect(st, &map_b_hi, &b_full[stage], tap * p.Cin + cc * 64, nt * p.BN);
+          if (NPROD == 3) tma_load_2d_elect(st + p.b_plane_bytes, &map_b_lo, &b_full[stage], tap * p.Cin + cc * 64, nt * p.BN);
+          }
+          if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, elected lane; see conv_tc_body) =====================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    // descriptors = base descriptor + byte offset / 16 (the address field holds address >> 4 and shared memory ends below 2^18):
+    // a stage or a tap is one 64-bit add.  Halo tile: 8-pixel groups 10 pixels (1280 B) apart; weights: 8 rows 1024 B apart.
+    const uint64_t a_base = make_desc(smem_u32(smem), 10u * 128u, 2u);
+    const uint64_t b_base = make_desc(smem_u32(smem_b), 1024u, 2u);
+    const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4, a_lo16 = p.a_plane_bytes >> 4, b_lo16 = p.b_plane_bytes >> 4;
+    // halo 1: pixel (y, x) of the halo sits at (y * 10 + x) * 128 B; halo 2: at (x * 10 + y) * 128 B  (units of 16 B below)
+    const uint32_t row16 = p.halo == 2 ? 8u : 80u, col16 = p.halo == 2 ? 80u : 8u;
+    int as = 0, bs = 0; uint32_t aph = 0, bph = 0; int it = 0;
+    uint32_t a_off16 = 0, b_off16 = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int cc = 0; cc < p.cchunks; ++cc) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          const uint64_t a_hi = a_base + (uint64_t)(a_off16 + (uint32_t)(tap / 3) * row16 + (uint32_t)(tap % 3) * col16);
+          const uint64_t b_hi = b_base + (uint64_t)b_off16;
+          if (!(p.dbg & 16))                                           // diagnostics: 16 = no MMAs
+            umma_chunk_elect<NPROD>(d_tmem, a_hi, a_hi + a_lo16, b_hi, b_hi + b_lo16, idesc, (cc | tap) != 0);
+          umma_commit_elect(&b_empty[bs]);
+          b_off16 += b_stage16;
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; b_off16 = 0; }
+        }
+        umma_commit_elect(&a_empty[as]);
+        a_off16 += a_stage16;
+        if (++as == p.a_stages) { as = 0; aph ^= 1; a_off16 = 0; }
+      }
+      umma_commit_elect(&tmem_full[acc]);
+    }
+  } else {
+    epilogue_warps(p, warp, lane, tmem_base, tmem_full, tmem_empty, s_stats);
   }
   tc_fence_before();
   __syncthreads();
@@ -491,6 +802,20 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   FSNET_REQUIRE(out->c_off % 4 == 0 && out->c_total % 4 == 0, "fsnet_conv: output channel slice must be 16-byte aligned");
   p.org = use_ring ? in->ring : 0;
   pick_tile(p.Ho, p.Wo, p.TH, p.TW);
+  // halo path (conv_halo_kernel) for 3x3 / stride-1 layers with 64-channel K chunks: 16 x 8 or 8 x 16 pixel tiles, whichever wastes
+  // fewer accumulator rows on this map size; small maps (6 x 20) stay on the per-tap path.  FSNET_CONV_HALO=0 switches it off.
+  static int halo_env = -1;
+  if (halo_env < 0) { const char* e = getenv("FSNET_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
+  p.halo = 0;
+  if (halo_env && KH == 3 && KW == 3 && stride == 1 && pad == 1 && Cin % 64 == 0 && (!use_ring || in->ring == 1)) {
+    auto eff = [&](int th, int tw) { return ((double)p.Ho / (ceil_div(p.Ho, th) * th)) * ((double)p.Wo / (ceil_div(p.Wo, tw) * tw)); };
+    const double ex = eff(16, 8), ey = eff(8, 16);
+    const double cur = ((double)p.Ho / (ceil_div(p.Ho, p.TH) * p.TH)) * ((double)p.Wo / (ceil_div(p.Wo, p.TW) * p.TW)) * (p.TH * p.TW / 128.0);
+    if ((ex > ey ? ex : ey) >= 0.7 * cur) {
+      p.halo = (halo_env == 3 || (halo_env != 2 && ex >= ey)) ? 1 : 2;      // FSNET_CONV_HALO = 2 / 3: force one orientation (diagnostics)
+      p.TH = p.halo == 1 ? 16 : 8; p.TW = p.halo == 1 ? 8 : 16;
+    }
+  }
   p.tiles_x = ceil_div(p.Wo, p.TW); p.tiles_y = ceil_div(p.Ho, p.TH);
   p.BN = Cout <= 128 ? Cout : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16)));
   FSNET_REQUIRE(Cout % p.BN == 0, "fsnet_conv: cannot tile Cout=%d", Cout);
@@ -555,7 +880,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     p.tx_bytes = (nprod == 3 ? 2u : 1u) * (rows * 128u + (uint32_t)KH * p.BN * 128u);
   }
   p.stage_bytes = (nprod == 3 ? 2u : 1u) * (p.a_bytes + p.b_bytes);
-  const uint32_t stats_bytes = stats ? 2u * Cout * 8u : 0u;
+  const uint32_t stats_bytes = stats ? 64u * (uint32_t)p.BN : 0u;      // 4 quadrants x (sum, sum of squares) x BN fp64 slots
   uint32_t cols = 32;
   while (cols < 2u * p.BN) cols <<= 1;
   p.tmem_cols = cols;
@@ -568,12 +893,101 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   if (occ_env < 0) { const char* e = getenv("FSNET_CONV_OCC"); occ_env = e ? atoi(e) : 1; }
   int occ = 1;
   if (occ_env > 0 && (occ_env >= 2 || p.stage_bytes <= 56u * 1024u)) {
-    for (int o = 4; o >= 2; --o) {
+    for (int o = 3; o >= 2; --o) {                     // 320 threads x ~66 registers: three CTAs fill the register file
       const uint32_t per_cta = 216u * 1024u / (uint32_t)o;
       if (per_cta < stats_bytes + 2048u) continue;
       const int st = (int)((per_cta - stats_bytes - 2048u) / p.stage_bytes);
       if (st >= 2 && (uint32_t)o * cols <= 512u && p.total_tiles >= 148 * o * 2) { occ = o; break; }
     }
+  }
+  // Thread-block clusters with TMA multicast.  These kernels are bound by the delivery of TMA bytes from L2 into the SMs (one
+  // 64-channel layer re-reads its input 9x and its weights once per 128-pixel tile: ~9.4 TB/s delivered at cfg2a).
+  // A cluster of cm x cn CTAs works on cm pixel tiles x cn channel tiles; each A box is fetched once per cluster row and each B
+  // box once per cluster column.  Shape = the one that minimises the bytes a CTA has to fetch itself (a/cn + b/cm) without
+  // padding the pixel-tile count by more than 10 % ghost tiles.  FSNET_CONV_MC = largest cluster (1 = off).
+  static int mc_env = -1;
+  if (mc_env < 0) { const char* e = getenv("FSNET_CONV_MC"); mc_env = e ? atoi(e) : 1; }
+  p.cm = p.cn = 1;
+  p.m_tiles = N * p.tiles_x * p.tiles_y;
+  if (mc_env > 1) {
+    const double a = (double)p.a_bytes, b = (double)p.b_bytes;
+    double best = a + b;
+    for (int cn = 1; cn <= 8; cn *= 2) {
+      if (cn > p.n_tiles || p.n_tiles % cn) continue;
+      for (int cm = 1; cm <= 8; cm *= 2) {
+        if (cm * cn > mc_env || cm * cn > 8 || cm * cn == 1 || cm > p.m_tiles) continue;
+        const double ghost = (double)(ceil_div(p.m_tiles, cm) * cm) / p.m_tiles;
+        if (ghost > 1.1) continue;
+        const double cost = (a / cn + b / cm) * ghost;
+        if (cost < best * 0.95) { best = cost; p.cm = cm; p.cn = cn; }
+      }
+    }
+  }
+  p.super_n = p.n_tiles / p.cn;
+  p.total_super = ceil_div(p.m_tiles, p.cm) * p.super_n;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  if (p.halo) {
+    const uint32_t planes = nprod == 3 ? 2u : 1u;
+    p.fold = 0; p.KC = 64; p.cchunks = Cin / 64; p.kiters = 9 * p.cchunks;
+    p.cm = p.cn = 1; p.super_n = p.n_tiles; p.total_super = p.total_tiles;
+    p.a_plane_bytes = 23552u;                          // 18 x 10 pixels x 128 B = 23040, rounded up to the 1024-byte swizzle atom
+    p.a_stage_bytes = planes * p.a_plane_bytes; p.a_tx = planes * 23040u;
+    p.b_plane_bytes = (uint32_t)p.BN * 128u;
+    p.b_stage_bytes = planes * p.b_plane_bytes; p.b_tx = p.b_stage_bytes;
+    const uint32_t budget = 220u * 1024u - stats_bytes;
+    p.a_stages = nprod == 3 ? 2 : 3;
+    { static int as_env = -1; if (as_env < 0) { const char* e = getenv("FSNET_CONV_HALO_ASTAGES"); as_env = e ? atoi(e) : 0; } if (as_env) p.a_stages = as_env; }
+    if (p.a_stages > p.cchunks + 1) p.a_stages = p.cchunks + 1;
+    int bst = (int)((budget - (uint32_t)p.a_stages * p.a_stage_bytes) / p.b_stage_bytes);
+    p.b_stages = bst > kHaloMaxB ? kHaloMaxB : bst;
+    FSNET_REQUIRE(p.b_stages >= 2, "fsnet_conv: halo tile does not fit shared memory");
+    p.stages = p.a_stages;
+    p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
+    p.out_ct = out->c_total; p.out_coff = out->c_off; p.accumulate = accumulate;
+    p.bias = bias; p.stats = stats; p.relu = relu;
+    { static int dbg_env = -1; if (dbg_env < 0) { const char* e = getenv("FSNET_CONV_DBG"); dbg_env = e ? atoi(e) : 0; } p.dbg = dbg_env; }
+    CUtensorMap ma[2], mb[2];
+    for (uint32_t pl = 0; pl < planes; ++pl) {
+      if (p.halo == 1) {
+        int rc = encode_act_map(&ma[pl], in, (int)pl, use_ring, 64, 10, 18, 1, "fsnet_conv(halo)");
+        if (rc) return rc;
+      } else {
+        const int pw = in->w + 2 * in->ring, ph = in->h + 2 * in->ring;
+        const size_t plane_elems = (size_t)in->n * ph * pw * in->c_total;
+        const char* base = (const char*)in->ptr + (plane_elems * pl + in->c_off) * 2;
+        if (!use_ring) base += ((size_t)in->ring * pw + in->ring) * in->c_total * 2;
+        const int Wm = use_ring ? pw : in->w, Hm = use_ring ? ph : in->h;
+        cuuint64_t dim[4] = {(cuuint64_t)in->c, (cuuint64_t)Hm, (cuuint64_t)Wm, (cuuint64_t)in->n};
+        cuuint64_t str[3] = {(cuuint64_t)pw * in->c_total * 2, (cuuint64_t)in->c_total * 2, (cuuint64_t)ph * pw * in->c_total * 2};
+        cuuint32_t box[4] = {64, 10, 18, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        FSNET_REQUIRE(((uintptr_t)base & 15) == 0, "fsnet_conv(halo): activation view is not 16-byte aligned");
+        CUresult r = enc(&ma[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv(halo): cuTensorMapEncodeTiled(A, rows fastest) failed with %d", (int)r);
+      }
+      const int Ktot = 9 * Cin;
+      cuuint64_t bdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+      cuuint64_t bstr[1] = {(cuuint64_t)Ktot * 2};
+      cuuint32_t bbox[2] = {64, (cuuint32_t)p.BN};
+      cuuint32_t bes[2] = {1, 1};
+      CUresult r = enc(&mb[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(pl ? w_lo : w_hi), bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv(halo): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    if (planes == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + stats_bytes + 1024;
+    auto kern = nprod == 3 ? conv_halo_kernel<3> : conv_halo_kernel<1>;
+    static bool halo_attr[2] = {false, false};
+    if (!halo_attr[nprod == 3]) {
+      FSNET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      halo_attr[nprod == 3] = true;
+    }
+    kern<<<grid, kHaloThreads, smem, (cudaStream_t)stream>>>(ma[0], ma[1], mb[0], mb[1], p);
+    FSNET_LAUNCH_OK();
+    return FSNET_OK;
   }
   const uint32_t smem_budget = occ == 1 ? 200u * 1024u : 216u * 1024u / (uint32_t)occ - 2048u;
   int stages = (int)((smem_budget - stats_bytes) / p.stage_bytes);
@@ -633,15 +1047,39 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv: cuTensorMapEncodeTiled(B lo) failed with %d", (int)r);
   }
 
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int grid = p.total_tiles < sms * occ ? p.total_tiles : sms * occ;
   const size_t smem = (size_t)p.stages * p.stage_bytes + stats_bytes + 1024;
-  auto kern = nprod == 3 ? conv_tc_kernel<3> : conv_tc_kernel<1>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[nprod == 3]) {
+  const int csz = p.cm * p.cn, ci = csz == 8 ? 3 : (csz == 4 ? 2 : (csz == 2 ? 1 : 0));
+  typedef void (*ConvKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvParams);
+  static const ConvKernel kernels[2][4] = {{conv_tc_kernel<1>, conv_tc_kernel_c2<1>, conv_tc_kernel_c4<1>, conv_tc_kernel_c8<1>},
+                                           {conv_tc_kernel<3>, conv_tc_kernel_c2<3>, conv_tc_kernel_c4<3>, conv_tc_kernel_c8<3>}};
+  ConvKernel kern = kernels[nprod == 3][ci];
+  static bool attr_set[2][4] = {};
+  if (!attr_set[nprod == 3][ci]) {
     FSNET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set[nprod == 3] = true;
+    if (csz == 8) FSNET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set[nprod == 3][ci] = true;
+  }
+  int grid = p.total_tiles < sms * occ ? p.total_tiles : sms * occ;
+  if (csz > 1) {
+    // persistent clusters: as many as the device can hold at once (GPCs whose SM count is no multiple of the cluster size lose a few)
+    static int slots[2][4][5] = {};                                  // [nprod][cluster size][CTAs per SM]
+    int& slot = slots[nprod == 3][ci][occ];
+    if (!slot) {
+      slot = sms * occ / csz;
+#ifndef FSNET_HOST_PLAN_ONLY
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(sms * occ / csz * csz)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) == cudaSuccess && n > 0) slot = n;
+      else cudaGetLastError();
+      if (getenv("FSNET_CONV_MC_PRINT")) fprintf(stderr, "fsnet_conv: cluster %d, %d CTAs/SM, %zu B smem: %d clusters resident\n", csz, occ, smem, slot);
+#endif
+    }
+    const int clusters = p.total_super < slot ? p.total_super : slot;
+    grid = clusters * csz;
   }
   kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   FSNET_LAUNCH_OK();

@@ -254,8 +254,8 @@ template <class K> static void plan_record(K, dim3 grid, dim3 block, size_t smem
                                            const fsnet::ConvParams& p) {
   const char* e = getenv("FSNET_PLAN_PRINT");
   if (!e || e[0] != '1') return;
-  printf("PLAN conv  N=%d %dx%d Cin=%d Cout=%d k=%d s=%d | tile %dx%d BN=%d fold=%d KC=%d kiters=%d stages=%d | tiles=%d grid=%u smem=%zu\n",
-         p.N, p.H, p.W, p.Cin, p.Cout, p.KH, p.stride, p.TH, p.TW, p.BN, p.fold, p.KC, p.kiters, p.stages, p.total_tiles, grid.x, smem);
+  printf("PLAN conv  N=%d %dx%d Cin=%d Cout=%d k=%d s=%d | tile %dx%d BN=%d fold=%d KC=%d kiters=%d stages=%d | tiles=%d cluster=%dx%d grid=%u smem=%zu\n",
+         p.N, p.H, p.W, p.Cin, p.Cout, p.KH, p.stride, p.TH, p.TW, p.BN, p.fold, p.KC, p.kiters, p.stages, p.total_tiles, p.cm, p.cn, grid.x, smem);
 }
 """
     text = text.replace('extern "C" int fsnet_conv(', recorder + 'extern "C" int fsnet_conv(', 1)

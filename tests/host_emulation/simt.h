@@ -23,6 +23,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __cluster_dims__(...)
+#define FSNET_HOST_PLAN_ONLY 1
 #define __shared__ static
 
 struct float2 { float x, y; };
@@ -51,7 +53,7 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static const int warpSize = 32;
 // runtime calls of the host-side planning code (conv_tc.cu): a 148-SM device, attributes always accepted
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributeNonPortableClusterSizeAllowed = 9 };
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
 static const unsigned long long cudaEnableDefault = 0;

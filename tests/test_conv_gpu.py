@@ -29,6 +29,12 @@ CASES = [
     (2, 64, 128, 24, 40, 3, 2, 1, "zero"),
     (2, 256, 512, 6, 10, 3, 1, 1, "zero"),
     (2, 128, 256, 12, 20, 1, 2, 0, "zero"),
+    # halo path (3x3 / stride 1, 64-channel chunks): 16 x 8 and 8 x 16 pixel tiles, several chunks, two channel tiles, partial tiles, ring
+    (2, 64, 64, 48, 40, 3, 1, 1, "zero"),
+    (2, 128, 128, 24, 80, 3, 1, 1, "zero"),
+    (2, 256, 256, 12, 40, 3, 1, 1, "zero"),
+    (2, 128, 64, 20, 36, 3, 1, 1, "rep"),
+    (3, 64, 32, 50, 70, 3, 1, 1, "rep"),
 ]
 
 
