@@ -35,6 +35,11 @@ WORKLOADS = {
     "cfg2b": dict(config="kitti_posenet_synthetic.py", B=12, H=192, W=640, fisheye=False, gflop_per_image=17.02 + 2 * 9.776,
                   text="cfg2b kitti_posenet_synthetic: MonoDepthMeta, ResNet-18 depth net + ResNet-18 PoseNet (2 pairs), 192x640, 4 scales, "
                        "fwd+bwd+clip(35)+Adam"),
+    # BASELINE.json configs[2] and [3] at their stated sizes (per-GPU batch 8); forward-convolution FLOPs are counted from the launches
+    "cfg3": dict(config="kitti360_r50_synthetic.py", B=8, H=192, W=768, fisheye=False, enc_convs=53,
+                 text="cfg3 kitti360_r50_synthetic: ResNet-50 depth net, 192x768, 4 scales, 16 bins, dataset poses, fwd+bwd+clip(35)+Adam"),
+    "cfg4": dict(config="nusc_wpose_synthetic.py", B=8, H=320, W=640, fisheye=False, enc_convs=20,
+                 text="cfg4 nusc_wpose_synthetic: ResNet-18 depth net, 320x640, 4 scales, 16 bins, dataset poses, fwd+bwd+clip(35)+Adam"),
     "cfg5": dict(config="kitti360_fisheye_synthetic.py", B=4, H=512, W=512, fisheye=True, gflop_per_image=18.95 + 24.16,
                  text="cfg5 kitti360_fisheye_synthetic: FishEyeDecoder (MEI camera), ResNet-18, 512x512, 4 scales, 64 bins, dataset poses, "
                       "is_log_image (default True), fwd+bwd+clip(1)+Adam"),
@@ -132,7 +137,7 @@ def run_reference(args, rank):
               "deviation from BASELINE.md: the CPU restatement of the reference (oracle/, pinned to the reference by 28 golden "
               "fixtures), not the reference package itself (/root/reference does not exist on the GPU box), at a bounded batch")
     line = {
-        "impl": "reference", "metric": "images/sec (640x192 triplets), full training step", "value": rate, "unit": "images/s",
+        "impl": "reference", "metric": f"images/sec ({W}x{H} triplets), full training step", "value": rate, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "cfg2a kitti_wpose 192x640 R18 4-scale n=16 (CPU restatement of the reference, oracle/)", "batch": batch},
@@ -190,6 +195,9 @@ def main():
     ap.add_argument("--prefetch", type=int, default=int(os.environ.get("FSNET_BENCH_PREFETCH", 1)),
                     help="e2e leg: upload batch k+1 on a side stream while step k runs (fsnet_b200.data.loading.DevicePrefetcher, "
                          "the default loader stage of scripts/train.py); 0 = the reference's serial upload inside the hook")
+    ap.add_argument("--e2e-input", default=os.environ.get("FSNET_BENCH_E2E_INPUT", "uint8"), choices=["uint8", "float32"],
+                    help="what the e2e leg uploads per step: uint8 frames + augmentation plan, normalised on the device by fsnet_augment_frames "
+                         "(SURVEY 8(f) N3, default) or the six float32 image tensors per sample the reference's loader delivers")
     ap.add_argument("--e2e-sync", type=int, default=0,
                     help="e2e leg: 1 = block on every step's loss (loss.item()); 0 (default) = copy every step's loss to pinned host "
                          "memory asynchronously and read it one step later, as a logging loop would")
@@ -244,9 +252,27 @@ def main():
     probe_hook = build(**dict(cfg.trainer.training_hook, cuda_graph=False))     # eager steps for per-kernel event timing
 
     host = (make_fisheye_batch if wl["fisheye"] else make_batch)(B_PER_GPU, H, W, seed=1234 + rank)
-    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    stage = None
+    if args.e2e_input == "uint8" and args.prefetch:
+        # the e2e leg's host batch: decoded uint8 frames, the 0/1 mask as uint8 and a 16-double plan per sample (identity geometry, no
+        # colour jitter) instead of ('image', f) / ('original_image', f) in float32 and an fp64 mask; the device stage rebuilds those
+        import types
+        import numpy as np
+        from fsnet_b200.data.device_augment import DeviceAugmentStage, GEOM_RESIZE, PLAN_SIZE
+        from fsnet_b200.data.synthetic import IMAGENET_MEAN, IMAGENET_STD
+        frames = [0, 1, -1]
+        u8 = torch.stack([(host[("original_image", f)] * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1) for f in frames], 1)
+        plan = torch.zeros(B_PER_GPU, PLAN_SIZE, dtype=torch.float64)
+        plan[:, 0], plan[:, 1], plan[:, 2], plan[:, 3], plan[:, 13], plan[:, 14], plan[:, 15] = 1.0, 1.0, W, H, H, W, GEOM_RESIZE
+        host_e2e = {k: v for k, v in host.items() if not (isinstance(k, tuple) and k[0] in ("image", "original_image")) and k != "patched_mask"}
+        host_e2e.update(frames_u8=u8.contiguous(), aug_plan=plan, mask_u8=host["patched_mask"].to(torch.uint8))
+        stage = DeviceAugmentStage(types.SimpleNamespace(frames=frames, output_h=H, output_w=W, mean=np.array(IMAGENET_MEAN, dtype=np.float32),
+                                                         std=np.array(IMAGENET_STD, dtype=np.float32)))
+    else:
+        host_e2e = host
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host_e2e.items()}
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_e2e.values() if torch.is_tensor(v))
 
     def barrier():
         if world > 1:
@@ -264,7 +290,7 @@ def main():
             # before step i is launched, so it runs on the copy engine under step i
             from fsnet_b200.data.loading import DevicePrefetcher
             reader = LossReader(args.e2e_sync)
-            for i, data in enumerate(DevicePrefetcher((dict(pinned) for _ in range(n)), dev)):
+            for i, data in enumerate(DevicePrefetcher((dict(pinned) for _ in range(n)), dev, device_transform=stage)):
                 out = hook(data, model, optimizer, None, None, i, 0)
                 reader.push(out["loss"])
             last = reader.last()
@@ -307,7 +333,12 @@ def main():
     # (is_log_image heads need the forward-only kernel for their hm outputs: forward and backward are separate launches)
     LOSS_ENTRY = "fsnet_warp_ssim_fwdbwd" if not wl["fisheye"] else "fsnet_warp_ssim_mei_bwd"
     _lib.profile_entry(LOSS_ENTRY, True)
-    _lib.profile_entry("fsnet_conv", True, tag=lambda a: a[9])       # a[9] = number of tensor-core products (3 = forward)
+    def conv_tag(a):
+        # (tensor-core products of the launch: 3 = forward, FLOPs 2*N*Ho*Wo*Cout*Cin*KH*KW from the call's own arguments; the network
+        # stems read 3 / 6 image channels padded to 8)
+        cin = a[0].c if a[0].c != 8 else 3
+        return a[9], 2.0 * a[12].n * a[12].h * a[12].w * a[4] * cin * a[5] * a[6]
+    _lib.profile_entry("fsnet_conv", True, tag=conv_tag)
     timed(min(args.steps, 5), False, probe_hook, head_start=True)
     kern_us = _lib.profile_results(LOSS_ENTRY)                       # per-launch CUDA-event times (us), scale order
     conv_rows = _lib.profile_results("fsnet_conv", with_tags=True)
@@ -331,8 +362,9 @@ def main():
         with open(prof) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     # tensor-bound leg: all forward convolutions of one step (34 launches), SURVEY.md 8(d): 17.02 GFLOP per image at cfg2
-    fwd_us = sum(t for t, tag in conv_rows if tag == 3) / max(probe_steps, 1)
-    conv_flops = wl["gflop_per_image"] * 1e9 * B_PER_GPU
+    fwd_us = sum(t for t, tag in conv_rows if tag[0] == 3) / max(probe_steps, 1)
+    counted_flops = sum(tag[1] for t, tag in conv_rows if tag[0] == 3) / max(probe_steps, 1)
+    conv_flops = wl["gflop_per_image"] * 1e9 * B_PER_GPU if "gflop_per_image" in wl else counted_flops
     tf_peak = 1364.9
     pk = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -340,20 +372,23 @@ def main():
             tf_peak = float(json.load(f).get("bf16_tflops_sustained", tf_peak))
     conv_tf = conv_flops / (fwd_us * 1e-6) / 1e12 if fwd_us > 0 else None
     # encoder only (what north_star's 50 % tensor-pipe target is quoted on): the first `enc_convs` forward launches of every step
-    fwd_rows = [t for t, tag in conv_rows if tag == 3]
+    fwd_rows = [t for t, tag in conv_rows if tag[0] == 3]
+    fwd_flops = [tag[1] for t, tag in conv_rows if tag[0] == 3]
     per_step = len(fwd_rows) // max(probe_steps, 1)
     enc_n = wl.get("enc_convs", 0)
     enc_us = (sum(sum(fwd_rows[i * per_step:i * per_step + enc_n]) for i in range(probe_steps)) / max(probe_steps, 1)) if (enc_n and per_step) else 0.0
-    enc_flops = wl.get("enc_gflop_per_image", 0.0) * 1e9 * B_PER_GPU
+    enc_flops = wl["enc_gflop_per_image"] * 1e9 * B_PER_GPU if "enc_gflop_per_image" in wl else (sum(fwd_flops[:enc_n]) if per_step else 0.0)
     enc_tf = enc_flops / (enc_us * 1e-6) / 1e12 if enc_us > 0 else None
     line = {
-        "metric": "images/sec (640x192 triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": f"images/sec ({W}x{H} triplets), full training step", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (convs: " + ops.precision_note() + ")", "data": "synthetic",
         "config": {"workload": wl["text"], "batch_per_gpu": B_PER_GPU, "global_batch": B_PER_GPU * world,
                    "parallelism": f"dp{world}" + (" (SyncBN statistics + flat gradient all-reduce over NCCL, inside the step graph)" if world > 1 else ""),
                    "conv_backend": "tc" if ops.COMPARATOR is None else "torch (comparator)",
                    "cuda_graph": use_graph, "e2e_prefetch": bool(args.prefetch),
+                   "e2e_input": ("uint8 frames + mask + augmentation plan, warped / normalised on the device (fsnet_augment_frames) on the upload stream"
+                                 if stage is not None else "float32 images (6 per sample) + fp64 mask, as the reference's loader delivers them"),
                    "e2e_loss_read": "blocking .item() per step" if args.e2e_sync else "async copy to pinned memory per step, read one step later",
                    "l2": "no explicit flush: one step touches >2 GB of activations, far beyond the 126 MB L2"},
         "roofline": {"kernel": "loss_pair_kernel<0> via fsnet_warp_ssim_fwdbwd (fused warp-SSIM forward+backward, one launch per scale)",
@@ -363,7 +398,7 @@ def main():
         "roofline_conv": {"kernel": "conv_tc_kernel<3> (all forward convolutions of one step, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
                           "bound": "tensor", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
                           "frac": (conv_tf / tf_peak) if conv_tf else None, "us_per_step": fwd_us,
-                          "algorithmic_flops_per_step": conv_flops,
+                          "algorithmic_flops_per_step": conv_flops, "flops_counted_from_launches": counted_flops,
                           "note": "useful fp32-equivalent FLOPs; the tensor pipe executes 3x as many (bf16x3 split)",
                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
         "roofline_conv_encoder": {"kernel": f"conv_tc_kernel<3>, the {enc_n} convolutions of the ResNet encoder (forward)", "bound": "tensor",

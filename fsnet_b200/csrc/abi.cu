@@ -1,5 +1,6 @@
 // Error reporting and version entry points of the C ABI (include/fsnet_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace fsnet {
@@ -9,6 +10,11 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FSNET_PDL"); on = e ? atoi(e) != 0 : 1; }
+  return on != 0;
 }
 }  // namespace fsnet
 

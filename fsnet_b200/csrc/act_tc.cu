@@ -133,6 +133,8 @@ __global__ void bn_finalize_kernel(double* __restrict__ stats, double count, con
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches, float momentum, float eps, int training, int C,
                                    float* __restrict__ scale_shift, float* __restrict__ mean_invstd) {
+  pdl_launch_dependents();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, invstd;
@@ -171,6 +173,8 @@ struct ActParams {
   V dst;                        // planes
 };
 __global__ void __launch_bounds__(256) act_planes_kernel(ActParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const V& s = p.raw;
   const unsigned total = (unsigned)s.n * s.h * s.w * (s.c >> 3);
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -327,6 +331,8 @@ __device__ __forceinline__ F8 masked_g8(const BnBwdParams& p, const Px& q, const
 // Each thread owns one 8-channel group and walks pixels; per-block partial sums go through shared-memory
 // float atomics, then one fp64 atomic per channel and block.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int pix_per_iter, int threads_used) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_acc[];           // [2*C]
   const V& r = p.raw;
   const int C = r.c, groups = C >> 3;
@@ -395,6 +401,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int p
 // per block from the fp64 sums into shared memory (round 1 read 16 doubles and converted them per 8 elements: the kernel sat
 // on the LSU queue, lg_throttle up to 3.9 per issue in ncu r2c8); persistent blocks walk the tensor.
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_coef[];          // A[C], B[C], K[C]
   const V& r = p.raw;
   const int C = r.c;
@@ -436,6 +444,33 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) d.v[k] = fmaf(A.v[k], g.v[k], fmaf(B.v[k], rv.v[k], K.v[k]));
     st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, q.n, q.y, q.x, q.c), d);
+  }
+  // ringed dy (thin replicate layers: the data gradient reads the zero padding of k-1 pixels as data): the ring is written here,
+  // r rows above and below and r columns left and right of every image, instead of a torch fill of the whole two-plane buffer
+  // before the launch (97 MB per full-resolution 16-channel layer, ~90 us per step)
+  if (p.dy.ring > 0) {
+    const int rg = p.dy.ring, pw = r.w + 2 * rg;
+    const unsigned top = (unsigned)(2 * rg * pw), side = (unsigned)(2 * rg * r.h), per_img = top + side, groups = (unsigned)(C >> 3);
+    const unsigned ring_total = (unsigned)r.n * per_img * groups;
+    F8 z;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z.v[k] = 0.f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ring_total; i += gridDim.x * blockDim.x) {
+      const unsigned cg = i % groups; unsigned px = i / groups;
+      const int n = (int)(px / per_img); px -= (unsigned)n * per_img;
+      int y, x;
+      if (px < top) {
+        const int row = (int)(px / pw);
+        x = (int)(px - row * pw) - rg;
+        y = row < rg ? row - rg : r.h + (row - rg);
+      } else {
+        px -= top;
+        y = (int)(px / (2 * rg));
+        const int xx = (int)(px - y * 2 * rg);
+        x = xx < rg ? xx - rg : r.w + (xx - rg);
+      }
+      st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, n, y, x, (int)cg * 8), z);
+    }
   }
 }
 
@@ -630,7 +665,7 @@ extern "C" int fsnet_bn_finalize(double* stats, double count, const float* gamma
                                  float* running_mean, float* running_var, long long* num_batches, float momentum, float eps,
                                  int training, int C, float* scale_shift, float* mean_invstd, void* stream) {
   FSNET_REQUIRE(scale_shift && C > 0 && (training ? stats != nullptr : (running_mean && running_var)), "fsnet_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, conv_bias, running_mean, running_var,
+  FSNET_LAUNCH_PDL(bn_finalize_kernel, ceil_div(C, 128), 128, 0, (cudaStream_t)stream, stats, count, gamma, beta, conv_bias, running_mean, running_var,
                                                                          num_batches, momentum, eps, training, C, scale_shift, mean_invstd);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
@@ -646,7 +681,7 @@ extern "C" int fsnet_act_planes(const fsnet_view* raw, const float* scale_shift,
   p.relu = relu; p.up = up; p.dst = *dst;
   FSNET_REQUIRE(raw->c % 8 == 0 && raw->c_off % 8 == 0 && dst->c_off % 8 == 0 && dst->c_total % 8 == 0, "fsnet_act_planes: channels must be multiples of 8");
   size_t total = (size_t)raw->n * raw->h * raw->w * (raw->c / 8);
-  act_planes_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_PDL(act_planes_kernel, blocks_for(total), 256, 0, (cudaStream_t)stream, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -711,7 +746,7 @@ extern "C" int fsnet_bn_bwd_reduce(const fsnet_view* g, int up, const fsnet_view
   // second, nearly empty one of the same length (ncu r2c8: 5 loop iterations per warp, the launch twice as long as a block)
   if (grid > 296u) grid = grid >= 592u ? 592u : 296u;
   if (grid == 0) grid = 1;
-  bn_bwd_reduce_kernel<<<grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p, pix_per_iter, threads_used);
+  FSNET_LAUNCH_PDL(bn_bwd_reduce_kernel, grid, 256, 2 * raw->c * sizeof(float), (cudaStream_t)stream, p, pix_per_iter, threads_used);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -730,7 +765,7 @@ extern "C" int fsnet_bn_bwd_apply(const fsnet_view* g, int up, const fsnet_view*
   FSNET_REQUIRE(raw->c <= 2048 && total < (1ull << 32), "fsnet_bn_bwd_apply: channels <= 2048, 32-bit indexing");
   unsigned grid = blocks_for(total);
   if (grid > 148u * 8u) grid = 148u * 8u;          // persistent blocks: the per-channel coefficients are built once per block
-  bn_bwd_apply_kernel<<<grid, 256, 3 * raw->c * sizeof(float), (cudaStream_t)stream>>>(p);
+  FSNET_LAUNCH_PDL(bn_bwd_apply_kernel, grid, 256, 3 * raw->c * sizeof(float), (cudaStream_t)stream, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

@@ -412,6 +412,8 @@ __device__ __forceinline__ void conv_tc_body(const CUtensorMap& map_a_hi, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();                       // everything above touched no global memory: it may overlap the previous kernel
+  pdl_wait();
   const int csz = p.cm * p.cn;
   const int crank = csz > 1 ? (int)cluster_ctarank() : 0;
   const int rank_m = crank / p.cn, rank_n = crank - rank_m * p.cn;
@@ -626,6 +628,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (p.dbg & 32) {
     // diagnostics: prologue and teardown only
@@ -985,7 +989,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
       FSNET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       halo_attr[nprod == 3] = true;
     }
-    kern<<<grid, kHaloThreads, smem, (cudaStream_t)stream>>>(ma[0], ma[1], mb[0], mb[1], p);
+    FSNET_LAUNCH_PDL(kern, grid, kHaloThreads, smem, (cudaStream_t)stream, ma[0], ma[1], mb[0], mb[1], p);
     FSNET_LAUNCH_OK();
     return FSNET_OK;
   }
@@ -1081,7 +1085,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     const int clusters = p.total_super < slot ? p.total_super : slot;
     grid = clusters * csz;
   }
-  kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  FSNET_LAUNCH_PDL(kern, grid, kThreads, smem, (cudaStream_t)stream, ma_hi, ma_lo, mb_hi, mb_lo, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }
@@ -1160,6 +1164,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     {   // whole warp converged, one elected lane issues (see conv_tc_kernel)
@@ -1191,14 +1197,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       // when fewer than 128/atomA atoms exist, LBO = 0 makes the missing atoms alias atom 0 (duplicate rows, never stored)
       const uint32_t lboA = (p.nA * p.atomA >= 128) ? p.a_atom_bytes : 0u;
       int stage = 0; uint32_t phase = 0;
+      // descriptors = base + byte offset / 16; four K-steps (16 pixels each) per statement with one election (see umma_chunk_elect)
+      const uint64_t da0 = make_desc_mn(smem_u32(smem), lboA, 8 * rowA, p.a_layout);
+      const uint64_t db0 = make_desc_mn(smem_u32(smem) + p.a_bytes, p.b_atom_bytes, 8 * rowB, p.b_layout);
+      const uint64_t stepA = rowA, stepB = rowB;                     // 16 pixel rows = 16 * row bytes = row bytes in units of 16 B
+      const uint32_t stage16 = p.stage_bytes >> 4;
       for (int i = 0; i < nchunks; ++i) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        for (int k = 0; k < p.pix / 16; ++k) {
-          const uint64_t da = make_desc_mn(st + k * 16 * rowA, lboA, 8 * rowA, p.a_layout);
-          const uint64_t db = make_desc_mn(st + p.a_bytes + k * 16 * rowB, p.b_atom_bytes, 8 * rowB, p.b_layout);
-          umma_bf16_elect(tmem_base, da, db, idesc, (i | k) != 0);
+        uint64_t da = da0 + (uint64_t)((uint32_t)stage * stage16), db = db0 + (uint64_t)((uint32_t)stage * stage16);
+        for (int k = 0; k < p.pix / 64; ++k) {
+          asm volatile(
+              "{\n"
+              ".reg .pred pe, pz, pt;\n"
+              ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+              "elect.sync _|pe, 0xffffffff;\n"
+              "setp.ne.b32 pz, %6, 0;\n"
+              "setp.eq.b32 pt, %6, %6;\n"
+              "add.u64 a1, %1, %4;\n add.u64 a2, a1, %4;\n add.u64 a3, a2, %4;\n"
+              "add.u64 b1, %2, %5;\n add.u64 b2, b1, %5;\n add.u64 b3, b2, %5;\n"
+              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pz;\n"
+              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, pt;\n"
+              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, pt;\n"
+              "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, pt;\n"
+              "}\n" ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "l"(stepA), "l"(stepB), "r"((uint32_t)((i | k) != 0)) : "memory");
+          da += 4 * stepA; db += 4 * stepB;
         }
         umma_commit_elect(&empty_bar[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -1343,7 +1366,7 @@ extern "C" int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_v
   }
   const int grid = base_items * p.ksplit;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
-  wgrad_tc_kernel<<<grid, kWgradThreads, smem, (cudaStream_t)stream>>>(mdy, mx, p);
+  FSNET_LAUNCH_PDL(wgrad_tc_kernel, grid, kWgradThreads, smem, (cudaStream_t)stream, mdy, mx, p);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
 }

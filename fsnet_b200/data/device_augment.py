@@ -197,10 +197,22 @@ class DeviceAugmentStage(object):
     """Device half: turns ``frames_u8`` / ``mask_u8`` / ``aug_plan`` of an uploaded batch into the model's inputs with one
     launch of ``fsnet_augment_frames``.  CUDA only."""
 
-    def __init__(self, augmentation: DeviceAugmentation):
+    def __init__(self, augmentation: DeviceAugmentation, ring: int = 2):
         self.frames = list(augmentation.frames)
         self.output_h, self.output_w = augmentation.output_h, augmentation.output_w
         self.mean_std = torch.tensor(np.concatenate([augmentation.mean, augmentation.std]), dtype=torch.float32)
+        # output buffers are kept and used round-robin, `ring` = the DevicePrefetcher's slots (depth + 1): a set is rewritten only
+        # after the prefetcher has seen the consumer release the slot it belongs to (no allocator traffic on the upload stream)
+        self._ring, self._sets, self._turn = max(int(ring), 1), {}, 0
+
+    def _buffers(self, key, dev, F, B, H, W, with_mask):
+        sets = self._sets.setdefault(key, [])
+        if len(sets) < self._ring:
+            sets.append((torch.empty(F, B, 3, H, W, device=dev, dtype=torch.float32), torch.empty(F, B, 3, H, W, device=dev, dtype=torch.float32),
+                         torch.empty(B, H, W, device=dev, dtype=torch.float64) if with_mask else None))
+            return sets[-1]
+        self._turn = (self._turn + 1) % self._ring
+        return sets[self._turn]
 
     def __call__(self, batch: Dict) -> Dict:
         from .. import _lib
@@ -214,9 +226,7 @@ class DeviceAugmentStage(object):
         if self.mean_std.device != dev:
             self.mean_std = self.mean_std.to(dev)
         H, W = self.output_h, self.output_w
-        image = torch.empty(F, B, 3, H, W, device=dev, dtype=torch.float32)
-        original = torch.empty(F, B, 3, H, W, device=dev, dtype=torch.float32)
-        mask_out = torch.empty(B, H, W, device=dev, dtype=torch.float64) if mask is not None else None
+        image, original, mask_out = self._buffers((B, F, H, W, mask is not None, str(dev)), dev, F, B, H, W, mask is not None)
         _lib.call("fsnet_augment_frames", frames.contiguous(), None if mask is None else mask.contiguous(), plan.double().contiguous(),
                   B, F, H0, W0, H, W, self.mean_std, image, original, mask_out)
         for i, f in enumerate(self.frames):

@@ -9,6 +9,7 @@ replayed in reverse.  Activations never leave the device-resident bf16 "planes" 
 Per convolution: forward   conv (tcgen05, bf16x3, BN statistics in the epilogue) -> bn_finalize -> act_planes
                  backward  bn_bwd_reduce -> bn_bwd_apply (-> dy plane) -> conv_wgrad + conv (data gradient)
 """
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -135,6 +136,13 @@ class Tape:
     # accumulators, so the bulk of the gradient bytes never goes through the hook's post-backward exchange.
     bucketed_allreduce = False
     N_BUCKETS = 4
+    # Weight gradients on a second stream.  In the backward walk of a layer, dy feeds two independent launches: the data gradient
+    # (which the rest of the walk waits for) and the weight gradient (needed only by the batched re-layout at the very end).  The
+    # 34 weight-gradient launches of a cfg2a step (1.1 ms, most of them small grids with K-split tails) run on a side stream
+    # that forks after dy is written and joins before the re-layout (and before a gradient bucket is exchanged), so they fill the
+    # SMs the main chain leaves idle; inside the step graph the fork/join become parallel branches.  FSNET_WGRAD_STREAM=0: off.
+    side_wgrad = os.environ.get("FSNET_WGRAD_STREAM", "1") != "0"
+    _side_streams: Dict = {}
 
     def __init__(self, states: Dict[int, LayerState], training: bool, need_grad: bool, weights_fresh=False):
         self.states, self.training, self.need_grad = states, training, need_grad
@@ -144,6 +152,20 @@ class Tape:
         self._pools = None
         self._sync_scaled: List[torch.Tensor] = []            # SyncBN affine gradients to divide by the world size (see _bn_bwd)
         self._sync_world = 1
+        self._side = None                                      # side stream with weight gradients in flight (None: joined)
+        self._side_keep: List = []                             # operands of those launches: not handed back to the allocator before the join
+
+    def _wgrad_side_stream(self, dev):
+        st = Tape._side_streams.get(dev)
+        if st is None:
+            st = Tape._side_streams[dev] = torch.cuda.Stream(device=dev)
+        return st
+
+    def _join_side(self):
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side = None
+            self._side_keep.clear()
 
     def _make_pools(self):
         """One zeroed workspace per backward pass instead of one fill kernel per layer: BN-backward sums (fp64),
@@ -316,7 +338,7 @@ class Tape:
             else:
                 dist.all_reduce(sums)
         fold_dgrad = st.replicate and st.kh == 3 and st.C < 64          # see fsnet_conv: folded x-taps need ring == pad
-        dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device, zero=fold_dgrad)
+        dy = Planes(raw.n, raw.h, raw.w, st.C, ring=2 if fold_dgrad else 0, device=raw.t.device)     # fsnet_bn_bwd_apply zeroes the ring
         gamma = st.padded(bn.weight, 1.0) if bn is not None else None
         C = st.c_real
         dgamma = dbeta = None
@@ -350,7 +372,16 @@ class Tape:
         conv = st.conv
         if conv.weight.requires_grad:
             use_ring = st.replicate or (x.zero_ring and x.planes.ring == st.pad)
-            tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=self._pool(st, "acc"))
+            acc = self._pool(st, "acc")                      # (the zeroed workspace is created on the main stream, before the fork)
+            if Tape.side_wgrad and dy.t.device.type == "cuda":
+                side = self._wgrad_side_stream(dy.t.device)
+                side.wait_stream(torch.cuda.current_stream())            # dy is written
+                with torch.cuda.stream(side):
+                    tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=acc)
+                self._side = side
+                self._side_keep.append((dy, x.planes))
+            else:
+                tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=acc)
             # the accumulator is re-laid out into this slice of the flat gradient buffer by ONE batched launch at the end
             # of the backward pass (run_backward)
             o_w = self._pools["gw_off"][id(st.conv)]
@@ -382,6 +413,7 @@ class Tape:
         bucket is final -- average it over the ranks now, concurrently with the rest of the backward pass."""
         rng = self._buckets.pop(key, None) if self._pools is not None else None
         if rng is not None:
+            self._join_side()                                # the bucket's accumulators are final only once their launches have run
             op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
             t = self._pools["acc"][rng[0]:rng[1]]
             self._works.append((dist.all_reduce(t, op=op, async_op=True), t, op))
@@ -473,6 +505,7 @@ class Tape:
         self.out_grads = out_grads
         for op in reversed(self.backward_ops):
             op()
+        self._join_side()
         if self._pools is not None and self._pools["gw_used"]:
             if self._buckets or self._works:
                 for key in list(self._buckets):              # buckets whose first layer has no weight gradient (frozen stages)

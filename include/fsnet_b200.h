@@ -304,7 +304,8 @@ int fsnet_conv_wgrad(const fsnet_view* x, int use_ring, const fsnet_view* dy, in
  *                          forward (may be NULL there) and read by the backward
  *   fsnet_bn_bwd_reduce / fsnet_bn_bwd_apply   gradient of (ReLU o BatchNorm): sums[2C] = (sum g, sum g*xhat);
  *                          dy (bf16 plane) = gamma*invstd*(g - mean g - xhat*mean g*xhat); mean_invstd == NULL
- *                          means "no BatchNorm" (dy = masked g); `up`=2 reads the gradient through the adjoint
+ *                          means "no BatchNorm" (dy = masked g); a dy view with ring > 0 gets its ring written as zeros
+ *                          (zero padding read as data by the folded data gradient); `up`=2 reads the gradient through the adjoint
  *                          of the nearest x2 up-sampling; res_mode 1/2 writes/accumulates the masked gradient
  *                          into another fp32 view (identity residual); dgamma / dbeta (fp32 [c_real], may be NULL) receive
  *                          the BatchNorm parameter gradients; the ReLU mask is `mask` (activation planes)
