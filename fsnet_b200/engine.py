@@ -117,7 +117,12 @@ class Inv:
         self.count = 1.0
 
 
+_DIAG_NO_SYNCBN = os.environ.get("FSNET_DIAG_NO_SYNCBN", "0") == "1"       # timing diagnostics only: local statistics (wrong numerics at N>1)
+
+
 def _sync_world(bn) -> int:
+    if _DIAG_NO_SYNCBN:
+        return 1
     if isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized():
         return dist.get_world_size()
     return 1
@@ -413,10 +418,16 @@ class Tape:
         bucket is final -- average it over the ranks now, concurrently with the rest of the backward pass."""
         rng = self._buckets.pop(key, None) if self._pools is not None else None
         if rng is not None:
-            self._join_side()                                # the bucket's accumulators are final only once their launches have run
             op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
             t = self._pools["acc"][rng[0]:rng[1]]
-            self._works.append((dist.all_reduce(t, op=op, async_op=True), t, op))
+            if self._side is not None:
+                # the bucket's accumulators are final once the side stream's weight-gradient launches have run: the collective is
+                # ordered behind THEM (issued from the side stream), the main chain does not wait
+                with torch.cuda.stream(self._side):
+                    work = dist.all_reduce(t, op=op, async_op=True)
+            else:
+                work = dist.all_reduce(t, op=op, async_op=True)
+            self._works.append((work, t, op))
 
     def _fold_if_needed(self, a: Act):
         if getattr(a, "ring_dirty", False):

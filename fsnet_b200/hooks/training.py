@@ -96,6 +96,8 @@ class BaseTrainingHook(object):
         buffer the executor did not reduce (all-reduced in place: parameter gradients are views of it, no copies)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
+        if os.environ.get("FSNET_DIAG_NO_GRADSYNC", "0") == "1":       # timing diagnostics only: ranks drift apart
+            return
         if isinstance(meta_arch, nn.parallel.DistributedDataParallel):
             return
         from .. import engine
@@ -131,7 +133,7 @@ class BaseTrainingHook(object):
         from .. import engine
         engine.Tape.bucketed_allreduce = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
                                           and not isinstance(meta_arch, nn.parallel.DistributedDataParallel)
-                                          and os.environ.get("FSNET_BUCKETED_ALLREDUCE", "1") != "0")
+                                          and os.environ.get("FSNET_BUCKETED_ALLREDUCE", "0") == "1")
         optimizer.zero_grad()
         output: dict = meta_arch(data, meta)
         output["loss"].mean().backward()

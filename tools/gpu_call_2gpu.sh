@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2-GPU call: N>1 parity on GPUs (SyncBN through NVLink peer memory and through NCCL, DDP wrapping) + N=2 bench A/B.
 mkdir -p gpurun_out
-O=gpurun_out/r2m3
+O=gpurun_out/r2m4
 nvidia-smi topo -m > ${O}_topo.txt 2>&1
 timeout 900 python -m pytest tests/test_multigpu_gpu.py -q -m gpu -rA -s --timeout 800 -p no:cacheprovider > ${O}_tests.txt 2>&1
 echo "rc=$?" >> ${O}_tests.txt
