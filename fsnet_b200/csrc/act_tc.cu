@@ -396,6 +396,32 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdParams p, int p
     if (v != 0.f) atomicAdd(p.sums + i, (double)v);
   }
 }
+// Ringed dy (thin replicate layers: the data gradient reads the zero padding of k-1 pixels as data): the ring -- r rows above and
+// below and r columns left and right of every image -- is written by the apply kernel instead of a torch fill of the whole
+// two-plane buffer before the launch (97 MB per full-resolution 16-channel layer, ~70 us per step).  Not inlined: inlined, its
+// index arithmetic took bn_bwd_apply_kernel from 48 to 100 registers and every layer's launch got 20-40 % slower.
+__device__ __noinline__ void zero_dy_ring(const V dy, int N, int H, int W, int C) {
+  const int rg = dy.ring, pw = W + 2 * rg;
+  const unsigned top = (unsigned)(2 * rg * pw), side = (unsigned)(2 * rg * H), per_img = top + side, groups = (unsigned)(C >> 3);
+  const unsigned ring_total = (unsigned)N * per_img * groups;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ring_total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % groups; unsigned px = i / groups;
+    const int n = (int)(px / per_img); px -= (unsigned)n * per_img;
+    int y, x;
+    if (px < top) {
+      const int row = (int)(px / pw);
+      x = (int)(px - row * pw) - rg;
+      y = row < rg ? row - rg : H + (row - rg);
+    } else {
+      px -= top;
+      y = (int)(px / (2 * rg));
+      const int xx = (int)(px - y * 2 * rg);
+      x = xx < rg ? xx - rg : W + (xx - rg);
+    }
+    *reinterpret_cast<uint4*>((__nv_bfloat16*)dy.ptr + vidx(dy, n, y, x, (int)cg * 8)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // dy = A * g + B * raw + K per channel: the BatchNorm input gradient gamma*inv*(g - mean(g) - xhat*mean(g*xhat)) with
 // xhat = (raw - mean)*inv, rearranged so that an element costs two FMAs.  The three coefficients per channel are built once
 // per block from the fp64 sums into shared memory (round 1 read 16 doubles and converted them per 8 elements: the kernel sat
@@ -445,33 +471,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdParams p) {
     for (int k = 0; k < 8; ++k) d.v[k] = fmaf(A.v[k], g.v[k], fmaf(B.v[k], rv.v[k], K.v[k]));
     st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, q.n, q.y, q.x, q.c), d);
   }
-  // ringed dy (thin replicate layers: the data gradient reads the zero padding of k-1 pixels as data): the ring is written here,
-  // r rows above and below and r columns left and right of every image, instead of a torch fill of the whole two-plane buffer
-  // before the launch (97 MB per full-resolution 16-channel layer, ~90 us per step)
-  if (p.dy.ring > 0) {
-    const int rg = p.dy.ring, pw = r.w + 2 * rg;
-    const unsigned top = (unsigned)(2 * rg * pw), side = (unsigned)(2 * rg * r.h), per_img = top + side, groups = (unsigned)(C >> 3);
-    const unsigned ring_total = (unsigned)r.n * per_img * groups;
-    F8 z;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) z.v[k] = 0.f;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ring_total; i += gridDim.x * blockDim.x) {
-      const unsigned cg = i % groups; unsigned px = i / groups;
-      const int n = (int)(px / per_img); px -= (unsigned)n * per_img;
-      int y, x;
-      if (px < top) {
-        const int row = (int)(px / pw);
-        x = (int)(px - row * pw) - rg;
-        y = row < rg ? row - rg : r.h + (row - rg);
-      } else {
-        px -= top;
-        y = (int)(px / (2 * rg));
-        const int xx = (int)(px - y * 2 * rg);
-        x = xx < rg ? xx - rg : r.w + (xx - rg);
-      }
-      st_split8((__nv_bfloat16*)p.dy.ptr, nullptr, vidx(p.dy, n, y, x, (int)cg * 8), z);
-    }
-  }
+  if (p.dy.ring > 0) zero_dy_ring(p.dy, r.n, r.h, r.w, C);
 }
 
 // ---- ring folding: adjoint of replicate padding on a ringed fp32 gradient ----------------------------------------------

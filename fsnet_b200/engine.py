@@ -160,15 +160,19 @@ class Tape:
         self._side = None                                      # side stream with weight gradients in flight (None: joined)
         self._side_keep: List = []                             # operands of those launches: not handed back to the allocator before the join
 
+    N_SIDE = int(os.environ.get("FSNET_WGRAD_STREAMS", "1"))     # side streams used round-robin
+
     def _wgrad_side_stream(self, dev):
-        st = Tape._side_streams.get(dev)
-        if st is None:
-            st = Tape._side_streams[dev] = torch.cuda.Stream(device=dev)
-        return st
+        pool = Tape._side_streams.get(dev)
+        if pool is None:
+            pool = Tape._side_streams[dev] = [torch.cuda.Stream(device=dev) for _ in range(max(Tape.N_SIDE, 1))]
+        self._side_turn = (getattr(self, "_side_turn", -1) + 1) % len(pool)
+        return pool[self._side_turn]
 
     def _join_side(self):
         if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)
+            for st in Tape._side_streams.get(self._side.device, []):
+                torch.cuda.current_stream().wait_stream(st)
             self._side = None
             self._side_keep.clear()
 
@@ -373,28 +377,37 @@ class Tape:
         return dy
 
     def _conv_bwd(self, x: Act, st: LayerState, dy: Planes, need_dgrad=True):
-        """Weight gradient and (accumulated) data gradient of one convolution."""
+        """Weight gradient and (accumulated) data gradient of one convolution.  Both read dy; the data gradient is issued first on
+        the main stream, the weight gradient on the side stream behind an event recorded BEFORE it: the block scheduler sees the
+        critical-path launch first, the weight gradient fills SMs as they free up."""
         conv = st.conv
-        if conv.weight.requires_grad:
-            use_ring = st.replicate or (x.zero_ring and x.planes.ring == st.pad)
-            acc = self._pool(st, "acc")                      # (the zeroed workspace is created on the main stream, before the fork)
-            if Tape.side_wgrad and dy.t.device.type == "cuda":
-                side = self._wgrad_side_stream(dy.t.device)
-                side.wait_stream(torch.cuda.current_stream())            # dy is written
-                with torch.cuda.stream(side):
-                    tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=acc)
-                self._side = side
-                self._side_keep.append((dy, x.planes))
-            else:
+        do_w = conv.weight.requires_grad
+        side = self._wgrad_side_stream(dy.t.device) if (do_w and Tape.side_wgrad and dy.t.device.type == "cuda") else None
+        acc = self._pool(st, "acc") if do_w else None            # (the zeroed workspace is created on the main stream, before the fork)
+        use_ring = st.replicate or (x.zero_ring and x.planes.ring == st.pad)
+        forked = None
+        if side is not None:
+            forked = torch.cuda.Event()
+            forked.record()                                      # dy is written
+        elif do_w:
+            tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=acc)
+        if need_dgrad and x.grad is not None:
+            self._conv_dgrad(x, st, dy)
+        if side is not None:
+            side.wait_event(forked)
+            with torch.cuda.stream(side):
                 tc.conv_wgrad(x.pview(), use_ring, dy.view(), st.w, st.stride, st.pad, acc=acc)
+            self._side = side
+            self._side_keep.append((dy, x.planes))
+        if do_w:
             # the accumulator is re-laid out into this slice of the flat gradient buffer by ONE batched launch at the end
             # of the backward pass (run_backward)
             o_w = self._pools["gw_off"][id(st.conv)]
             self.param_grads[id(conv.weight)] = self._pools["gw"][o_w:o_w + conv.weight.numel()].view_as(conv.weight)
             self._pools["gw_used"] = True
         self._reduce_bucket(id(conv))
-        if not need_dgrad or x.grad is None:
-            return
+
+    def _conv_dgrad(self, x: Act, st: LayerState, dy: Planes):
         k = st.kh
         if st.replicate:
             # x_pad = replicate_pad(x): gradient of the padded tensor (pad k-1 correlation), then fold the ring
@@ -423,6 +436,9 @@ class Tape:
             if self._side is not None:
                 # the bucket's accumulators are final once the side stream's weight-gradient launches have run: the collective is
                 # ordered behind THEM (issued from the side stream), the main chain does not wait
+                for st in Tape._side_streams.get(self._side.device, []):
+                    if st is not self._side:
+                        self._side.wait_stream(st)
                 with torch.cuda.stream(self._side):
                     work = dist.all_reduce(t, op=op, async_op=True)
             else:

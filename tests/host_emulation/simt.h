@@ -24,6 +24,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __cluster_dims__(...)
+#define __noinline__
 #define FSNET_HOST_PLAN_ONLY 1
 #define __shared__ static
 
