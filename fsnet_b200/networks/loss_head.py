@@ -6,6 +6,8 @@ conventions (every extra kwarg becomes an attribute read with ``getattr(self, na
 ``{'loss','loss_dict','hm'}`` are the reference's.  The loss itself is NOT a PyTorch graph: it is one
 fused CUDA kernel per scale plus small helpers (fsnet_b200/functional.py -> csrc/warp_ssim.cu).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -67,6 +69,20 @@ class MonoDepth2Decoder(nn.Module):
         if getattr(self, "distillation_loss_weight", 0) > 0 and getattr(self, "is_unscaled_distill", False):
             raise NotImplementedError("is_unscaled_distill=True is not implemented (no shipped config enables it)")
 
+    def prefetch_loss_terms(self, input_dict):
+        """Called by the meta-architectures at the START of a training step: everything the loss needs from the batch alone
+        (identity photometric terms, packed frames, mask sums, colour pyramid, tie-break noise) is launched on a side stream and
+        runs under the encoder (functional.prefetch_batch_terms).  Optional: without it the loss computes these itself."""
+        self._pre = None
+        tgt = input_dict.get(("original_image", 0))
+        if (not self.training or os.environ.get("FSNET_LOSS_PREFETCH", "1") == "0" or len(self.frame_ids) != 3
+                or tgt is None or tgt.device.type != "cuda" or not torch.is_grad_enabled()):
+            return
+        f1, f2 = self.frame_ids[1], self.frame_ids[2]
+        draw = input_dict.get("motion_mask") is None and self.tie_break_noise is None
+        self._pre = Fn.prefetch_batch_terms(tgt, input_dict[("original_image", f1)], input_dict[("original_image", f2)],
+                                            input_dict.get("patched_mask"), self.scales, getattr(self, "is_log_image", True), draw)
+
     def compute_total_reprojection_loss(self, output_dict, input_dict):
         """Returns (losses, hm, total) like monodepth2_decoder.py:205-304."""
         if len(self.frame_ids) != 3:
@@ -77,10 +93,16 @@ class MonoDepth2Decoder(nn.Module):
         depths = [output_dict[("depth", s, s)] for s in self.scales]
         disps = [output_dict[("disp", s)] for s in self.scales]
         motion = input_dict.get("motion_mask")
+        pre, self._pre = getattr(self, "_pre", None), None
         noise = None
         if motion is None:
             if self.tie_break_noise is not None:
                 noise = [self.tie_break_noise[s].to(tgt.device) for s in self.scales]
+            elif pre is not None and pre.noise is not None:
+                torch.cuda.current_stream().wait_event(pre.event)      # drawn on the side stream at step start
+                noise = pre.noise
+                for n_ in noise:
+                    n_.record_stream(torch.cuda.current_stream())
             else:   # the reference draws on the CPU and uploads (:258-259); same distribution, drawn on the device
                 noise = list(torch.randn(self.num_scales, B, 2, H, W, device=tgt.device).unbind(0))
         log_image = getattr(self, "is_log_image", True)
@@ -88,7 +110,7 @@ class MonoDepth2Decoder(nn.Module):
         total, stats, sel, pred0 = Fn.reprojection_loss(
             depths, disps, output_dict[("cam_T_cam", f1)], output_dict[("cam_T_cam", f2)], input_dict["P2"], tgt,
             input_dict[("original_image", f1)], input_dict[("original_image", f2)], input_dict.get("patched_mask"), motion,
-            noise, scales=self.scales, overlapped_mask=getattr(self, "overlapped_mask", False), log_image=log_image, mei=mei)
+            noise, scales=self.scales, overlapped_mask=getattr(self, "overlapped_mask", False), log_image=log_image, mei=mei, pre=pre)
         S = self.num_scales
         losses = {}
         for i, s in enumerate(self.scales):

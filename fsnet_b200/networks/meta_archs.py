@@ -36,6 +36,7 @@ class MonoDepthMeta(BaseMetaArch):
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
 
     def forward_train(self, data, meta):
+        self.head.prefetch_loss_terms(data)
         features = self.depth_backbone(data[("image", 0)])
         outputs = self.head.forward_depth(features)
         for f_i in self.train_cfg.frame_ids[1:]:
@@ -72,6 +73,7 @@ class MonoDepthWPose(BaseMetaArch):
                                       "reference repository (its shipped PoseDecoder rejects the call)")
 
     def forward_train(self, data, meta):
+        self.head.prefetch_loss_terms(data)
         features = self.depth_backbone(data[("image", 0)])
         outputs = self.head.forward_depth(features, data["P2"])
         for f_i in self.train_cfg.frame_ids[1:]:
@@ -130,6 +132,7 @@ class DistillWPoseMeta(BaseMetaArch):
         return self
 
     def forward_train(self, data, meta):
+        self.head.prefetch_loss_terms(data)
         image_0 = data[("image", 0)]
         outputs = self.head.forward_depth(self.depth_backbone(image_0), data["P2"])
         outputs.update(self.teacher_net.compute_teacher_depth(image_0))
