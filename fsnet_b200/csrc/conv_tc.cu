@@ -55,7 +55,7 @@ struct ConvParams {
   // halo path (conv_halo_kernel): 3x3 / stride 1, 64-channel K chunks.  The (TH+2) x (TW+2) halo of a 128-pixel tile is loaded ONCE per
   // chunk and plane; tap (r, s) is the same shared-memory tile read from a start address shifted by whole pixels.
   // halo = 1: 16 rows x 8 pixels (box [64, 10, 18]);  halo = 2: 8 rows x 16 pixels, y fastest in shared memory (box [64 ch, 10 rows, 18 cols])
-  int halo, a_stages, b_stages;
+  int halo, a_stages, b_stages, b_resident;
   uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes, a_tx, b_tx;
   int dbg;                     // diagnostics (FSNET_CONV_DBG, tools/bench_conv.py): 1 skip the accumulate read, 2 skip the stores, 4 skip the statistics
 };
@@ -158,50 +158,87 @@ __device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc
 // hi*lo) K-steps back to back, descriptor advances (32 B = 2 units per K-step) done in PTX.  The tensor pipe's queue is shallow:
 // whatever the issuing warp executes between two tcgen05.mma (an election per MMA, 64-bit descriptor assembly per tap: ~400 cycles
 // per stage in the first version) showed up as idle pipe time on top of the MMAs (profiles/r2_conv_halo.md, DBG ablation).
-template <int NPROD>
+template <int NPROD, int KS = 4>
 __device__ __forceinline__ void umma_chunk_elect(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                                  uint32_t idesc, uint32_t accumulate_first) {
+  // KS = K-steps of 16 elements in the chunk (4: 64-channel rows, 2: 32, 1: 16); products hi*hi, then lo*hi, then hi*lo
+#define FSNET_MMA(A, B, P) "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " P ";\n"
   if (NPROD == 3) {
-    asm volatile(
-        "{\n"
-        ".reg .pred pe, pz, pt;\n"
-        ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "setp.ne.b32 pz, %6, 0;\n"
-        "setp.eq.b32 pt, %6, %6;\n"
-        "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
-        "add.u64 al1, %2, 2;\n add.u64 al2, %2, 4;\n add.u64 al3, %2, 6;\n"
-        "add.u64 bh1, %3, 2;\n add.u64 bh2, %3, 4;\n add.u64 bh3, %3, 6;\n"
-        "add.u64 bl1, %4, 2;\n add.u64 bl2, %4, 4;\n add.u64 bl3, %4, 6;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, pz;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bh3, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al1, bh1, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al2, bh2, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], al3, bh3, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bl1, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bl2, %5, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bl3, %5, pt;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    if (KS == 4) {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz, pt;\n"
+          ".reg .b64 ah1, ah2, ah3, al1, al2, al3, bh1, bh2, bh3, bl1, bl2, bl3;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          "setp.eq.b32 pt, %6, %6;\n"
+          "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
+          "add.u64 al1, %2, 2;\n add.u64 al2, %2, 4;\n add.u64 al3, %2, 6;\n"
+          "add.u64 bh1, %3, 2;\n add.u64 bh2, %3, 4;\n add.u64 bh3, %3, 6;\n"
+          "add.u64 bl1, %4, 2;\n add.u64 bl2, %4, 4;\n add.u64 bl3, %4, 6;\n"
+          FSNET_MMA("%1", "%3", "pz") FSNET_MMA("ah1", "bh1", "pt") FSNET_MMA("ah2", "bh2", "pt") FSNET_MMA("ah3", "bh3", "pt")
+          FSNET_MMA("%2", "%3", "pt") FSNET_MMA("al1", "bh1", "pt") FSNET_MMA("al2", "bh2", "pt") FSNET_MMA("al3", "bh3", "pt")
+          FSNET_MMA("%1", "%4", "pt") FSNET_MMA("ah1", "bl1", "pt") FSNET_MMA("ah2", "bl2", "pt") FSNET_MMA("ah3", "bl3", "pt")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    } else if (KS == 2) {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz, pt;\n"
+          ".reg .b64 ah1, al1, bh1, bl1;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          "setp.eq.b32 pt, %6, %6;\n"
+          "add.u64 ah1, %1, 2;\n add.u64 al1, %2, 2;\n add.u64 bh1, %3, 2;\n add.u64 bl1, %4, 2;\n"
+          FSNET_MMA("%1", "%3", "pz") FSNET_MMA("ah1", "bh1", "pt")
+          FSNET_MMA("%2", "%3", "pt") FSNET_MMA("al1", "bh1", "pt")
+          FSNET_MMA("%1", "%4", "pt") FSNET_MMA("ah1", "bl1", "pt")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz, pt;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          "setp.eq.b32 pt, %6, %6;\n"
+          FSNET_MMA("%1", "%3", "pz") FSNET_MMA("%2", "%3", "pt") FSNET_MMA("%1", "%4", "pt")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    }
   } else {
-    asm volatile(
-        "{\n"
-        ".reg .pred pe, pz, pt;\n"
-        ".reg .b64 ah1, ah2, ah3, bh1, bh2, bh3;\n"
-        "elect.sync _|pe, 0xffffffff;\n"
-        "setp.ne.b32 pz, %4, 0;\n"
-        "setp.eq.b32 pt, %4, %4;\n"
-        "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
-        "add.u64 bh1, %2, 2;\n add.u64 bh2, %2, 4;\n add.u64 bh3, %2, 6;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pz;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah1, bh1, %3, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah2, bh2, %3, pt;\n"
-        "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], ah3, bh3, %3, pt;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(b_hi), "r"(idesc), "r"(accumulate_first) : "memory");
+    // (operand numbering as above: %2 / %4, the lo planes, are unused)
+    if (KS == 4) {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz, pt;\n"
+          ".reg .b64 ah1, ah2, ah3, bh1, bh2, bh3;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          "setp.eq.b32 pt, %6, %6;\n"
+          "add.u64 ah1, %1, 2;\n add.u64 ah2, %1, 4;\n add.u64 ah3, %1, 6;\n"
+          "add.u64 bh1, %3, 2;\n add.u64 bh2, %3, 4;\n add.u64 bh3, %3, 6;\n"
+          FSNET_MMA("%1", "%3", "pz") FSNET_MMA("ah1", "bh1", "pt") FSNET_MMA("ah2", "bh2", "pt") FSNET_MMA("ah3", "bh3", "pt")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    } else if (KS == 2) {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz, pt;\n"
+          ".reg .b64 ah1, bh1;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          "setp.eq.b32 pt, %6, %6;\n"
+          "add.u64 ah1, %1, 2;\n add.u64 bh1, %3, 2;\n"
+          FSNET_MMA("%1", "%3", "pz") FSNET_MMA("ah1", "bh1", "pt")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred pe, pz;\n"
+          "elect.sync _|pe, 0xffffffff;\n"
+          "setp.ne.b32 pz, %6, 0;\n"
+          FSNET_MMA("%1", "%3", "pz")
+          "}\n" ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first) : "memory");
+    }
   }
+#undef FSNET_MMA
 }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
@@ -335,6 +372,14 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
     const int oy = ty * p.TH + py, ox = tx * p.TW + px;
     const bool valid = (m < p.TH * p.TW) && oy < p.Ho && ox < p.Wo && mt < p.m_tiles;
     float* orow = p.out + (((size_t)img * p.out_ph + oy + p.out_ring) * p.out_pw + ox + p.out_ring) * p.out_ct + p.out_coff + nt * p.BN;
+    // accumulating launches (a gradient buffer with a second consumer): the old values of this warp's first 16-column group are
+    // requested BEFORE the wait for the accumulator, so their latency hides behind the tile's MMAs
+    float4 old0[4];
+    const bool pre_old = p.accumulate && !(p.dbg & 1) && valid && half * 16 < p.BN;
+    if (pre_old) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) old0[j] = *reinterpret_cast<const float4*>(orow + half * 16 + 4 * j);
+    }
     mbar_wait(&tmem_full[acc], ((uint32_t)it >> 1) & 1);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -361,7 +406,10 @@ __device__ __forceinline__ void epilogue_warps(const ConvParams& p, int warp, in
         for (int j = 0; j < 16; j += 4) {
           float4* dst = reinterpret_cast<float4*>(orow + c0 + j);
           float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.accumulate && !(p.dbg & 1)) { float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          if (p.accumulate && !(p.dbg & 1)) {
+            const float4 old = (g == 0 && pre_old) ? old0[j / 4] : *dst;
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
           *dst = o;
         }
       }
@@ -595,30 +643,36 @@ FSNET_CONV_KERNEL(conv_tc_kernel_c8, __cluster_dims__(8, 1, 1))
 // A and the per-tap weight tiles ride in two separate rings with their own producer warps (0: weights, 10: halo tiles).
 // ---------------------------------------------------------------------------------------------------------------------------------
 constexpr int kHaloThreads = 352;      // warp 0 weight producer, 1 MMA issuer, 2-9 epilogue, 10 halo producer
-constexpr int kHaloMaxA = 4, kHaloMaxB = 8;
+constexpr int kHaloMaxA = 8, kHaloMaxB = 8;
 
-template <int NPROD>
+// KS = K-steps per tap = channels per chunk / 16: 4 (64-channel chunks, 128-byte rows / swizzle), 2 (32, 64 B), 1 (16, 32 B).
+template <int NPROD, int KS>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kHaloMaxA], a_empty[kHaloMaxA], b_full[kHaloMaxB], b_empty[kHaloMaxB], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_smem;
+  constexpr int KC = 16 * KS;                    // channels per chunk
+  constexpr uint32_t RB = 2 * KC;                // bytes per pixel row of the halo tile / per weight row
+  constexpr uint32_t LAYOUT = KS == 4 ? 2u : (KS == 2 ? 4u : 6u);
 
   // dynamic smem: [a_stages * a_stage_bytes | b_stages * b_stage_bytes | 4 x 2*BN fp64 statistics slots]
+  // (b_resident: b_stages = 9 * cchunks, every (chunk, tap) weight tile is loaded once per CTA and stays)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + (size_t)p.a_stages * p.a_stage_bytes;
   double* s_stats = reinterpret_cast<double*>(smem_b + (size_t)p.b_stages * p.b_stage_bytes);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
+  const int n_bbar = p.b_resident ? 1 : p.b_stages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
     tma_prefetch_desc(&map_b_hi);
     if (NPROD == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < n_bbar; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
     fence_barrier_init();
   }
@@ -634,13 +688,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   if (p.dbg & 32) {
     // diagnostics: prologue and teardown only
   } else if (warp == 10) {
-    // ===================== halo producer: one box per (tile, 64-channel chunk, plane) =====================
+    // ===================== halo producer: one box per (tile, channel chunk, plane) =====================
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles;
       const int tx = mt % p.tiles_x; const int rest = mt / p.tiles_x;
       const int ty = rest % p.tiles_y; const int img = rest / p.tiles_y;
-      const int x0 = tx * p.TW - 1 + p.org, y0 = ty * p.TH - 1 + p.org;
+      const int x0 = tx * p.TW - p.pad + p.org, y0 = ty * p.TH - p.pad + p.org;
       const int c1 = p.halo == 2 ? y0 : x0, c2 = p.halo == 2 ? x0 : y0;          // halo 2: the tensor map's dimension 1 is the image row
       for (int cc = 0; cc < p.cchunks; ++cc) {
         mbar_wait(&a_empty[stage], phase ^ 1);
@@ -648,28 +702,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (p.dbg & 8) { if (lane == 0) mbar_arrive(&a_full[stage]); __syncwarp(); }      // diagnostics: no loads
         else {
         mbar_expect_tx_elect(&a_full[stage], p.a_tx);
-        tma_load_4d_elect(st, &map_a_hi, &a_full[stage], cc * 64, c1, c2, img);
-        if (NPROD == 3) tma_load_4d_elect(st + p.a_plane_bytes, &map_a_lo, &a_full[stage], cc * 64, c1, c2, img);
+        tma_load_4d_elect(st, &map_a_hi, &a_full[stage], cc * KC, c1, c2, img);
+        if (NPROD == 3) tma_load_4d_elect(st + p.a_plane_bytes, &map_a_lo, &a_full[stage], cc * KC, c1, c2, img);
         }
         if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 0) {
-    // ===================== weight producer: one [BN x 64] box per (chunk, tap, plane) =====================
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      for (int cc = 0; cc < p.cchunks; ++cc) {
-        for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
-          uint8_t* st = smem_b + (size_t)stage * p.b_stage_bytes;
-          if (p.dbg & 8) { if (lane == 0) mbar_arrive(&b_full[stage]); __syncwarp(); }
-          else {
-          mbar_expect_tx_elect(&b_full[stage], p.b_tx);
-          tma_load_2d_elect(st, &map_b_hi, &b_full[stage], tap * p.Cin + cc * 64, nt * p.BN);
-          if (NPROD == 3) tma_load_2d_elect(st + p.b_plane_bytes, &map_b_lo, &b_full[stage], tap * p.Cin + cc * 64, nt * p.BN);
+    // ===================== weight producer: one [BN x KC] box per (chunk, tap, plane) =====================
+    if (p.b_resident) {
+      // thin layers: all 9 * cchunks weight tiles of the (single) channel tile fit next to the halo ring: loaded once per CTA
+      if (!(p.dbg & 8)) {
+        mbar_expect_tx_elect(&b_full[0], p.b_tx * 9u * (uint32_t)p.cchunks);
+        for (int cc = 0; cc < p.cchunks; ++cc)
+          for (int tap = 0; tap < 9; ++tap) {
+            uint8_t* st = smem_b + (size_t)(cc * 9 + tap) * p.b_stage_bytes;
+            tma_load_2d_elect(st, &map_b_hi, &b_full[0], tap * p.Cin + cc * KC, 0);
+            if (NPROD == 3) tma_load_2d_elect(st + p.b_plane_bytes, &map_b_lo, &b_full[0], tap * p.Cin + cc * KC, 0);
           }
-          if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+      } else { if (lane == 0) mbar_arrive(&b_full[0]); __syncwarp(); }
+    } else {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            uint8_t* st = smem_b + (size_t)stage * p.b_stage_bytes;
+            if (p.dbg & 8) { if (lane == 0) mbar_arrive(&b_full[stage]); __syncwarp(); }
+            else {
+            mbar_expect_tx_elect(&b_full[stage], p.b_tx);
+            tma_load_2d_elect(st, &map_b_hi, &b_full[stage], tap * p.Cin + cc * KC, nt * p.BN);
+            if (NPROD == 3) tma_load_2d_elect(st + p.b_plane_bytes, &map_b_lo, &b_full[stage], tap * p.Cin + cc * KC, nt * p.BN);
+            }
+            if (++stage == p.b_stages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -677,33 +744,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     // ===================== MMA issuer (converged warp, elected lane; see conv_tc_body) =====================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
     // descriptors = base descriptor + byte offset / 16 (the address field holds address >> 4 and shared memory ends below 2^18):
-    // a stage or a tap is one 64-bit add.  Halo tile: 8-pixel groups 10 pixels (1280 B) apart; weights: 8 rows 1024 B apart.
-    const uint64_t a_base = make_desc(smem_u32(smem), 10u * 128u, 2u);
-    const uint64_t b_base = make_desc(smem_u32(smem_b), 1024u, 2u);
+    // a stage or a tap is one 64-bit add.  Halo tile: 8-pixel groups 10 pixels apart; weights: 8 rows of RB bytes.
+    const uint64_t a_base = make_desc(smem_u32(smem), 10u * RB, LAYOUT);
+    const uint64_t b_base = make_desc(smem_u32(smem_b), 8u * RB, LAYOUT);
     const uint32_t a_stage16 = p.a_stage_bytes >> 4, b_stage16 = p.b_stage_bytes >> 4, a_lo16 = p.a_plane_bytes >> 4, b_lo16 = p.b_plane_bytes >> 4;
-    // halo 1: pixel (y, x) of the halo sits at (y * 10 + x) * 128 B; halo 2: at (x * 10 + y) * 128 B  (units of 16 B below)
-    const uint32_t row16 = p.halo == 2 ? 8u : 80u, col16 = p.halo == 2 ? 80u : 8u;
+    // halo 1: pixel (y, x) of the halo sits at (y * 10 + x) * RB; halo 2: at (x * 10 + y) * RB  (units of 16 B below)
+    const uint32_t row16 = p.halo == 2 ? RB / 16u : 10u * RB / 16u, col16 = p.halo == 2 ? 10u * RB / 16u : RB / 16u;
     int as = 0, bs = 0; uint32_t aph = 0, bph = 0; int it = 0;
     uint32_t a_off16 = 0, b_off16 = 0;
+    if (p.b_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       mbar_wait(&tmem_empty[acc], (((uint32_t)it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      if (p.b_resident) b_off16 = 0;
       for (int cc = 0; cc < p.cchunks; ++cc) {
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&b_full[bs], bph);
-          tc_fence_after();
+          if (!p.b_resident) { mbar_wait(&b_full[bs], bph); tc_fence_after(); }
           const uint64_t a_hi = a_base + (uint64_t)(a_off16 + (uint32_t)(tap / 3) * row16 + (uint32_t)(tap % 3) * col16);
           const uint64_t b_hi = b_base + (uint64_t)b_off16;
           if (!(p.dbg & 16))                                           // diagnostics: 16 = no MMAs
-            umma_chunk_elect<NPROD>(d_tmem, a_hi, a_hi + a_lo16, b_hi, b_hi + b_lo16, idesc, (cc | tap) != 0);
-          umma_commit_elect(&b_empty[bs]);
+            umma_chunk_elect<NPROD, KS>(d_tmem, a_hi, a_hi + a_lo16, b_hi, b_hi + b_lo16, idesc, (cc | tap) != 0);
           b_off16 += b_stage16;
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1; b_off16 = 0; }
+          if (!p.b_resident) {
+            umma_commit_elect(&b_empty[bs]);
+            if (++bs == p.b_stages) { bs = 0; bph ^= 1; b_off16 = 0; }
+          }
         }
         umma_commit_elect(&a_empty[as]);
         a_off16 += a_stage16;
@@ -811,7 +881,10 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   static int halo_env = -1;
   if (halo_env < 0) { const char* e = getenv("FSNET_CONV_HALO"); halo_env = e ? atoi(e) : 1; }
   p.halo = 0;
-  if (halo_env && KH == 3 && KW == 3 && stride == 1 && pad == 1 && Cin % 64 == 0 && (!use_ring || in->ring == 1)) {
+  // (FSNET_CONV_HALO=4: only the 64-channel-chunk layers, the thin ones stay on the folded-tap path)
+  const bool halo_pad_ok = (pad == 1 && (!use_ring || in->ring == 1)) || (pad == 2 && use_ring && in->ring == 2);
+  if (halo_env && KH == 3 && KW == 3 && stride == 1 && halo_pad_ok && Cin % 16 == 0 && (Cin % 64 == 0 || halo_env != 4) &&
+      in->c_off % 8 == 0) {
     auto eff = [&](int th, int tw) { return ((double)p.Ho / (ceil_div(p.Ho, th) * th)) * ((double)p.Wo / (ceil_div(p.Wo, tw) * tw)); };
     const double ex = eff(16, 8), ey = eff(8, 16);
     const double cur = ((double)p.Ho / (ceil_div(p.Ho, p.TH) * p.TH)) * ((double)p.Wo / (ceil_div(p.Wo, p.TW) * p.TW)) * (p.TH * p.TW / 128.0);
@@ -851,7 +924,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   // run in NHWC, read as 64-element slices through an overlapping-stride tensor map (pixel stride = Cin elements)
   static int fold_env = -1;
   if (fold_env < 0) { const char* e = getenv("FSNET_CONV_FOLD"); fold_env = e ? atoi(e) : 2; }
-  p.fold = fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
+  p.fold = !p.halo && fold_env && stride == 1 && use_ring && in->ring == pad && (pad == 1 || pad == 2) && KH == 3 && KW == 3 && in->c_off == 0 &&
            in->c == in->c_total && (Cin < 64 || Cin == 96);
   // the 7x7 / stride-2 stem on 8-channel (3 or 6 real) image planes with a materialised zero ring: the 7 taps x 8 channels of a
   // kernel row are 56 contiguous elements = ONE 64-element slice (K = 7 x 64 for a real K of 147; 16-channel planes needed two
@@ -933,19 +1006,30 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   if (p.halo) {
     const uint32_t planes = nprod == 3 ? 2u : 1u;
-    p.fold = 0; p.KC = 64; p.cchunks = Cin / 64; p.kiters = 9 * p.cchunks;
+    p.fold = 0; p.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16); p.cchunks = Cin / p.KC; p.kiters = 9 * p.cchunks;
+    const uint32_t rb = 2u * (uint32_t)p.KC;             // bytes per pixel row (= per weight row) of a chunk
     p.cm = p.cn = 1; p.super_n = p.n_tiles; p.total_super = p.total_tiles;
-    p.a_plane_bytes = 23552u;                          // 18 x 10 pixels x 128 B = 23040, rounded up to the 1024-byte swizzle atom
-    p.a_stage_bytes = planes * p.a_plane_bytes; p.a_tx = planes * 23040u;
-    p.b_plane_bytes = (uint32_t)p.BN * 128u;
+    p.a_plane_bytes = (180u * rb + 1023u) & ~1023u;      // 18 x 10 pixels, rounded up to the 1024-byte atom of the widest swizzle
+    p.a_stage_bytes = planes * p.a_plane_bytes; p.a_tx = planes * 180u * rb;
+    p.b_plane_bytes = (uint32_t)p.BN * rb;
     p.b_stage_bytes = planes * p.b_plane_bytes; p.b_tx = p.b_stage_bytes;
     const uint32_t budget = 220u * 1024u - stats_bytes;
-    p.a_stages = nprod == 3 ? 2 : 3;
-    { static int as_env = -1; if (as_env < 0) { const char* e = getenv("FSNET_CONV_HALO_ASTAGES"); as_env = e ? atoi(e) : 0; } if (as_env) p.a_stages = as_env; }
-    if (p.a_stages > p.cchunks + 1) p.a_stages = p.cchunks + 1;
-    int bst = (int)((budget - (uint32_t)p.a_stages * p.a_stage_bytes) / p.b_stage_bytes);
-    p.b_stages = bst > kHaloMaxB ? kHaloMaxB : bst;
-    FSNET_REQUIRE(p.b_stages >= 2, "fsnet_conv: halo tile does not fit shared memory");
+    // weights resident in shared memory when all 9 * cchunks tap tiles of the (single) channel tile fit beside a halo ring of >= 3
+    // stages: the thin layers (16..96 input channels) then receive nothing but their halo tiles
+    const uint32_t all_b = 9u * (uint32_t)p.cchunks * p.b_stage_bytes;
+    p.b_resident = p.n_tiles == 1 && all_b + 3u * p.a_stage_bytes <= budget && all_b <= 128u * 1024u;
+    if (p.b_resident) {
+      p.b_stages = 9 * p.cchunks;
+      int ast = (int)((budget - all_b) / p.a_stage_bytes);
+      p.a_stages = ast > kHaloMaxA ? kHaloMaxA : ast;
+    } else {
+      p.a_stages = nprod == 3 ? 2 : 3;
+      if (p.a_stages > p.cchunks + 1) p.a_stages = p.cchunks + 1;
+      { static int as_env = -1; if (as_env < 0) { const char* e = getenv("FSNET_CONV_HALO_ASTAGES"); as_env = e ? atoi(e) : 0; } if (as_env) p.a_stages = as_env; }
+      int bst = (int)((budget - (uint32_t)p.a_stages * p.a_stage_bytes) / p.b_stage_bytes);
+      p.b_stages = bst > kHaloMaxB ? kHaloMaxB : bst;
+    }
+    FSNET_REQUIRE(p.b_stages >= 2 && p.a_stages >= 2, "fsnet_conv: halo tile does not fit shared memory");
     p.stages = p.a_stages;
     p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
     p.out_ct = out->c_total; p.out_coff = out->c_off; p.accumulate = accumulate;
@@ -954,7 +1038,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
     CUtensorMap ma[2], mb[2];
     for (uint32_t pl = 0; pl < planes; ++pl) {
       if (p.halo == 1) {
-        int rc = encode_act_map(&ma[pl], in, (int)pl, use_ring, 64, 10, 18, 1, "fsnet_conv(halo)");
+        int rc = encode_act_map(&ma[pl], in, (int)pl, use_ring, p.KC, 10, 18, 1, "fsnet_conv(halo)");
         if (rc) return rc;
       } else {
         const int pw = in->w + 2 * in->ring, ph = in->h + 2 * in->ring;
@@ -964,30 +1048,34 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
         const int Wm = use_ring ? pw : in->w, Hm = use_ring ? ph : in->h;
         cuuint64_t dim[4] = {(cuuint64_t)in->c, (cuuint64_t)Hm, (cuuint64_t)Wm, (cuuint64_t)in->n};
         cuuint64_t str[3] = {(cuuint64_t)pw * in->c_total * 2, (cuuint64_t)in->c_total * 2, (cuuint64_t)ph * pw * in->c_total * 2};
-        cuuint32_t box[4] = {64, 10, 18, 1};
+        cuuint32_t box[4] = {(cuuint32_t)p.KC, 10, 18, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         FSNET_REQUIRE(((uintptr_t)base & 15) == 0, "fsnet_conv(halo): activation view is not 16-byte aligned");
         CUresult r = enc(&ma[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv(halo): cuTensorMapEncodeTiled(A, rows fastest) failed with %d", (int)r);
       }
       const int Ktot = 9 * Cin;
       cuuint64_t bdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
       cuuint64_t bstr[1] = {(cuuint64_t)Ktot * 2};
-      cuuint32_t bbox[2] = {64, (cuuint32_t)p.BN};
+      cuuint32_t bbox[2] = {(cuuint32_t)p.KC, (cuuint32_t)p.BN};
       cuuint32_t bes[2] = {1, 1};
       CUresult r = enc(&mb[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)(pl ? w_lo : w_hi), bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                       swizzle_for(p.KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv(halo): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     if (planes == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
     const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + stats_bytes + 1024;
-    auto kern = nprod == 3 ? conv_halo_kernel<3> : conv_halo_kernel<1>;
-    static bool halo_attr[2] = {false, false};
-    if (!halo_attr[nprod == 3]) {
+    typedef void (*HaloKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvParams);
+    static const HaloKernel kernels[2][3] = {{conv_halo_kernel<1, 1>, conv_halo_kernel<1, 2>, conv_halo_kernel<1, 4>},
+                                             {conv_halo_kernel<3, 1>, conv_halo_kernel<3, 2>, conv_halo_kernel<3, 4>}};
+    const int ki = p.KC == 64 ? 2 : (p.KC == 32 ? 1 : 0);
+    HaloKernel kern = kernels[nprod == 3][ki];
+    static bool halo_attr[2][3] = {};
+    if (!halo_attr[nprod == 3][ki]) {
       FSNET_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      halo_attr[nprod == 3] = true;
+      halo_attr[nprod == 3][ki] = true;
     }
     FSNET_LAUNCH_PDL(kern, grid, kHaloThreads, smem, (cudaStream_t)stream, ma[0], ma[1], mb[0], mb[1], p);
     FSNET_LAUNCH_OK();

@@ -13,7 +13,7 @@
 #include <math.h>
 #include <vector>
 
-constexpr int TH = 16, TW = 8, HR = TH + 2, HC = TW + 2, C = 64, NOUT = 64;
+constexpr int TH = 16, TW = 8, HR = TH + 2, HC = TW + 2, NOUT = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -32,27 +32,30 @@ __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* map, uint64
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo, uint32_t base_off) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo, uint32_t base_off, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)(base_off & 7) << 49;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
 // out[variant 0..3][tap 0..8][128][64]
+template <int C>
 __global__ void __launch_bounds__(128, 1) shift_kernel(const __grid_constant__ CUtensorMap map_dense, const __grid_constant__ CUtensorMap map_row,
                                                        const __grid_constant__ CUtensorMap map_b, float* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t ld_bar, mma_bar;
   __shared__ uint32_t tmem_base_smem;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_dense = smem;                       // 18 * 10 * 128 = 23040 B -> 23552
-  uint8_t* a_pad = smem + 23552;                 // 18 * 2048 = 36864
-  uint8_t* b_sm = smem + 23552 + 36864;          // 64 * 128 = 8192
+  constexpr uint32_t RB = C * 2;                 // bytes per pixel row: 128 / 64 / 32
+  constexpr uint32_t LAYOUT = C == 64 ? 2u : (C == 32 ? 4u : 6u);
+  uint8_t* a_dense = smem;                       // 18 * 10 * RB <= 23040 B -> 23552
+  uint8_t* a_pad = smem + 23552;                 // 18 * 16 * RB <= 36864
+  uint8_t* b_sm = smem + 23552 + 36864;          // 64 * RB <= 8192
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { mbar_init(&ld_bar, 1); mbar_init(&mma_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {
@@ -67,25 +70,25 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __grid_constant__ C
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_smem;
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&ld_bar, HR * HC * 128 * 2 + NOUT * 128);
+    mbar_expect_tx(&ld_bar, HR * HC * RB * 2 + NOUT * RB);
     tma_3d(a_dense, &map_dense, &ld_bar, 0, 0, 0);
-    for (int y = 0; y < HR; ++y) tma_3d(a_pad + y * 2048, &map_row, &ld_bar, 0, 0, y);
+    for (int y = 0; y < HR; ++y) tma_3d(a_pad + y * 16 * RB, &map_row, &ld_bar, 0, 0, y);
     tma_2d(b_sm, &map_b, &ld_bar, 0, 0);
   }
   mbar_wait(&ld_bar, 0);
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NOUT >> 3) << 17) | ((128u >> 4) << 24);
   uint32_t ph = 0;
   for (int variant = 0; variant < 4; ++variant) {
-    const uint32_t pitch = (variant & 1) ? 2048u : 1280u;
+    const uint32_t pitch = (variant & 1) ? 16u * RB : 10u * RB;
     const uint8_t* a_base = (variant & 1) ? a_pad : a_dense;
     for (int tap = 0; tap < 9; ++tap) {
       const int r = tap / 3, s = tap % 3;
       if (threadIdx.x == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t start = smem_u32(a_base) + r * pitch + s * 128;
+        const uint32_t start = smem_u32(a_base) + r * pitch + s * RB;
         const uint32_t boff = (variant & 2) ? ((start >> 7) & 7) : 0;
-        const uint64_t ad = make_desc(start, pitch, boff), bd = make_desc(smem_u32(b_sm), 1024, 0);
-        for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = make_desc(start, pitch, boff, LAYOUT), bd = make_desc(smem_u32(b_sm), 8 * RB, 0, LAYOUT);
+        for (int k = 0; k < C / 16; ++k) {
           asm volatile("{\n.reg .pred pa;\nsetp.ne.b32 pa, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n}\n"
                        ::"r"(tmem), "l"(ad + 2 * k), "l"(bd + 2 * k), "r"(idesc), "r"(k > 0 ? 1u : 0u) : "memory");
         }
@@ -115,10 +118,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-int main() {
-  void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
-  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
-  EncodeTiledFn enc = (EncodeTiledFn)ptr;
+template <int C>
+int run(EncodeTiledFn enc) {
   std::vector<__nv_bfloat16> hx(HR * HC * C), hb(NOUT * C);
   std::vector<float> fx(HR * HC * C), fb(NOUT * C);
   srand(7);
@@ -130,18 +131,19 @@ int main() {
   CUtensorMap md, mr, mb;
   cuuint64_t dim[3] = {C, HC, HR}; cuuint64_t str[2] = {C * 2, HC * C * 2}; cuuint32_t es[3] = {1, 1, 1};
   cuuint32_t boxd[3] = {C, HC, HR}, boxr[3] = {C, HC, 1};
-  CUresult r1 = enc(&md, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dim, str, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CUresult r2 = enc(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dim, str, boxr, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r1 = enc(&md, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dim, str, boxd, es, CU_TENSOR_MAP_INTERLEAVE_NONE, (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&mr, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dx, dim, str, boxr, es, CU_TENSOR_MAP_INTERLEAVE_NONE, (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   cuuint64_t bdim[2] = {C, NOUT}; cuuint64_t bstr[1] = {C * 2}; cuuint32_t bbox[2] = {C, NOUT}; cuuint32_t bes[2] = {1, 1};
-  CUresult r3 = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, db, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r3 = enc(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, db, bdim, bstr, bbox, bes, CU_TENSOR_MAP_INTERLEAVE_NONE, (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r1 || r2 || r3) { printf("encode failed %d %d %d\n", (int)r1, (int)r2, (int)r3); return 1; }
   const int smem = 23552 + 36864 + 8192 + 1024;
-  CK(cudaFuncSetAttribute(shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  shift_kernel<<<1, 128, smem>>>(md, mr, mb, dout);
+  CK(cudaFuncSetAttribute(shift_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  shift_kernel<C><<<1, 128, smem>>>(md, mr, mb, dout);
   CK(cudaDeviceSynchronize());
   std::vector<float> ho(4 * 9 * 128 * NOUT);
   CK(cudaMemcpy(ho.data(), dout, ho.size() * 4, cudaMemcpyDeviceToHost));
-  const char* names[4] = {"pitch1280 boff=0", "pitch2048 boff=0", "pitch1280 boff=addr", "pitch2048 boff=addr"};
+  printf("channels per pixel row %d (row %d B):\n", C, C * 2);
+  const char* names[4] = {"pitch 10 px boff=0", "pitch 16 px boff=0", "pitch 10 px boff=addr", "pitch 16 px boff=addr"};
   for (int v = 0; v < 4; ++v) {
     printf("%-20s:", names[v]);
     for (int tap = 0; tap < 9; ++tap) {
@@ -162,4 +164,11 @@ int main() {
     printf("\n");
   }
   return 0;
+}
+
+int main() {
+  void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q));
+  EncodeTiledFn enc = (EncodeTiledFn)ptr;
+  return run<64>(enc) | run<32>(enc) | run<16>(enc);
 }
