@@ -647,7 +647,7 @@ constexpr int kHaloMaxA = 8, kHaloMaxB = 8;
 
 // KS = K-steps per tap = channels per chunk / 16: 4 (64-channel chunks, 128-byte rows / swizzle), 2 (32, 64 B), 1 (16, 32 B).
 template <int NPROD, int KS>
-__global__ void __launch_bounds__(kHaloThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, KS == 4 ? 1 : 2)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1029,6 +1029,19 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
       int bst = (int)((budget - (uint32_t)p.a_stages * p.a_stage_bytes) / p.b_stage_bytes);
       p.b_stages = bst > kHaloMaxB ? kHaloMaxB : bst;
     }
+    // thin layers with resident weights: two CTAs per SM (a tile is ~1.2 K cycles of MMAs between ~400 cycles of hand-overs; the
+    // second CTA's MMAs fill them).  FSNET_CONV_HALO_OCC=1 keeps one CTA per SM.
+    static int hocc_env = -1;
+    if (hocc_env < 0) { const char* e = getenv("FSNET_CONV_HALO_OCC"); hocc_env = e ? atoi(e) : 2; }
+    int hocc = 1;
+    if (hocc_env >= 2 && p.b_resident && p.KC < 64 && p.total_tiles >= 4 * sms && 2u * p.tmem_cols <= 512u) {
+      const uint32_t per_cta = 108u * 1024u - stats_bytes;
+      if (all_b + 3u * p.a_stage_bytes <= per_cta) {
+        hocc = 2;
+        int ast = (int)((per_cta - all_b) / p.a_stage_bytes);
+        p.a_stages = ast > kHaloMaxA ? kHaloMaxA : ast;
+      }
+    }
     FSNET_REQUIRE(p.b_stages >= 2 && p.a_stages >= 2, "fsnet_conv: halo tile does not fit shared memory");
     p.stages = p.a_stages;
     p.out = (float*)out->ptr; p.out_pw = out->w + 2 * out->ring; p.out_ph = out->h + 2 * out->ring; p.out_ring = out->ring;
@@ -1065,7 +1078,7 @@ extern "C" int fsnet_conv(const fsnet_view* in, int use_ring, const void* w_hi, 
       FSNET_REQUIRE(r == CUDA_SUCCESS, "fsnet_conv(halo): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     if (planes == 1) { ma[1] = ma[0]; mb[1] = mb[0]; }
-    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const int grid = p.total_tiles < sms * hocc ? p.total_tiles : sms * hocc;
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + stats_bytes + 1024;
     typedef void (*HaloKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvParams);
     static const HaloKernel kernels[2][3] = {{conv_halo_kernel<1, 1>, conv_halo_kernel<1, 2>, conv_halo_kernel<1, 4>},
