@@ -5,6 +5,8 @@ fallback.  Reference citations (file:line) are relative to the FSNet checkout.
 """
 from typing import List, Optional, Sequence
 
+import os
+
 import torch
 
 from . import _lib
@@ -175,6 +177,29 @@ class _ReprojectionLoss(torch.autograd.Function):
         if fused:
             unit = torch.full((1,), 1.0 / S, device=dev, dtype=torch.float32)
             unit_gP = torch.zeros(B, 2, 12, device=dev, dtype=torch.float32) if ctx.need_pose else None
+        # Smoothness term on a side stream, under the frame-pair kernels (which are issue bound and leave the memory system idle):
+        # forward sums and -- in training steps -- the backward for the unit upstream gradient, which backward() rescales like
+        # the fused photometric gradients.  Joined before the loss is finalised.
+        side = _SIDE.get(dev) if (dev.type == "cuda" and os.environ.get("FSNET_SMOOTH_STREAM", "1") != "0") else None
+        if side is None and dev.type == "cuda" and os.environ.get("FSNET_SMOOTH_STREAM", "1") != "0":
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        unit_gs = [None] * S
+        unit_smooth = need_grad and side is not None
+
+        def smooth_terms():
+            for i, s in enumerate(cfg["scales"]):
+                h, w = disps[i].shape[-2:]
+                wgt = float(cfg["smooth_weight"] / (2 ** s))
+                _lib.call("fsnet_smooth_fwd", disps[i], colour[i], B, h, w, h, w, wgt, sums[i], acc[i, 2:])
+                if unit_smooth:
+                    unit_gs[i] = torch.empty(disps[i].shape, device=dev, dtype=torch.float32)
+                    _lib.call("fsnet_smooth_bwd", disps[i], colour[i], B, h, w, h, w, wgt, sums[i], unit_s, unit_gs[i])
+
+        if side is not None:
+            unit_s = torch.full((1,), 1.0 / S, device=dev, dtype=torch.float32)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                smooth_terms()
         for i, s in enumerate(cfg["scales"]):
             hs, ws = depths[i].shape[-2:]
             want_log = sel is not None and s == 0
@@ -187,13 +212,20 @@ class _ReprojectionLoss(torch.autograd.Function):
                 _lib.call(warp_fwd, *lut_args, depths[i], hs, ws, packed, mask_c, mdt, cam, ident, noise_c[i],
                           motion_c, _lib.ctypes.c_uint(flags), B, H, W, acc[i], sel if want_log else None,
                           pred0 if want_log else None)
-            h, w = disps[i].shape[-2:]
-            _lib.call("fsnet_smooth_fwd", disps[i], colour[i], B, h, w, h, w, float(cfg["smooth_weight"] / (2 ** s)), sums[i], acc[i, 2:])
+        if side is not None:
+            main = torch.cuda.current_stream()
+            main.wait_stream(side)
+            for t_ in unit_gs:
+                if t_ is not None:
+                    t_.record_stream(main)
+        else:
+            smooth_terms()
         stats = torch.empty(2 * S + 2, device=dev, dtype=torch.float64)
         _lib.call("fsnet_loss_finalize", acc, S, stats)
         ctx.S, ctx.cfg, ctx.flags, ctx.mdt = S, cfg, flags, mdt
         ctx.shapes = (B, H, W)
         ctx.unit_grads = (unit_gd, unit_gP)
+        ctx.unit_gs = unit_gs
         ctx.colour = colour
         ctx.save_for_backward(*depths, *disps, tgt, packed, cam, P2c, acc, sums,
                               *( [ident] if ident is not None else []), *( [mask_c] if mask_c is not None else []),
@@ -240,6 +272,9 @@ class _ReprojectionLoss(torch.autograd.Function):
                 _lib.call(warp_bwd, *lut_args, depths[i], hs, ws, packed, mask_c, ctx.mdt, cam, ident, noise_c[i],
                           motion_c, _lib.ctypes.c_uint(ctx.flags), B, H, W, acc[i], gout, gd, gP)
                 g_depths.append(gd)
+            if ctx.unit_gs[i] is not None:                       # computed under the forward's pair kernels for d total / d loss = 1
+                g_disps.append(ctx.unit_gs[i] * gscale)
+                continue
             h, w = disps[i].shape[-2:]
             gs = torch.empty(disps[i].shape, device=dev, dtype=torch.float32)
             _lib.call("fsnet_smooth_bwd", disps[i], ctx.colour[i], B, h, w, h, w, float(cfg["smooth_weight"] / (2 ** s)), sums[i], gout, gs)
