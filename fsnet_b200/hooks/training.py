@@ -114,15 +114,21 @@ class BaseTrainingHook(object):
                 continue
             st = grads[0].untyped_storage()
             n = sum(g.numel() for g in grads)
-            if len(grads) > 1 and n * 4 == st.nbytes() and all(g.dtype == torch.float32 and g.is_contiguous() for g in grads):
+            # the executor's flat gradient buffer: every gradient is a view of ONE storage -> one in-place all-reduce of the whole
+            # storage (slots of parameters without a gradient ride along; they are never read)
+            if len(grads) > 1 and n * 4 <= st.nbytes() and all(g.dtype == torch.float32 and g.is_contiguous() for g in grads):
+                n = st.nbytes() // 4
                 flat = torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, 0, (n,))     # the whole pool, in place
                 dist.all_reduce(flat, op=op)
                 if not avg:
                     flat.div_(world)
             else:
                 small += grads
+        if os.environ.get("FSNET_DEBUG_SYNC"):
+            print(f"[fsnet_b200] sync_gradients: {len(by_storage)} storages, reduced earlier {len(engine.REDUCED_STORAGES)}, "
+                  f"small tensors {len(small)} ({sum(g.numel() for g in small)} elements)", flush=True)
         engine.REDUCED_STORAGES.clear()
-        if small:
+        if small and os.environ.get("FSNET_DIAG_NO_GRADSYNC", "0") != "small":       # ("small": timing diagnostics only)
             flat = torch.cat([g.reshape(-1) for g in small])
             dist.all_reduce(flat, op=op)
             if not avg:
