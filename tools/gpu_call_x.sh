@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/r2c27
-for v in "FSNET_X=1" "FSNET_SMOOTH_STREAM=0"; do
+O=gpurun_out/r2c28
+for v in "FSNET_X=1" "FSNET_FUSE_BN_ACT=0"; do
 env $v timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > ${O}_bench.txt 2>&1; python - <<PY
 import json
 try:
@@ -11,4 +11,4 @@ except Exception as e:
     print("$v failed"); print(open("${O}_bench.txt").read()[-2000:])
 PY
 done
-timeout 900 python -m pytest tests/test_loss_gpu.py tests/test_model_gpu.py tests/test_fullsize_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > ${O}_tests_all.txt; tail -3 ${O}_tests_all.txt
