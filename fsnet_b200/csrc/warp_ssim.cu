@@ -10,6 +10,7 @@
 // shared memory and no block-level barrier exists.  The halo lanes/rows recompute the warp of the
 // reflected pixel, exactly what ReflectionPad2d(1) on the *warped* image means.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace fsnet {
@@ -874,7 +875,7 @@ struct PairRow {
 template <int CAM>
 __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams p) {
   __shared__ float s_cam[2][20];                // per frame: M = P[:, :3] K^-1 (9), t = P[:, 3] (3), MEI intrinsics (7)
-  __shared__ float s_ring[2][3][9][32];         // per frame: the last three rows of (target 3, warped 3, d warped / d D 3)
+  __shared__ float s_ring[2][4][9][32];         // per frame: a ring of four rows (three live) of (target 3, warped 3, d warped / d D 3)
   __shared__ float s_ex[2][2][2][32];           // [row parity][frame][photometric | identity][lane]
   const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, W = p.W, HW = H * W;
@@ -1007,59 +1008,47 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
     return r;
   };
 
-  float h1[15], h2[15], g1[9], g2[9];
+  // ---- the row walk ---------------------------------------------------------------------------------------------------
+  // Iteration yy: (A) moments of raw row yy, (B) SSIM + arg-min at centre row yy - 1, (C) adjoint + chain at row yy - 2.
+  // Rows y_begin-1, y_begin run A only, rows y_begin+1 .. y_end all three, two more iterations C only: three code paths
+  // instantiated from one generic lambda, so the steady-state loop carries no phase predicates.  Vertical 3-row sums are
+  // kept as PAIR sums (hP = h(yy-2) + h(yy-1)): S = hP + h(yy), then hP = h(yy-1) + h(yy) -- with the loop unrolled by two the
+  // roles of the two row buffers alternate and nothing is ever moved between registers (the rotation of 2 x 15 + 2 x 9
+  // registers per row was 84 of the 686 instructions of an iteration, profiles/r2_loss_pair_ncu.json).
+  float hX[15], hY[15], hP[15], gX[9], gY[9], gP[9];
 #pragma unroll
-  for (int i = 0; i < 15; ++i) { h1[i] = 0.f; h2[i] = 0.f; }
+  for (int i = 0; i < 15; ++i) { hX[i] = 0.f; hY[i] = 0.f; hP[i] = 0.f; }
 #pragma unroll
-  for (int i = 0; i < 9; ++i) { g1[i] = 0.f; g2[i] = 0.f; }
+  for (int i = 0; i < 9; ++i) { gX[i] = 0.f; gY[i] = 0.f; gP[i] = 0.f; }
   float l1_prev = 0.f, gf_prev = 0.f, acc_num = 0.f, c_m_prev = 1.f;
   bool valid_prev = true;
-
-  const int y_first = y_begin - 1, y_stop = y_end + 2;
-  // prologue: row y_first is requested here (one exposed round trip per CTA), the depth of row y_first + 1 is in flight
-  PairRow cur;
-#if LOSS_PAIR_PIPELINE
-  {
-    const DepthRaw d0 = request_depth(reflect_idx(y_first, H));
-    cur = request_row(y_first, blend_depth(d0), d0.ray, false);
-  }
-  DepthRaw dnext = request_depth(reflect_idx(min(y_first + 1, y_end), H));
-#else
+  const int y_first = y_begin - 1;
   DepthRaw dnext = request_depth(reflect_idx(y_first, H));
-#endif
+  using T_ = std::true_type;
+  using F_ = std::false_type;
 
-  int itn = 0;
-#pragma unroll 1
-  for (int yy = y_first; yy <= y_stop; ++yy, ++itn) {
-    const bool rowA = yy <= y_end;                       // moments of raw row yy
-    const bool rowB = yy >= y_begin + 1 && yy <= y_end;  // SSIM + arg-min at centre row yc = yy - 1
-    const bool rowC = yy >= y_begin + 1;                 // adjoint + chain at row yq = yy - 2
+  auto iter = [&](auto fA, auto fB, auto fC, auto fPar, int yy) {
+    constexpr bool rowA = decltype(fA)::value, rowB = decltype(fB)::value, rowC = decltype(fC)::value;
+    constexpr int par = decltype(fPar)::value;
+    float(&hcur)[15] = par ? hY : hX;            // this row's horizontal sums land here; the other buffer holds the previous row's
+    float(&hprev)[15] = par ? hX : hY;
+    float(&gcur)[9] = par ? gY : gX;
+    float(&gprev)[9] = par ? gX : gY;
     const bool centre = rowB && own_col;
     float c_id = 0.f, c_gate = 1.f, c_m_next = 1.f;
-    const float c_m = c_m_prev;                          // target row yy - 1 was consumed one iteration ago
-    float h[15];
+    const float c_m = c_m_prev;                          // centre row yy - 1: target mask, L1 and validity from one iteration ago
+    const float l1_c = l1_prev;
+    const bool valid_c = valid_prev;
     float l1 = 0.f;
     bool valid = true;
     float ph = 0.f, da[3], db[3], dc[3];
-#if LOSS_PAIR_PIPELINE
-    PairRow nxt = cur;
-#endif
     if (rowA) {
-#if LOSS_PAIR_PIPELINE
-      // ---- load phase: everything row yy + 1 needs (its depth arrived during the previous iteration) ---------------
-      if (yy + 1 <= y_end) {
-        nxt = request_row(yy + 1, blend_depth(dnext), dnext.ray, yy + 1 >= y_begin + 1 && own_col);
-        dnext = request_depth(reflect_idx(min(yy + 2, y_end), H));
-      }
-#else
       // ---- load phase: this row's gathers (its depth was requested one iteration ago), then the next row's depth ---
-      cur = request_row(yy, blend_depth(dnext), dnext.ray, centre);
+      const PairRow cur = request_row(yy, blend_depth(dnext), dnext.ray, centre);
       dnext = request_depth(reflect_idx(min(yy + 1, y_end), H));
-#endif
-      // ---- A: bilinear blend of the corners requested one iteration ago ------------------------------------------
+      // ---- A: bilinear blend of the corners ------------------------------------------------------------------------
       // (every component of the 128-bit pixels is used: a dead 4th component lets the register allocator reuse that register
-      // while the load is in flight, and the write-after-write hazard exposes the full memory latency behind every gather --
-      // 1250 + 1210 of 11 470 stall samples sat on two such instructions in the first versions, profiles/r2_loss_pair.md)
+      // while the load is in flight, and the write-after-write hazard exposes the full memory latency behind every gather)
       if (use_ident) c_id = fmaf(cur.nz, 1e-5f, cur.id); else c_gate = 1.f - cur.nz;
       c_m_next = cur.tq.w;                                   // patched mask of the pixel that is the centre one iteration later
       {
@@ -1070,7 +1059,7 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
       const float a_nw[3] = {cur.nw.x, cur.nw.y, cur.nw.z}, a_ne[3] = {cur.ne.x, cur.ne.y, cur.ne.z};
       const float a_sw[3] = {cur.sw.x, cur.sw.y, cur.sw.z}, a_se[3] = {cur.se.x, cur.se.y, cur.se.z};
       float pred[3];
-      float(*slot)[32] = s_ring[k][(yy + 3) % 3];
+      float(*slot)[32] = s_ring[k][yy & 3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float dxt = a_ne[c] - a_nw[c], dxb = a_se[c] - a_sw[c];
@@ -1083,25 +1072,28 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
         slot[6 + c][lane] = fmaf(dix, cur.du, dyv * cur.dv);    // d pred_c / d D
         l1 += fabsf(tt[c] - pred[c]);
       }
-      hsum15(tt, pred, h);
+      hsum15(tt, pred, hcur);
       // ---- B (first half): SSIM value and partials at the centre row from the three rows of horizontal sums ---
       if (rowB) {
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          s += ssim_sums_grad(h2[6 + c] + h1[6 + c] + h[6 + c], h2[9 + c] + h1[9 + c] + h[9 + c], h2[12 + c] + h1[12 + c] + h[12 + c],
-                              h2[c] + h1[c] + h[c], h2[3 + c] + h1[3 + c] + h[3 + c], da[c], db[c], dc[c]);
-        ph = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_prev);
-        if (overlap && !valid_prev) ph = 100.f;
+          s += ssim_sums_grad(hP[6 + c] + hcur[6 + c], hP[9 + c] + hcur[9 + c], hP[12 + c] + hcur[12 + c],
+                              hP[c] + hcur[c], hP[3 + c] + hcur[3 + c], da[c], db[c], dc[c]);
+        ph = fmaf(0.85f / 3.f, s, (0.15f / 3.f) * l1_c);
+        if (overlap && !valid_c) ph = 100.f;
       }
+#pragma unroll
+      for (int i = 0; i < 15; ++i) hP[i] = hprev[i] + hcur[i];
+      l1_prev = l1; valid_prev = valid; c_m_prev = c_m_next;
     }
-    s_ex[itn & 1][k][0][lane] = ph;
-    s_ex[itn & 1][k][1][lane] = c_id;
-    __syncthreads();
     // ---- B (second half): arg-min over [identity(+1), identity(-1), reprojection(+1), reprojection(-1)] ----------
     float ws_ = 0.f, gf = 0.f;
     if (rowB) {
-      const float ph_o = s_ex[itn & 1][1 - k][0][lane], id_o = s_ex[itn & 1][1 - k][1][lane];
+      s_ex[par][k][0][lane] = ph;
+      s_ex[par][k][1][lane] = c_id;
+      __syncthreads();
+      const float ph_o = s_ex[par][1 - k][0][lane], id_o = s_ex[par][1 - k][1][lane];
       const float p0 = k == 0 ? ph : ph_o, p1 = k == 0 ? ph_o : ph;
       float best;
       int arg;
@@ -1118,39 +1110,37 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
       }
       if (centre) {
         if (k == 0 && p.accum != nullptr) acc_num = fmaf(best, c_m, acc_num);
-        if (arg == k && (!overlap || valid_prev)) {
+        if (arg == k && (!overlap || valid_c)) {
           gf = gbase * c_m * c_gate;
           ws_ = (0.85f / 3.f) * gf;
         }
       }
     }
     // ---- C: adjoint of the 3x3 box filter over the OWNED centres, chain to the depth at row yq = yy - 2 ----------
-    // (rows in which no lane of the warp won for three centre rows carry no gradient: the whole phase is skipped)
-    const bool any_w = __any_sync(0xffffffffu, ws_ != 0.f);
-    float hw[9];
-    if (any_w) {
+    // (rows in which no lane of the warp won carry no gradient: the products are skipped)
+    if (rowB && __any_sync(0xffffffffu, ws_ != 0.f)) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         // (halo lanes 0 and 31 hold w = 0 and a shuffle from outside the warp returns the lane's own value: no edge case)
         const float w0 = ws_ * da[c], w1 = ws_ * db[c], w2 = ws_ * dc[c];
-        hw[c] = __shfl_up_sync(0xffffffffu, w0, 1) + w0 + __shfl_down_sync(0xffffffffu, w0, 1);
-        hw[3 + c] = __shfl_up_sync(0xffffffffu, w1, 1) + w1 + __shfl_down_sync(0xffffffffu, w1, 1);
-        hw[6 + c] = __shfl_up_sync(0xffffffffu, w2, 1) + w2 + __shfl_down_sync(0xffffffffu, w2, 1);
+        gcur[c] = __shfl_up_sync(0xffffffffu, w0, 1) + w0 + __shfl_down_sync(0xffffffffu, w0, 1);
+        gcur[3 + c] = __shfl_up_sync(0xffffffffu, w1, 1) + w1 + __shfl_down_sync(0xffffffffu, w1, 1);
+        gcur[6 + c] = __shfl_up_sync(0xffffffffu, w2, 1) + w2 + __shfl_down_sync(0xffffffffu, w2, 1);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) hw[i] = 0.f;
+      for (int i = 0; i < 9; ++i) gcur[i] = 0.f;
     }
     if (rowC) {
       const int yq = yy - 2;
-      float(*slot)[32] = s_ring[k][(yq + 3) % 3];
+      float(*slot)[32] = s_ring[k][yq & 3];
       float gD = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float t = slot[c][lane], pr = slot[3 + c][lane];
         const float d = t - pr;
         const float sgn = (d > 0.f ? 1.f : 0.f) - (d < 0.f ? 1.f : 0.f);
-        float gp = fmaf(2.f * pr, g2[3 + c] + g1[3 + c] + hw[3 + c], fmaf(t, g2[6 + c] + g1[6 + c] + hw[6 + c], g2[c] + g1[c] + hw[c]));
+        float gp = fmaf(2.f * pr, gP[3 + c] + gcur[3 + c], fmaf(t, gP[6 + c] + gcur[6 + c], gP[c] + gcur[c]));
         gp = fmaf(-(0.15f / 3.f) * gf_prev, sgn, gp);
         gD = fmaf(gp, slot[6 + c][lane], gD);
       }
@@ -1169,16 +1159,26 @@ __global__ void __launch_bounds__(64, LOSS_PAIR_OCC) loss_pair_kernel(LossParams
       }
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { g2[i] = g1[i]; g1[i] = hw[i]; }
-    if (rowA) {
-#pragma unroll
-      for (int i = 0; i < 15; ++i) { h2[i] = h1[i]; h1[i] = h[i]; }
-      l1_prev = l1; valid_prev = valid; c_m_prev = c_m_next;
-    }
+    for (int i = 0; i < 9; ++i) gP[i] = gprev[i] + gcur[i];
     gf_prev = gf;
-#if LOSS_PAIR_PIPELINE
-    cur = nxt;
-#endif
+  };
+  using P0_ = std::integral_constant<int, 0>;
+  using P1_ = std::integral_constant<int, 1>;
+  iter(T_{}, F_{}, F_{}, P0_{}, y_first);
+  iter(T_{}, F_{}, F_{}, P1_{}, y_first + 1);
+  int yy = y_begin + 1;
+#pragma unroll 1
+  for (; yy + 1 <= y_end; yy += 2) {
+    iter(T_{}, T_{}, T_{}, P0_{}, yy);
+    iter(T_{}, T_{}, T_{}, P1_{}, yy + 1);
+  }
+  if (yy <= y_end) {                               // odd number of rows in the chunk: the buffers' roles stay alternating
+    iter(T_{}, T_{}, T_{}, P0_{}, yy);
+    iter(F_{}, F_{}, T_{}, P1_{}, yy + 1);
+    iter(F_{}, F_{}, T_{}, P0_{}, yy + 2);
+  } else {
+    iter(F_{}, F_{}, T_{}, P0_{}, yy);
+    iter(F_{}, F_{}, T_{}, P1_{}, yy + 1);
   }
   if (k == 0 && p.accum != nullptr) {
     const double n = warp_sum((double)acc_num);
