@@ -395,13 +395,13 @@ def main():
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                      "traffic": traffic, "peak_source": peak_src, "launches_timed": len(kern_us), "avg_launch_us": avg_us,
                      "algorithmic_bytes_per_launch": bytes_per_launch},
-        "roofline_conv": {"kernel": "conv_tc_kernel<3> (all forward convolutions of one step, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
+        "roofline_conv": {"kernel": "conv_halo_kernel<3,*> + conv_tc_kernel<3> (all forward convolutions of one step, tcgen05 implicit GEMM, 3 bf16 products per K-step)",
                           "bound": "tensor", "achieved": conv_tf, "peak": tf_peak, "unit": "TFLOP/s",
                           "frac": (conv_tf / tf_peak) if conv_tf else None, "us_per_step": fwd_us,
                           "algorithmic_flops_per_step": conv_flops, "flops_counted_from_launches": counted_flops,
                           "note": "useful fp32-equivalent FLOPs; the tensor pipe executes 3x as many (bf16x3 split)",
                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
-        "roofline_conv_encoder": {"kernel": f"conv_tc_kernel<3>, the {enc_n} convolutions of the ResNet encoder (forward)", "bound": "tensor",
+        "roofline_conv_encoder": {"kernel": f"conv_halo_kernel<3,4> + conv_tc_kernel<3>, the {enc_n} convolutions of the ResNet encoder (forward)", "bound": "tensor",
                                   "achieved": enc_tf, "achieved_on_pipe": (3 * enc_tf) if enc_tf else None, "peak": tf_peak, "unit": "TFLOP/s",
                                   "frac": (enc_tf / tf_peak) if enc_tf else None, "frac_on_pipe": (3 * enc_tf / tf_peak) if enc_tf else None,
                                   "us_per_step": enc_us, "algorithmic_flops_per_step": enc_flops,
@@ -412,11 +412,12 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2a":
         split = {}
-        rate, sec = oracle_step_rate(4, 2, 1, split)
+        # the same workload (B=12 per step), 1 warm-up + 8 timed full steps: ~10-15 s of CPU work on the box's host cores
+        rate, sec = oracle_step_rate(B_PER_GPU, 8, 1, split)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "B=4 of 12 triplets per step, 1 warm-up + 2 timed full steps (oracle/ = CPU restatement of the "
-                                          "reference in torch fp32, pinned by reference-generated goldens; not the reference package, "
-                                          "which does not travel to the GPU box)",
+                                "sample": f"B={B_PER_GPU} triplets per step (the bench workload), 1 warm-up + 8 timed full steps of {sec:.2f} s "
+                                          "(oracle/ = CPU restatement of the reference in torch fp32, pinned by reference-generated "
+                                          "goldens; not the reference package, which does not travel to the GPU box)",
                                 "seconds_per_step_split": split}
     print(json.dumps(line), flush=True)
     _finish(world)
