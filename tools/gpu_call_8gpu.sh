@@ -1,7 +1,7 @@
 #!/bin/bash
 # multi-GPU scaling of the default arm at N = $NGPU
 mkdir -p gpurun_out
-O=gpurun_out/r2s3
+O=gpurun_out/r2s4
 N=${NGPU:-8}
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > ${O}_n${N}.txt 2>&1
 tail -1 ${O}_n${N}.txt | python -c "
