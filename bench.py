@@ -233,8 +233,9 @@ def main():
         sys.path.insert(0, os.path.join(REPO, "tools"))
         import torch_reference_backend
         torch_reference_backend.enable()
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    tf32 = os.environ.get("FSNET_BENCH_TF32", "0") == "1"     # comparator only: what stock PyTorch does by default on this GPU class
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
     cfg = cfg_from_file(CONFIG)
     set_random_seed(123)
     model = build(**cfg.meta_arch)
@@ -419,8 +420,27 @@ def main():
                                           "(oracle/ = CPU restatement of the reference in torch fp32, pinned by reference-generated "
                                           "goldens; not the reference package, which does not travel to the GPU box)",
                                 "seconds_per_step_split": split}
+        # informational: the SAME module tree and loss kernels with the convolutions / BatchNorm / activations through stock PyTorch
+        # (cuDNN), eager, on this GPU -- fp32 as this arm computes, and TF32 as PyTorch runs convolutions by default
+        line["gpu_reference"] = gpu_reference(args)
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def gpu_reference(args):
+    import subprocess
+    out = {"what": "same modules, parameters and loss kernels; network arithmetic through torch.nn.functional / cuDNN (tools/torch_reference_backend.py), "
+                   "eager, batch resident in HBM; a comparator, not a product path"}
+    for name, flag in (("cudnn_fp32", "0"), ("cudnn_tf32", "1")):
+        try:
+            env = dict(os.environ, FSNET_BENCH_TF32=flag)
+            res = subprocess.run([sys.executable, os.path.abspath(__file__), "--backend", "torch", "--steps", "5", "--warmup", "3", "--no-cpu-baseline",
+                                  "--workload", args.workload], env=env, capture_output=True, text=True, timeout=300)
+            d = json.loads(res.stdout.strip().splitlines()[-1])
+            out[name] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"]}
+        except Exception as e:       # noqa: BLE001 -- informational leg: never fails the bench line
+            out[name] = {"unavailable": repr(e)[:200]}
+    return out
 
 
 def _finish(world):
