@@ -552,16 +552,20 @@ __global__ void weight_planes_kernel(const float* __restrict__ w, int Cout, int 
 // index across threads: [co][tap][ci] for the forward planes (hi, lo) and [ci][flipped tap][co] for the data gradient.
 // (The scalar version wrote the transposed layout with 2-byte scattered stores: 288 us per step at cfg2.)
 constexpr int kWpTile = 4608;                // floats of shared memory per brick
-__global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_weight_desc* __restrict__ table) {
-  __shared__ float s_w[kWpTile];
-  const fsnet_weight_desc d = table[blockIdx.y];
-  const int T = d.kh * d.kw;
-  const int CI_T = d.cin_pad < 32 ? d.cin_pad : 32;
+// (TT = taps as a compile-time constant for the 3x3 and 1x1 layers, 0 = run-time: with run-time divisors the index arithmetic --
+// six integer divisions per element -- made both batched re-layout kernels compute bound: 128 + 87 us per step for 117 + 102 MB)
+template <int TT>
+__device__ __forceinline__ void weight_planes_tiles(const fsnet_weight_desc& d, float* s_w) {
+  const int T = TT ? TT : d.kh * d.kw;
+  const int CI_T = d.cin_pad < 32 ? d.cin_pad : 32;          // 8, 16 or 32: a power of two
+  int cs = 0;
+  while ((1 << cs) < CI_T) ++cs;
   int CO_T = kWpTile / (CI_T * T);
   CO_T = CO_T > 16 ? 16 : (CO_T < 1 ? 1 : CO_T);
+  if (TT) CO_T = 16;                                         // 4608 / (32 * 9) = 16 and more for thinner layers
   if (CI_T * T > kWpTile) return;            // host guarantees this never happens (taps <= 49, CI_T <= 32)
   const int ci_tiles = (d.cin_pad + CI_T - 1) / CI_T, co_tiles = (d.cout_pad + CO_T - 1) / CO_T;
-  const int brick = CO_T * CI_T * T, run = CI_T * T;
+  const int brick = CO_T * CI_T * T;
   __nv_bfloat16* fh = (__nv_bfloat16*)d.fwd_hi;
   __nv_bfloat16* fl = (__nv_bfloat16*)d.fwd_lo;
   __nv_bfloat16* dg = (__nv_bfloat16*)d.dgrad_hi;
@@ -569,13 +573,13 @@ __global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_
     const int co0 = (tile / ci_tiles) * CO_T, ci0 = (tile % ci_tiles) * CI_T;
     __syncthreads();
     for (int i = threadIdx.x; i < brick; i += 256) {
-      const int co_l = i / run, rem = i - co_l * run, ci_l = rem / T;
+      const int q = i / T, co_l = q >> cs, ci_l = q & (CI_T - 1), rem = i - co_l * (CI_T * T);      // i = (co_l * CI_T + ci_l) * T + tap
       const int co = co0 + co_l, ci = ci0 + ci_l;
       s_w[i] = (co < d.cout && ci < d.cin) ? __ldg(d.w + ((size_t)co * d.cin + ci0) * T + rem) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < brick; i += 256) {         // forward layout: ci fastest
-      const int ci_l = i % CI_T, t2 = i / CI_T, tap = t2 % T, co_l = t2 / T;
+      const int ci_l = i & (CI_T - 1), t2 = i >> cs, co_l = t2 / T, tap = t2 - co_l * T;
       const int co = co0 + co_l, ci = ci0 + ci_l;
       if (co < d.cout_pad && ci < d.cin_pad) {
         const float v = s_w[(co_l * CI_T + ci_l) * T + tap];
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_
     }
     if (dg) {
       for (int i = threadIdx.x; i < brick; i += 256) {       // data-gradient layout: co fastest, taps flipped
-        const int co_l = i % CO_T, t2 = i / CO_T, tap = t2 % T, ci_l = t2 / T;
+        const int co_l = i % CO_T, t2 = i / CO_T, ci_l = t2 / T, tap = t2 - ci_l * T;
         const int co = co0 + co_l, ci = ci0 + ci_l;
         if (co < d.cout_pad && ci < d.cin_pad)
           dg[((size_t)ci * T + (T - 1 - tap)) * d.cout_pad + co] = __float2bfloat16_rn(s_w[(co_l * CI_T + ci_l) * T + tap]);
@@ -595,38 +599,57 @@ __global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_
     }
   }
 }
+__global__ void __launch_bounds__(256) weight_planes_batched_kernel(const fsnet_weight_desc* __restrict__ table) {
+  __shared__ float s_w[kWpTile];
+  const fsnet_weight_desc d = table[blockIdx.y];
+  const int T = d.kh * d.kw;
+  if (T == 9) weight_planes_tiles<9>(d, s_w);
+  else if (T == 1) weight_planes_tiles<1>(d, s_w);
+  else weight_planes_tiles<0>(d, s_w);
+}
 // All layers' accumulators -> parameter-gradient layout in one launch (blockIdx.y = layer): a [co tile][tap][ci tile]
 // brick of the padded fp32 accumulator [Cout_pad, KH, KW, Cin_pad] goes through shared memory and comes out as the
 // contiguous [co][ci][tap] run of the nn.Conv2d weight gradient.  Offsets are relative to the two base pointers, so the
 // table is static across steps.
-__global__ void __launch_bounds__(256) wgrad_to_param_batched_kernel(const fsnet_wgrad_desc* __restrict__ table,
-                                                                     const float* __restrict__ acc_base, float* __restrict__ grad_base) {
-  __shared__ float s_w[kWpTile];
-  const fsnet_wgrad_desc d = table[blockIdx.y];
-  const int T = d.kh * d.kw;
+template <int TT>
+__device__ __forceinline__ void wgrad_to_param_tiles(const fsnet_wgrad_desc& d, const float* __restrict__ acc_base, float* __restrict__ grad_base,
+                                                     float* s_w) {
+  const int T = TT ? TT : d.kh * d.kw;
   const int CI_T = d.cin_pad < 32 ? d.cin_pad : 32;
+  int cs = 0;
+  while ((1 << cs) < CI_T) ++cs;
   int CO_T = kWpTile / (CI_T * T);
   CO_T = CO_T > 16 ? 16 : (CO_T < 1 ? 1 : CO_T);
+  if (TT) CO_T = 16;
   if (CI_T * T > kWpTile) return;
   const int ci_tiles = (d.cin + CI_T - 1) / CI_T, co_tiles = (d.cout + CO_T - 1) / CO_T;
-  const int brick = CO_T * CI_T * T, run = CI_T * T;
+  const int brick = CO_T * CI_T * T;
   const float* acc = acc_base + d.acc_off;
   float* grad = grad_base + d.grad_off;
   for (int tile = blockIdx.x; tile < ci_tiles * co_tiles; tile += gridDim.x) {
     const int co0 = (tile / ci_tiles) * CO_T, ci0 = (tile % ci_tiles) * CI_T;
     __syncthreads();
     for (int i = threadIdx.x; i < brick; i += 256) {         // accumulator layout: ci fastest
-      const int ci_l = i % CI_T, t2 = i / CI_T, tap = t2 % T, co_l = t2 / T;
+      const int ci_l = i & (CI_T - 1), t2 = i >> cs, co_l = t2 / T, tap = t2 - co_l * T;
       const int co = co0 + co_l, ci = ci0 + ci_l;
       s_w[(co_l * CI_T + ci_l) * T + tap] = (co < d.cout && ci < d.cin) ? acc[((size_t)co * T + tap) * d.cin_pad + ci] : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < brick; i += 256) {         // parameter layout: (ci, tap) contiguous
-      const int co_l = i / run, rem = i - co_l * run, ci_l = rem / T;
+      const int q = i / T, co_l = q >> cs, ci_l = q & (CI_T - 1), rem = i - co_l * (CI_T * T);
       const int co = co0 + co_l, ci = ci0 + ci_l;
       if (co < d.cout && ci < d.cin) grad[((size_t)co * d.cin + ci0) * T + rem] = s_w[i];
     }
   }
+}
+__global__ void __launch_bounds__(256) wgrad_to_param_batched_kernel(const fsnet_wgrad_desc* __restrict__ table,
+                                                                     const float* __restrict__ acc_base, float* __restrict__ grad_base) {
+  __shared__ float s_w[kWpTile];
+  const fsnet_wgrad_desc d = table[blockIdx.y];
+  const int T = d.kh * d.kw;
+  if (T == 9) wgrad_to_param_tiles<9>(d, acc_base, grad_base, s_w);
+  else if (T == 1) wgrad_to_param_tiles<1>(d, acc_base, grad_base, s_w);
+  else wgrad_to_param_tiles<0>(d, acc_base, grad_base, s_w);
 }
 __global__ void wgrad_to_param_kernel(const float* __restrict__ acc, int Cout, int Cin, int KH, int KW, int Cout_pad, int Cin_pad,
                                       float* __restrict__ grad, int accumulate) {
