@@ -6,6 +6,7 @@
 // buffer with a one-pixel ring (replicate padding of the interior), so that tcgen05 convolutions read
 // it directly with TMA.  All views are described by fsnet_view (include/fsnet_b200.h).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace fsnet {
@@ -670,6 +671,13 @@ inline unsigned blocks_for(size_t total, int threads = 256) { return (unsigned)(
 
 using namespace fsnet;
 
+// blocks per layer of the two batched re-layout kernels (blockIdx.y = layer; blocks of small layers exit at once)
+static unsigned relayout_grid_x() {
+  static int g = 0;
+  if (!g) { const char* e = getenv("FSNET_RELAYOUT_GRID"); g = e ? atoi(e) : 148; if (g < 1) g = 148; }
+  return (unsigned)g;
+}
+
 extern "C" int fsnet_image_to_planes_ring(const float* img, int C, const fsnet_view* dst, int zero_ring, void* stream) {
   FSNET_REQUIRE(img && dst && dst->ptr && C <= dst->c, "fsnet_image_to_planes: bad arguments");
   FSNET_REQUIRE(dst->c % 8 == 0 && dst->c_off == 0 && dst->c == dst->c_total, "fsnet_image_to_planes: destination must be a whole buffer with channels % 8 == 0");
@@ -830,7 +838,7 @@ extern "C" int fsnet_weight_planes(const float* w, int Cout, int Cin, int KH, in
 
 extern "C" int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device, int n_layers, void* stream) {
   FSNET_REQUIRE(table_device && n_layers > 0, "fsnet_weight_planes_batched: bad arguments");
-  dim3 grid(148, n_layers);
+  dim3 grid(relayout_grid_x(), n_layers);
   weight_planes_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_device);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
@@ -839,7 +847,7 @@ extern "C" int fsnet_weight_planes_batched(const fsnet_weight_desc* table_device
 extern "C" int fsnet_wgrad_to_param_batched(const fsnet_wgrad_desc* table_device, int n_layers, const float* acc_base, float* grad_base,
                                             void* stream) {
   FSNET_REQUIRE(table_device && n_layers > 0 && acc_base && grad_base, "fsnet_wgrad_to_param_batched: bad arguments");
-  dim3 grid(148, n_layers);
+  dim3 grid(relayout_grid_x(), n_layers);
   wgrad_to_param_batched_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_device, acc_base, grad_base);
   FSNET_LAUNCH_OK();
   return FSNET_OK;
