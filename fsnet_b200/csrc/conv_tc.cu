@@ -18,6 +18,10 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 =
 // epilogue (TMEM lane quadrant = warp_id % 4, two warps per quadrant on alternate 16-column groups).
+//
+// Three kernels in this file: conv_tc_kernel (the per-tap scheme above: stem, stride-2 and 1x1 layers, small maps; optional
+// cluster multicast), conv_halo_kernel (every 3x3 / stride-1 layer: one halo tile per chunk feeds all nine taps through shifted
+// operand descriptors, weights in their own ring or resident) and wgrad_tc_kernel (weight gradient, MN-major operands).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
