@@ -251,6 +251,12 @@ def test_whole_training_step_through_the_executor_under_emulation(emulated, gold
     if topo.distill:
         assert {f"distilation/{s}" for s in topo.scales} <= set(ret["loss_dict"])
         assert all(torch.equal(teacher_before[k], v) for k, v in model.teacher_net.state_dict().items())
+    # the executor hands its gradients to autograd without keeping a reference: p.grad ARE the views of the per-network flat
+    # buffers (plus the shared all-zero buffer of BatchNorm-cancelled conv biases), not one private clone per parameter --
+    # which is what makes the data-parallel exchange a single in-place all-reduce (hooks/training.py::sync_gradients)
+    # (the PoseNet runs twice per step with shared weights: autograd sums its two gradients into fresh tensors first)
+    storages = {p.grad.untyped_storage().data_ptr() for k, p in params.items() if p.grad is not None and "pose" not in k}
+    assert len(storages) <= 4, len(storages)
 
 
 @pytest.mark.parametrize("H,W,B,scales,fisheye", [(40, 72, 2, (0, 1, 2), False), (24, 40, 1, (0, 3), False), (56, 104, 1, (0, 1), True)])
