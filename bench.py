@@ -280,7 +280,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, use_host, hook=hook, head_start=False):
+    pinned_f32 = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()} if stage is not None else None
+
+    def timed(n, use_host, hook=hook, head_start=False, pinned=pinned, stage=stage):
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
@@ -328,6 +330,11 @@ def main():
     launches = launches_per_step * args.steps
     timed(2, True)
     ms_e2e, last_loss = timed(args.steps, True)
+    # informational: the same e2e leg fed with what the reference's loader delivers (six float32 images + fp64 mask per sample)
+    ms_e2e_f32 = None
+    if pinned_f32 is not None:
+        timed(2, True, pinned=pinned_f32, stage=None)
+        ms_e2e_f32, _ = timed(args.steps, True, pinned=pinned_f32, stage=None)
     clocks = sampler.stop() if rank == 0 else None          # sampled over both timed regions (value and e2e)
     # roofline leg: the same training steps run eagerly so that the kernels can be bracketed with CUDA events on their
     # stream (events cannot be read back from inside a replayed graph)
@@ -408,7 +415,11 @@ def main():
                                   "us_per_step": enc_us, "algorithmic_flops_per_step": enc_flops,
                                   "note": "achieved = useful fp32-equivalent FLOPs; on_pipe = x3 (three bf16 products per K-step)"},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+                "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss,
+                "float32_input": (None if ms_e2e_f32 is None else
+                                  {"value": imgs / (ms_e2e_f32 / 1e3), "ms_per_step": ms_e2e_f32 / args.steps,
+                                   "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v)),
+                                   "note": "informational: the same leg uploading the reference loader's float32 tensors"})},
         "gpu_launches": launches, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2a":
